@@ -1,0 +1,93 @@
+/* b200blas.h -- the C ABI of libb200blas.so, a B200-native drop-in for the BLAS hot path of
+ * Prince781/libgpublas ("blas2cuda").  Plain C: pointers and sizes only.
+ *
+ * The library is meant to be LD_PRELOADed (reference scripts/blas2cuda.sh:27, tests/netlib/
+ * test.py:28) or linked ahead of the CPU BLAS.  It exports exactly the symbols the reference's
+ * interposer exports for this path, with the CPU BLAS's own (gfortran) calling convention:
+ *
+ *   1. Fortran BLAS symbols  (reference blas.h:202-314, blas_level3/[star].cc F77_xxx wrappers;
+ *      Level 1/2 follow the CPU BLAS ABI because blas.h:11-198 is unreliable)
+ *   2. CBLAS symbols         (reference cblas.h:46-824; complex scalars by pointer as in
+ *      standard CBLAS, not by value as cblas.h:662-677 mis-declares)
+ *   3. allocator symbols     (reference lib/obj_tracker.c:789,842,902,948)
+ *   4. a small control API   (b200blas_[star]) for embedding, tests and benchmarks.
+ *
+ * Operands may live in: tracked managed memory (from the interposed malloc/calloc), any other
+ * CUDA managed or device memory (used in place), or ordinary host memory (staged).  Every entry
+ * point returns only after results are visible to the CPU (unless b200blas_set_sync(0)).
+ * Illegal arguments call xerbla_(SRNAME,INFO) with netlib numbering and return; device failures
+ * print to fd 2 and abort() (reference runtime.c:208-213).  There is no CPU fallback.
+ */
+#ifndef B200BLAS_H
+#define B200BLAS_H
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { float re, im; } b200_c32;     /* == float _Complex, interleaved (re,im) */
+typedef struct { double re, im; } b200_c64;    /* == double _Complex */
+
+/* ------------------------------ 1. Fortran BLAS ABI ------------------------------ */
+/* Level 3 -- reference blas.h:202-215 (gemm), :268-274 (syrk), :290-301 (trmm), :303-314 (trsm),
+ * :254-266 (symm), :276-288 (syr2k), :217-227 (hemm), :230-239 (herk), :242-252 (her2k) */
+B200_API void sgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k, const float* alpha, const float* a, const int* lda, const float* b, const int* ldb, const float* beta, float* c, const int* ldc);
+B200_API void dgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k, const double* alpha, const double* a, const int* lda, const double* b, const int* ldb, const double* beta, double* c, const int* ldc);
+B200_API void cgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k, const b200_c32* alpha, const b200_c32* a, const int* lda, const b200_c32* b, const int* ldb, const b200_c32* beta, b200_c32* c, const int* ldc);
+B200_API void zgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k, const b200_c64* alpha, const b200_c64* a, const int* lda, const b200_c64* b, const int* ldb, const b200_c64* beta, b200_c64* c, const int* ldc);
+
+/* ------------------------------ 2. CBLAS ABI ------------------------------ */
+/* enums: reference cblas.h:21-25 */
+enum CBLAS_ORDER { CblasRowMajor = 101, CblasColMajor = 102 };
+typedef enum CBLAS_ORDER CBLAS_LAYOUT;
+enum CBLAS_TRANSPOSE { CblasNoTrans = 111, CblasTrans = 112, CblasConjTrans = 113 };
+enum CBLAS_UPLO { CblasUpper = 121, CblasLower = 122 };
+enum CBLAS_DIAG { CblasNonUnit = 131, CblasUnit = 132 };
+enum CBLAS_SIDE { CblasLeft = 141, CblasRight = 142 };
+typedef size_t CBLAS_INDEX;
+
+B200_API void cblas_sgemm(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE transa, enum CBLAS_TRANSPOSE transb, int m, int n, int k, float alpha, const float* a, int lda, const float* b, int ldb, float beta, float* c, int ldc);
+B200_API void cblas_dgemm(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE transa, enum CBLAS_TRANSPOSE transb, int m, int n, int k, double alpha, const double* a, int lda, const double* b, int ldb, double beta, double* c, int ldc);
+B200_API void cblas_cgemm(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE transa, enum CBLAS_TRANSPOSE transb, int m, int n, int k, const void* alpha, const void* a, int lda, const void* b, int ldb, const void* beta, void* c, int ldc);
+B200_API void cblas_zgemm(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE transa, enum CBLAS_TRANSPOSE transb, int m, int n, int k, const void* alpha, const void* a, int lda, const void* b, int ldb, const void* beta, void* c, int ldc);
+
+/* ------------------------------ 3. allocator symbols ------------------------------ */
+/* malloc / calloc / realloc / free are exported with their libc prototypes (<stdlib.h>);
+ * reference lib/obj_tracker.c:789 (malloc), :842 (calloc), :902 (realloc), :948 (free). */
+
+/* ------------------------------ 4. control API ------------------------------ */
+struct b200blas_stats {
+    uint64_t hits, misses;           /* operands used in place / staged (reference b2c_hits, b2c_misses) */
+    uint64_t calls, h2d_bytes, d2h_bytes, prefetch_bytes;
+    uint64_t managed_allocs, managed_frees, managed_bytes_live;
+};
+typedef void (*b200blas_xerbla_fn)(const char* srname, int* info, size_t srname_len);
+
+B200_API int b200blas_version(void);
+B200_API void b200blas_set_options(const char* opts);            /* same grammar as BLAS2CUDA_OPTIONS */
+B200_API void b200blas_set_xerbla(b200blas_xerbla_fn fn);        /* NULL: look xerbla_ up by symbol (default) */
+B200_API void b200blas_set_stream(void* cuda_stream);            /* run this thread's calls on a caller stream (0 = legacy default stream) */
+B200_API void b200blas_reset_stream(void);                       /* back to the library's own per-thread stream */
+B200_API void b200blas_set_sync(int on);                         /* 0: do not wait for completion before returning */
+B200_API void b200blas_synchronize(void);
+B200_API const char* b200blas_last_variant(void);                /* kernel variant the calling thread's last call used */
+B200_API void b200blas_force_variant(const char* name);          /* NULL/"auto": size-based selection */
+B200_API void b200blas_get_stats(struct b200blas_stats* out);
+B200_API void* b200blas_malloc_managed(size_t bytes);            /* tracked managed block (what malloc() hands out) */
+B200_API void b200blas_free_managed(void* p);
+B200_API int b200blas_is_tracked(const void* p);
+B200_API int b200blas_device_count(void);
+B200_API void b200blas_entry(void);                              /* ELF entry: prints option help (reference entry.c) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200BLAS_H */

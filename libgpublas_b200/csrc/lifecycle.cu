@@ -1,0 +1,146 @@
+// lifecycle.cu -- library constructor/destructor, BLAS2CUDA_OPTIONS, statistics.csv and the
+// control half of the C ABI (reference blas2cuda.c:59-124, :178-277; entry.c:4-11).
+#include "abi_common.h"
+#include "../../include/b200blas.h"
+#include <dlfcn.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <unistd.h>
+
+using namespace b200;
+
+static void print_help() {
+    b200_writef(STDERR_FILENO,
+        "b200blas options (set BLAS2CUDA_OPTIONS):\n"
+        "   You can chain these options with a semicolon (;)\n"
+        "   help            -- print help\n"
+        "   debug_execfail  -- debug kernel failures (synchronise and check after every call)\n"
+        "   debug_exec      -- debug kernel invocations (one line per BLAS call: shapes, variant)\n"
+        "   trace_copy      -- trace copies between CPU and GPU\n"
+        "   heuristic=<val> -- one of: 'size' (default), 'random', 'true', 'false', or:\n"
+        "                      'oracle:<filename>', where <filename> is the name of an object trace\n"
+        "   threshold=<n>   -- heuristic=size: allocations of >= n bytes become managed (default 65536)\n"
+        "   variant=<name>  -- force a kernel variant: generic_tile | dmma_tma | dmma_ldg | auto\n"
+        "   devices=<n>     -- GPUs used for partitioned Level-3 calls (default 1)\n"
+        "   sync=<0|1>      -- block until results are visible before returning (default 1)\n"
+        "   prefetch=<0|1>  -- cudaMemPrefetchAsync managed operands to the device (default 1)\n");
+}
+
+static int variant_from_name(const char* n) {
+    if (!strcmp(n, "generic_tile")) return VAR_GENERIC_TILE;
+    if (!strcmp(n, "dmma_tma")) return VAR_DMMA_TMA;
+    if (!strcmp(n, "dmma_ldg")) return VAR_DMMA_LDG;
+    if (!strcmp(n, "tf32x3_tcgen05")) return VAR_TF32X3_TCGEN05;
+    return VAR_NONE;
+}
+
+static void set_options(const char* env) {
+    if (!env) return;
+    char* copy = strdup(env);
+    char* save = nullptr;
+    for (char* opt = strtok_r(copy, ";", &save); opt; opt = strtok_r(nullptr, ";", &save)) {
+        if (!strcmp(opt, "help")) print_help();
+        else if (!strcmp(opt, "debug_execfail")) g_opts.debug_execfail = true;
+        else if (!strcmp(opt, "debug_exec")) g_opts.debug_exec = true;
+        else if (!strcmp(opt, "trace_copy")) g_opts.trace_copy = true;
+        else if (!strncmp(opt, "heuristic=", 10)) {
+            const char* h = opt + 10;
+            if (!strncmp(h, "random", 6)) tracker_set_heuristic(B200_H_RANDOM);
+            else if (!strncmp(h, "true", 4)) tracker_set_heuristic(B200_H_TRUE);
+            else if (!strncmp(h, "false", 5)) tracker_set_heuristic(B200_H_FALSE);
+            else if (!strncmp(h, "size", 4)) tracker_set_heuristic(B200_H_SIZE);
+            else if (!strncmp(h, "oracle:", 7)) {
+                if (!tracker_load_oracle_file(h + 7)) {
+                    b200_writef(STDERR_FILENO, "b200blas:oracle: failed to load '%s'\n", h + 7);
+                    abort();
+                }
+                tracker_set_heuristic(B200_H_ORACLE);
+            } else {
+                b200_writef(STDERR_FILENO, "b200blas: unsupported heuristic '%s'\n", h);
+                abort();
+            }
+            b200_writef(STDERR_FILENO, "b200blas: selecting heuristic %s\n", h);
+        }
+        else if (!strncmp(opt, "threshold=", 10)) { g_opts.managed_threshold = strtoull(opt + 10, nullptr, 0); tracker_set_threshold(g_opts.managed_threshold); }
+        else if (!strncmp(opt, "variant=", 8)) force_variant = variant_from_name(opt + 8);
+        else if (!strncmp(opt, "devices=", 8)) g_opts.devices = atoi(opt + 8);
+        else if (!strncmp(opt, "sync=", 5)) g_opts.sync = atoi(opt + 5) != 0;
+        else if (!strncmp(opt, "prefetch=", 9)) g_opts.prefetch = atoi(opt + 9) != 0;
+        else b200_writef(STDERR_FILENO, "b200blas: unknown option '%s'. Set BLAS2CUDA_OPTIONS=help.\n", opt);
+    }
+    free(copy);
+}
+
+// Constructor: cheap on purpose.  The reference creates the cuBLAS handle and prints device
+// properties in every process that loads it (blas2cuda.c:178-242); here the device comes up lazily
+// at the first BLAS call or first managed allocation, so preloading into `sh`, `make`, ... is free.
+__attribute__((constructor)) static void b200blas_ctor() {
+    set_options(getenv("BLAS2CUDA_OPTIONS"));
+    tracker_set_tracking(1);
+}
+
+__attribute__((destructor)) static void b200blas_dtor() {
+    tracker_set_tracking(0);
+    if (g_stats.calls == 0) return;
+    // reference blas2cuda.c:266-273: ./statistics.csv with the hit/miss counters
+    const char* path = getenv("B200BLAS_STATS_FILE");
+    if (!path) path = "statistics.csv";
+    FILE* f = fopen(path, "w");
+    if (f) {
+        fprintf(f, "Hits, Misses, Calls, H2D bytes, D2H bytes, Prefetched bytes\n%llu, %llu, %llu, %llu, %llu, %llu\n",
+                g_stats.hits, g_stats.misses, g_stats.calls, g_stats.h2d_bytes, g_stats.d2h_bytes, g_stats.prefetch_bytes);
+        fclose(f);
+    }
+}
+
+// ---- xerbla plumbing ----
+static b200blas_xerbla_fn g_xerbla_override = nullptr;
+namespace b200 {
+void call_xerbla(const char* routine, int info) {
+    char srname[8];
+    int i = 0;
+    for (; i < 6 && routine[i] && routine[i] != '_'; i++) {
+        char c = routine[i];
+        srname[i] = (c >= 'a' && c <= 'z') ? c - 32 : c;
+    }
+    for (; i < 6; i++) srname[i] = ' ';
+    srname[6] = 0;
+    if (g_xerbla_override) { g_xerbla_override(srname, &info, 6); return; }
+    typedef void (*xerbla_t)(const char*, int*, size_t);
+    xerbla_t x = (xerbla_t)dlsym(RTLD_DEFAULT, "xerbla_");
+    if (x) { x(srname, &info, 6); return; }
+    // netlib XERBLA's message; netlib stops the program, the CPU BLAS in this image returns
+    b200_writef(STDERR_FILENO, " ** On entry to %s parameter number %2d had an illegal value\n", srname, info);
+}
+}  // namespace b200
+
+extern "C" {
+
+int b200blas_version(void) { return 100; }
+void b200blas_set_xerbla(b200blas_xerbla_fn fn) { g_xerbla_override = fn; }
+void b200blas_set_stream(void* stream) { set_thread_stream((cudaStream_t)stream, true); }
+void b200blas_reset_stream(void) { set_thread_stream(nullptr, false); }
+void b200blas_set_sync(int on) { g_opts.sync = on != 0; }
+void b200blas_set_options(const char* opts) { set_options(opts); }
+const char* b200blas_last_variant(void) { return variant_name(last_variant); }
+void b200blas_force_variant(const char* name) { force_variant = name ? variant_from_name(name) : VAR_NONE; }
+void b200blas_get_stats(struct b200blas_stats* out) {
+    out->hits = g_stats.hits; out->misses = g_stats.misses; out->calls = g_stats.calls;
+    out->h2d_bytes = g_stats.h2d_bytes; out->d2h_bytes = g_stats.d2h_bytes; out->prefetch_bytes = g_stats.prefetch_bytes;
+    b200_tracker_stats ts; tracker_get_stats(&ts);
+    out->managed_allocs = ts.managed_allocs; out->managed_frees = ts.managed_frees; out->managed_bytes_live = ts.managed_bytes_live;
+}
+void* b200blas_malloc_managed(size_t bytes) { TrackerGuard g; return tracker_alloc_managed(bytes); }
+void b200blas_free_managed(void* p) { TrackerGuard g; tracker_free_managed(p); }
+int b200blas_is_tracked(const void* p) { return tracker_lookup(p, nullptr, nullptr); }
+int b200blas_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+void b200blas_synchronize(void) { B200_CUDA(cudaStreamSynchronize(current_stream())); }
+
+// Running the shared object itself prints the option help (reference entry.c:4-11, meson.build:25).
+void b200blas_entry(void) {
+    print_help();
+    _exit(0);
+}
+
+}  // extern "C"

@@ -1,0 +1,268 @@
+// runtime.cu -- see runtime.h.
+#include "runtime.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "tracker.h"
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unistd.h>
+#include <sys/syscall.h>
+
+extern "C" void b200_writef(int fd, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    int n = vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (n < 0) return;
+    if (n > (int)sizeof buf - 1) n = sizeof buf - 1;
+    syscall(SYS_write, fd, buf, (size_t)n);
+}
+
+namespace b200 {
+
+Options g_opts;
+Stats g_stats = {0, 0, 0, 0, 0, 0};
+thread_local int last_variant = VAR_NONE;
+int force_variant = VAR_NONE;
+
+const char* variant_name(int v) {
+    switch (v) {
+        case VAR_SCALE_ONLY: return "scale_only";
+        case VAR_GENERIC_TILE: return "generic_tile";
+        case VAR_DMMA_TMA: return "dmma_tma";
+        case VAR_DMMA_LDG: return "dmma_ldg";
+        case VAR_TF32X3_TCGEN05: return "tf32x3_tcgen05";
+        default: return "none";
+    }
+}
+
+void fatal(const char* what, const char* file, int line, const char* detail) {
+    b200_writef(STDERR_FILENO, "b200blas: fatal: %s failed at %s:%d: %s\n", what, file, line, detail ? detail : "");
+    abort();
+}
+
+// ---------------------------------------------------------------------------------------------
+static std::once_flag g_init_once;
+static bool g_ready = false;
+static int g_sms = 0;
+static int g_device = 0;
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn g_encode = nullptr;
+
+static void do_init() {
+    TrackerGuard guard;   // CUDA's own allocations must not be routed to managed memory
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        fatal("cudaGetDeviceCount", __FILE__, __LINE__,
+              "no CUDA device: libb200blas has no CPU fallback (by design); unset LD_PRELOAD to run on the CPU BLAS");
+    const char* dev_env = getenv("B200BLAS_DEVICE");
+    g_device = dev_env ? atoi(dev_env) : -1;
+    if (g_device < 0) {
+        // keep whatever device the process already selected (torch.cuda.set_device under torchrun)
+        B200_CUDA(cudaGetDevice(&g_device));
+    } else {
+        B200_CUDA(cudaSetDevice(g_device));
+    }
+    cudaDeviceProp prop;
+    B200_CUDA(cudaGetDeviceProperties(&prop, g_device));
+    g_sms = prop.multiProcessorCount;
+    if (prop.major != 10)
+        b200_writef(STDERR_FILENO, "b200blas: warning: device %s is sm_%d%d; kernels are built for sm_100a only\n",
+                    prop.name, prop.major, prop.minor);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+        g_encode = (encode_tiled_fn)fn;
+    if (g_opts.debug_exec)
+        b200_writef(STDERR_FILENO, "b200blas: device %d %s, %d SMs, %zu MiB, concurrentManagedAccess=%d, tma=%d\n",
+                    g_device, prop.name, g_sms, prop.totalGlobalMem >> 20, prop.concurrentManagedAccess, g_encode != nullptr);
+    g_ready = true;
+}
+
+void ensure_init() { std::call_once(g_init_once, do_init); }
+bool device_ready() { return g_ready; }
+int sm_count() { return g_sms; }
+bool tma_available() { return g_encode != nullptr; }
+
+bool encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, void* base, const cuuint64_t* gdim,
+                       const cuuint64_t* gstride_bytes, const cuuint32_t* box, const cuuint32_t* estride,
+                       CUtensorMapSwizzle swz) {
+    if (!g_encode) return false;
+    CUresult r = g_encode(map, dt, (cuuint32_t)rank, base, gdim, gstride_bytes, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct ThreadCtx {
+    cudaStream_t stream = nullptr;      // library-owned, non-blocking
+    cudaStream_t ext = nullptr;         // caller-provided (b200blas_set_stream)
+    bool external_stream = false;
+    char* ws = nullptr; size_t ws_cap = 0, ws_used = 0;
+    // blocks retired because the workspace had to grow mid-call; freed at the next reset
+    void* retired[16]; int nretired = 0;
+    void* pinned = nullptr; void* dscalar = nullptr;
+};
+static thread_local ThreadCtx t_ctx;
+
+cudaStream_t current_stream() {
+    ensure_init();
+    if (t_ctx.external_stream) return t_ctx.ext;
+    if (!t_ctx.stream) {
+        TrackerGuard guard;
+        B200_CUDA(cudaSetDevice(g_device));
+        B200_CUDA(cudaStreamCreateWithFlags(&t_ctx.stream, cudaStreamNonBlocking));
+    }
+    return t_ctx.stream;
+}
+void set_thread_stream(cudaStream_t s, bool external) {
+    ensure_init();
+    t_ctx.ext = s;               // may legitimately be 0: the legacy default stream
+    t_ctx.external_stream = external;
+}
+
+void ws_reset() {
+    ThreadCtx& c = t_ctx;
+    if (c.nretired) {
+        TrackerGuard guard;
+        B200_CUDA(cudaStreamSynchronize(current_stream()));
+        for (int i = 0; i < c.nretired; i++) cudaFree(c.retired[i]);
+        c.nretired = 0;
+    }
+    c.ws_used = 0;
+}
+void* ws_alloc(size_t bytes) {
+    ThreadCtx& c = t_ctx;
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (c.ws_used + bytes > c.ws_cap) {
+        TrackerGuard guard;
+        // grow: earlier sub-allocations of this call may still be in use by queued work, so the old
+        // block is retired (freed at the next call) rather than freed now.
+        size_t ncap = c.ws_cap ? c.ws_cap : (size_t)64 << 20;
+        while (ncap < bytes + (c.ws ? 0 : 0)) ncap *= 2;
+        if (c.ws) {
+            if (c.nretired == 16) fatal("workspace growth", __FILE__, __LINE__, "too many regrowths in one call");
+            c.retired[c.nretired++] = c.ws;
+        }
+        B200_CUDA(cudaMalloc((void**)&c.ws, ncap));
+        c.ws_cap = ncap; c.ws_used = 0;
+    }
+    void* p = c.ws + c.ws_used;
+    c.ws_used += bytes;
+    return p;
+}
+void* pinned_scalar() {
+    if (!t_ctx.pinned) { TrackerGuard guard; B200_CUDA(cudaMallocHost(&t_ctx.pinned, 256)); }
+    return t_ctx.pinned;
+}
+void* device_scalar() {
+    if (!t_ctx.dscalar) { TrackerGuard guard; B200_CUDA(cudaMalloc(&t_ctx.dscalar, 256)); }
+    return t_ctx.dscalar;
+}
+
+void finish_call() {
+    // BLAS is synchronous: results must be visible to the CPU when the symbol returns.  The
+    // reference skips this on concurrentManagedAccess devices (runtime.h:33-34) and so races
+    // with the caller on every modern GPU; here the per-thread stream is drained unless the
+    // caller opted out (device-resident pipelines, b200blas_set_sync(0)).
+    if (g_opts.sync) {
+        B200_CUDA(cudaStreamSynchronize(current_stream()));
+    } else if (g_opts.debug_execfail) {
+        B200_CUDA(cudaStreamSynchronize(current_stream()));
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) fatal("kernel launch", __FILE__, __LINE__, cudaGetErrorString(e));
+    __atomic_fetch_add(&g_stats.calls, 1ull, __ATOMIC_RELAXED);
+}
+
+void log_exec(const char* routine, const char* fmt, ...) {
+    if (!g_opts.debug_exec) return;
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    b200_writef(STDERR_FILENO, "b200blas: %s %s variant=%s\n", routine, buf, variant_name(last_variant));
+}
+
+// ---------------------------------------------------------------------------------------------
+Residency classify(const void* p) {
+    // 1. the tracker knows every managed block it handed out (reference obj_tracker_objinfo_subptr,
+    //    lib/obj_tracker.c:602-637) -- a lock-free range lookup, no CUDA call
+    if (tracker_lookup(p, nullptr, nullptr)) return RES_MANAGED;
+    // 2. anything else: ask the driver (device pointers from cudaMalloc/torch, managed memory
+    //    allocated by the application itself, pinned host memory)
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return RES_HOST_PAGEABLE; }
+    switch (at.type) {
+        case cudaMemoryTypeDevice: return RES_DEVICE;
+        case cudaMemoryTypeManaged: return RES_MANAGED;
+        case cudaMemoryTypeHost: return RES_HOST_PINNED;
+        default: return RES_HOST_PAGEABLE;
+    }
+}
+
+Operand::Operand(const void* host, int64_t rows, int64_t cols, int64_t ld, size_t elem, int access)
+    : host_(host), dev_(nullptr), rows_(rows), cols_(cols), ld_(ld), dld_(ld), elem_(elem), access_(access),
+      staged_(false), done_(false) {
+    if (rows <= 0 || cols <= 0 || host == nullptr) { dev_ = (void*)host; done_ = true; return; }
+    Residency r = classify(host);
+    cudaStream_t s = current_stream();
+    if (r == RES_DEVICE || r == RES_MANAGED) {
+        dev_ = (void*)host;
+        __atomic_fetch_add(&g_stats.hits, 1ull, __ATOMIC_RELAXED);
+        if (r == RES_MANAGED && g_opts.prefetch) {
+            // bulk-migrate instead of faulting page by page; no-op when already resident
+            size_t bytes = (size_t)((cols - 1) * ld + rows) * elem;
+            if (bytes >= (size_t)2 << 20) {
+                TrackerGuard guard;
+                int dev; cudaGetDevice(&dev);
+                if (cudaMemPrefetchAsync(host, bytes, dev, s) == cudaSuccess)
+                    __atomic_fetch_add(&g_stats.prefetch_bytes, (unsigned long long)bytes, __ATOMIC_RELAXED);
+                else
+                    cudaGetLastError();
+            }
+        }
+        done_ = true;   // nothing to write back
+        return;
+    }
+    // miss: stage a compact copy.  Leading dimension rounded so that rows*elem is a multiple of 16 B
+    // (TMA-addressable) -- an unaligned host lda never forces the slow loader.
+    __atomic_fetch_add(&g_stats.misses, 1ull, __ATOMIC_RELAXED);
+    staged_ = true;
+    int64_t per16 = 16 / (int64_t)elem; if (per16 < 1) per16 = 1;
+    dld_ = (rows + per16 - 1) / per16 * per16;
+    dev_ = ws_alloc((size_t)dld_ * cols * elem);
+    if (access & ACC_IN) {
+        TrackerGuard guard;
+        B200_CUDA(cudaMemcpy2DAsync(dev_, (size_t)dld_ * elem, host, (size_t)ld * elem, (size_t)rows * elem, (size_t)cols,
+                                    cudaMemcpyHostToDevice, s));
+        __atomic_fetch_add(&g_stats.h2d_bytes, (unsigned long long)(rows * cols * elem), __ATOMIC_RELAXED);
+        if (g_opts.trace_copy)
+            b200_writef(STDOUT_FILENO, "b200blas: copy %zu B from %p (CPU) ---> %p (GPU)\n", (size_t)(rows * cols * elem), host, dev_);
+    }
+}
+
+void Operand::release() {
+    if (done_) return;
+    done_ = true;
+    if (staged_ && (access_ & ACC_OUT)) {
+        TrackerGuard guard;
+        B200_CUDA(cudaMemcpy2DAsync((void*)host_, (size_t)ld_ * elem_, dev_, (size_t)dld_ * elem_, (size_t)rows_ * elem_,
+                                    (size_t)cols_, cudaMemcpyDeviceToHost, current_stream()));
+        __atomic_fetch_add(&g_stats.d2h_bytes, (unsigned long long)(rows_ * cols_ * elem_), __ATOMIC_RELAXED);
+        if (g_opts.trace_copy)
+            b200_writef(STDOUT_FILENO, "b200blas: copy %zu B from %p (GPU) ---> %p (CPU)\n", (size_t)(rows_ * cols_ * elem_), dev_, host_);
+    }
+}
+
+}  // namespace b200

@@ -1,0 +1,72 @@
+// runtime.h -- host runtime of libb200blas: lazy device init, per-thread stream + workspace,
+// operand residency (the replacement for the reference's gpuptr<T>, runtime-mem.hpp:19-176, and
+// call_kernel, runtime.h:28-36), options and statistics (blas2cuda.c:59-124, :266-273).
+#pragma once
+#include <cuda_runtime_api.h>
+#include <cuda.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace b200 {
+
+struct Options {
+    bool debug_exec = false;       // reference key: log every kernel invocation
+    bool debug_execfail = false;   // reference key: sync + check after every launch
+    bool trace_copy = false;       // reference key: log host<->device copies
+    bool sync = true;              // block until results are visible before returning (BLAS semantics)
+    bool prefetch = true;          // cudaMemPrefetchAsync managed operands to the device
+    size_t managed_threshold = 64 * 1024;   // tracker: allocations >= this go to managed memory
+    int devices = 1;               // GPUs used by partitioned Level-3 calls
+    size_t multi_gpu_min_dim = 8192;
+};
+extern Options g_opts;
+
+struct Stats {
+    unsigned long long hits, misses;        // reference b2c_hits / b2c_misses (runtime-mem.hpp:83,112)
+    unsigned long long calls, h2d_bytes, d2h_bytes, prefetch_bytes;
+};
+extern Stats g_stats;
+
+void ensure_init();                 // idempotent, thread-safe; aborts if no CUDA device
+bool device_ready();                // true once ensure_init() has succeeded
+int sm_count();
+cudaStream_t current_stream();      // per-thread stream (or the one set by b200blas_set_stream)
+void set_thread_stream(cudaStream_t s, bool external);
+void finish_call();                 // the synchronous-return step (replaces call_kernel's tail)
+
+bool tma_available();
+bool encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, void* base, const cuuint64_t* gdim,
+                       const cuuint64_t* gstride_bytes, const cuuint32_t* box, const cuuint32_t* estride,
+                       CUtensorMapSwizzle swz);
+
+// Per-thread grow-only device scratch: bump allocator reset at the start of every BLAS call.
+void* ws_alloc(size_t bytes);       // 256-B aligned device memory valid until the call returns
+void ws_reset();
+void* pinned_scalar();              // 64 B of pinned host memory for scalar results (per thread)
+void* device_scalar();              // 64 B of device memory for scalar results (per thread)
+
+enum Access { ACC_IN = 1, ACC_OUT = 2, ACC_INOUT = 3 };
+enum Residency { RES_DEVICE = 0, RES_MANAGED = 1, RES_HOST_PINNED = 2, RES_HOST_PAGEABLE = 3 };
+Residency classify(const void* p);
+
+// A column-major matrix operand (vectors are 1 x n with ld = |inc|) made device-accessible.
+// Tracked-managed / device pointers are used in place (hit); host pointers are staged into the
+// workspace with a 2-D copy that also re-packs them to a TMA-friendly leading dimension (miss),
+// and written back on release if the access mode says so.
+class Operand {
+public:
+    Operand(const void* host, int64_t rows, int64_t cols, int64_t ld, size_t elem, int access);
+    void* dev() const { return dev_; }
+    int64_t ld() const { return dld_; }
+    void release();                 // enqueue write-back (if any); idempotent
+    bool staged() const { return staged_; }
+private:
+    const void* host_; void* dev_; int64_t rows_, cols_, ld_, dld_; size_t elem_; int access_; bool staged_, done_;
+};
+
+void log_exec(const char* routine, const char* fmt, ...);
+
+}  // namespace b200
+
+// async-signal-safe formatted write (reference common.h:15-28 writef): usable inside malloc
+extern "C" void b200_writef(int fd, const char* fmt, ...);

@@ -1,0 +1,250 @@
+// tracker.cpp -- (host-only translation unit: nvcc refuses to redefine malloc/free)
+// see tracker.h.  Differences from the reference, all on purpose:
+//  * the real allocator is reached through glibc's exported __libc_* entry points, not
+//    dlsym(RTLD_NEXT) at first use (obj_tracker.c:142-223), so there is no bootstrap recursion;
+//  * managed blocks carry no in-band header (the reference stores the size in an 8-byte header and
+//    returns base+8, blas2cuda.c:127-148, which breaks 16-byte alignment and therefore TMA):
+//    sizes live in the registry and the caller gets the cudaMallocManaged base itself;
+//  * the registry is a sorted array under a rwlock with an address-range pre-filter, so free() of
+//    ordinary heap pointers never takes the lock (the reference does a tsearch under a rwlock for
+//    every free, obj_tracker.c:948-982);
+//  * the default heuristic is size-based, not random (obj_tracker.c:52).
+#include "tracker.h"
+#include "runtime.h"
+#include <cuda_runtime_api.h>
+#include <errno.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+extern "C" {
+void* __libc_malloc(size_t);
+void* __libc_calloc(size_t, size_t);
+void* __libc_realloc(void*, size_t);
+void __libc_free(void*);
+}
+
+namespace {
+
+struct Block { uintptr_t base; size_t size; };
+
+pthread_rwlock_t g_lock = PTHREAD_RWLOCK_INITIALIZER;
+Block* g_blocks = nullptr;
+size_t g_nblocks = 0, g_cap = 0;
+volatile uintptr_t g_lo = UINTPTR_MAX, g_hi = 0;   // address envelope of all blocks ever handed out
+
+__thread int t_inside = 0;
+volatile int g_tracking = 0;
+volatile int g_heuristic = B200_H_SIZE;
+volatile size_t g_threshold = 64 * 1024;
+volatile int g_initialising = 0;
+uint64_t g_nth = 0;
+b200_tracker_stats g_tstats = {0, 0, 0, 0, 0};
+
+uint8_t* g_decisions = nullptr;   // oracle bitmap: bit n set => n-th allocation is managed
+size_t g_ndecisions = 0;
+
+// index of the block containing p, or -1.  caller holds the lock.
+long find_block(uintptr_t p) {
+    size_t lo = 0, hi = g_nblocks;   // half-open; (the reference's in_excluded_region search has an
+    while (lo < hi) {                //  off-by-one on exactly this, obj_tracker.c:409-424)
+        size_t mid = lo + (hi - lo) / 2;
+        if (p < g_blocks[mid].base) hi = mid;
+        else if (p >= g_blocks[mid].base + g_blocks[mid].size) lo = mid + 1;
+        else return (long)mid;
+    }
+    return -1;
+}
+
+bool registry_insert(uintptr_t base, size_t size) {
+    pthread_rwlock_wrlock(&g_lock);
+    if (g_nblocks == g_cap) {
+        size_t ncap = g_cap ? g_cap * 2 : 256;
+        Block* nb = (Block*)__libc_realloc(g_blocks, ncap * sizeof(Block));
+        if (!nb) { pthread_rwlock_unlock(&g_lock); return false; }
+        g_blocks = nb; g_cap = ncap;
+    }
+    size_t pos = g_nblocks;
+    while (pos > 0 && g_blocks[pos - 1].base > base) { g_blocks[pos] = g_blocks[pos - 1]; pos--; }
+    g_blocks[pos].base = base; g_blocks[pos].size = size;
+    g_nblocks++;
+    if (base < g_lo) g_lo = base;
+    if (base + size > g_hi) g_hi = base + size;
+    g_tstats.managed_allocs++;
+    g_tstats.managed_bytes_live += size;
+    if (g_tstats.managed_bytes_live > g_tstats.managed_bytes_peak) g_tstats.managed_bytes_peak = g_tstats.managed_bytes_live;
+    pthread_rwlock_unlock(&g_lock);
+    return true;
+}
+
+// removes the block whose BASE is p; returns its size or 0
+size_t registry_remove(uintptr_t p) {
+    size_t sz = 0;
+    pthread_rwlock_wrlock(&g_lock);
+    long i = find_block(p);
+    if (i >= 0 && g_blocks[i].base == p) {
+        sz = g_blocks[i].size;
+        memmove(&g_blocks[i], &g_blocks[i + 1], (g_nblocks - i - 1) * sizeof(Block));
+        g_nblocks--;
+        g_tstats.managed_frees++;
+        g_tstats.managed_bytes_live -= sz;
+    }
+    pthread_rwlock_unlock(&g_lock);
+    return sz;
+}
+
+bool should_manage(size_t request, uint64_t nth) {
+    switch (g_heuristic) {
+        case B200_H_TRUE: return true;
+        case B200_H_FALSE: return false;
+        case B200_H_RANDOM: return (random() & 1) != 0;
+        case B200_H_ORACLE: return nth < g_ndecisions && (g_decisions[nth / 8] & (1u << (nth % 8)));
+        default: return request >= g_threshold;
+    }
+}
+
+void* managed_new(size_t request) {
+    // first qualifying allocation brings the device up; allocations made meanwhile (by CUDA itself,
+    // on this or on helper threads) see t_inside / g_initialising and go to glibc
+    if (!b200::device_ready()) {
+        if (__sync_lock_test_and_set(&g_initialising, 1)) return nullptr;
+        t_inside++;
+        b200::ensure_init();
+        t_inside--;
+        __sync_lock_release(&g_initialising);
+    }
+    void* p = nullptr;
+    t_inside++;
+    cudaError_t e = cudaMallocManaged(&p, request ? request : 1, cudaMemAttachGlobal);
+    t_inside--;
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        b200_writef(STDERR_FILENO, "b200blas: cudaMallocManaged(%zu) failed: %s -- falling back to the heap\n", request,
+                    cudaGetErrorString(e));
+        return nullptr;
+    }
+    if (!registry_insert((uintptr_t)p, request ? request : 1)) {
+        t_inside++; cudaFree(p); t_inside--;
+        return nullptr;
+    }
+    return p;
+}
+
+bool bypass() { return t_inside || !g_tracking || g_initialising; }
+
+}  // namespace
+
+extern "C" {
+
+int tracker_lookup(const void* ptr, void** base, size_t* size) {
+    uintptr_t p = (uintptr_t)ptr;
+    if (p < g_lo || p >= g_hi) return 0;
+    int found = 0;
+    pthread_rwlock_rdlock(&g_lock);
+    long i = find_block(p);
+    if (i >= 0) {
+        found = 1;
+        if (base) *base = (void*)g_blocks[i].base;
+        if (size) *size = g_blocks[i].size;
+    }
+    pthread_rwlock_unlock(&g_lock);
+    return found;
+}
+void tracker_enter(void) { t_inside++; }
+void tracker_leave(void) { t_inside--; }
+void tracker_set_tracking(int on) { g_tracking = on; }
+int tracker_get_tracking(void) { return g_tracking; }
+void tracker_set_heuristic(int h) { g_heuristic = h; }
+void tracker_set_threshold(size_t bytes) { g_threshold = bytes; }
+void tracker_get_stats(struct b200_tracker_stats* out) {
+    pthread_rwlock_rdlock(&g_lock);
+    *out = g_tstats;
+    out->allocs_seen = g_nth;
+    pthread_rwlock_unlock(&g_lock);
+}
+
+int tracker_load_oracle_file(const char* filename) {
+    // trace line format "H #<nth> ..." / "D #<nth> ..." (reference oracle.c:41); D = place on device
+    t_inside++;
+    FILE* f = fopen(filename, "r");
+    if (!f) { t_inside--; return 0; }
+    char line[4096];
+    size_t cap = 0;
+    uint8_t* bits = nullptr;
+    size_t maxn = 0;
+    while (fgets(line, sizeof line, f)) {
+        char c; unsigned long long nth;
+        if (sscanf(line, " %c #%llu", &c, &nth) != 2 || (c != 'H' && c != 'D')) continue;
+        if (nth / 8 >= cap) {
+            size_t ncap = cap ? cap : 1024;
+            while (nth / 8 >= ncap) ncap *= 2;
+            uint8_t* nb = (uint8_t*)__libc_realloc(bits, ncap);
+            if (!nb) break;
+            memset(nb + cap, 0, ncap - cap);
+            bits = nb; cap = ncap;
+        }
+        if (c == 'D') bits[nth / 8] |= (uint8_t)(1u << (nth % 8));
+        if (nth + 1 > maxn) maxn = nth + 1;
+    }
+    fclose(f);
+    g_decisions = bits; g_ndecisions = maxn;
+    t_inside--;
+    return 1;
+}
+
+void* tracker_alloc_managed(size_t bytes) { return managed_new(bytes); }
+int tracker_free_managed(void* p) {
+    if (!registry_remove((uintptr_t)p)) return 0;
+    t_inside++;
+    cudaFree(p);
+    t_inside--;
+    return 1;
+}
+
+// ---- the interposed allocator symbols (reference obj_tracker.c:789,842,902,948) ----
+void* malloc(size_t request) noexcept {
+    if (bypass()) return __libc_malloc(request);
+    uint64_t nth = __sync_fetch_and_add(&g_nth, 1);
+    if (request && should_manage(request, nth)) {
+        void* p = managed_new(request);
+        if (p) return p;
+    }
+    return __libc_malloc(request);
+}
+
+void* calloc(size_t nmemb, size_t size) noexcept {
+    if (bypass()) return __libc_calloc(nmemb, size);
+    uint64_t nth = __sync_fetch_and_add(&g_nth, 1);
+    size_t total;
+    if (__builtin_mul_overflow(nmemb, size, &total)) { errno = ENOMEM; return nullptr; }
+    if (total && should_manage(total, nth)) {
+        void* p = managed_new(total);
+        if (p) { memset(p, 0, total); return p; }   // reference calloc_managed, blas2cuda.c:150-154
+    }
+    return __libc_calloc(nmemb, size);
+}
+
+void* realloc(void* ptr, size_t request) noexcept {
+    if (ptr == nullptr) return malloc(request);
+    void* base; size_t old;
+    if (!tracker_lookup(ptr, &base, &old) || base != ptr) return __libc_realloc(ptr, request);
+    if (request == 0) { tracker_free_managed(ptr); return nullptr; }
+    // reference realloc_managed (blas2cuda.c:156-166): new block, copy, free -- stays managed
+    void* np = managed_new(request);
+    if (!np) np = __libc_malloc(request);
+    if (!np) return nullptr;
+    memcpy(np, ptr, old < request ? old : request);
+    tracker_free_managed(ptr);
+    return np;
+}
+
+void free(void* ptr) noexcept {
+    if (!ptr) return;
+    uintptr_t p = (uintptr_t)ptr;
+    if (p >= g_lo && p < g_hi && tracker_free_managed(ptr)) return;
+    __libc_free(ptr);
+}
+
+}  // extern "C"

@@ -12,6 +12,8 @@ import sys
 
 import numpy as np
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB_PATH = os.path.join(ROOT, "libgpublas_b200", "libb200blas.so")
@@ -68,66 +70,14 @@ def load_openblas():
     return _openblas
 
 
+from libgpublas_b200._ffi import DevPtr, as_ptr as _as_ptr, f77call, routine_prec  # noqa: E402,F401
+
 _PREC = {"s": (ctypes.c_float, np.float32), "d": (ctypes.c_double, np.float64),
          "c": (ctypes.c_float, np.complex64), "z": (ctypes.c_double, np.complex128)}
 
 
-def routine_prec(name):
-    """precision letter of a BLAS routine name: dgemm_->d, idamax_->d, dznrm2_->z, scnrm2_->c."""
-    n = name.lower()
-    if n.startswith("cblas_"):
-        n = n[6:]
-    if n[0] == "i":
-        return n[1]
-    if n[:2] in ("dz", "sc"):
-        return n[1]
-    return n[0]
-
-
-class DevPtr:
-    """A raw (device or managed) address passed through unchanged."""
-
-    def __init__(self, addr):
-        self.addr = int(addr)
-
-
-def _as_ptr(a):
-    if isinstance(a, np.ndarray):
-        return ctypes.c_void_p(a.ctypes.data)
-    if isinstance(a, DevPtr):
-        return ctypes.c_void_p(a.addr)
-    if hasattr(a, "data_ptr"):
-        return ctypes.c_void_p(a.data_ptr())
-    raise TypeError(type(a))
-
-
 def f77(lib, name, *args, restype=None):
-    """Call Fortran-ABI symbol `name` in `lib`: every argument by reference.
-    str -> CHARACTER*1, int -> INTEGER, float/complex -> scalar of the routine's precision,
-    np.float32/np.float64 -> that exact real type, arrays/tensors/DevPtr -> address."""
-    creal, _ = _PREC[routine_prec(name)]
-    fn = getattr(lib, name)
-    fn.restype = restype
-    keep, cargs = [], []
-    for a in args:
-        if isinstance(a, str):
-            c = ctypes.c_char(a.encode())
-        elif isinstance(a, (bool, int, np.integer)):
-            c = ctypes.c_int(int(a))
-        elif isinstance(a, np.float32):
-            c = ctypes.c_float(float(a))
-        elif isinstance(a, np.float64):
-            c = ctypes.c_double(float(a))
-        elif isinstance(a, float):
-            c = creal(a)
-        elif isinstance(a, complex):
-            c = (creal * 2)(a.real, a.imag)
-        else:
-            cargs.append(_as_ptr(a))
-            continue
-        keep.append(c)
-        cargs.append(ctypes.byref(c))
-    return fn(*cargs)
+    return f77call(lib, name, *args, restype=restype)
 
 
 def oracle_call(name, *args, restype=ctypes.c_int):

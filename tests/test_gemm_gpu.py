@@ -1,0 +1,192 @@
+"""GPU parity tests for the GEMM family through the C ABI (Fortran symbols), against the oracle.
+
+Tolerances (SURVEY.md section 8c / BASELINE.json north_star):
+  * Frobenius bound  ||C - C_ref||_F <= c * k * eps * ||A||_F * ||B||_F   with c = 2 (d, s), 4 (z, c)
+  * netlib DMMCH element-wise ratio  max |C - C_ref| / (eps * (|alpha| |A||B| + |beta||C|)) < 16
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import libgpublas_b200 as g
+from helpers import f77, fro, oracle_call, splitmix_uniform
+
+pytestmark = pytest.mark.gpu
+
+DT = {"s": np.float32, "d": np.float64, "c": np.complex64, "z": np.complex128}
+EPS = {"s": 2.0 ** -24, "d": 2.0 ** -53, "c": 2.0 ** -24, "z": 2.0 ** -53}
+CFRO = {"s": 2, "d": 2, "c": 4, "z": 4}
+
+
+def F(x):
+    return np.array(x, order="F")
+
+
+def op(x, t):
+    return x if t == "N" else (x.T if t == "T" else x.conj().T)
+
+
+def check_gemm(p, ta, tb, m, n, k, alpha, beta, A, B, C0, C):
+    """C (result of the library) against the float64/complex128 numpy product and the oracle."""
+    hi = np.complex128 if p in "cz" else np.float64
+    a = op(A.astype(hi)[: (m if ta == "N" else k), : (k if ta == "N" else m)], ta)
+    b = op(B.astype(hi)[: (k if tb == "N" else n), : (n if tb == "N" else k)], tb)
+    ref = alpha * (a @ b) + (beta * C0.astype(hi)[:m, :n] if beta != 0 else 0)
+    err = np.abs(C.astype(hi)[:m, :n] - ref)
+    gbound = abs(alpha) * (np.abs(a) @ np.abs(b)) + abs(beta) * np.abs(C0.astype(hi)[:m, :n])
+    ratio = float((err / (EPS[p] * np.maximum(gbound, np.finfo(np.float64).tiny))).max()) if err.size else 0.0
+    frob = fro(err)
+    bound = CFRO[p] * (k + 2) * EPS[p] * (abs(alpha) * fro(a) * fro(b) + abs(beta) * fro(C0[:m, :n]))
+    assert frob <= bound, (frob, bound)
+    assert ratio < 16.0, ratio
+    # rows m..ldc-1 (padding) and columns >= n must be untouched (netlib LDERES)
+    assert np.array_equal(C[m:, :], C0[m:, :])
+    assert np.array_equal(C[:, n:], C0[:, n:])
+
+
+SHAPES = [(1, 1, 1), (2, 3, 5), (9, 9, 9), (37, 29, 41), (64, 64, 64), (129, 127, 65), (200, 300, 17), (256, 128, 512)]
+
+
+@pytest.mark.parametrize("variant", ["auto", "generic_tile", "dmma_tma", "dmma_ldg"])
+@pytest.mark.parametrize("ta,tb", [("N", "N"), ("T", "N"), ("N", "T"), ("T", "T"), ("C", "N")])
+def test_dgemm_host_operands(variant, ta, tb):
+    lib = g.load()
+    g.force_variant(variant)
+    try:
+        for (m, n, k) in SHAPES:
+            for (alpha, beta) in [(1.0, 0.0), (0.7, 1.3)]:
+                ra, ca = (m, k) if ta == "N" else (k, m)
+                rb, cb = (k, n) if tb == "N" else (n, k)
+                lda, ldb, ldc = ra + 1, rb + 3, m + 2
+                A = splitmix_uniform(11, (lda, ca)); B = splitmix_uniform(12, (ldb, cb)); C0 = splitmix_uniform(13, (ldc, n + 1))
+                C = F(C0)
+                f77(lib, "dgemm_", ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc)
+                check_gemm("d", ta, tb, m, n, k, alpha, beta, A, B, C0, C)
+                # and bit-level agreement in structure with the oracle's own restatement
+                C2 = F(C0)
+                assert oracle_call("dgemm", ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C2, ldc) == 0
+                assert np.allclose(C[:m, :n], C2[:m, :n], rtol=1e-11, atol=1e-11)
+    finally:
+        g.force_variant("auto")
+
+
+@pytest.mark.parametrize("p", ["s", "c", "z"])
+@pytest.mark.parametrize("ta,tb", [("N", "N"), ("T", "N"), ("N", "C"), ("C", "T")])
+def test_other_gemm_host_operands(p, ta, tb):
+    lib = g.load()
+    dt = DT[p]
+    for (m, n, k) in [(1, 1, 1), (5, 9, 3), (37, 29, 41), (130, 70, 90)]:
+        alpha, beta = ((0.7 - 0.9j), (1.3 - 1.1j)) if p in "cz" else (0.7, 1.3)
+        ra, ca = (m, k) if ta == "N" else (k, m)
+        rb, cb = (k, n) if tb == "N" else (n, k)
+        lda, ldb, ldc = ra + 1, rb + 1, m + 1
+        A = splitmix_uniform(21, (lda, ca), dt); B = splitmix_uniform(22, (ldb, cb), dt); C0 = splitmix_uniform(23, (ldc, n), dt)
+        C = F(C0)
+        f77(lib, p + "gemm_", ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc)
+        check_gemm(p, ta, tb, m, n, k, alpha, beta, A, B, C0, C)
+
+
+def test_dgemm_quick_returns_and_scaling():
+    lib = g.load()
+    m, n, k = 33, 17, 9
+    A = splitmix_uniform(1, (m, k)); B = splitmix_uniform(2, (k, n)); C0 = splitmix_uniform(3, (m + 1, n))
+    # alpha == 0: C := beta*C without reading A/B; beta == 0 must overwrite NaN
+    C = F(C0); f77(lib, "dgemm_", "N", "N", m, n, k, 0.0, A, m, B, k, 1.3, C, m + 1)
+    assert np.allclose(C[:m], 1.3 * C0[:m]) and np.array_equal(C[m:], C0[m:])
+    C = F(C0); C[:m] = np.nan; f77(lib, "dgemm_", "N", "N", m, n, k, 0.0, A, m, B, k, 0.0, C, m + 1)
+    assert np.all(C[:m] == 0.0)
+    C = F(C0); C[:m] = np.nan; f77(lib, "dgemm_", "N", "N", m, n, k, 1.0, A, m, B, k, 0.0, C, m + 1)
+    assert np.allclose(C[:m], A @ B)
+    # k == 0 and beta == 1, m == 0, n == 0: untouched
+    for (mm, nn, kk, be) in [(m, n, 0, 1.0), (0, n, k, 0.5), (m, 0, k, 0.5)]:
+        C = F(C0); f77(lib, "dgemm_", "N", "N", mm, nn, kk, 1.0, A, m, B, k, be, C, m + 1)
+        assert np.array_equal(C, C0)
+
+
+def test_gemm_error_exits():
+    """netlib DCHKE-style: each illegal argument reports its INFO through XERBLA and leaves C alone
+    (reference gemm.cc:96-111 numbering; tests/netlib/dblat3.f DCHKE)."""
+    lib = g.load()
+    seen = []
+    CB = ctypes.CFUNCTYPE(None, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.c_size_t)
+    cb = CB(lambda name, info, ln: seen.append((name[:6].decode(), info[0])))
+    lib.b200blas_set_xerbla(cb)
+    try:
+        A = np.zeros((4, 4), order="F"); C = np.ones((4, 4), order="F")
+        cases = [(("X", "N", 2, 2, 2, 2, 2, 2), 1), (("N", "X", 2, 2, 2, 2, 2, 2), 2), (("N", "N", -1, 2, 2, 2, 2, 2), 3),
+                 (("N", "N", 2, -1, 2, 2, 2, 2), 4), (("N", "N", 2, 2, -1, 2, 2, 2), 5), (("N", "N", 2, 2, 2, 1, 2, 2), 8),
+                 (("T", "N", 2, 2, 3, 2, 3, 2), 8), (("N", "N", 2, 2, 2, 2, 1, 2), 10), (("N", "T", 2, 3, 2, 2, 2, 2), 10),
+                 (("N", "N", 2, 2, 2, 2, 2, 1), 13)]
+        for (ta, tb, m, n, k, lda, ldb, ldc), want in cases:
+            for p in "sdcz":
+                seen.clear()
+                al = 1.0 if p in "sd" else 1.0 + 0j
+                f77(lib, p + "gemm_", ta, tb, m, n, k, al, A, lda, A, ldb, al, C, ldc)
+                assert seen == [((p + "gemm").upper().ljust(6), want)], (p, seen, want)
+                assert np.all(C == 1.0)
+    finally:
+        lib.b200blas_set_xerbla(CB(0))
+
+
+def test_dgemm_golden_fixture_1024():
+    """BASELINE config 1 / reference tests/c/gemm.c:29-35 restated in f64: A[i,j]=i, B[i,j]=j,
+    alpha=1, beta=0 => C[i,j] = k*i*j exactly (all partial sums < 2^53)."""
+    lib = g.load()
+    n = 1024
+    i = np.arange(n, dtype=np.float64)
+    A = F(np.repeat(i[:, None], n, axis=1)); B = F(np.repeat(i[None, :], n, axis=0)); C = np.zeros((n, n), order="F")
+    f77(lib, "dgemm_", "N", "N", n, n, n, 1.0, A, n, B, n, 0.0, C, n)
+    assert g.last_variant() == "dmma_tma"
+    assert np.array_equal(C, n * np.outer(i, i))
+    # same through CBLAS, column- and row-major
+    for order in (102, 101):
+        C[:] = -1
+        lib.cblas_dgemm(ctypes.c_int(order), ctypes.c_int(111), ctypes.c_int(111), n, n, n, ctypes.c_double(1.0),
+                        A.ctypes.data_as(ctypes.c_void_p), n, B.ctypes.data_as(ctypes.c_void_p), n, ctypes.c_double(0.0),
+                        C.ctypes.data_as(ctypes.c_void_p), n)
+        want = n * np.outer(i, i) if order == 102 else (A.T @ B.T).T   # row-major view of the same buffers
+        assert np.array_equal(C, want)
+
+
+def test_dgemm_device_resident_vs_oracle_and_unaligned():
+    """Operands already on the device (torch tensors) are used in place; odd lda / 8-byte-offset
+    base pointers route to the LDG-staged DMMA variant and must agree."""
+    import torch
+    lib = g.load()
+    m, n, k = 300, 260, 190
+    for (ta, tb) in [("N", "N"), ("T", "N"), ("N", "T"), ("T", "T")]:
+        for (lda_pad, off) in [(0, 0), (1, 0), (0, 1), (3, 1)]:
+            ra, ca = (m, k) if ta == "N" else (k, m)
+            rb, cb = (k, n) if tb == "N" else (n, k)
+            lda, ldb, ldc = ra + lda_pad, rb + lda_pad, m + lda_pad
+            A = splitmix_uniform(31, (lda, ca)); B = splitmix_uniform(32, (ldb, cb)); C0 = splitmix_uniform(33, (ldc, n))
+            dA = torch.zeros(lda * ca + 2, dtype=torch.float64, device="cuda"); dA[off:off + lda * ca] = torch.from_numpy(A.ravel(order="F")).cuda()
+            dB = torch.zeros(ldb * cb + 2, dtype=torch.float64, device="cuda"); dB[off:off + ldb * cb] = torch.from_numpy(B.ravel(order="F")).cuda()
+            dC = torch.zeros(ldc * n + 2, dtype=torch.float64, device="cuda"); dC[off:off + ldc * n] = torch.from_numpy(C0.ravel(order="F")).cuda()
+            torch.cuda.synchronize()
+            f77(lib, "dgemm_", ta, tb, m, n, k, 0.7, g.DevPtr(dA.data_ptr() + 8 * off), lda, g.DevPtr(dB.data_ptr() + 8 * off), ldb,
+                1.3, g.DevPtr(dC.data_ptr() + 8 * off), ldc)
+            want = "dmma_tma" if (lda_pad % 2 == 0 and off == 0) else "dmma_ldg"
+            assert g.last_variant() == want, (g.last_variant(), want)
+            C = dC[off:off + ldc * n].cpu().numpy().reshape((ldc, n), order="F")
+            check_gemm("d", ta, tb, m, n, k, 0.7, 1.3, A, B, C0, C)
+
+
+def test_dgemm_large_property_linearity():
+    """Size-independent property at a size the oracle cannot reach: (A1+A2)B == A1 B + A2 B to
+    rounding, and agreement with an independent fp64 product (torch/cuBLAS) within the bound."""
+    import torch
+    lib = g.load()
+    n = 2048
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.rand((n, n), dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+    B = torch.rand((n, n), dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+    C = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    # torch tensors are row-major: as column-major buffers they are A^T, B^T; C^T = B^T A^T
+    f77(lib, "dgemm_", "N", "N", n, n, n, 1.0, B, n, A, n, 0.0, C, n)
+    ref = A @ B
+    err = torch.linalg.norm(C - ref).item()
+    bound = 2 * n * 2.0 ** -53 * torch.linalg.norm(A).item() * torch.linalg.norm(B).item()
+    assert err <= bound, (err, bound)
