@@ -44,6 +44,55 @@ B200_API void dgemm_(const char* transa, const char* transb, const int* m, const
 B200_API void cgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k, const b200_c32* alpha, const b200_c32* a, const int* lda, const b200_c32* b, const int* ldb, const b200_c32* beta, b200_c32* c, const int* ldc);
 B200_API void zgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k, const b200_c64* alpha, const b200_c64* a, const int* lda, const b200_c64* b, const int* ldb, const b200_c64* beta, b200_c64* c, const int* ldc);
 
+/* Level 1 -- gfortran ABI of the CPU BLAS (functions return their result; complex results by value):
+ * reference blas_level1/dot.cc:38-48, dotc.cc, dotu.cc, nrm2.cc:31-54, asum.cc, amax.cc:32-56, axpy.cc:44-59,
+ * scal.cc, copy.cc, swap.cc (dead wrappers naming the routines).  i?amax_ is 1-based, 0 if n<1 or incx<=0.
+ * Level 2 -- reference blas_level2/gemv.cc:11-118, trsv.cc:11-114. */
+B200_API float sdot_(const int* n, const float* x, const int* incx, const float* y, const int* incy);
+B200_API double ddot_(const int* n, const double* x, const int* incx, const double* y, const int* incy);
+B200_API b200_c32 cdotu_(const int* n, const b200_c32* x, const int* incx, const b200_c32* y, const int* incy);
+B200_API b200_c32 cdotc_(const int* n, const b200_c32* x, const int* incx, const b200_c32* y, const int* incy);
+B200_API b200_c64 zdotu_(const int* n, const b200_c64* x, const int* incx, const b200_c64* y, const int* incy);
+B200_API b200_c64 zdotc_(const int* n, const b200_c64* x, const int* incx, const b200_c64* y, const int* incy);
+B200_API float snrm2_(const int* n, const float* x, const int* incx);
+B200_API double dnrm2_(const int* n, const double* x, const int* incx);
+B200_API float scnrm2_(const int* n, const b200_c32* x, const int* incx);
+B200_API double dznrm2_(const int* n, const b200_c64* x, const int* incx);
+B200_API float sasum_(const int* n, const float* x, const int* incx);
+B200_API double dasum_(const int* n, const double* x, const int* incx);
+B200_API float scasum_(const int* n, const b200_c32* x, const int* incx);
+B200_API double dzasum_(const int* n, const b200_c64* x, const int* incx);
+B200_API int isamax_(const int* n, const float* x, const int* incx);
+B200_API int idamax_(const int* n, const double* x, const int* incx);
+B200_API int icamax_(const int* n, const b200_c32* x, const int* incx);
+B200_API int izamax_(const int* n, const b200_c64* x, const int* incx);
+B200_API void saxpy_(const int* n, const float* alpha, const float* x, const int* incx, float* y, const int* incy);
+B200_API void daxpy_(const int* n, const double* alpha, const double* x, const int* incx, double* y, const int* incy);
+B200_API void caxpy_(const int* n, const b200_c32* alpha, const b200_c32* x, const int* incx, b200_c32* y, const int* incy);
+B200_API void zaxpy_(const int* n, const b200_c64* alpha, const b200_c64* x, const int* incx, b200_c64* y, const int* incy);
+B200_API void sscal_(const int* n, const float* alpha, float* x, const int* incx);
+B200_API void dscal_(const int* n, const double* alpha, double* x, const int* incx);
+B200_API void cscal_(const int* n, const b200_c32* alpha, b200_c32* x, const int* incx);
+B200_API void zscal_(const int* n, const b200_c64* alpha, b200_c64* x, const int* incx);
+B200_API void csscal_(const int* n, const float* alpha, b200_c32* x, const int* incx);
+B200_API void zdscal_(const int* n, const double* alpha, b200_c64* x, const int* incx);
+B200_API void scopy_(const int* n, const float* x, const int* incx, float* y, const int* incy);
+B200_API void dcopy_(const int* n, const double* x, const int* incx, double* y, const int* incy);
+B200_API void ccopy_(const int* n, const b200_c32* x, const int* incx, b200_c32* y, const int* incy);
+B200_API void zcopy_(const int* n, const b200_c64* x, const int* incx, b200_c64* y, const int* incy);
+B200_API void sswap_(const int* n, float* x, const int* incx, float* y, const int* incy);
+B200_API void dswap_(const int* n, double* x, const int* incx, double* y, const int* incy);
+B200_API void cswap_(const int* n, b200_c32* x, const int* incx, b200_c32* y, const int* incy);
+B200_API void zswap_(const int* n, b200_c64* x, const int* incx, b200_c64* y, const int* incy);
+B200_API void sgemv_(const char* trans, const int* m, const int* n, const float* alpha, const float* a, const int* lda, const float* x, const int* incx, const float* beta, float* y, const int* incy);
+B200_API void dgemv_(const char* trans, const int* m, const int* n, const double* alpha, const double* a, const int* lda, const double* x, const int* incx, const double* beta, double* y, const int* incy);
+B200_API void cgemv_(const char* trans, const int* m, const int* n, const b200_c32* alpha, const b200_c32* a, const int* lda, const b200_c32* x, const int* incx, const b200_c32* beta, b200_c32* y, const int* incy);
+B200_API void zgemv_(const char* trans, const int* m, const int* n, const b200_c64* alpha, const b200_c64* a, const int* lda, const b200_c64* x, const int* incx, const b200_c64* beta, b200_c64* y, const int* incy);
+B200_API void strsv_(const char* uplo, const char* trans, const char* diag, const int* n, const float* a, const int* lda, float* x, const int* incx);
+B200_API void dtrsv_(const char* uplo, const char* trans, const char* diag, const int* n, const double* a, const int* lda, double* x, const int* incx);
+B200_API void ctrsv_(const char* uplo, const char* trans, const char* diag, const int* n, const b200_c32* a, const int* lda, b200_c32* x, const int* incx);
+B200_API void ztrsv_(const char* uplo, const char* trans, const char* diag, const int* n, const b200_c64* a, const int* lda, b200_c64* x, const int* incx);
+
 /* ------------------------------ 2. CBLAS ABI ------------------------------ */
 /* enums: reference cblas.h:21-25 */
 enum CBLAS_ORDER { CblasRowMajor = 101, CblasColMajor = 102 };
@@ -58,6 +107,38 @@ B200_API void cblas_sgemm(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE transa, e
 B200_API void cblas_dgemm(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE transa, enum CBLAS_TRANSPOSE transb, int m, int n, int k, double alpha, const double* a, int lda, const double* b, int ldb, double beta, double* c, int ldc);
 B200_API void cblas_cgemm(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE transa, enum CBLAS_TRANSPOSE transb, int m, int n, int k, const void* alpha, const void* a, int lda, const void* b, int ldb, const void* beta, void* c, int ldc);
 B200_API void cblas_zgemm(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE transa, enum CBLAS_TRANSPOSE transb, int m, int n, int k, const void* alpha, const void* a, int lda, const void* b, int ldb, const void* beta, void* c, int ldc);
+
+/* CBLAS Level 1 / 2 -- reference cblas.h:46-656; cblas_i?amax is 0-based */
+B200_API float cblas_sdot(int n, const float* x, int incx, const float* y, int incy);
+B200_API double cblas_ddot(int n, const double* x, int incx, const double* y, int incy);
+B200_API void cblas_cdotu_sub(int n, const void* x, int incx, const void* y, int incy, void* out);
+B200_API void cblas_cdotc_sub(int n, const void* x, int incx, const void* y, int incy, void* out);
+B200_API void cblas_zdotu_sub(int n, const void* x, int incx, const void* y, int incy, void* out);
+B200_API void cblas_zdotc_sub(int n, const void* x, int incx, const void* y, int incy, void* out);
+B200_API float cblas_snrm2(int n, const float* x, int incx);
+B200_API double cblas_dnrm2(int n, const double* x, int incx);
+B200_API float cblas_scnrm2(int n, const void* x, int incx);
+B200_API double cblas_dznrm2(int n, const void* x, int incx);
+B200_API float cblas_sasum(int n, const float* x, int incx);
+B200_API double cblas_dasum(int n, const double* x, int incx);
+B200_API CBLAS_INDEX cblas_isamax(int n, const float* x, int incx);
+B200_API CBLAS_INDEX cblas_idamax(int n, const double* x, int incx);
+B200_API CBLAS_INDEX cblas_icamax(int n, const void* x, int incx);
+B200_API CBLAS_INDEX cblas_izamax(int n, const void* x, int incx);
+B200_API void cblas_saxpy(int n, float alpha, const float* x, int incx, float* y, int incy);
+B200_API void cblas_daxpy(int n, double alpha, const double* x, int incx, double* y, int incy);
+B200_API void cblas_caxpy(int n, const void* alpha, const void* x, int incx, void* y, int incy);
+B200_API void cblas_zaxpy(int n, const void* alpha, const void* x, int incx, void* y, int incy);
+B200_API void cblas_sscal(int n, float alpha, float* x, int incx);
+B200_API void cblas_dscal(int n, double alpha, double* x, int incx);
+B200_API void cblas_scopy(int n, const float* x, int incx, float* y, int incy);
+B200_API void cblas_dcopy(int n, const double* x, int incx, double* y, int incy);
+B200_API void cblas_sswap(int n, float* x, int incx, float* y, int incy);
+B200_API void cblas_dswap(int n, double* x, int incx, double* y, int incy);
+B200_API void cblas_sgemv(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE trans, int m, int n, float alpha, const float* a, int lda, const float* x, int incx, float beta, float* y, int incy);
+B200_API void cblas_dgemv(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE trans, int m, int n, double alpha, const double* a, int lda, const double* x, int incx, double beta, double* y, int incy);
+B200_API void cblas_strsv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const float* a, int lda, float* x, int incx);
+B200_API void cblas_dtrsv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const double* a, int lda, double* x, int incx);
 
 /* ------------------------------ 3. allocator symbols ------------------------------ */
 /* malloc / calloc / realloc / free are exported with their libc prototypes (<stdlib.h>);

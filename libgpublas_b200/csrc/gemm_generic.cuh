@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include <cuComplex.h>
+#include <type_traits>
 
 namespace b200 {
 
@@ -18,6 +19,7 @@ template <> struct num<float> {
     static __device__ float mul(float a, float b) { return a * b; }
     static __device__ float fma(float a, float b, float c) { return fmaf(a, b, c); }
     static __device__ float add(float a, float b) { return a + b; }
+    static __device__ float sub(float a, float b) { return a - b; }
     static __host__ __device__ bool is_zero(float a) { return a == 0.f; }
     static __host__ __device__ bool is_one(float a) { return a == 1.f; }
 };
@@ -27,6 +29,7 @@ template <> struct num<double> {
     static __device__ double mul(double a, double b) { return a * b; }
     static __device__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
     static __device__ double add(double a, double b) { return a + b; }
+    static __device__ double sub(double a, double b) { return a - b; }
     static __host__ __device__ bool is_zero(double a) { return a == 0.0; }
     static __host__ __device__ bool is_one(double a) { return a == 1.0; }
 };
@@ -42,6 +45,7 @@ template <> struct num<cuFloatComplex> {
         return c;
     }
     static __device__ cuFloatComplex add(cuFloatComplex a, cuFloatComplex b) { return make_cuFloatComplex(a.x + b.x, a.y + b.y); }
+    static __device__ cuFloatComplex sub(cuFloatComplex a, cuFloatComplex b) { return make_cuFloatComplex(a.x - b.x, a.y - b.y); }
     static __host__ __device__ bool is_zero(cuFloatComplex a) { return a.x == 0.f && a.y == 0.f; }
     static __host__ __device__ bool is_one(cuFloatComplex a) { return a.x == 1.f && a.y == 0.f; }
 };
@@ -57,6 +61,7 @@ template <> struct num<cuDoubleComplex> {
         return c;
     }
     static __device__ cuDoubleComplex add(cuDoubleComplex a, cuDoubleComplex b) { return make_cuDoubleComplex(a.x + b.x, a.y + b.y); }
+    static __device__ cuDoubleComplex sub(cuDoubleComplex a, cuDoubleComplex b) { return make_cuDoubleComplex(a.x - b.x, a.y - b.y); }
     static __host__ __device__ bool is_zero(cuDoubleComplex a) { return a.x == 0.0 && a.y == 0.0; }
     static __host__ __device__ bool is_one(cuDoubleComplex a) { return a.x == 1.0 && a.y == 0.0; }
 };

@@ -36,6 +36,22 @@ void cgemm_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, cuFloatCom
                int64_t lda, const cuFloatComplex* B, int64_t ldb, cuFloatComplex beta, cuFloatComplex* C,
                int64_t ldc, int mask = MASK_FULL);
 
-template <typename T> struct Scalar { using type = T; };
+// ---- Level 1 ----  x, y device-accessible; incx/incy are the BLAS increments (may be negative where
+// netlib allows it).  Reductions write their result to `out` (device memory) deterministically:
+// fixed grid, fixed combination order, independent of scheduling.
+template <typename T> void dot_dev(cudaStream_t s, int64_t n, const T* x, int64_t incx, const T* y, int64_t incy, T* out, bool conj_x);
+template <typename T, typename R> void nrm2_dev(cudaStream_t s, int64_t n, const T* x, int64_t incx, R* out);
+template <typename T, typename R> void asum_dev(cudaStream_t s, int64_t n, const T* x, int64_t incx, R* out);
+template <typename T> void iamax_dev(cudaStream_t s, int64_t n, const T* x, int64_t incx, long long* out);   // 0-based, -1 if none
+template <typename T> void axpy_dev(cudaStream_t s, int64_t n, T alpha, const T* x, int64_t incx, T* y, int64_t incy);
+template <typename T, typename S> void scal_dev(cudaStream_t s, int64_t n, S alpha, T* x, int64_t incx);
+template <typename T> void copy_dev(cudaStream_t s, int64_t n, const T* x, int64_t incx, T* y, int64_t incy);
+template <typename T> void swap_dev(cudaStream_t s, int64_t n, T* x, int64_t incx, T* y, int64_t incy);
+
+// ---- Level 2 ----
+template <typename T> void gemv_dev(cudaStream_t s, char trans, int m, int n, T alpha, const T* A, int64_t lda, const T* x,
+                                    int64_t incx, T beta, T* y, int64_t incy);
+template <typename T> void trsv_dev(cudaStream_t s, char uplo, char trans, char diag, int n, const T* A, int64_t lda, T* x,
+                                    int64_t incx);
 
 }  // namespace b200

@@ -164,7 +164,11 @@ void* pinned_scalar() {
     return t_ctx.pinned;
 }
 void* device_scalar() {
-    if (!t_ctx.dscalar) { TrackerGuard guard; B200_CUDA(cudaMalloc(&t_ctx.dscalar, 256)); }
+    if (!t_ctx.dscalar) {
+        TrackerGuard guard;
+        B200_CUDA(cudaMalloc(&t_ctx.dscalar, 256));
+        B200_CUDA(cudaMemset(t_ctx.dscalar, 0, 256));   // bytes 128.. hold the "last block" tickets of the reductions
+    }
     return t_ctx.dscalar;
 }
 
