@@ -44,6 +44,19 @@ B200_API void dgemm_(const char* transa, const char* transb, const int* m, const
 B200_API void cgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k, const b200_c32* alpha, const b200_c32* a, const int* lda, const b200_c32* b, const int* ldb, const b200_c32* beta, b200_c32* c, const int* ldc);
 B200_API void zgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k, const b200_c64* alpha, const b200_c64* a, const int* lda, const b200_c64* b, const int* ldb, const b200_c64* beta, b200_c64* c, const int* ldc);
 
+B200_API void ssyrk_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha, const float* a, const int* lda, const float* beta, float* c, const int* ldc);
+B200_API void dsyrk_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const double* a, const int* lda, const double* beta, double* c, const int* ldc);
+B200_API void csyrk_(const char* uplo, const char* trans, const int* n, const int* k, const b200_c32* alpha, const b200_c32* a, const int* lda, const b200_c32* beta, b200_c32* c, const int* ldc);
+B200_API void zsyrk_(const char* uplo, const char* trans, const int* n, const int* k, const b200_c64* alpha, const b200_c64* a, const int* lda, const b200_c64* beta, b200_c64* c, const int* ldc);
+B200_API void strsm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n, const float* alpha, const float* a, const int* lda, float* b, const int* ldb);
+B200_API void strmm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n, const float* alpha, const float* a, const int* lda, float* b, const int* ldb);
+B200_API void dtrsm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n, const double* alpha, const double* a, const int* lda, double* b, const int* ldb);
+B200_API void dtrmm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n, const double* alpha, const double* a, const int* lda, double* b, const int* ldb);
+B200_API void ctrsm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n, const b200_c32* alpha, const b200_c32* a, const int* lda, b200_c32* b, const int* ldb);
+B200_API void ctrmm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n, const b200_c32* alpha, const b200_c32* a, const int* lda, b200_c32* b, const int* ldb);
+B200_API void ztrsm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n, const b200_c64* alpha, const b200_c64* a, const int* lda, b200_c64* b, const int* ldb);
+B200_API void ztrmm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n, const b200_c64* alpha, const b200_c64* a, const int* lda, b200_c64* b, const int* ldb);
+
 /* Level 1 -- gfortran ABI of the CPU BLAS (functions return their result; complex results by value):
  * reference blas_level1/dot.cc:38-48, dotc.cc, dotu.cc, nrm2.cc:31-54, asum.cc, amax.cc:32-56, axpy.cc:44-59,
  * scal.cc, copy.cc, swap.cc (dead wrappers naming the routines).  i?amax_ is 1-based, 0 if n<1 or incx<=0.

@@ -49,6 +49,60 @@ void gemm_entry(const char* name, const char* transa, const char* transb, const 
     log_exec(name, "%c%c m=%d n=%d k=%d lda=%d ldb=%d ldc=%d", ta, tb, *m, *n, *k, *lda, *ldb, *ldc);
 }
 
+// reference syrk.cc:78-146 (syrk_check: info 1,2,3,4,7,10) + :43-76.  The reference's alpha==0 host
+// loops are replaced by the device scale kernel (and its upper/beta!=0 loop, syrk.cc:124-128, which
+// scales the wrong triangle, is not reproduced).  Complex SYRK rejects 'C' like netlib ZSYRK.
+template <typename T>
+void syrk_entry(const char* name, bool cplx, const char* uplo, const char* trans, const int* n, const int* k, const T* alpha,
+                const T* a, const int* lda, const T* beta, T* c, const int* ldc) {
+    const bool upper = lsame(uplo, 'U'), nota = lsame(trans, 'N');
+    const int nrowa = nota ? *n : *k;
+    int info = 0;
+    if (!upper && !lsame(uplo, 'L')) info = 1;
+    else if (!nota && !lsame(trans, 'T') && (cplx || !lsame(trans, 'C'))) info = 2;
+    else if (*n < 0) info = 3;
+    else if (*k < 0) info = 4;
+    else if (*lda < imax(1, nrowa)) info = 7;
+    else if (*ldc < imax(1, *n)) info = 10;
+    if (info) { call_xerbla(name, info); return; }
+    if (*n == 0 || ((is0(*alpha) || *k == 0) && is1(*beta))) return;
+    CallScope scope;
+    const bool scale_only = is0(*alpha) || *k == 0;
+    Operand oa(scale_only ? nullptr : a, nrowa, nota ? *k : *n, *lda, sizeof(T), ACC_IN);
+    // C is read even when beta == 0: the unreferenced triangle must survive a staged round trip
+    Operand oc(c, *n, *n, *ldc, sizeof(T), ACC_INOUT);
+    syrk_dev<T>(current_stream(), upper ? 'U' : 'L', nota ? 'N' : 'T', *n, *k, *alpha, (const T*)oa.dev(), oa.ld(), *beta, (T*)oc.dev(), oc.ld());
+    oc.release();
+    log_exec(name, "%c%c n=%d k=%d lda=%d ldc=%d", upper ? 'U' : 'L', nota ? 'N' : 'T', *n, *k, *lda, *ldc);
+}
+
+// reference trsm.cc:76-132 / trmm.cc:81-137 (info 1,2,3,4,5,6,9,11) + trsm.cc:40-73 / trmm.cc:42-79
+template <typename T>
+void tr_entry(const char* name, bool solve, const char* side, const char* uplo, const char* transa, const char* diag, const int* m,
+              const int* n, const T* alpha, const T* a, const int* lda, T* b, const int* ldb) {
+    const bool lside = lsame(side, 'L'), upper = lsame(uplo, 'U');
+    const int nrowa = lside ? *m : *n;
+    int info = 0;
+    if (!lside && !lsame(side, 'R')) info = 1;
+    else if (!upper && !lsame(uplo, 'L')) info = 2;
+    else if (!lsame(transa, 'N') && !lsame(transa, 'T') && !lsame(transa, 'C')) info = 3;
+    else if (!lsame(diag, 'U') && !lsame(diag, 'N')) info = 4;
+    else if (*m < 0) info = 5;
+    else if (*n < 0) info = 6;
+    else if (*lda < imax(1, nrowa)) info = 9;
+    else if (*ldb < imax(1, *m)) info = 11;
+    if (info) { call_xerbla(name, info); return; }
+    if (*m == 0 || *n == 0) return;
+    CallScope scope;
+    const char t = lsame(transa, 'N') ? 'N' : (lsame(transa, 'T') ? 'T' : 'C');
+    Operand oa(is0(*alpha) ? nullptr : a, nrowa, nrowa, *lda, sizeof(T), ACC_IN);
+    Operand ob(b, *m, *n, *ldb, sizeof(T), is0(*alpha) ? ACC_OUT : ACC_INOUT);
+    if (solve) trsm_dev<T>(current_stream(), lside ? 'L' : 'R', upper ? 'U' : 'L', t, lsame(diag, 'U') ? 'U' : 'N', *m, *n, *alpha, (const T*)oa.dev(), oa.ld(), (T*)ob.dev(), ob.ld());
+    else trmm_dev<T>(current_stream(), lside ? 'L' : 'R', upper ? 'U' : 'L', t, lsame(diag, 'U') ? 'U' : 'N', *m, *n, *alpha, (const T*)oa.dev(), oa.ld(), (T*)ob.dev(), ob.ld());
+    ob.release();
+    log_exec(name, "%c%c%c%c m=%d n=%d lda=%d ldb=%d", lside ? 'L' : 'R', upper ? 'U' : 'L', t, lsame(diag, 'U') ? 'U' : 'N', *m, *n, *lda, *ldb);
+}
+
 }  // namespace
 
 extern "C" {
@@ -71,5 +125,28 @@ void zgemm_(const char* transa, const char* transb, const int* m, const int* n, 
     gemm_entry<cuDoubleComplex>("zgemm_", transa, transb, m, n, k, (const cuDoubleComplex*)alpha, (const cuDoubleComplex*)a, lda,
                                 (const cuDoubleComplex*)b, ldb, (const cuDoubleComplex*)beta, (cuDoubleComplex*)c, ldc);
 }
+
+#define B200_SYRK(P, T, CT, CPLX)                                                                                       \
+    void P##syrk_(const char* uplo, const char* trans, const int* n, const int* k, const T* alpha, const T* a, const int* lda, \
+                  const T* beta, T* c, const int* ldc) {                                                                \
+        syrk_entry<CT>(#P "syrk_", CPLX, uplo, trans, n, k, (const CT*)alpha, (const CT*)a, lda, (const CT*)beta, (CT*)c, ldc); \
+    }
+B200_SYRK(s, float, float, false)
+B200_SYRK(d, double, double, false)
+B200_SYRK(c, b200_c32, cuFloatComplex, true)
+B200_SYRK(z, b200_c64, cuDoubleComplex, true)
+#define B200_TR(P, T, CT)                                                                                               \
+    void P##trsm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n, \
+                  const T* alpha, const T* a, const int* lda, T* b, const int* ldb) {                                   \
+        tr_entry<CT>(#P "trsm_", true, side, uplo, transa, diag, m, n, (const CT*)alpha, (const CT*)a, lda, (CT*)b, ldb); \
+    }                                                                                                                   \
+    void P##trmm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n, \
+                  const T* alpha, const T* a, const int* lda, T* b, const int* ldb) {                                   \
+        tr_entry<CT>(#P "trmm_", false, side, uplo, transa, diag, m, n, (const CT*)alpha, (const CT*)a, lda, (CT*)b, ldb); \
+    }
+B200_TR(s, float, float)
+B200_TR(d, double, double)
+B200_TR(c, b200_c32, cuFloatComplex)
+B200_TR(z, b200_c64, cuDoubleComplex)
 
 }  // extern "C"

@@ -15,6 +15,7 @@ namespace b200 {
 template <typename T> struct num;
 template <> struct num<float> {
     static __host__ __device__ float zero() { return 0.f; }
+    static __host__ __device__ float real(double r) { return (float)r; }
     static __device__ float conj(float a) { return a; }
     static __device__ float mul(float a, float b) { return a * b; }
     static __device__ float fma(float a, float b, float c) { return fmaf(a, b, c); }
@@ -25,6 +26,7 @@ template <> struct num<float> {
 };
 template <> struct num<double> {
     static __host__ __device__ double zero() { return 0.0; }
+    static __host__ __device__ double real(double r) { return r; }
     static __device__ double conj(double a) { return a; }
     static __device__ double mul(double a, double b) { return a * b; }
     static __device__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
@@ -35,6 +37,7 @@ template <> struct num<double> {
 };
 template <> struct num<cuFloatComplex> {
     static __host__ __device__ cuFloatComplex zero() { return make_cuFloatComplex(0.f, 0.f); }
+    static __host__ __device__ cuFloatComplex real(double r) { return make_cuFloatComplex((float)r, 0.f); }
     static __device__ cuFloatComplex conj(cuFloatComplex a) { return make_cuFloatComplex(a.x, -a.y); }
     static __device__ cuFloatComplex mul(cuFloatComplex a, cuFloatComplex b) {
         return make_cuFloatComplex(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -51,6 +54,7 @@ template <> struct num<cuFloatComplex> {
 };
 template <> struct num<cuDoubleComplex> {
     static __host__ __device__ cuDoubleComplex zero() { return make_cuDoubleComplex(0.0, 0.0); }
+    static __host__ __device__ cuDoubleComplex real(double r) { return make_cuDoubleComplex(r, 0.0); }
     static __device__ cuDoubleComplex conj(cuDoubleComplex a) { return make_cuDoubleComplex(a.x, -a.y); }
     static __device__ cuDoubleComplex mul(cuDoubleComplex a, cuDoubleComplex b) {
         return make_cuDoubleComplex(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);

@@ -36,6 +36,19 @@ void cgemm_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, cuFloatCom
                int64_t lda, const cuFloatComplex* B, int64_t ldb, cuFloatComplex beta, cuFloatComplex* C,
                int64_t ldc, int mask = MASK_FULL);
 
+// typed front door to the four GEMMs
+template <typename T> void gemm_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, T alpha, const T* A, int64_t lda, const T* B,
+                                    int64_t ldb, T beta, T* C, int64_t ldc, int mask = MASK_FULL);
+// C := alpha*op(A)*op(A)^T + beta*C on one triangle (trans 'N': A n x k; 'T': A k x n).  herm: C/A^H variant.
+template <typename T> void syrk_dev(cudaStream_t s, char uplo, char trans, int n, int k, T alpha, const T* A, int64_t lda, T beta, T* C,
+                                    int64_t ldc);
+// B := alpha*op(A)*B (side 'L') or alpha*B*op(A) ('R'), A triangular; in place, blocked on the GEMM tiles
+template <typename T> void trmm_dev(cudaStream_t s, char side, char uplo, char trans, char diag, int m, int n, T alpha, const T* A,
+                                    int64_t lda, T* B, int64_t ldb);
+// solve op(A)*X = alpha*B ('L') or X*op(A) = alpha*B ('R'), X overwrites B
+template <typename T> void trsm_dev(cudaStream_t s, char side, char uplo, char trans, char diag, int m, int n, T alpha, const T* A,
+                                    int64_t lda, T* B, int64_t ldb);
+
 // ---- Level 1 ----  x, y device-accessible; incx/incy are the BLAS increments (may be negative where
 // netlib allows it).  Reductions write their result to `out` (device memory) deterministically:
 // fixed grid, fixed combination order, independent of scheduling.

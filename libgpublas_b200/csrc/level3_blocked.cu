@@ -1,0 +1,279 @@
+// level3_blocked.cu -- SYRK, TRMM and TRSM as blocked recursions onto the GEMM tile engine
+// (reference blas_level3/syrk.cc:43-76, trmm.cc:42-79, trsm.cc:40-73 forward to cublas<t>syrk /
+// trmm / trsm; north_star (1): "SYRK and TRSM are built as blocked recursions onto the same GEMM
+// tiles").
+//
+//  SYRK  one masked GEMM launch: tiles entirely outside the referenced triangle exit at once,
+//        diagonal tiles store only the referenced half; nothing outside the triangle is written.
+//  TRMM  recursive 2x2 splitting in place; off-diagonal blocks are GEMMs; a diagonal block of
+//        <= 256 is copied to scratch with the unreferenced triangle zeroed (and the unit diagonal
+//        made explicit), multiplied out of place by the GEMM kernel and copied back.
+//  TRSM  same recursion; the 64x64 diagonal blocks are inverted once up front by a small kernel
+//        (one CTA per block, exact substitution on the identity), so every leaf solve is a GEMM
+//        with the inverted block, and every update is a GEMM.
+#include "common.cuh"
+#include "kernels.h"
+#include "gemm_generic.cuh"
+#include "runtime.h"
+
+namespace b200 {
+
+template <> void gemm_dev<float>(cudaStream_t s, char ta, char tb, int m, int n, int k, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int mask) { sgemm_dev(s, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mask); }
+template <> void gemm_dev<double>(cudaStream_t s, char ta, char tb, int m, int n, int k, double alpha, const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int mask) { dgemm_dev(s, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mask); }
+template <> void gemm_dev<cuFloatComplex>(cudaStream_t s, char ta, char tb, int m, int n, int k, cuFloatComplex alpha, const cuFloatComplex* A, int64_t lda, const cuFloatComplex* B, int64_t ldb, cuFloatComplex beta, cuFloatComplex* C, int64_t ldc, int mask) { cgemm_dev(s, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mask); }
+template <> void gemm_dev<cuDoubleComplex>(cudaStream_t s, char ta, char tb, int m, int n, int k, cuDoubleComplex alpha, const cuDoubleComplex* A, int64_t lda, const cuDoubleComplex* B, int64_t ldb, cuDoubleComplex beta, cuDoubleComplex* C, int64_t ldc, int mask) { zgemm_dev(s, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mask); }
+
+// ------------------------------------------------------------------ SYRK
+template <typename T>
+void syrk_dev(cudaStream_t s, char uplo, char trans, int n, int k, T alpha, const T* A, int64_t lda, T beta, T* C, int64_t ldc) {
+    const int mask = (uplo == 'U' || uplo == 'u') ? MASK_UPPER : MASK_LOWER;
+    const bool nota = op_code(trans) == 0;
+    // netlib xSYRK: trans 'T' and (real types) 'C' both mean A^T A -- never a conjugate
+    gemm_dev<T>(s, nota ? 'N' : 'T', nota ? 'T' : 'N', n, n, k, alpha, A, lda, A, lda, beta, C, ldc, mask);
+}
+template void syrk_dev<float>(cudaStream_t, char, char, int, int, float, const float*, int64_t, float, float*, int64_t);
+template void syrk_dev<double>(cudaStream_t, char, char, int, int, double, const double*, int64_t, double, double*, int64_t);
+template void syrk_dev<cuFloatComplex>(cudaStream_t, char, char, int, int, cuFloatComplex, const cuFloatComplex*, int64_t, cuFloatComplex, cuFloatComplex*, int64_t);
+template void syrk_dev<cuDoubleComplex>(cudaStream_t, char, char, int, int, cuDoubleComplex, const cuDoubleComplex*, int64_t, cuDoubleComplex, cuDoubleComplex*, int64_t);
+
+// ------------------------------------------------------------------ helpers
+// dst (nb x nb, ld = ldd) := the referenced triangle of src with zeros elsewhere; unit => diagonal = 1
+template <typename T>
+__global__ void tri_copy_kernel(int nb, const T* __restrict__ src, int64_t lds, T* __restrict__ dst, int64_t ldd, bool upper, bool unit) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= nb || j >= nb) return;
+    T v = num<T>::zero();
+    if (i == j) v = unit ? num<T>::real(1.0) : src[i + (int64_t)j * lds];
+    else if (upper ? i < j : i > j) v = src[i + (int64_t)j * lds];
+    dst[i + (int64_t)j * ldd] = v;
+}
+template <typename T>
+__global__ void copy_matrix_kernel(int m, int n, const T* __restrict__ src, int64_t lds, T* __restrict__ dst, int64_t ldd) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    for (int64_t j = blockIdx.y; j < n; j += gridDim.y) dst[i + j * ldd] = src[i + j * lds];
+}
+template <typename T> static void copy_matrix(cudaStream_t s, int m, int n, const T* src, int64_t lds, T* dst, int64_t ldd) {
+    if (m <= 0 || n <= 0) return;
+    dim3 grd((m + 255) / 256, n > 65535 ? 65535 : n);
+    copy_matrix_kernel<T><<<grd, 256, 0, s>>>(m, n, src, lds, dst, ldd);
+}
+static inline int split_point(int n, int align) {
+    int h = ((n / 2 + align - 1) / align) * align;
+    if (h >= n) h = ((n - 1) / align) * align;
+    return h;
+}
+static inline int64_t even_ld(int64_t rows, size_t elem) { int64_t per = 16 / (int64_t)elem; if (per < 1) per = 1; return (rows + per - 1) / per * per; }
+
+// ------------------------------------------------------------------ TRMM
+constexpr int TRMM_BASE = 256;
+
+template <typename T> struct TrCtx {
+    cudaStream_t s; bool left, upper /*stored triangle*/, unit; char trans; const T* A; int64_t lda; T* B; int64_t ldb;
+    T* triw; T* outw;   // scratch: TRMM_BASE^2 triangle copy, and the out-of-place product
+    int64_t ldo;
+};
+
+// sub-block accessors: A(i0.., j0..) of the stored triangular matrix
+template <typename T> static inline const T* Aat(const TrCtx<T>& c, int i, int j) { return c.A + i + (int64_t)j * c.lda; }
+
+// B[r0:r0+mr, c0:c0+nc] := alpha * op(T[d0:d0+nd]) * B_blk   (left: rows d0.., nd = mr)   or   B_blk * op(T) (right: cols d0.., nd = nc)
+template <typename T>
+static void trmm_rec(const TrCtx<T>& c, T alpha, int d0, int nd, int other /* n for left, m for right */) {
+    const bool opupper = (op_code(c.trans) == 0) ? c.upper : !c.upper;
+    if (nd <= TRMM_BASE) {
+        dim3 blk(32, 8), grd((nd + 31) / 32, (nd + 7) / 8);
+        const int64_t ldt = even_ld(nd, sizeof(T));
+        tri_copy_kernel<T><<<grd, blk, 0, c.s>>>(nd, Aat(c, d0, d0), c.lda, c.triw, ldt, c.upper, c.unit);
+        if (c.left) {
+            T* Bb = c.B + d0;
+            gemm_dev<T>(c.s, c.trans, 'N', nd, other, nd, alpha, c.triw, ldt, Bb, c.ldb, num<T>::zero(), c.outw, c.ldo);
+            copy_matrix<T>(c.s, nd, other, c.outw, c.ldo, Bb, c.ldb);
+        } else {
+            T* Bb = c.B + (int64_t)d0 * c.ldb;
+            gemm_dev<T>(c.s, 'N', c.trans, other, nd, nd, alpha, Bb, c.ldb, c.triw, ldt, num<T>::zero(), c.outw, c.ldo);
+            copy_matrix<T>(c.s, other, nd, c.outw, c.ldo, Bb, c.ldb);
+        }
+        return;
+    }
+    const int n1 = split_point(nd, 128), n2 = nd - n1;
+    const int a = d0, b = d0 + n1;          // block 1 = [a, b), block 2 = [b, d0+nd)
+    const T one = num<T>::real(1.0);
+    // off-diagonal block of the STORED matrix: lower -> A21 = A(b.., a..) (n2 x n1); upper -> A12 = A(a.., b..) (n1 x n2)
+    const T* Aoff = c.upper ? Aat(c, a, b) : Aat(c, b, a);
+    const bool notr = op_code(c.trans) == 0;
+    if (c.left) {
+        T* B1 = c.B + a; T* B2 = c.B + b;
+        if (!opupper) {   // op(A) lower: B2 = T22 B2 + T21 B1 ; B1 = T11 B1   (B2 first: it needs the old B1)
+            trmm_rec(c, alpha, b, n2, other);
+            // T21 = op(A)(b.., a..): stored lower & 'N' -> A21 ; stored upper & 'T' -> A12^T
+            gemm_dev<T>(c.s, notr ? 'N' : c.trans, 'N', n2, other, n1, alpha, Aoff, c.lda, B1, c.ldb, one, B2, c.ldb);
+            trmm_rec(c, alpha, a, n1, other);
+        } else {          // op(A) upper: B1 = T11 B1 + T12 B2 ; B2 = T22 B2
+            trmm_rec(c, alpha, a, n1, other);
+            gemm_dev<T>(c.s, notr ? 'N' : c.trans, 'N', n1, other, n2, alpha, Aoff, c.lda, B2, c.ldb, one, B1, c.ldb);
+            trmm_rec(c, alpha, b, n2, other);
+        }
+    } else {
+        T* B1 = c.B + (int64_t)a * c.ldb; T* B2 = c.B + (int64_t)b * c.ldb;
+        if (!opupper) {   // op(A) lower: B1 = B1 T11 + B2 T21 ; B2 = B2 T22   (B1 first)
+            trmm_rec(c, alpha, a, n1, other);
+            gemm_dev<T>(c.s, 'N', notr ? 'N' : c.trans, other, n1, n2, alpha, B2, c.ldb, Aoff, c.lda, one, B1, c.ldb);
+            trmm_rec(c, alpha, b, n2, other);
+        } else {          // op(A) upper: B2 = B1 T12 + B2 T22 ; B1 = B1 T11   (B2 first)
+            trmm_rec(c, alpha, b, n2, other);
+            gemm_dev<T>(c.s, 'N', notr ? 'N' : c.trans, other, n2, n1, alpha, B1, c.ldb, Aoff, c.lda, one, B2, c.ldb);
+            trmm_rec(c, alpha, a, n1, other);
+        }
+    }
+}
+
+template <typename T>
+void trmm_dev(cudaStream_t s, char side, char uplo, char trans, char diag, int m, int n, T alpha, const T* A, int64_t lda, T* B,
+              int64_t ldb) {
+    if (m <= 0 || n <= 0) return;
+    if (num<T>::is_zero(alpha)) { scale_matrix<T>(s, m, n, num<T>::zero(), B, ldb, MASK_FULL); last_variant = VAR_SCALE_ONLY; return; }
+    TrCtx<T> c;
+    c.s = s; c.left = (side == 'L' || side == 'l'); c.upper = (uplo == 'U' || uplo == 'u'); c.unit = (diag == 'U' || diag == 'u');
+    c.trans = op_code(trans) == 0 ? 'N' : (op_code(trans) == 1 ? 'T' : 'C');
+    c.A = A; c.lda = lda; c.B = B; c.ldb = ldb;
+    const int nd = c.left ? m : n, other = c.left ? n : m;
+    const int base = nd < TRMM_BASE ? nd : TRMM_BASE;
+    c.triw = (T*)ws_alloc((size_t)even_ld(base, sizeof(T)) * base * sizeof(T));
+    c.ldo = even_ld(c.left ? base : other, sizeof(T));
+    c.outw = (T*)ws_alloc((size_t)c.ldo * (c.left ? other : base) * sizeof(T));
+    trmm_rec(c, alpha, 0, nd, other);
+}
+template void trmm_dev<float>(cudaStream_t, char, char, char, char, int, int, float, const float*, int64_t, float*, int64_t);
+template void trmm_dev<double>(cudaStream_t, char, char, char, char, int, int, double, const double*, int64_t, double*, int64_t);
+template void trmm_dev<cuFloatComplex>(cudaStream_t, char, char, char, char, int, int, cuFloatComplex, const cuFloatComplex*, int64_t, cuFloatComplex*, int64_t);
+template void trmm_dev<cuDoubleComplex>(cudaStream_t, char, char, char, char, int, int, cuDoubleComplex, const cuDoubleComplex*, int64_t, cuDoubleComplex*, int64_t);
+
+// ------------------------------------------------------------------ TRSM
+constexpr int TRSM_NB = 64;
+
+template <typename T> __device__ __forceinline__ T tdiv(T a, T b);
+template <> __device__ __forceinline__ float tdiv(float a, float b) { return a / b; }
+template <> __device__ __forceinline__ double tdiv(double a, double b) { return a / b; }
+template <> __device__ __forceinline__ cuFloatComplex tdiv(cuFloatComplex a, cuFloatComplex b) { return cuCdivf(a, b); }
+template <> __device__ __forceinline__ cuDoubleComplex tdiv(cuDoubleComplex a, cuDoubleComplex b) { return cuCdiv(a, b); }
+
+// One CTA per 64x64 diagonal block: inv := T^{-1} by substitution on the identity.  Thread j owns column j
+// of the inverse (columns are independent); T sits in shared memory.  Output is a full nb x nb block with
+// exact zeros in the unreferenced triangle, so it can be fed to the GEMM kernel.
+template <typename T>
+__global__ void __launch_bounds__(TRSM_NB) tri_inverse_kernel(int n, const T* __restrict__ A, int64_t lda, bool upper, bool unit,
+                                                             T* __restrict__ inv /* [nblk][NB*NB] */) {
+    extern __shared__ __align__(16) unsigned char smem_inv[];
+    T* sT = (T*)smem_inv;                       // sT[i + l*NB]
+    T* sX = sT + TRSM_NB * TRSM_NB;             // sX[i + j*(NB+1)]: column j of the inverse (padded: bank-conflict-free)
+    const int b0 = blockIdx.x * TRSM_NB, nb = min(TRSM_NB, n - b0), j = threadIdx.x;
+    const T* Ab = A + b0 + (int64_t)b0 * lda;
+    for (int l = 0; l < nb; l++)
+        if (j < nb) sT[j + l * TRSM_NB] = Ab[j + (int64_t)l * lda];
+    __syncthreads();
+    if (j < nb) {
+        T* x = sX + j * (TRSM_NB + 1);
+        for (int i = 0; i < nb; i++) x[i] = num<T>::zero();
+        if (!upper) {   // forward substitution, rows j..nb-1 (rows < j of column j are zero)
+            for (int i = j; i < nb; i++) {
+                T sacc = (i == j) ? num<T>::real(1.0) : num<T>::zero();
+                for (int l = j; l < i; l++) sacc = num<T>::sub(sacc, num<T>::mul(sT[i + l * TRSM_NB], x[l]));
+                x[i] = unit ? sacc : tdiv<T>(sacc, sT[i + i * TRSM_NB]);
+            }
+        } else {        // back substitution, rows j..0
+            for (int i = j; i >= 0; i--) {
+                T sacc = (i == j) ? num<T>::real(1.0) : num<T>::zero();
+                for (int l = i + 1; l <= j; l++) sacc = num<T>::sub(sacc, num<T>::mul(sT[i + l * TRSM_NB], x[l]));
+                x[i] = unit ? sacc : tdiv<T>(sacc, sT[i + i * TRSM_NB]);
+            }
+        }
+    }
+    __syncthreads();
+    T* out = inv + (int64_t)blockIdx.x * TRSM_NB * TRSM_NB;
+    for (int l = 0; l < TRSM_NB; l++)
+        out[j + l * TRSM_NB] = (j < nb && l < nb) ? sX[j + l * (TRSM_NB + 1)] : num<T>::zero();
+}
+
+template <typename T> struct TsCtx {
+    cudaStream_t s; bool left, upper, unit; char trans; const T* A; int64_t lda; T* B; int64_t ldb;
+    const T* inv; T* outw; int64_t ldo;
+};
+
+template <typename T>
+static void trsm_rec(const TsCtx<T>& c, T alpha, int d0, int nd, int other) {
+    const bool notr = op_code(c.trans) == 0;
+    const bool opupper = notr ? c.upper : !c.upper;
+    if (nd <= TRSM_NB) {
+        const T* invb = c.inv + (int64_t)(d0 / TRSM_NB) * TRSM_NB * TRSM_NB;
+        if (c.left) {   // X = alpha * op(T)^{-1} B_blk = alpha * op(T^{-1}) B_blk
+            T* Bb = c.B + d0;
+            gemm_dev<T>(c.s, c.trans, 'N', nd, other, nd, alpha, invb, TRSM_NB, Bb, c.ldb, num<T>::zero(), c.outw, c.ldo);
+            copy_matrix<T>(c.s, nd, other, c.outw, c.ldo, Bb, c.ldb);
+        } else {        // X = alpha * B_blk * op(T^{-1})
+            T* Bb = c.B + (int64_t)d0 * c.ldb;
+            gemm_dev<T>(c.s, 'N', c.trans, other, nd, nd, alpha, Bb, c.ldb, invb, TRSM_NB, num<T>::zero(), c.outw, c.ldo);
+            copy_matrix<T>(c.s, other, nd, c.outw, c.ldo, Bb, c.ldb);
+        }
+        return;
+    }
+    const int n1 = split_point(nd, TRSM_NB), n2 = nd - n1;
+    const int a = d0, b = d0 + n1;
+    const T one = num<T>::real(1.0), mone = num<T>::real(-1.0);
+    const T* Aoff = c.upper ? (c.A + a + (int64_t)b * c.lda) : (c.A + b + (int64_t)a * c.lda);
+    const char to = notr ? 'N' : c.trans;
+    if (c.left) {
+        T* B1 = c.B + a; T* B2 = c.B + b;
+        if (!opupper) {   // [T11 0; T21 T22][X1;X2] = alpha [B1;B2]
+            trsm_rec(c, alpha, a, n1, other);
+            gemm_dev<T>(c.s, to, 'N', n2, other, n1, mone, Aoff, c.lda, B1, c.ldb, alpha, B2, c.ldb);
+            trsm_rec(c, one, b, n2, other);
+        } else {          // [T11 T12; 0 T22]
+            trsm_rec(c, alpha, b, n2, other);
+            gemm_dev<T>(c.s, to, 'N', n1, other, n2, mone, Aoff, c.lda, B2, c.ldb, alpha, B1, c.ldb);
+            trsm_rec(c, one, a, n1, other);
+        }
+    } else {
+        T* B1 = c.B + (int64_t)a * c.ldb; T* B2 = c.B + (int64_t)b * c.ldb;
+        if (!opupper) {   // [X1 X2][T11 0; T21 T22] = alpha [B1 B2]:  X2 T22 = aB2 ; X1 T11 = aB1 - X2 T21
+            trsm_rec(c, alpha, b, n2, other);
+            gemm_dev<T>(c.s, 'N', to, other, n1, n2, mone, B2, c.ldb, Aoff, c.lda, alpha, B1, c.ldb);
+            trsm_rec(c, one, a, n1, other);
+        } else {          // X1 T11 = aB1 ; X2 T22 = aB2 - X1 T12
+            trsm_rec(c, alpha, a, n1, other);
+            gemm_dev<T>(c.s, 'N', to, other, n2, n1, mone, B1, c.ldb, Aoff, c.lda, alpha, B2, c.ldb);
+            trsm_rec(c, one, b, n2, other);
+        }
+    }
+}
+
+template <typename T>
+void trsm_dev(cudaStream_t s, char side, char uplo, char trans, char diag, int m, int n, T alpha, const T* A, int64_t lda, T* B,
+              int64_t ldb) {
+    if (m <= 0 || n <= 0) return;
+    if (num<T>::is_zero(alpha)) { scale_matrix<T>(s, m, n, num<T>::zero(), B, ldb, MASK_FULL); last_variant = VAR_SCALE_ONLY; return; }
+    TsCtx<T> c;
+    c.s = s; c.left = (side == 'L' || side == 'l'); c.upper = (uplo == 'U' || uplo == 'u'); c.unit = (diag == 'U' || diag == 'u');
+    c.trans = op_code(trans) == 0 ? 'N' : (op_code(trans) == 1 ? 'T' : 'C');
+    c.A = A; c.lda = lda; c.B = B; c.ldb = ldb;
+    const int nd = c.left ? m : n, other = c.left ? n : m;
+    const int nblk = (nd + TRSM_NB - 1) / TRSM_NB;
+    T* inv = (T*)ws_alloc((size_t)nblk * TRSM_NB * TRSM_NB * sizeof(T));
+    c.inv = inv;
+    const int smem = (2 * TRSM_NB + 1) * TRSM_NB * sizeof(T);
+    static bool attr_done = false;
+    if (!attr_done) {
+        B200_CUDA(cudaFuncSetAttribute(tri_inverse_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    tri_inverse_kernel<T><<<nblk, TRSM_NB, smem, s>>>(nd, A, lda, c.upper, c.unit, inv);
+    c.ldo = even_ld(c.left ? TRSM_NB : other, sizeof(T));
+    c.outw = (T*)ws_alloc((size_t)c.ldo * (c.left ? other : TRSM_NB) * sizeof(T));
+    trsm_rec(c, alpha, 0, nd, other);
+}
+template void trsm_dev<float>(cudaStream_t, char, char, char, char, int, int, float, const float*, int64_t, float*, int64_t);
+template void trsm_dev<double>(cudaStream_t, char, char, char, char, int, int, double, const double*, int64_t, double*, int64_t);
+template void trsm_dev<cuFloatComplex>(cudaStream_t, char, char, char, char, int, int, cuFloatComplex, const cuFloatComplex*, int64_t, cuFloatComplex*, int64_t);
+template void trsm_dev<cuDoubleComplex>(cudaStream_t, char, char, char, char, int, int, cuDoubleComplex, const cuDoubleComplex*, int64_t, cuDoubleComplex*, int64_t);
+
+}  // namespace b200
