@@ -179,6 +179,7 @@ B200_API void* b200blas_malloc_managed(size_t bytes);            /* tracked mana
 B200_API void b200blas_free_managed(void* p);
 B200_API int b200blas_is_tracked(const void* p);
 B200_API int b200blas_device_count(void);
+B200_API void b200blas_print_help(void);
 B200_API void b200blas_entry(void);                              /* ELF entry: prints option help (reference entry.c) */
 
 #ifdef __cplusplus

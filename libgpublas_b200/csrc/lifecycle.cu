@@ -137,10 +137,6 @@ int b200blas_is_tracked(const void* p) { return tracker_lookup(p, nullptr, nullp
 int b200blas_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 void b200blas_synchronize(void) { B200_CUDA(cudaStreamSynchronize(current_stream())); }
 
-// Running the shared object itself prints the option help (reference entry.c:4-11, meson.build:25).
-void b200blas_entry(void) {
-    print_help();
-    _exit(0);
-}
+void b200blas_print_help(void) { print_help(); }
 
 }  // extern "C"

@@ -85,6 +85,14 @@ static void do_init() {
         b200_writef(STDERR_FILENO, "b200blas: device %d %s, %d SMs, %zu MiB, concurrentManagedAccess=%d, tma=%d\n",
                     g_device, prop.name, g_sms, prop.totalGlobalMem >> 20, prop.concurrentManagedAccess, g_encode != nullptr);
     g_ready = true;
+    // Registered after the CUDA runtime registered its own teardown, so it runs BEFORE it (LIFO): stdio
+    // buffers that the interposed malloc placed in managed memory (heuristic=true, or a large setvbuf)
+    // are flushed and detached while the context still exists; later allocations use the heap.
+    atexit([] {
+        tracker_set_tracking(0);
+        fflush(NULL);
+        if (tracker_lookup(stdout->_IO_buf_base, nullptr, nullptr)) setvbuf(stdout, nullptr, _IONBF, 0);
+    });
 }
 
 void ensure_init() { std::call_once(g_init_once, do_init); }

@@ -12,6 +12,7 @@
 #include "tracker.h"
 #include "runtime.h"
 #include <cuda_runtime_api.h>
+#include <dlfcn.h>
 #include <errno.h>
 #include <pthread.h>
 #include <stdio.h>
@@ -35,7 +36,7 @@ Block* g_blocks = nullptr;
 size_t g_nblocks = 0, g_cap = 0;
 volatile uintptr_t g_lo = UINTPTR_MAX, g_hi = 0;   // address envelope of all blocks ever handed out
 
-__thread int t_inside = 0;
+__thread int t_inside __attribute__((tls_model("initial-exec"))) = 0;   // no lazy TLS allocation inside malloc
 volatile int g_tracking = 0;
 volatile int g_heuristic = B200_H_SIZE;
 volatile size_t g_threshold = 64 * 1024;
@@ -203,6 +204,40 @@ int tracker_free_managed(void* p) {
     return 1;
 }
 
+// ---- threads created by CUDA itself never get managed memory ----
+// The reference keeps CUDA's own allocations out of the managed allocator by return address ("excluded
+// regions" scanned from /proc/self/maps, obj_tracker.c:352-424), which misses allocations CUDA makes through
+// libc helpers.  Here every thread that is created while a thread is inside the library (i.e. by the CUDA
+// runtime / driver during one of our calls) is marked "inside" for its whole life, so a driver worker
+// thread can never re-enter cudaMallocManaged from malloc and deadlock on the driver's own locks.
+struct ThreadStart { void* (*fn)(void*); void* arg; };
+static void* cuda_thread_trampoline(void* p) {
+    ThreadStart ts = *(ThreadStart*)p;
+    __libc_free(p);
+    t_inside = 1 << 20;
+    return ts.fn(ts.arg);
+}
+typedef int (*pthread_create_t)(pthread_t*, const pthread_attr_t*, void* (*)(void*), void*);
+__attribute__((visibility("default"))) int pthread_create(pthread_t* thread, const pthread_attr_t* attr, void* (*fn)(void*), void* arg) {
+    static pthread_create_t real = nullptr;
+    if (!real) {
+        t_inside++;
+        real = (pthread_create_t)dlsym(RTLD_NEXT, "pthread_create");
+        t_inside--;
+        if (!real) { b200_writef(STDERR_FILENO, "b200blas: cannot resolve pthread_create\n"); abort(); }
+    }
+    if (t_inside > 0 || g_initialising) {
+        ThreadStart* ts = (ThreadStart*)__libc_malloc(sizeof(ThreadStart));
+        if (ts) {
+            ts->fn = fn; ts->arg = arg;
+            int rc = real(thread, attr, cuda_thread_trampoline, ts);
+            if (rc != 0) __libc_free(ts);
+            return rc;
+        }
+    }
+    return real(thread, attr, fn, arg);
+}
+
 // ---- the interposed allocator symbols (reference obj_tracker.c:789,842,902,948) ----
 void* malloc(size_t request) noexcept {
     if (bypass()) return __libc_malloc(request);
@@ -248,3 +283,17 @@ void free(void* ptr) noexcept {
 }
 
 }  // extern "C"
+
+// Makes the shared object directly executable (`./libb200blas.so` prints the option help through
+// b200blas_entry, lifecycle.cu): the kernel needs a program interpreter to relocate it
+// (reference entry.c:4, same mechanism).
+extern "C" {
+__attribute__((used, visibility("default"), section(".interp"))) const char b200blas_interp[] = "/lib64/ld-linux-x86-64.so.2";
+void b200blas_print_help(void);
+// ELF entry point (-e b200blas_entry): entered without a return address on the stack, so the stack
+// must be re-aligned before calling into libc.
+__attribute__((force_align_arg_pointer, visibility("default"))) void b200blas_entry(void) {
+    b200blas_print_help();
+    _exit(0);
+}
+}

@@ -1,0 +1,150 @@
+"""The drop-in boundary itself: C programs that call BLAS and malloc through the PLT, run (a) plain on the
+CPU BLAS they are linked with and (b) under LD_PRELOAD=libb200blas.so (reference scripts/blas2cuda.sh:27,
+tests/netlib/test.py:28).  CPU-only part: the drivers build and run on the CPU BLAS, and the library
+exports every symbol include/b200blas.h declares."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+from helpers import LIB_PATH, ROOT, find_openblas
+
+DRV = os.path.join(ROOT, "tests", "drivers")
+BUILD = os.path.join(DRV, "_build")
+
+
+def build_driver(name):
+    ob = find_openblas()
+    if ob is None:
+        pytest.skip("no CPU BLAS in this image")
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, name)
+    src = os.path.join(DRV, name + ".c")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
+        d = os.path.dirname(ob)
+        subprocess.check_call(["gcc", "-O2", "-o", exe, src, "-L" + d, "-l:" + os.path.basename(ob), "-Wl,-rpath," + d, "-Wl,--disable-new-dtags",
+                               "-Wl,--allow-shlib-undefined", "-ldl", "-lm"])
+    return exe
+
+
+def run(exe, args=(), preload=False, env_extra=None, cwd=None, timeout=300):
+    env = dict(os.environ)
+    env.setdefault("OPENBLAS_CORETYPE", "SkylakeX")
+    env["OPENBLAS_NUM_THREADS"] = str(os.cpu_count() or 1)
+    ob = find_openblas()
+    if ob:   # OpenBLAS's private libgfortran / libquadmath live beside it
+        env["LD_LIBRARY_PATH"] = os.path.dirname(ob) + ":" + env.get("LD_LIBRARY_PATH", "")
+    if preload:
+        env["LD_PRELOAD"] = LIB_PATH
+    if env_extra:
+        env.update(env_extra)
+    out = subprocess.run([exe] + [str(a) for a in args], env=env, cwd=cwd, capture_output=True, text=True, timeout=timeout)
+    assert out.returncode == 0, (out.returncode, out.stdout[-2000:], out.stderr[-2000:])
+    return out.stdout, out.stderr
+
+
+def fields(line):
+    return dict(kv.split("=", 1) for kv in line.split()[1:])
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b200blas.h")).read()
+    declared = set(re.findall(r"^B200_API [^;(]*?(\w+)\(", hdr, re.M)) | {"malloc", "calloc", "realloc", "free"}
+    assert len(declared) > 100
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", LIB_PATH], text=True)
+    exported = {l.split()[-1] for l in syms.splitlines() if " T " in l or " W " in l}
+    missing = sorted(declared - exported)
+    assert not missing, missing
+    # and it loads (no unresolved dependencies) on a machine without a GPU
+    import libgpublas_b200 as g
+    assert g.load().b200blas_version() >= 100
+
+
+def test_so_is_executable_and_prints_help():
+    """reference entry.c:4-11 / meson.build:25: running the .so prints the option help."""
+    out = subprocess.run([LIB_PATH], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "BLAS2CUDA_OPTIONS" in out.stderr and "heuristic=" in out.stderr
+
+
+def test_gemm_fixture_on_cpu_blas():
+    exe = build_driver("gemm_fixture")
+    out, _ = run(exe, [256, 3])
+    res = [fields(l) for l in out.splitlines() if l.startswith("RESULT")]
+    assert len(res) == 2 and all(float(r["max_abs_err"]) == 0.0 for r in res)
+    assert "STATS none" in out
+
+
+def test_cg_chain_on_cpu_blas():
+    exe = build_driver("cg_chain")
+    out, _ = run(exe, [512, 10])
+    r = fields([l for l in out.splitlines() if l.startswith("RESULT")][0])
+    assert float(r["rnorm"]) < 1e-10
+
+
+def test_allocs_on_glibc():
+    exe = build_driver("allocs")
+    out, _ = run(exe)
+    assert "RESULT ok=1 tracked=0" in out
+
+
+# ------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_gemm_fixture_under_preload(tmp_path):
+    """BASELINE config 1: DGEMM 1024^3 through the interposer == the closed form, via dgemm_ and cblas_dgemm;
+    operands come from the interposed calloc, so every operand is a tracker hit (no staging copies)."""
+    exe = build_driver("gemm_fixture")
+    out, err = run(exe, [1024, 11], preload=True, cwd=str(tmp_path))
+    res = [fields(l) for l in out.splitlines() if l.startswith("RESULT")]
+    assert len(res) == 2 and all(float(r["max_abs_err"]) == 0.0 for r in res), out
+    st = fields([l for l in out.splitlines() if l.startswith("STATS")][0])
+    assert int(st["misses"]) == 0 and int(st["hits"]) == 2 * 11 * 3 and int(st["h2d"]) == 0
+    assert int(st["managed_allocs"]) >= 2 * 11 * 3
+    cpu_out, _ = run(exe, [1024, 3])
+    cpu = [fields(l) for l in cpu_out.splitlines() if l.startswith("RESULT")]
+    assert cpu[0]["checksum"] == res[0]["checksum"]
+    # reference blas2cuda.c:266-273: statistics.csv with the hit/miss counters is written at exit
+    stats = open(os.path.join(str(tmp_path), "statistics.csv")).read().splitlines()
+    assert stats[0].startswith("Hits, Misses") and stats[1].split(",")[1].strip() == "0"
+
+
+@pytest.mark.gpu
+def test_cg_chain_under_preload(tmp_path):
+    """BASELINE config 3 (scaled for the test): chained Level-1/2 calls on tracked managed buffers agree with
+    the CPU BLAS run of the same binary and never stage a copy."""
+    exe = build_driver("cg_chain")
+    # 2048 doubles = 16 KiB per vector: below the default 64 KiB rule, so lower it (north_star (3): size-based selector)
+    gout, _ = run(exe, [2048, 25], preload=True, env_extra={"BLAS2CUDA_OPTIONS": "threshold=8192"}, cwd=str(tmp_path))
+    cout, _ = run(exe, [2048, 25])
+    gr = fields([l for l in gout.splitlines() if l.startswith("RESULT")][0])
+    cr = fields([l for l in cout.splitlines() if l.startswith("RESULT")][0])
+    assert float(gr["rnorm"]) < 1e-10 and float(cr["rnorm"]) < 1e-10
+    assert abs(float(gr["xsum"]) - float(cr["xsum"])) <= 1e-12 * max(1.0, abs(float(cr["xsum"])))
+    assert gr["imax"] == cr["imax"]
+    st = fields([l for l in gout.splitlines() if l.startswith("STATS")][0])
+    assert int(st["h2d"]) == 0 and int(st["d2h"]) == 0 and int(st["hits"]) > 0
+
+
+@pytest.mark.gpu
+def test_allocs_under_preload(tmp_path):
+    exe = build_driver("allocs")
+    out, _ = run(exe, preload=True, cwd=str(tmp_path), timeout=90)
+    r = fields([l for l in out.splitlines() if l.startswith("RESULT")][0])
+    assert r["ok"] == "1" and int(r["tracked"]) > 300          # blocks >= 64 KiB are managed
+    out, _ = run(exe, preload=True, env_extra={"BLAS2CUDA_OPTIONS": "heuristic=false"}, cwd=str(tmp_path), timeout=90)
+    assert "RESULT ok=1 tracked=0" in out
+    out, _ = run(exe, preload=True, env_extra={"BLAS2CUDA_OPTIONS": "heuristic=true"}, cwd=str(tmp_path), timeout=90)
+    assert "RESULT ok=1 tracked=512" in out
+
+
+@pytest.mark.gpu
+def test_preload_untracked_operands_are_staged(tmp_path):
+    """heuristic=false: operands stay on the glibc heap -> every operand is a miss, staged through the
+    workspace and copied back (the reference's gpuptr miss path, runtime-mem.hpp:84-135); result identical."""
+    exe = build_driver("gemm_fixture")
+    out, _ = run(exe, [512, 2], preload=True, env_extra={"BLAS2CUDA_OPTIONS": "heuristic=false"}, cwd=str(tmp_path))
+    res = [fields(l) for l in out.splitlines() if l.startswith("RESULT")]
+    assert all(float(r["max_abs_err"]) == 0.0 for r in res)
+    st = fields([l for l in out.splitlines() if l.startswith("STATS")][0])
+    assert int(st["hits"]) == 0 and int(st["misses"]) == 2 * 2 * 3 and int(st["h2d"]) > 0 and int(st["d2h"]) > 0
