@@ -110,6 +110,8 @@ def main():
     ap.add_argument("--ksample", type=int, default=1024)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="N>1: check the partitioned result against the 1-GPU kernel on rank 0")
+    ap.add_argument("--kchunk", type=int, default=2048)
     args = ap.parse_args()
     n = args.n
     rank = int(os.environ.get("RANK", "0"))
@@ -182,7 +184,7 @@ def main():
         ref = (A.T[:, :64].T @ B.T[:64, :].T) if False else None
         scaling, parallelism = "strong", "single"
     else:
-        tg = TiledGemm(n, n, n, dev, rank, world)
+        tg = TiledGemm(n, n, n, dev, rank, world, kchunk=args.kchunk)
         tg.make_inputs(seed=2)
         for _ in range(args.warmup):
             tg.run()
@@ -207,6 +209,15 @@ def main():
         variant = g.last_variant()
         launches = args.steps * tg.kernels_per_step
         scaling, parallelism = "strong", tg.describe()
+        verified = None
+        if args.verify and rank == 0:
+            ref = torch.empty(n * n, dtype=torch.float64, device=dev)
+            g.call("dgemm_", "N", "N", n, n, n, 1.0, tg.A, n, tg.B, n, 0.0, ref, n)
+            torch.cuda.synchronize()
+            got = tg.home_c()
+            verified = {"max_abs_diff_vs_1gpu": float((got - ref).abs().max().item()),
+                        "bound": 2 * n * 2.0 ** -53 * float(torch.linalg.norm(tg.A[: n * 64]).item()) ** 2 / 64}
+            del ref, got
 
     # ---- end-to-end through the C ABI with pinned host buffers (N = 1) ----
     e2e = None
@@ -256,6 +267,8 @@ def main():
                                             % (FP64_PEAK_MEASURED, peaks.get("bf16_tflops", 0), peaks.get("hbm_gbs", 0)),
                              "kernel_ms": kernel_ms},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        if world > 1 and verified is not None:
+            line["verified"] = verified
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -179,6 +179,14 @@ B200_API void* b200blas_malloc_managed(size_t bytes);            /* tracked mana
 B200_API void b200blas_free_managed(void* p);
 B200_API int b200blas_is_tracked(const void* p);
 B200_API int b200blas_device_count(void);
+/* D := alpha*op(A)*op(B) + beta*C on device pointers with a separate output (may be peer-mapped) */
+B200_API void b200blas_dgemm_out(char transa, char transb, int m, int n, int k, double alpha, const double* a, long long lda, const double* b, long long ldb, double beta, const double* c, long long ldc, double* d, long long ldd);
+/* raw device memory + CUDA IPC: lets another process's GEMM epilogue store C tiles into this allocation */
+B200_API void* b200blas_device_malloc(size_t bytes);
+B200_API void b200blas_device_free(void* p);
+B200_API int b200blas_ipc_get_handle(void* dev_ptr, void* handle64);   /* returns handle size (64) or -1 */
+B200_API void* b200blas_ipc_open(const void* handle64);                /* peer-mapped pointer or NULL */
+B200_API void b200blas_ipc_close(void* p);
 B200_API void b200blas_print_help(void);
 B200_API void b200blas_entry(void);                              /* ELF entry: prints option help (reference entry.c) */
 

@@ -107,6 +107,14 @@ void tr_entry(const char* name, bool solve, const char* side, const char* uplo, 
 
 extern "C" {
 
+// D := alpha*op(A)*op(B) + beta*C on DEVICE pointers, D distinct from C allowed (and D may be a CUDA-IPC
+// peer mapping).  Building block of the partitioned multi-GPU GEMM; arguments by value, no staging.
+void b200blas_dgemm_out(char transa, char transb, int m, int n, int k, double alpha, const double* a, long long lda,
+                        const double* b, long long ldb, double beta, const double* c, long long ldc, double* d, long long ldd) {
+    CallScope scope;
+    dgemm_out_dev(current_stream(), transa, transb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, d, ldd, MASK_FULL);
+}
+
 void sgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k, const float* alpha,
             const float* a, const int* lda, const float* b, const int* ldb, const float* beta, float* c, const int* ldc) {
     gemm_entry<float>("sgemm_", transa, transb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);

@@ -43,7 +43,8 @@ struct DgemmParams {
     double alpha, beta;
     const double* A; int64_t lda;
     const double* B; int64_t ldb;
-    double* C; int64_t ldc;
+    double* C; int64_t ldc;      // C-in (read when beta != 0)
+    double* D; int64_t ldd;      // output; == C for plain BLAS, a peer-mapped tile for partitioned calls
     int mask;
     int tiles_m, tiles_n;
 };
@@ -210,14 +211,15 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         for (int c = 0; c < 2; c++) {
             const int64_t col = n0 + wn0 + 8 * j + 2 * tig + c;
             if (col >= p.n) continue;
-            double* cp = p.C + col * p.ldc;
+            const double* cp = p.C + col * p.ldc;
+            double* dp = p.D + col * p.ldd;
 #pragma unroll
             for (int i = 0; i < MB; i++) {
                 const int64_t row = m0 + wm0 + 8 * i + g;
                 if (row >= p.m || !tri_keep(p.mask, row, col)) continue;
                 double v = p.alpha * acc[i][j][c];
                 if (!beta0) v = fma(p.beta, cp[row], v);
-                cp[row] = v;
+                dp[row] = v;
             }
         }
     }
@@ -276,8 +278,17 @@ static void dgemm_dmma_dispatch(cudaStream_t s, bool nota, bool notb, bool tma, 
 
 void dgemm_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, double alpha, const double* A, int64_t lda,
                const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int mask) {
+    dgemm_out_dev(s, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, C, ldc, mask);
+}
+
+// D := alpha*op(A)*op(B) + beta*C with D possibly distinct from C (D may be a peer-mapped pointer: the
+// epilogue then stores the tile over NVLink -- the fused compute + C-return of the partitioned GEMM).
+void dgemm_out_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, double alpha, const double* A, int64_t lda,
+                   const double* B, int64_t ldb, double beta, const double* Cin, int64_t ldc, double* D, int64_t ldd, int mask) {
+    double* C = const_cast<double*>(Cin);
     if (m <= 0 || n <= 0) return;
-    if (alpha == 0.0 || k <= 0) {
+    const bool separate_out = (D != C);
+    if ((alpha == 0.0 || k <= 0) && !separate_out) {
         scale_matrix<double>(s, m, n, beta, C, ldc, mask);
         last_variant = VAR_SCALE_ONLY;
         return;
@@ -291,6 +302,7 @@ void dgemm_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, double alp
         const double work = (double)m * n * k;
         variant = (work < 32.0 * 32.0 * 32.0) ? VAR_GENERIC_TILE : VAR_DMMA_TMA;
     }
+    if (separate_out) variant = (variant == VAR_DMMA_LDG) ? VAR_DMMA_LDG : VAR_DMMA_TMA;   // only the DMMA kernel has a D operand
     if (variant == VAR_GENERIC_TILE) {
         gemm_generic_launch<double>(s, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mask);
         return;
@@ -300,7 +312,7 @@ void dgemm_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, double alp
                         lda * 8 < ((int64_t)1 << 40) && ldb * 8 < ((int64_t)1 << 40);
     DgemmParams p;
     p.m = m; p.n = n; p.k = k; p.alpha = alpha; p.beta = beta;
-    p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.mask = mask;
+    p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.D = D; p.ldd = ldd; p.mask = mask;
     p.tiles_m = p.tiles_n = 0;
     dgemm_dmma_dispatch<8, 4>(s, nota, notb, tma_ok, p);
 }

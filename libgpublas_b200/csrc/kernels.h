@@ -27,6 +27,9 @@ extern int force_variant;                  // BLAS2CUDA_OPTIONS variant=...; VAR
 // ---- Level 3 ----  C := alpha*op(A)*op(B) + beta*C on the part of C selected by `mask`
 void dgemm_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, double alpha, const double* A, int64_t lda,
                const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int mask = MASK_FULL);
+void dgemm_out_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, double alpha, const double* A, int64_t lda,
+                   const double* B, int64_t ldb, double beta, const double* Cin, int64_t ldc, double* D, int64_t ldd,
+                   int mask = MASK_FULL);
 void sgemm_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, float alpha, const float* A, int64_t lda,
                const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int mask = MASK_FULL);
 void zgemm_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, cuDoubleComplex alpha,

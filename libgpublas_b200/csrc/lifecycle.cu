@@ -139,4 +139,35 @@ void b200blas_synchronize(void) { B200_CUDA(cudaStreamSynchronize(current_stream
 
 void b200blas_print_help(void) { print_help(); }
 
+// ---- raw device memory + CUDA IPC, for partitioned Level-3 calls across processes (one process per
+// GPU): the home rank exports C, every other rank maps it and its GEMM epilogue stores its C tile
+// straight into the home allocation over NVLink (SURVEY.md section 8e "C-tile return fused into the
+// epilogue (peer stores)"). ----
+void* b200blas_device_malloc(size_t bytes) {
+    ensure_init();
+    TrackerGuard g;
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void b200blas_device_free(void* p) { TrackerGuard g; cudaFree(p); }
+int b200blas_ipc_get_handle(void* dev_ptr, void* handle64) {
+    ensure_init();
+    TrackerGuard g;
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, dev_ptr) != cudaSuccess) { cudaGetLastError(); return -1; }
+    memcpy(handle64, &h, sizeof h);
+    return (int)sizeof h;
+}
+void* b200blas_ipc_open(const void* handle64) {
+    ensure_init();
+    TrackerGuard g;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void b200blas_ipc_close(void* p) { TrackerGuard g; cudaIpcCloseMemHandle(p); }
+
 }  // extern "C"
