@@ -36,7 +36,31 @@ Block* g_blocks = nullptr;
 size_t g_nblocks = 0, g_cap = 0;
 volatile uintptr_t g_lo = UINTPTR_MAX, g_hi = 0;   // address envelope of all blocks ever handed out
 
-__thread int t_inside __attribute__((tls_model("initial-exec"))) = 0;   // no lazy TLS allocation inside malloc
+// Per-thread re-entrancy depth WITHOUT thread-local storage.  A TLS variable read inside malloc must be
+// initial-exec (a general-dynamic access may itself call malloc to allocate the module's TLS block), but one
+// initial-exec variable marks the whole shared object DF_STATIC_TLS, and the statically linked CUDA runtime
+// carries a 4 KiB-aligned TLS block that does not fit glibc's static-TLS surplus -- dlopen() of the library
+// (ctypes, Octave, Python extensions) would fail.  So the counter lives in a fixed open-addressing table keyed
+// by the thread pointer (%fs:0, the TCB address: unique per live thread, readable without any allocation).
+struct ThreadSlot { volatile uintptr_t tp; int inside; };
+constexpr size_t kSlots = 4096;                 // live threads beyond this are simply never tracked
+ThreadSlot g_slots[kSlots];
+int g_overflow_inside = 1;
+
+inline int& inside_ref() {
+    const uintptr_t tp = (uintptr_t)__builtin_thread_pointer();
+    size_t h = (size_t)(((tp >> 6) * 0x9E3779B97F4A7C15ull) >> 52);
+    for (size_t probe = 0; probe < kSlots; probe++, h = (h + 1) & (kSlots - 1)) {
+        uintptr_t cur = g_slots[h].tp;
+        if (cur == tp) return g_slots[h].inside;
+        if (cur == 0) {
+            if (__sync_bool_compare_and_swap(&g_slots[h].tp, (uintptr_t)0, tp)) return g_slots[h].inside;
+            if (g_slots[h].tp == tp) return g_slots[h].inside;
+        }
+    }
+    return g_overflow_inside;
+}
+#define t_inside (inside_ref())
 volatile int g_tracking = 0;
 volatile int g_heuristic = B200_H_SIZE;
 volatile size_t g_threshold = 64 * 1024;
@@ -210,11 +234,12 @@ int tracker_free_managed(void* p) {
 // libc helpers.  Here every thread that is created while a thread is inside the library (i.e. by the CUDA
 // runtime / driver during one of our calls) is marked "inside" for its whole life, so a driver worker
 // thread can never re-enter cudaMallocManaged from malloc and deadlock on the driver's own locks.
-struct ThreadStart { void* (*fn)(void*); void* arg; };
-static void* cuda_thread_trampoline(void* p) {
+// (A TCB address is reused once its thread has exited, so every new thread re-initialises its slot.)
+struct ThreadStart { void* (*fn)(void*); void* arg; int depth; };
+static void* thread_trampoline(void* p) {
     ThreadStart ts = *(ThreadStart*)p;
     __libc_free(p);
-    t_inside = 1 << 20;
+    t_inside = ts.depth;
     return ts.fn(ts.arg);
 }
 typedef int (*pthread_create_t)(pthread_t*, const pthread_attr_t*, void* (*)(void*), void*);
@@ -226,16 +251,13 @@ __attribute__((visibility("default"))) int pthread_create(pthread_t* thread, con
         t_inside--;
         if (!real) { b200_writef(STDERR_FILENO, "b200blas: cannot resolve pthread_create\n"); abort(); }
     }
-    if (t_inside > 0 || g_initialising) {
-        ThreadStart* ts = (ThreadStart*)__libc_malloc(sizeof(ThreadStart));
-        if (ts) {
-            ts->fn = fn; ts->arg = arg;
-            int rc = real(thread, attr, cuda_thread_trampoline, ts);
-            if (rc != 0) __libc_free(ts);
-            return rc;
-        }
-    }
-    return real(thread, attr, fn, arg);
+    ThreadStart* ts = (ThreadStart*)__libc_malloc(sizeof(ThreadStart));
+    if (!ts) return real(thread, attr, fn, arg);
+    ts->fn = fn; ts->arg = arg;
+    ts->depth = (t_inside > 0 || g_initialising) ? (1 << 20) : 0;
+    int rc = real(thread, attr, thread_trampoline, ts);
+    if (rc != 0) __libc_free(ts);
+    return rc;
 }
 
 // ---- the interposed allocator symbols (reference obj_tracker.c:789,842,902,948) ----
