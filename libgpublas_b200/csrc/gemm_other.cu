@@ -1,4 +1,4 @@
-// gemm_other.cu -- SGEMM / CGEMM / ZGEMM launchers (reference gemm.cc:143-160, :181-217).
+// gemm_other.cu -- SGEMM / CGEMM launchers (reference gemm.cc:143-160, :181-198); ZGEMM lives in gemm_z.cu.
 #include "gemm_generic.cuh"
 #include "runtime.h"
 
@@ -17,12 +17,4 @@ void cgemm_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, cuFloatCom
     if (num<cuFloatComplex>::is_zero(alpha) || k <= 0) { scale_matrix<cuFloatComplex>(s, m, n, beta, C, ldc, mask); last_variant = VAR_SCALE_ONLY; return; }
     gemm_generic_launch<cuFloatComplex>(s, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mask);
 }
-void zgemm_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, cuDoubleComplex alpha, const cuDoubleComplex* A,
-               int64_t lda, const cuDoubleComplex* B, int64_t ldb, cuDoubleComplex beta, cuDoubleComplex* C,
-               int64_t ldc, int mask) {
-    if (m <= 0 || n <= 0) return;
-    if (num<cuDoubleComplex>::is_zero(alpha) || k <= 0) { scale_matrix<cuDoubleComplex>(s, m, n, beta, C, ldc, mask); last_variant = VAR_SCALE_ONLY; return; }
-    gemm_generic_launch<cuDoubleComplex>(s, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mask);
-}
-
 }  // namespace b200

@@ -190,3 +190,51 @@ def test_dgemm_large_property_linearity():
     err = torch.linalg.norm(C - ref).item()
     bound = 2 * n * 2.0 ** -53 * torch.linalg.norm(A).item() * torch.linalg.norm(B).item()
     assert err <= bound, (err, bound)
+
+
+@pytest.mark.parametrize("ta", ["N", "T", "C"])
+@pytest.mark.parametrize("tb", ["N", "T", "C"])
+def test_zgemm_dmma_all_ops(ta, tb):
+    """ZGEMM on the DMMA pipeline: every transpose/conjugate pair, ragged tiles and k tails,
+    c = 4 Frobenius bound and the netlib ratio test; must agree with the generic tile kernel too."""
+    lib = g.load()
+    for (m, n, k) in [(64, 128, 8), (65, 129, 9), (130, 200, 77), (300, 70, 160)]:
+        alpha, beta = (0.7 - 0.9j), (1.3 - 1.1j)                  # input.zblat3:11-14
+        ra, ca = (m, k) if ta == "N" else (k, m)
+        rb, cb = (k, n) if tb == "N" else (n, k)
+        lda, ldb, ldc = ra + 1, rb + 2, m + 3
+        A = splitmix_uniform(41, (lda, ca), np.complex128); B = splitmix_uniform(42, (ldb, cb), np.complex128)
+        C0 = splitmix_uniform(43, (ldc, n + 1), np.complex128)
+        C = F(C0)
+        f77(lib, "zgemm_", ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc)
+        assert g.last_variant() == "dmma_tma"
+        check_gemm("z", ta, tb, m, n, k, alpha, beta, A, B, C0, C)
+        g.force_variant("generic_tile")
+        try:
+            C2 = F(C0)
+            f77(lib, "zgemm_", ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C2, ldc)
+            assert g.last_variant() == "generic_tile"
+        finally:
+            g.force_variant("auto")
+        assert np.allclose(C[:m, :n], C2[:m, :n], rtol=1e-12, atol=1e-12)
+
+
+def test_zgemm_large_device_resident():
+    """BASELINE config 5 shape family at a size the host check finishes quickly: device-resident
+    operands, beta = 0 must not read C (NaN-filled), spot-checked rows/columns against numpy."""
+    import torch
+    lib = g.load()
+    n = 1536
+    gen = torch.Generator(device="cuda").manual_seed(10)
+    A = torch.rand((n, n), dtype=torch.complex128, device="cuda", generator=gen) - (0.5 + 0.5j)
+    B = torch.rand((n, n), dtype=torch.complex128, device="cuda", generator=gen) - (0.5 + 0.5j)
+    C = torch.full((n, n), float("nan"), dtype=torch.complex128, device="cuda")
+    # torch tensors are row-major: the column-major view of A is A^T, so C_cm = A_cm * B_cm  <=>  C^T = A^T B^T
+    f77(lib, "zgemm_", "N", "C", n, n, n, 1.0 + 0.0j, A, n, B, n, 0.0 + 0.0j, C, n)
+    torch.cuda.synchronize()
+    assert g.last_variant() == "dmma_tma"
+    Acm, Bcm, Ccm = A.T, B.T, C.T
+    ref = Acm @ Bcm.conj().T
+    err = (Ccm - ref).abs().max().item()
+    bound = 4 * n * 2.0 ** -53 * float(torch.linalg.norm(Acm[0]).item()) * float(torch.linalg.norm(Bcm[0]).item()) * 4
+    assert err <= bound, (err, bound)
