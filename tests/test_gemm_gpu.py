@@ -238,3 +238,25 @@ def test_zgemm_large_device_resident():
     err = (Ccm - ref).abs().max().item()
     bound = 4 * n * 2.0 ** -53 * float(torch.linalg.norm(Acm[0]).item()) * float(torch.linalg.norm(Bcm[0]).item()) * 4
     assert err <= bound, (err, bound)
+
+
+@pytest.mark.parametrize("ta,tb", [("N", "N"), ("T", "N"), ("N", "T"), ("T", "T"), ("C", "N")])
+def test_sgemm_tf32x3_tcgen05(ta, tb):
+    """SGEMM on tcgen05 (3xTF32 split, TMEM accumulators) must hold FP32 accuracy: the c=4 Frobenius
+    bound with eps = 2^-24 AND the netlib DMMCH element-wise ratio test (< 16 eps-units of sum|a||b|)."""
+    lib = g.load()
+    g.force_variant("tf32x3_tcgen05")
+    try:
+        for (m, n, k) in [(128, 128, 32), (128, 128, 64), (129, 131, 40), (300, 260, 515), (64, 1000, 77)]:
+            for (alpha, beta) in [(1.0, 0.0), (0.7, 1.3)]:
+                ra, ca = (m, k) if ta == "N" else (k, m)
+                rb, cb = (k, n) if tb == "N" else (n, k)
+                lda, ldb, ldc = ra + 1, rb + 3, m + 2
+                A = splitmix_uniform(51, (lda, ca), np.float32); B = splitmix_uniform(52, (ldb, cb), np.float32)
+                C0 = splitmix_uniform(53, (ldc, n + 1), np.float32)
+                C = F(C0)
+                f77(lib, "sgemm_", ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc)
+                assert g.last_variant() == "tf32x3_tcgen05"
+                check_gemm("s", ta, tb, m, n, k, alpha, beta, A, B, C0, C)
+    finally:
+        g.force_variant("auto")
