@@ -9,8 +9,9 @@
 //  2. GEMM: CTA tile 128 x BN, BK = 32 floats (one 128-byte swizzle row).  Warp 0 = TMA producer
 //     (one 3-D box per operand per stage brings hi and lo planes together), warp 1 = MMA issuer
 //     (one thread; per 8-wide k step three tcgen05.mma into the same TMEM accumulator:
-//     lo*hi, hi*lo, hi*hi -- small terms first), warps 2..5 = epilogue (tcgen05.ld 32x32b, each
-//     thread owns one row of the tile, so a warp stores 32 consecutive rows of a C column = 128 B).
+//     lo*hi, hi*lo, hi*hi -- small terms first), warps 2..9 = epilogue (tcgen05.ld 32x32b.x64: lane
+//     quarter x column half; each thread owns one row of the tile, so a warp stores 32 consecutive
+//     rows of a C column = 128 B).
 //     smem ring: mbarrier full[] armed by TMA bytes, empty[] released by tcgen05.commit.
 //  The dropped lo*lo term is O(2^-22) relative; products are exact in the tensor core, accumulation
 //  is fp32 in TMEM.
@@ -23,6 +24,7 @@
 namespace b200 {
 
 constexpr int SG_BM = 128, SG_BK = 32, SG_STAGES = 3;
+constexpr int SG_THREADS = 64 + 256;      // TMA warp, MMA warp, 8 epilogue warps (lane quarter x column half)
 constexpr int SG_CHUNK_STAGES = 4;      // k per TMEM accumulation chunk = 4 * 32 = 128 (see the epilogue comment)
 
 struct SgemmParams {
@@ -101,6 +103,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
@@ -124,7 +132,7 @@ template <int BN> __host__ __device__ constexpr uint32_t sg_idesc() {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(SG_THREADS, 1)
 sgemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const SgemmParams p) {
     constexpr int A_PLANE = SG_BM * SG_BK * 4, B_PLANE = BN * SG_BK * 4;     // one (hi or lo) tile
     constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;
@@ -158,7 +166,7 @@ sgemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 
     if (tid == 0) {
         for (int s = 0; s < SG_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(accfull0 + 8 * b, 1); mbar_init(accempty0 + 8 * b, 128); }
+        for (int b = 0; b < 2; b++) { mbar_init(accfull0 + 8 * b, 1); mbar_init(accempty0 + 8 * b, 256); }
         mbar_fence_init();
         tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB);
     }
@@ -218,37 +226,35 @@ sgemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
         __syncwarp();
     } else {
-        // =========================== epilogue warps 2..5 ===========================
+        // =========================== epilogue warps 2..9 ===========================
         // The tensor core accumulates in fp32 with truncation, a bias that grows linearly with the number of
         // accumulation steps.  So the k loop is cut into chunks of SG_CHUNK_STAGES*32; each chunk is summed in
         // TMEM from zero and folded into per-thread register accumulators here with round-to-nearest FADDs,
         // while the MMA warp is already filling the other TMEM accumulator.
+        static_assert(BN == 128, "epilogue: two column halves of 64");
         const int q = warp & 3;                       // TMEM lane quarter this warp may read
-        float acc[BN];
+        const int half = (warp - 2) >> 2;             // which 64 columns of the tile
+        float acc[64];
 #pragma unroll
-        for (int j = 0; j < BN; j++) acc[j] = 0.f;
+        for (int j = 0; j < 64; j++) acc[j] = 0.f;
         for (int c = 0; c < nchunks; c++) {
             const int buf = c & 1;
             mbar_wait(accfull0 + 8 * buf, (c >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tsrc = tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * BN);
-#pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tsrc + (uint32_t)c0, v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int j = 0; j < 32; j++) acc[c0 + j] += __uint_as_float(v[j]);
-            }
+            uint32_t v[64];
+            tmem_ld64(tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * BN + half * 64), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(accempty0 + 8 * buf);
+            mbar_arrive(accempty0 + 8 * buf);         // values are in registers: the MMA warp may overwrite the buffer
+#pragma unroll
+            for (int j = 0; j < 64; j++) acc[j] += __uint_as_float(v[j]);
         }
         const int64_t row = (int64_t)m0 + 32 * q + lane;
         const bool beta0 = p.beta == 0.f;
         if (row < p.m) {
 #pragma unroll
-            for (int j = 0; j < BN; j++) {
-                const int64_t col = (int64_t)n0 + j;
+            for (int j = 0; j < 64; j++) {
+                const int64_t col = (int64_t)n0 + half * 64 + j;
                 if (col < p.n && tri_keep(p.mask, row, col)) {
                     float* cp = p.C + row + col * p.ldc;
                     float r = p.alpha * acc[j];
@@ -282,7 +288,7 @@ template <int BN> static void launch_sg(cudaStream_t s, const CUtensorMap& ma, c
     }
     p.tiles_m = (p.m + SG_BM - 1) / SG_BM;
     p.tiles_n = (p.n + BN - 1) / BN;
-    sgemm_tf32x3_kernel<BN><<<p.tiles_m * p.tiles_n, 192, SMEM, s>>>(ma, mb, p);
+    sgemm_tf32x3_kernel<BN><<<p.tiles_m * p.tiles_n, SG_THREADS, SMEM, s>>>(ma, mb, p);
 }
 
 static bool sgemm_tf32x3(cudaStream_t s, int oa, int ob, int m, int n, int k, float alpha, const float* A, int64_t lda,

@@ -114,7 +114,7 @@ struct ThreadCtx {
     cudaStream_t stream = nullptr;      // library-owned, non-blocking
     cudaStream_t ext = nullptr;         // caller-provided (b200blas_set_stream)
     bool external_stream = false;
-    char* ws = nullptr; size_t ws_cap = 0, ws_used = 0;
+    char* ws = nullptr; size_t ws_cap = 0, ws_used = 0, call_bytes = 0;
     // blocks retired because the workspace had to grow mid-call; freed at the next reset
     void* retired[16]; int nretired = 0;
     void* pinned = nullptr; void* dscalar = nullptr;
@@ -146,6 +146,7 @@ void ws_reset() {
         c.nretired = 0;
     }
     c.ws_used = 0;
+    c.call_bytes = 0;
 }
 void* ws_alloc(size_t bytes) {
     ThreadCtx& c = t_ctx;
@@ -154,8 +155,10 @@ void* ws_alloc(size_t bytes) {
         TrackerGuard guard;
         // grow: earlier sub-allocations of this call may still be in use by queued work, so the old
         // block is retired (freed at the next call) rather than freed now.
+        // The new block is sized for everything this call has asked for so far, so the NEXT call of the same
+        // shape fits in one block and allocates nothing (steady state: zero cudaMalloc/cudaFree per call).
         size_t ncap = c.ws_cap ? c.ws_cap : (size_t)64 << 20;
-        while (ncap < bytes + (c.ws ? 0 : 0)) ncap *= 2;
+        while (ncap < c.call_bytes + bytes) ncap *= 2;
         if (c.ws) {
             if (c.nretired == 16) fatal("workspace growth", __FILE__, __LINE__, "too many regrowths in one call");
             c.retired[c.nretired++] = c.ws;
@@ -165,6 +168,7 @@ void* ws_alloc(size_t bytes) {
     }
     void* p = c.ws + c.ws_used;
     c.ws_used += bytes;
+    c.call_bytes += bytes;
     return p;
 }
 void* pinned_scalar() {

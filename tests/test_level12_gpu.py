@@ -226,6 +226,7 @@ def test_level1_large_device_resident():
     # nrm2(x)^2 == dot(x,x) to rounding
     assert abs(nr * nr - f77(lib, "ddot_", n, x, 1, x, 1, restype=ctypes.c_double)) <= 1e-12 * nr * nr
     y0 = y.clone()
+    torch.cuda.synchronize()      # the library runs on its own stream: the clone must have finished reading y
     f77(lib, "daxpy_", n, 0.7, x, 1, y, 1); f77(lib, "daxpy_", n, -0.7, x, 1, y, 1)
     assert (y - y0).abs().max().item() <= 4 * 2.0 ** -53 * 2
     del y0

@@ -19,7 +19,7 @@ def F(x):
 def test_syrk_vs_oracle(p):
     lib = g.load(); dt = DT[p]
     al, be = ((0.7 - 0.9j), (1.3 - 1.1j)) if p in "cz" else (0.7, 1.3)
-    for (n, k) in [(70, 33), (129, 200), (300, 64), (257, 1)]:
+    for (n, k) in [(70, 33), (129, 200), (300, 64), (257, 1), (390, 300)]:   # the last one reaches the tensor-core SGEMM tiles
         for uplo in "UL":
             for tr in "NT":
                 ra, ca = (n, k) if tr == "N" else (k, n)
