@@ -3,6 +3,7 @@
 // return.  No size cutoff to a CPU BLAS (reference gemm.cc:129-141 gemm_perf_check): small
 // problems pick a small-tile GPU variant instead.
 #include "abi_common.h"
+#include "staged_gemm.cuh"
 #include "../../include/b200blas.h"
 
 using namespace b200;
@@ -38,6 +39,11 @@ void gemm_entry(const char* name, const char* transa, const char* transb, const 
     const bool scale_only = is0(*alpha) || *k == 0;
     const char ta = nota ? 'N' : (lsame(transa, 'T') ? 'T' : 'C');
     const char tb = notb ? 'N' : (lsame(transb, 'T') ? 'T' : 'C');
+    // large host-resident operands: chunked staging overlapped with the multiply (staged_gemm.cuh)
+    if (!scale_only && gemm_pipelined<T>(GemmDev<T>::fn, ta, tb, *m, *n, *k, *alpha, a, (int64_t)*lda, b, (int64_t)*ldb, *beta, c, (int64_t)*ldc)) {
+        log_exec(name, "%c%c m=%d n=%d k=%d lda=%d ldb=%d ldc=%d (pipelined staging)", ta, tb, *m, *n, *k, *lda, *ldb, *ldc);
+        return;
+    }
     // A is lda x (nota ? k : m), B is ldb x (notb ? n : k)  (reference compute_size, gemm.cc:36-44,
     // done in 64-bit here: the reference's int byte counts overflow at n=16384)
     Operand oa(scale_only ? nullptr : a, nrowa, nota ? *k : *m, *lda, sizeof(T), ACC_IN);

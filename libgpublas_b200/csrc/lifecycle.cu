@@ -24,7 +24,9 @@ static void print_help() {
         "   variant=<name>  -- force a kernel variant: generic_tile | dmma_tma | dmma_ldg | auto\n"
         "   devices=<n>     -- GPUs used for partitioned Level-3 calls (default 1)\n"
         "   sync=<0|1>      -- block until results are visible before returning (default 1)\n"
-        "   prefetch=<0|1>  -- cudaMemPrefetchAsync managed operands to the device (default 1)\n");
+        "   prefetch=<0|1>  -- cudaMemPrefetchAsync managed operands to the device (default 1)\n"
+        "   pipeline_min=<n> -- host-resident GEMM operands of >= n bytes in total are staged in chunks\n"
+        "                      overlapped with compute (default 64 MiB)\n");
 }
 
 static int variant_from_name(const char* n) {
@@ -67,6 +69,7 @@ static void set_options(const char* env) {
         else if (!strncmp(opt, "devices=", 8)) g_opts.devices = atoi(opt + 8);
         else if (!strncmp(opt, "sync=", 5)) g_opts.sync = atoi(opt + 5) != 0;
         else if (!strncmp(opt, "prefetch=", 9)) g_opts.prefetch = atoi(opt + 9) != 0;
+        else if (!strncmp(opt, "pipeline_min=", 13)) g_opts.pipeline_min_bytes = strtoull(opt + 13, nullptr, 0);
         else b200_writef(STDERR_FILENO, "b200blas: unknown option '%s'. Set BLAS2CUDA_OPTIONS=help.\n", opt);
     }
     free(copy);

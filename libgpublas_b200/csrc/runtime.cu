@@ -118,6 +118,8 @@ struct ThreadCtx {
     // blocks retired because the workspace had to grow mid-call; freed at the next reset
     void* retired[16]; int nretired = 0;
     void* pinned = nullptr; void* dscalar = nullptr;
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaEvent_t events[64]; int nevents = 0;
 };
 static thread_local ThreadCtx t_ctx;
 
@@ -135,6 +137,27 @@ void set_thread_stream(cudaStream_t s, bool external) {
     ensure_init();
     t_ctx.ext = s;               // may legitimately be 0: the legacy default stream
     t_ctx.external_stream = external;
+}
+
+cudaStream_t aux_stream(int which) {
+    ensure_init();
+    ThreadCtx& c = t_ctx;
+    if (!c.aux[which]) {
+        TrackerGuard guard;
+        B200_CUDA(cudaSetDevice(g_device));
+        B200_CUDA(cudaStreamCreateWithFlags(&c.aux[which], cudaStreamNonBlocking));
+    }
+    return c.aux[which];
+}
+cudaEvent_t pooled_event(int idx) {
+    ThreadCtx& c = t_ctx;
+    if (idx >= 64) fatal("pooled_event", __FILE__, __LINE__, "event pool exhausted");
+    while (c.nevents <= idx) {
+        TrackerGuard guard;
+        B200_CUDA(cudaEventCreateWithFlags(&c.events[c.nevents], cudaEventDisableTiming));
+        c.nevents++;
+    }
+    return c.events[idx];
 }
 
 void ws_reset() {

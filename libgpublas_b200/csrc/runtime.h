@@ -18,6 +18,7 @@ struct Options {
     size_t managed_threshold = 64 * 1024;   // tracker: allocations >= this go to managed memory
     int devices = 1;               // GPUs used by partitioned Level-3 calls
     size_t multi_gpu_min_dim = 8192;
+    size_t pipeline_min_bytes = (size_t)64 << 20;   // host-resident GEMM operands above this are staged in overlapped chunks
 };
 extern Options g_opts;
 
@@ -33,6 +34,10 @@ int sm_count();
 cudaStream_t current_stream();      // per-thread stream (or the one set by b200blas_set_stream)
 void set_thread_stream(cudaStream_t s, bool external);
 void finish_call();                 // the synchronous-return step (replaces call_kernel's tail)
+// Per-thread helper streams (0 = host->device copies, 1 = device->host copies) and a pool of timing-less
+// events, for calls that overlap staging with compute (staged_gemm.cu).  Created lazily, never destroyed.
+cudaStream_t aux_stream(int which);
+cudaEvent_t pooled_event(int idx);
 
 bool tma_available();
 bool encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, void* base, const cuuint64_t* gdim,

@@ -260,3 +260,54 @@ def test_sgemm_tf32x3_tcgen05(ta, tb):
                 check_gemm("s", ta, tb, m, n, k, alpha, beta, A, B, C0, C)
     finally:
         g.force_variant("auto")
+
+
+@pytest.mark.parametrize("p", ["d", "s", "z"])
+@pytest.mark.parametrize("ta,tb", [("N", "N"), ("T", "N"), ("N", "T"), ("C", "T")])
+def test_gemm_pipelined_staging_host_operands(p, ta, tb):
+    """Host-resident operands above pipeline_min bytes are staged in k-chunks / column panels overlapped
+    with the multiply (staged_gemm.cuh): ragged last chunk and panel, odd leading dimensions,
+    beta != 0 (C goes in and out), same numerical bar as the plain path."""
+    lib = g.load()
+    dt = DT[p]
+    lib.b200blas_set_options(b"pipeline_min=1000")
+    try:
+        m, n, k = 384, 2304, 2200
+        alpha, beta = ((0.7 - 0.9j), (1.3 - 1.1j)) if p == "z" else (0.7, 1.3)
+        ra, ca = (m, k) if ta == "N" else (k, m)
+        rb, cb = (k, n) if tb == "N" else (n, k)
+        lda, ldb, ldc = ra + 1, rb + 3, m + 2
+        A = splitmix_uniform(61, (lda, ca), dt); B = splitmix_uniform(62, (ldb, cb), dt); C0 = splitmix_uniform(63, (ldc, n + 1), dt)
+        for (al, be) in [(alpha, beta), (alpha, 0.0 * alpha)]:
+            C = F(C0)
+            s0 = g.stats()
+            f77(lib, p + "gemm_", ta, tb, m, n, k, al, A, lda, B, ldb, be, C, ldc)
+            s1 = g.stats()
+            check_gemm(p, ta, tb, m, n, k, al, be, A, B, C0, C)
+            es = np.dtype(dt).itemsize
+            assert s1["h2d_bytes"] - s0["h2d_bytes"] == (m * k + k * n + (m * n if be != 0 else 0)) * es
+            assert s1["d2h_bytes"] - s0["d2h_bytes"] == m * n * es
+    finally:
+        lib.b200blas_set_options(b"pipeline_min=67108864")
+
+
+def test_dgemm_pipelined_mixed_residency():
+    """A on the device (used in place), B and C in host memory (staged): same schedule, no copies for A."""
+    import torch
+    lib = g.load()
+    lib.b200blas_set_options(b"pipeline_min=1000")
+    try:
+        m, n, k = 256, 1536, 1280
+        gen = torch.Generator(device="cuda").manual_seed(5)
+        At = torch.rand((k, m), dtype=torch.float64, device="cuda", generator=gen) * 2 - 1     # row-major (k,m) == column-major m x k
+        B = splitmix_uniform(71, (k, n)); C0 = splitmix_uniform(72, (m, n)); C = F(C0)
+        torch.cuda.synchronize()
+        s0 = g.stats()
+        f77(lib, "dgemm_", "N", "N", m, n, k, 1.0, At, m, B, k, 0.5, C, m)
+        s1 = g.stats()
+        Ah = At.cpu().numpy().T                                                                   # m x k
+        ref = Ah @ B + 0.5 * C0
+        assert np.abs(C - ref).max() <= 16 * 2.0 ** -53 * k
+        assert s1["h2d_bytes"] - s0["h2d_bytes"] == (k * n + m * n) * 8 and s1["hits"] - s0["hits"] == 1
+    finally:
+        lib.b200blas_set_options(b"pipeline_min=67108864")
