@@ -177,7 +177,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the SGEMM/ZGEMM/Level-1/2 lines of BASELINE.json's metric")
     ap.add_argument("--verify", action="store_true", help="N>1: check the partitioned result against the 1-GPU kernel on rank 0")
-    ap.add_argument("--kchunk", type=int, default=2048)
+    ap.add_argument("--kchunk", type=int, default=1024)
+    ap.add_argument("--distribute", default=None, help="N>1: p2p_push (default on CUDA) | bcast")
     args = ap.parse_args()
     n = args.n
     rank = int(os.environ.get("RANK", "0"))
@@ -250,7 +251,7 @@ def main():
         ref = (A.T[:, :64].T @ B.T[:64, :].T) if False else None
         scaling, parallelism = "strong", "single"
     else:
-        tg = TiledGemm(n, n, n, dev, rank, world, kchunk=args.kchunk)
+        tg = TiledGemm(n, n, n, dev, rank, world, kchunk=args.kchunk, distribute=args.distribute)
         tg.make_inputs(seed=2)
         for _ in range(args.warmup):
             tg.run()
@@ -266,6 +267,12 @@ def main():
         e1.record()
         torch.cuda.synchronize(); dist.barrier()
         clocks = sampler.stop() if rank == 0 else {}
+        if os.environ.get("B200_MG_TRACE"):
+            tg.run(trace=True)
+            for r in range(world):
+                if r == rank:
+                    sys.stderr.write("rank %d trace: %s\n" % (rank, tg.trace))
+                dist.barrier()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = t.item()

@@ -181,6 +181,14 @@ B200_API int b200blas_is_tracked(const void* p);
 B200_API int b200blas_device_count(void);
 /* D := alpha*op(A)*op(B) + beta*C on device pointers with a separate output (may be peer-mapped) */
 B200_API void b200blas_dgemm_out(char transa, char transb, int m, int n, int k, double alpha, const double* a, long long lda, const double* b, long long ldb, double beta, const double* c, long long ldc, double* d, long long ldd);
+/* the same for a rank whose operand panels are still arriving over NVLink: a tile reads rows [g*a_group, ...) of op(A) only
+ * after aflags[g] >= epoch and columns [h*b_group, ...) of op(B) only after bflags[h] >= epoch (flags: device memory of this
+ * GPU, written remotely; group sizes multiples of 128) */
+B200_API void b200blas_dgemm_out_flagged(char transa, char transb, int m, int n, int k, double alpha, const double* a, long long lda, const double* b, long long ldb, double beta, const double* c, long long ldc, double* d, long long ldd, const unsigned* aflags, int a_group, const unsigned* bflags, int b_group, unsigned epoch);
+/* copy-engine building blocks of the panel push: strided device->device (peer) copy, stream-ordered flag write, memset */
+B200_API void b200blas_copy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t height, void* cuda_stream);
+B200_API void b200blas_write_flag_async(void* dst_flag, unsigned value, void* cuda_stream);
+B200_API void b200blas_memset_async(void* dst, int byte, size_t bytes, void* cuda_stream);
 /* raw device memory + CUDA IPC: lets another process's GEMM epilogue store C tiles into this allocation */
 B200_API void* b200blas_device_malloc(size_t bytes);
 B200_API void b200blas_device_free(void* p);

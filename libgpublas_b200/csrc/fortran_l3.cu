@@ -121,6 +121,19 @@ void b200blas_dgemm_out(char transa, char transb, int m, int n, int k, double al
     dgemm_out_dev(current_stream(), transa, transb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, d, ldd, MASK_FULL);
 }
 
+// Same, for a rank of the partitioned GEMM whose operand panels are still arriving: a CTA reads its tile's rows of
+// op(A) only after aflags[row / a_group] >= epoch and its columns of op(B) only after bflags[col / b_group] >= epoch
+// (flags live in this device's memory and are written remotely by the home GPU's copy engine).
+void b200blas_dgemm_out_flagged(char transa, char transb, int m, int n, int k, double alpha, const double* a, long long lda,
+                                const double* b, long long ldb, double beta, const double* c, long long ldc, double* d, long long ldd,
+                                const unsigned* aflags, int a_group, const unsigned* bflags, int b_group, unsigned epoch) {
+    CallScope scope;
+    if ((aflags && (a_group <= 0 || a_group % 128)) || (bflags && (b_group <= 0 || b_group % 128)))
+        fatal("b200blas_dgemm_out_flagged", __FILE__, __LINE__, "flag group sizes must be positive multiples of 128");
+    dgemm_set_panel_flags(aflags, a_group, bflags, b_group, epoch);
+    dgemm_out_dev(current_stream(), transa, transb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, d, ldd, MASK_FULL);
+}
+
 void sgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k, const float* alpha,
             const float* a, const int* lda, const float* b, const int* ldb, const float* beta, float* c, const int* ldc) {
     gemm_entry<float>("sgemm_", transa, transb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);

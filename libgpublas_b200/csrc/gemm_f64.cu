@@ -47,7 +47,22 @@ struct DgemmParams {
     double* D; int64_t ldd;      // output; == C for plain BLAS, a peer-mapped tile for partitioned calls
     int mask;
     int tiles_m, tiles_n;
+    // Optional panel-readiness flags (partitioned multi-GPU GEMM): rows [g*a_group, (g+1)*a_group) of op(A) may be read
+    // only once aflags[g] >= flag_epoch, columns [h*b_group, (h+1)*b_group) of op(B) once bflags[h] >= flag_epoch.
+    // The flags are written by the home GPU's copy engine over NVLink after the corresponding panel piece has landed,
+    // in the order the tile schedule consumes them, so ONE launch overlaps transfer and compute.
+    const uint32_t* aflags; const uint32_t* bflags; int a_group, b_group; uint32_t flag_epoch;
 };
+
+__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch) {
+    uint32_t v;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= epoch) break;
+        __nanosleep(200);
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");   // order the async-proxy (TMA) reads after the acquire
+}
 
 template <int MB, int NB, int LAYA, int LAYB, bool USE_TMA>
 __global__ void __launch_bounds__(384, 1)
@@ -99,6 +114,8 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         if (USE_TMA) {
             if (tid == 0) {
                 int stage = 0; uint32_t phase = 0;
+                if (p.aflags) wait_flag(p.aflags + m0 / p.a_group, p.flag_epoch);   // group sizes are multiples of the tile
+                if (p.bflags) wait_flag(p.bflags + n0 / p.b_group, p.flag_epoch);
                 for (int kt = 0; kt < ktiles; kt++) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t fb = full0 + 8 * stage;
@@ -123,6 +140,8 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         } else {
             // LDG staging for operands TMA cannot describe (lda odd / base not 16-B aligned)
             int stage = 0; uint32_t phase = 0;
+            if (p.aflags) wait_flag(p.aflags + m0 / p.a_group, p.flag_epoch);
+            if (p.bflags) wait_flag(p.bflags + n0 / p.b_group, p.flag_epoch);
             for (int kt = 0; kt < ktiles; kt++) {
                 mbar_wait(empty0 + 8 * stage, phase ^ 1);
                 uint8_t* sA = smem + stage * STAGE_BYTES;
@@ -281,6 +300,16 @@ void dgemm_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, double alp
     dgemm_out_dev(s, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, C, ldc, mask);
 }
 
+static thread_local const uint32_t* t_aflags = nullptr;
+static thread_local const uint32_t* t_bflags = nullptr;
+static thread_local int t_a_group = 0, t_b_group = 0;
+static thread_local uint32_t t_flag_epoch = 0;
+// The next dgemm_out_dev call of this thread polls the panel flags (see DgemmParams::aflags); group sizes must be
+// multiples of the 128-wide CTA tile.
+void dgemm_set_panel_flags(const uint32_t* aflags, int a_group, const uint32_t* bflags, int b_group, uint32_t epoch) {
+    t_aflags = aflags; t_bflags = bflags; t_a_group = a_group; t_b_group = b_group; t_flag_epoch = epoch;
+}
+
 // D := alpha*op(A)*op(B) + beta*C with D possibly distinct from C (D may be a peer-mapped pointer: the
 // epilogue then stores the tile over NVLink -- the fused compute + C-return of the partitioned GEMM).
 void dgemm_out_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, double alpha, const double* A, int64_t lda,
@@ -302,7 +331,7 @@ void dgemm_out_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, double
         const double work = (double)m * n * k;
         variant = (work < 32.0 * 32.0 * 32.0) ? VAR_GENERIC_TILE : VAR_DMMA_TMA;
     }
-    if (separate_out) variant = (variant == VAR_DMMA_LDG) ? VAR_DMMA_LDG : VAR_DMMA_TMA;   // only the DMMA kernel has a D operand
+    if (separate_out || t_aflags || t_bflags) variant = (variant == VAR_DMMA_LDG) ? VAR_DMMA_LDG : VAR_DMMA_TMA;   // only the DMMA kernel has a D operand / flags
     if (variant == VAR_GENERIC_TILE) {
         gemm_generic_launch<double>(s, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mask);
         return;
@@ -314,6 +343,8 @@ void dgemm_out_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, double
     p.m = m; p.n = n; p.k = k; p.alpha = alpha; p.beta = beta;
     p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.D = D; p.ldd = ldd; p.mask = mask;
     p.tiles_m = p.tiles_n = 0;
+    p.aflags = t_aflags; p.bflags = t_bflags; p.a_group = t_a_group; p.b_group = t_b_group; p.flag_epoch = t_flag_epoch;
+    t_aflags = t_bflags = nullptr;
     dgemm_dmma_dispatch<8, 4>(s, nota, notb, tma_ok, p);
 }
 

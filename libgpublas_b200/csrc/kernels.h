@@ -30,6 +30,7 @@ void dgemm_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, double alp
 void dgemm_out_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, double alpha, const double* A, int64_t lda,
                    const double* B, int64_t ldb, double beta, const double* Cin, int64_t ldc, double* D, int64_t ldd,
                    int mask = MASK_FULL);
+void dgemm_set_panel_flags(const uint32_t* aflags, int a_group, const uint32_t* bflags, int b_group, uint32_t epoch);   // applies to this thread's next dgemm_out_dev
 void sgemm_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, float alpha, const float* A, int64_t lda,
                const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int mask = MASK_FULL);
 void zgemm_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, cuDoubleComplex alpha,

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <unistd.h>
+#include <mutex>
 
 using namespace b200;
 
@@ -172,5 +173,35 @@ void* b200blas_ipc_open(const void* handle64) {
     return p;
 }
 void b200blas_ipc_close(void* p) { TrackerGuard g; cudaIpcCloseMemHandle(p); }
+
+// ---- building blocks of the copy-engine panel push (libgpublas_b200/multigpu.py) ----
+// 2-D strided device->device copy on a caller stream; dst may be a CUDA-IPC peer mapping (then the bytes
+// cross NVLink on a copy engine, no SM involved).
+void b200blas_copy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t height, void* stream) {
+    ensure_init();
+    TrackerGuard g;
+    B200_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, height, cudaMemcpyDefault, (cudaStream_t)stream));
+}
+// Stream-ordered 32-bit flag write (value < 65536) into local or peer-mapped device memory: a 4-byte DMA from a
+// device-resident table of constants, so it is ordered after the panel copies queued before it on `stream`.
+void b200blas_write_flag_async(void* dst_flag, unsigned value, void* stream) {
+    ensure_init();
+    TrackerGuard g;
+    static unsigned* table = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        unsigned* host = (unsigned*)malloc(65536 * sizeof(unsigned));
+        for (unsigned i = 0; i < 65536; i++) host[i] = i;
+        B200_CUDA(cudaMalloc((void**)&table, 65536 * sizeof(unsigned)));
+        B200_CUDA(cudaMemcpy(table, host, 65536 * sizeof(unsigned), cudaMemcpyHostToDevice));
+        free(host);
+    });
+    B200_CUDA(cudaMemcpyAsync(dst_flag, table + (value & 0xffffu), sizeof(unsigned), cudaMemcpyDefault, (cudaStream_t)stream));
+}
+void b200blas_memset_async(void* dst, int byte, size_t bytes, void* stream) {
+    ensure_init();
+    TrackerGuard g;
+    B200_CUDA(cudaMemsetAsync(dst, byte, bytes, (cudaStream_t)stream));
+}
 
 }  // extern "C"

@@ -44,7 +44,7 @@ def block_range(total, parts, idx):
 class TiledGemm:
     """C(m x n) := alpha * A(m x k) * B(k x n) + beta * C, column-major, operands on rank 0."""
 
-    def __init__(self, m, n, k, device, rank, world, kchunk=2048, dtype=torch.float64, gemm=None, c_return=None):
+    def __init__(self, m, n, k, device, rank, world, kchunk=2048, dtype=torch.float64, gemm=None, c_return=None, distribute=None):
         self.m, self.n, self.k = m, n, k
         self.dev, self.rank, self.world, self.dtype = device, rank, world, dtype
         self.P, self.Q = grid_for(world)
@@ -56,16 +56,24 @@ class TiledGemm:
         self.cuda = device.type == "cuda"
         self.gemm = gemm or self._lib_gemm
         self.c_return = c_return or ("peer_store" if self.cuda else "sendrecv")
-        self.kernels_per_step = self.nchunks
+        # how the operand panels reach the ranks: "p2p_push" = home GPU's copy engines write each rank's A row-panel and
+        # B column-panel slice by slice into that rank's memory over NVLink and raise a flag per slice, every rank runs
+        # ONE GEMM launch whose TMA producer polls the flags (CUDA only, beta == 0); "bcast" = chunked collective
+        # broadcast + one GEMM launch per chunk (any backend; the CPU/gloo tests and the beta != 0 case)
+        self.distribute = distribute or ("p2p_push" if (self.cuda and self.c_return == "peer_store" and dtype == torch.float64) else "bcast")
+        self.kernels_per_step = 1 if self.distribute == "p2p_push" else self.nchunks
+        self.epoch = 0
+        self.trace = None
         self._kernel_ms = None
         # column-major matrices are held as 1-D buffers; element (i, j) of an ld-strided matrix is buf[i + j*ld]
         self.A = self.B = self.C = None
         self.peerC = None
         self._home_c_ptr = None
-        # double-buffered chunk landing zones on every rank
-        self.abuf = [torch.empty(m * self.kchunk, dtype=dtype, device=device) for _ in range(2)]
-        self.bbuf = [torch.empty(self.kchunk * n, dtype=dtype, device=device) for _ in range(2)]
-        self.ctile = torch.empty((self.r1 - self.r0) * (self.c1 - self.c0), dtype=dtype, device=device)
+        if self.distribute == "bcast":
+            # double-buffered chunk landing zones on every rank
+            self.abuf = [torch.empty(m * self.kchunk, dtype=dtype, device=device) for _ in range(2)]
+            self.bbuf = [torch.empty(self.kchunk * n, dtype=dtype, device=device) for _ in range(2)]
+            self.ctile = torch.empty((self.r1 - self.r0) * (self.c1 - self.c0), dtype=dtype, device=device)
         if self.cuda:
             self.comm_stream = torch.cuda.Stream(device=device)
             self.ready = [torch.cuda.Event() for _ in range(2)]
@@ -111,8 +119,137 @@ class TiledGemm:
                 self.peerC = lib.b200blas_ipc_open(ctypes.create_string_buffer(handle[0], 64))
                 if not self.peerC:
                     raise RuntimeError("cudaIpcOpenMemHandle failed: peer access to the home GPU is required")
+            if self.distribute == "p2p_push":
+                self._setup_push(lib)
         elif self.rank == 0:
             self.C = C if C is not None else torch.zeros(self.m * self.n, dtype=self.dtype, device=self.dev)
+
+    def _setup_push(self, lib):
+        """Every non-home rank allocates its A row-panel (tm x k), B column-panel (k x tn) and one flag per k-slice and
+        exports them through CUDA IPC; the home rank maps them and creates one push stream per peer."""
+        es = 8
+        tm, tn = self.r1 - self.r0, self.c1 - self.c0
+        lib.b200blas_copy2d_async.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p]
+        lib.b200blas_copy2d_async.restype = None
+        lib.b200blas_write_flag_async.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p]
+        lib.b200blas_write_flag_async.restype = None
+        lib.b200blas_memset_async.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p]
+        lib.b200blas_memset_async.restype = None
+        lib.b200blas_dgemm_out_flagged.argtypes = [ctypes.c_char, ctypes.c_char, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                                   ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_double,
+                                                   ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong,
+                                                   ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_uint]
+        lib.b200blas_dgemm_out_flagged.restype = None
+        mine = None
+        self.nflags = 4096
+        if self.rank != 0 and tm > 0 and tn > 0:
+            self.panelA = lib.b200blas_device_malloc(max(1, tm * self.k * es))
+            self.panelB = lib.b200blas_device_malloc(max(1, self.k * tn * es))
+            self.flags = lib.b200blas_device_malloc(4 * self.nflags)     # [0, 2048): A row-groups, [2048, 4096): B column-bands
+            assert self.panelA and self.panelB and self.flags, "device allocation of the operand panels failed"
+            lib.b200blas_memset_async(ctypes.c_void_p(self.flags), 0, 4 * self.nflags, None)
+            torch.cuda.synchronize()
+            hs = []
+            for ptr in (self.panelA, self.panelB, self.flags):
+                buf = ctypes.create_string_buffer(64)
+                assert lib.b200blas_ipc_get_handle(ctypes.c_void_p(ptr), buf) == 64
+                hs.append(bytes(buf.raw))
+            mine = tuple(hs)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, mine)
+        self.peers = {}
+        if self.rank == 0:
+            for r, hs in enumerate(gathered):
+                if r == 0 or hs is None:
+                    continue
+                ptrs = [lib.b200blas_ipc_open(ctypes.create_string_buffer(h, 64)) for h in hs]
+                if not all(ptrs):
+                    raise RuntimeError("cudaIpcOpenMemHandle failed: peer access from the home GPU is required")
+                self.peers[r] = (ptrs[0], ptrs[1], ptrs[2], torch.cuda.Stream(device=self.dev))
+        dist.barrier()
+
+    @staticmethod
+    def _groups(tm):
+        """(A row-group, B column-band) sizes of the readiness flags: ~16 row-groups per panel, bands of 16 CTA tiles
+        (the kernel's tile schedule walks bands of 16 x 128 columns), both multiples of the 128-wide tile."""
+        return max(128, (tm // 16 + 127) // 128 * 128), 2048
+
+    def _run_push(self, trace=False):
+        import libgpublas_b200 as g
+        lib = g.load()
+        m, n, k, kc = self.m, self.n, self.k, self.kchunk
+        es = 8
+        tm, tn = self.r1 - self.r0, self.c1 - self.c0
+        comp = torch.cuda.current_stream(self.dev)
+        if self.epoch >= 65535:            # flag values are 16-bit table entries: restart the epoch counter
+            if self.rank != 0 and tm > 0 and tn > 0:
+                lib.b200blas_memset_async(ctypes.c_void_p(self.flags), 0, 4 * self.nflags, ctypes.c_void_p(comp.cuda_stream))
+            torch.cuda.synchronize(); dist.barrier()
+            self.epoch = 0
+        self.epoch += 1
+        if trace:
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True); t0.record(comp)
+        if self.rank == 0:
+            inputs_ready = torch.cuda.Event(); inputs_ready.record(comp)
+            a0, b0 = self.A.data_ptr(), self.B.data_ptr()
+            for r, (pA, pB, pF, st) in self.peers.items():
+                st.wait_event(inputs_ready)
+            if trace:
+                push_ev = {r: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for r in self.peers}
+                for r, (pA, pB, pF, st) in self.peers.items():
+                    push_ev[r][0].record(st)
+            # Push order = consumption order of the tile schedule (bands of 16 tile-columns walked down the rows):
+            # B column-band 0, then A row-groups top to bottom, then the remaining B bands.  A first wave of tiles can
+            # start after ~1/4 of a rank's data has landed; from then on arrival stays ahead of compute.
+            # The copy engines serve queued copies roughly in issue order, so the pieces are issued round-robin over the
+            # peers (piece-major): every rank gets its first pieces at the same time.
+            queues = []
+            for r, (pA, pB, pF, st) in self.peers.items():
+                p, q = r // self.Q, r % self.Q
+                r0, r1 = block_range(m, self.P, p); c0, c1 = block_range(n, self.Q, q)
+                rtm, rtn = r1 - r0, c1 - c0
+                ag, bg = self._groups(rtm)
+                sh = ctypes.c_void_p(st.cuda_stream)
+
+                def push_b(h, pB=pB, pF=pF, sh=sh, c0=c0, rtn=rtn, bg=bg):
+                    j0 = h * bg; jj = min(bg, rtn - j0)      # B[:, c0+j0 : c0+j0+jj] is contiguous (ld = k on both sides)
+                    lib.b200blas_copy2d_async(ctypes.c_void_p(pB + es * j0 * k), k * es, ctypes.c_void_p(b0 + es * (c0 + j0) * k), k * es, k * es, jj, sh)
+                    lib.b200blas_write_flag_async(ctypes.c_void_p(pF + 4 * (2048 + h)), self.epoch, sh)
+
+                def push_a(gi, pA=pA, pF=pF, sh=sh, r0=r0, rtm=rtm, ag=ag):
+                    i0 = gi * ag; ii = min(ag, rtm - i0)     # A[r0+i0 : r0+i0+ii, :]  ->  panelA[i0:i0+ii, :]   (ld m -> ld rtm)
+                    lib.b200blas_copy2d_async(ctypes.c_void_p(pA + es * i0), rtm * es, ctypes.c_void_p(a0 + es * (r0 + i0)), m * es, ii * es, k, sh)
+                    lib.b200blas_write_flag_async(ctypes.c_void_p(pF + 4 * gi), self.epoch, sh)
+
+                items = [(push_b, 0)] + [(push_a, gi) for gi in range((rtm + ag - 1) // ag)] + [(push_b, h) for h in range(1, (rtn + bg - 1) // bg)]
+                queues.append(items)
+            for i in range(max(len(qu) for qu in queues) if queues else 0):
+                for qu in queues:
+                    if i < len(qu):
+                        qu[i][0](qu[i][1])
+            if trace:
+                for r, (pA, pB, pF, st) in self.peers.items():
+                    push_ev[r][1].record(st)
+            if tm > 0 and tn > 0:
+                self._gemm_out(tm, tn, k, self.alpha, a0 + es * self.r0, m, b0 + es * self.c0 * k, k, 0.0,
+                               self.peerC + es * (self.r0 + self.c0 * m), m, self.peerC + es * (self.r0 + self.c0 * m), m)
+            for r, (pA, pB, pF, st) in self.peers.items():
+                comp.wait_stream(st)
+        elif tm > 0 and tn > 0:
+            d = self.peerC + es * (self.r0 + self.c0 * m)
+            ag, bg = self._groups(tm)
+            lib.b200blas_dgemm_out_flagged(b"N", b"N", tm, tn, k, float(self.alpha), self.panelA, tm, self.panelB, k, 0.0, d, m, d, m,
+                                           self.flags, ag, self.flags + 4 * 2048, bg, self.epoch)
+        if trace:
+            t1.record(comp)
+        # the home rank must not report completion (or push the next product's panels) before every peer's
+        # kernel has finished reading its panels and storing its C tile
+        dist.barrier()
+        if trace:
+            torch.cuda.synchronize()
+            self.trace = [("gemm_ms", t0.elapsed_time(t1))]
+            if self.rank == 0:
+                self.trace += [("push_to_%d_ms" % r, push_ev[r][0].elapsed_time(push_ev[r][1])) for r in self.peers]
 
     def home_c(self):
         """The result on rank 0 as a (n, m) row-major == (m, n) column-major torch view (CUDA peer_store path: a
@@ -129,7 +266,11 @@ class TiledGemm:
         return self.C
 
     def describe(self):
-        return "2d-tile %dx%d, k-chunk %d, nccl broadcast of A/B chunks overlapped with compute, C via %s" % (
+        if self.distribute == "p2p_push":
+            return ("2d-tile %dx%d; A row-groups / B column-bands pushed in tile-schedule order by the home GPU's copy engines over "
+                    "NVLink (CUDA IPC) with a flag per piece; one DMMA GEMM launch per rank whose TMA producer polls the flags; C tiles "
+                    "stored to the home allocation by the kernel epilogue (%s)" % (self.P, self.Q, self.c_return))
+        return "2d-tile %dx%d, k-chunk %d, collective broadcast of A/B chunks overlapped with compute, C via %s" % (
             self.P, self.Q, self.kchunk, self.c_return)
 
     # ------------------------------------------------------------------ back ends
@@ -138,14 +279,21 @@ class TiledGemm:
         g.call("dgemm_", "N", "N", m, n, k, float(alpha), g.DevPtr(a_ptr), lda, g.DevPtr(b_ptr), ldb, float(beta), g.DevPtr(c_ptr), ldc)
 
     def _esize(self):
-        return self.abuf[0].element_size()
+        return torch.empty((), dtype=self.dtype).element_size()
 
     # ------------------------------------------------------------------ one full product
-    def run(self):
+    def run(self, trace=False):
+        """One full product.  trace=True (CUDA only) records per-chunk events on both streams and leaves a
+        list of (chunk, comm_ms, compute_ms, compute_start_ms) in self.trace after a synchronize."""
+        if self.distribute == "p2p_push":
+            return self._run_push(trace)
         m, n, k, kc = self.m, self.n, self.k, self.kchunk
         es = self._esize()
         tm, tn = self.r1 - self.r0, self.c1 - self.c0
         comp = torch.cuda.current_stream(self.dev) if self.cuda else None
+        tr = [] if (trace and self.cuda) else None
+        if tr is not None:
+            t_begin = torch.cuda.Event(enable_timing=True); t_begin.record(comp)
         for c in range(self.nchunks):
             slot = c % 2
             k0 = c * kc
@@ -161,6 +309,9 @@ class TiledGemm:
             else:
                 ctx = _Null()
             with ctx:
+                if tr is not None:
+                    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                    ev[0].record(self.comm_stream)
                 if self.rank == 0:
                     a_dst.copy_(self.A[k0 * m:(k0 + kk) * m])                       # A[:, chunk]: contiguous column block
                     b_dst.view(n, kk).copy_(self.B.view(n, k)[:, k0:k0 + kk])       # B[chunk, :] packed: column j -> kk contiguous values
@@ -168,9 +319,13 @@ class TiledGemm:
                 dist.broadcast(b_dst, src=0)
                 if self.cuda:
                     self.ready[slot].record(self.comm_stream)
+                if tr is not None:
+                    ev[1].record(self.comm_stream)
             # ---- compute on chunk c (compute stream) ----
             if self.cuda:
                 comp.wait_event(self.ready[slot])
+            if tr is not None:
+                ev[2].record(comp)
             last = c == self.nchunks - 1
             beta = self.beta if c == 0 else 1.0
             a_ptr = a_dst.data_ptr() + es * self.r0                  # rows r0.. of the m x kk chunk (ld = m)
@@ -185,11 +340,17 @@ class TiledGemm:
                     self.gemm(tm, tn, kk, self.alpha, a_ptr, m, b_ptr, kk, beta, self.ctile.data_ptr(), tm)
             if self.cuda:
                 self.consumed[slot].record(comp)
+            if tr is not None:
+                ev[3].record(comp); tr.append(ev)
         if self.c_return == "sendrecv":
             self._gather_sendrecv(tm, tn)
         elif self.cuda:
             # the home rank must not report completion before every peer's stores have landed
             dist.barrier()
+        if tr is not None:
+            torch.cuda.synchronize()
+            self.trace = [(i, e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3]), t_begin.elapsed_time(e[2]), t_begin.elapsed_time(e[0]))
+                          for i, e in enumerate(tr)]
 
     def _gemm_out(self, m, n, k, alpha, a_ptr, lda, b_ptr, ldb, beta, c_ptr, ldc, d_ptr, ldd):
         import libgpublas_b200 as g
