@@ -1,0 +1,134 @@
+"""Blocked right-looking Cholesky (lower) -- the workload of BASELINE.json configs[3]: per panel a diagonal-block
+factorisation, a DTRSM on the panel below it and a DSYRK trailing update, all issued through the interposed Fortran
+symbols exactly as a LAPACK-style caller would (SURVEY.md section 8d "C4").
+
+    blocked_cholesky(n, A, lda, nb)            one GPU, A device/managed/host
+    TiledCholesky(n, nb, device, rank, world)  one process per GPU: 1-D block-cyclic column ownership, the owner
+                                               factors its panel and broadcasts it, every rank updates the block
+                                               columns it owns (look-ahead: the next panel's column first)
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import DevPtr, call, load
+
+
+def _ptr(A):
+    if isinstance(A, DevPtr):
+        return A.addr
+    if hasattr(A, "data_ptr"):
+        return A.data_ptr()
+    return A.ctypes.data
+
+
+def potrf_lower(n, A, lda):
+    """In-place lower Cholesky of an n x n column-major block (device, managed or host memory); returns LAPACK info."""
+    lib = load()
+    lib.b200blas_dpotrf_lower.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong]
+    lib.b200blas_dpotrf_lower.restype = ctypes.c_int
+    return lib.b200blas_dpotrf_lower(n, ctypes.c_void_p(_ptr(A)), lda)
+
+
+def blocked_cholesky(n, A, lda, nb=2048):
+    """A := L (lower triangle) with A = L L^T, column-major, leading dimension lda.  Returns LAPACK info."""
+    base = _ptr(A)
+    at = lambda i, j: DevPtr(base + 8 * (i + j * lda))
+    for j in range(0, n, nb):
+        jb = min(nb, n - j)
+        info = potrf_lower(jb, at(j, j), lda)
+        if info:
+            return info + j
+        rest = n - j - jb
+        if rest > 0:
+            call("dtrsm_", "R", "L", "T", "N", rest, jb, 1.0, at(j, j), lda, at(j + jb, j), lda)
+            call("dsyrk_", "L", "N", rest, jb, -1.0, at(j + jb, j), lda, 1.0, at(j + jb, j + jb), lda)
+    return 0
+
+
+class TiledCholesky:
+    """Strong-scaled lower Cholesky of one n x n matrix over `world` GPUs (one process each).
+
+    Block column J (nb wide) is owned by rank J % world.  Every rank holds a full-size copy of the matrix but keeps
+    only its own block columns up to date.  Step J: the owner factors the diagonal block and solves the panel below
+    it, then the panel is broadcast; every rank applies the rank-nb update to the block columns it owns.  The owner
+    of column J+1 updates that column FIRST and factors/broadcasts it on a second stream while its remaining
+    columns are still being updated (look-ahead of one panel).  Every rank ends up with the complete factor: the
+    panels arrive in the broadcasts anyway, so there is no separate gather."""
+
+    def __init__(self, n, nb, device, rank, world):
+        self.n, self.nb, self.dev, self.rank, self.world = n, nb, device, rank, world
+        self.nblk = (n + nb - 1) // nb
+        self.A = None
+
+    def owner(self, J):
+        return J % self.world
+
+    def set_matrix(self, A):
+        """A: torch float64 1-D buffer of n*n (column-major, ld = n) on every rank; rank 0's content is the input."""
+        self.A = A
+        dist.broadcast(self.A, src=0)
+
+    def run(self):
+        import libgpublas_b200 as g
+        n, nb, A = self.n, self.nb, self.A
+        base = A.data_ptr()
+        at = lambda i, j: DevPtr(base + 8 * (i + j * n))
+        cuda = self.dev.type == "cuda"
+        main = torch.cuda.current_stream(self.dev) if cuda else None
+        if cuda and not hasattr(self, "panel_stream"):
+            self.panel_stream = torch.cuda.Stream(device=self.dev)
+        info = 0
+
+        class on:                       # run the enclosed BLAS calls / collectives on the given stream
+            def __init__(s, stream): s.stream = stream
+            def __enter__(s):
+                if cuda:
+                    s.ctx = torch.cuda.stream(s.stream); s.ctx.__enter__(); g.use_torch_stream()
+            def __exit__(s, *a):
+                if cuda:
+                    s.ctx.__exit__(*a); g.use_torch_stream()
+
+        def factor_panel(J):
+            j = J * nb; jb = min(nb, n - j); rest = n - j - jb
+            r = potrf_lower(jb, at(j, j), n)
+            if rest > 0 and r == 0:
+                call("dtrsm_", "R", "L", "T", "N", rest, jb, 1.0, at(j, j), n, at(j + jb, j), n)
+            return r + j if r else 0
+
+        if cuda:
+            self.panel_stream.wait_stream(main)
+        if self.owner(0) == self.rank:
+            with on(self.panel_stream if cuda else None):
+                info = factor_panel(0)
+        for J in range(self.nblk):
+            j = J * nb; jb = min(nb, n - j); rest = n - j - jb
+            # panel J = rows j.. of columns j..j+jb; the column block [j*n, (j+jb)*n) is one contiguous range
+            with on(self.panel_stream if cuda else None):
+                dist.broadcast(A[j * n:(j + jb) * n], src=self.owner(J))
+                if cuda:
+                    arrived = torch.cuda.Event(); arrived.record(self.panel_stream)
+            if rest <= 0:
+                continue
+            if cuda:
+                main.wait_event(arrived)
+            # trailing update of the block columns this rank owns; the next panel's column goes first so that its
+            # owner can factor and broadcast it on the panel stream while the remaining columns are still updating
+            mine = [K for K in range(J + 1, self.nblk) if self.owner(K) == self.rank]
+            for K in mine:
+                kcol = K * nb; kb = min(nb, n - kcol); below = n - kcol - kb
+                call("dsyrk_", "L", "N", kb, jb, -1.0, at(kcol, j), n, 1.0, at(kcol, kcol), n)
+                if below > 0:
+                    call("dgemm_", "N", "T", below, kb, jb, -1.0, at(kcol + kb, j), n, at(kcol, j), n, 1.0, at(kcol + kb, kcol), n)
+                if K == J + 1 and cuda:
+                    ready = torch.cuda.Event(); ready.record(main)
+                    self.panel_stream.wait_event(ready)
+            if mine and mine[0] == J + 1 and info == 0:
+                with on(self.panel_stream if cuda else None):
+                    info = factor_panel(J + 1)
+        if cuda:
+            main.wait_stream(self.panel_stream)
+        t = torch.tensor([info], device=self.dev, dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return int(t.item())

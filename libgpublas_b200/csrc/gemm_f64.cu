@@ -64,8 +64,11 @@ __device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch) 
     asm volatile("fence.proxy.async;" ::: "memory");   // order the async-proxy (TMA) reads after the acquire
 }
 
+// MB*NB >= 32 (the 128x128 tile): one CTA per SM, registers moved from the producer group to the consumers.
+// Smaller tiles (64x64, 64x32; used when a 128x128 tiling would leave most SMs without a tile): the consumers
+// need few registers, so two CTAs share an SM and setmaxnreg is skipped.
 template <int MB, int NB, int LAYA, int LAYB, bool USE_TMA>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(384, (MB * NB >= 32) ? 1 : 2)
 dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                   const DgemmParams p) {
     constexpr int BM = 16 * MB, BN = 32 * NB;          // 2 consumer warps along m, 4 along n
@@ -110,7 +113,7 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 
     if (warp < 4) {
         // =========================== producer warp-group ===========================
-        setmaxnreg_dec<40>();
+        if (MB * NB >= 32) setmaxnreg_dec<40>();
         if (USE_TMA) {
             if (tid == 0) {
                 int stage = 0; uint32_t phase = 0;
@@ -175,7 +178,7 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
 
     // =============================== consumer warps ===============================
-    setmaxnreg_inc<232>();
+    if (MB * NB >= 32) setmaxnreg_inc<232>();
     const int cw = warp - 4;
     const int wm0 = (cw & 1) * (8 * MB), wn0 = (cw >> 1) * (8 * NB);
     const int g = lane >> 2, tig = lane & 3;
@@ -344,8 +347,16 @@ void dgemm_out_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, double
     p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.D = D; p.ldd = ldd; p.mask = mask;
     p.tiles_m = p.tiles_n = 0;
     p.aflags = t_aflags; p.bflags = t_bflags; p.a_group = t_a_group; p.b_group = t_b_group; p.flag_epoch = t_flag_epoch;
+    const bool flagged = t_aflags || t_bflags;
     t_aflags = t_bflags = nullptr;
-    dgemm_dmma_dispatch<8, 4>(s, nota, notb, tma_ok, p);
+    // Tile shape by available parallelism: a CTA streams its whole k range at one SM's DMMA rate (2.1 us per
+    // 16-deep step of a 128x128 tile), so when a 128x128 tiling yields fewer tiles than SMs -- panel updates,
+    // triangular-solve leaves, Cholesky diagonal blocks -- smaller tiles finish sooner although each is less efficient.
+    const int64_t sms = sm_count() > 0 ? sm_count() : 148;
+    auto ntiles = [&](int bm, int bn) { return (int64_t)((m + bm - 1) / bm) * ((n + bn - 1) / bn); };
+    if (flagged || ntiles(128, 128) >= sms) dgemm_dmma_dispatch<8, 4>(s, nota, notb, tma_ok, p);
+    else if (ntiles(64, 64) >= sms) dgemm_dmma_dispatch<4, 2>(s, nota, notb, tma_ok, p);
+    else dgemm_dmma_dispatch<4, 1>(s, nota, notb, tma_ok, p);
 }
 
 }  // namespace b200

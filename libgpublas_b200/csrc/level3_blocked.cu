@@ -172,6 +172,9 @@ __global__ void __launch_bounds__(TRSM_NB) tri_inverse_kernel(int n, const T* __
     for (int l = 0; l < nb; l++)
         if (j < nb) sT[j + l * TRSM_NB] = Ab[j + (int64_t)l * lda];
     __syncthreads();
+    // one division per row instead of one per (row, column): thread j replaces T(j,j) by its reciprocal
+    if (j < nb && !unit) sT[j + j * TRSM_NB] = tdiv<T>(num<T>::real(1.0), sT[j + j * TRSM_NB]);
+    __syncthreads();
     if (j < nb) {
         T* x = sX + j * (TRSM_NB + 1);
         for (int i = 0; i < nb; i++) x[i] = num<T>::zero();
@@ -179,13 +182,13 @@ __global__ void __launch_bounds__(TRSM_NB) tri_inverse_kernel(int n, const T* __
             for (int i = j; i < nb; i++) {
                 T sacc = (i == j) ? num<T>::real(1.0) : num<T>::zero();
                 for (int l = j; l < i; l++) sacc = num<T>::sub(sacc, num<T>::mul(sT[i + l * TRSM_NB], x[l]));
-                x[i] = unit ? sacc : tdiv<T>(sacc, sT[i + i * TRSM_NB]);
+                x[i] = unit ? sacc : num<T>::mul(sacc, sT[i + i * TRSM_NB]);
             }
         } else {        // back substitution, rows j..0
             for (int i = j; i >= 0; i--) {
                 T sacc = (i == j) ? num<T>::real(1.0) : num<T>::zero();
                 for (int l = i + 1; l <= j; l++) sacc = num<T>::sub(sacc, num<T>::mul(sT[i + l * TRSM_NB], x[l]));
-                x[i] = unit ? sacc : tdiv<T>(sacc, sT[i + i * TRSM_NB]);
+                x[i] = unit ? sacc : num<T>::mul(sacc, sT[i + i * TRSM_NB]);
             }
         }
     }

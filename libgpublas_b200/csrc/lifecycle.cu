@@ -8,6 +8,8 @@
 #include <cstring>
 #include <unistd.h>
 #include <mutex>
+#include <execinfo.h>
+#include <signal.h>
 
 using namespace b200;
 
@@ -79,13 +81,22 @@ static void set_options(const char* env) {
 // Constructor: cheap on purpose.  The reference creates the cuBLAS handle and prints device
 // properties in every process that loads it (blas2cuda.c:178-242); here the device comes up lazily
 // at the first BLAS call or first managed allocation, so preloading into `sh`, `make`, ... is free.
+static void segv_backtrace(int sig) {
+    void* frames[64];
+    int n = backtrace(frames, 64);
+    b200_writef(STDERR_FILENO, "b200blas: signal %d, backtrace:\n", sig);
+    backtrace_symbols_fd(frames, n, STDERR_FILENO);
+    _exit(128 + sig);
+}
+
 __attribute__((constructor)) static void b200blas_ctor() {
+    if (getenv("B200BLAS_DEBUG_SEGV")) { signal(SIGSEGV, segv_backtrace); signal(SIGABRT, segv_backtrace); }
     set_options(getenv("BLAS2CUDA_OPTIONS"));
     tracker_set_tracking(1);
 }
 
 __attribute__((destructor)) static void b200blas_dtor() {
-    tracker_set_tracking(0);
+    tracker_set_shutdown();
     if (g_stats.calls == 0) return;
     // reference blas2cuda.c:266-273: ./statistics.csv with the hit/miss counters
     const char* path = getenv("B200BLAS_STATS_FILE");

@@ -89,7 +89,7 @@ static void do_init() {
     // buffers that the interposed malloc placed in managed memory (heuristic=true, or a large setvbuf)
     // are flushed and detached while the context still exists; later allocations use the heap.
     atexit([] {
-        tracker_set_tracking(0);
+        tracker_set_shutdown();
         fflush(NULL);
         if (tracker_lookup(stdout->_IO_buf_base, nullptr, nullptr)) setvbuf(stdout, nullptr, _IONBF, 0);
     });

@@ -65,6 +65,7 @@ volatile int g_tracking = 0;
 volatile int g_heuristic = B200_H_SIZE;
 volatile size_t g_threshold = 64 * 1024;
 volatile int g_initialising = 0;
+volatile int g_shutdown = 0;      // set at exit, before the CUDA runtime tears itself down
 uint64_t g_nth = 0;
 b200_tracker_stats g_tstats = {0, 0, 0, 0, 0};
 
@@ -222,11 +223,16 @@ int tracker_load_oracle_file(const char* filename) {
 void* tracker_alloc_managed(size_t bytes) { return managed_new(bytes); }
 int tracker_free_managed(void* p) {
     if (!registry_remove((uintptr_t)p)) return 0;
+    // Once the process is exiting, blocks are dropped rather than returned: exit-time destructors (including the
+    // CUDA runtime's own, which run after its context is gone) still call free() on tracked blocks, and re-entering
+    // a half-destroyed runtime crashes.  The driver reclaims everything at process end.
+    if (g_shutdown) return 1;
     t_inside++;
     cudaFree(p);
     t_inside--;
     return 1;
 }
+void tracker_set_shutdown(void) { g_shutdown = 1; g_tracking = 0; }
 
 // ---- threads created by CUDA itself never get managed memory ----
 // The reference keeps CUDA's own allocations out of the managed allocator by return address ("excluded

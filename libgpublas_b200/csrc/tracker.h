@@ -22,6 +22,7 @@ void tracker_enter(void);
 void tracker_leave(void);
 void tracker_set_tracking(int on);          // reference obj_tracker_set_tracking
 int tracker_get_tracking(void);
+void tracker_set_shutdown(void);             // process is exiting: stop tracking, never call into CUDA from free() again
 void tracker_set_heuristic(int h);
 void tracker_set_threshold(size_t bytes);
 int tracker_load_oracle_file(const char* filename);   // reference oracle_load_file, oracle.c:26-72
