@@ -47,6 +47,31 @@ def blocked_cholesky(n, A, lda, nb=2048):
     return 0
 
 
+class LibBlas:
+    """The four block operations of the workload on a column-major n x n buffer (ld = n), through the library's
+    Fortran symbols.  TiledCholesky takes any object with these methods, so its host logic (ownership, ordering,
+    broadcasts) can be exercised on CPU with gloo by injecting a reference back end (tests/test_multigpu_cpu.py)."""
+
+    def __init__(self, A, n):
+        self.base, self.n = A.data_ptr(), n
+
+    def at(self, i, j):
+        return DevPtr(self.base + 8 * (i + j * self.n))
+
+    def potrf(self, j, jb):
+        return potrf_lower(jb, self.at(j, j), self.n)
+
+    def trsm(self, j, jb, rest):                  # A[j+jb:, j:j+jb] := A[j+jb:, j:j+jb] * L(j,j)^-T
+        call("dtrsm_", "R", "L", "T", "N", rest, jb, 1.0, self.at(j, j), self.n, self.at(j + jb, j), self.n)
+
+    def syrk(self, kcol, kb, j, jb):              # A[kcol:kcol+kb, kcol:kcol+kb] -= P P^T (lower), P = A[kcol:kcol+kb, j:j+jb]
+        call("dsyrk_", "L", "N", kb, jb, -1.0, self.at(kcol, j), self.n, 1.0, self.at(kcol, kcol), self.n)
+
+    def gemm(self, kcol, kb, below, j, jb):       # A[kcol+kb:, kcol:kcol+kb] -= A[kcol+kb:, j:j+jb] * A[kcol:kcol+kb, j:j+jb]^T
+        call("dgemm_", "N", "T", below, kb, jb, -1.0, self.at(kcol + kb, j), self.n, self.at(kcol, j), self.n, 1.0,
+             self.at(kcol + kb, kcol), self.n)
+
+
 class TiledCholesky:
     """Strong-scaled lower Cholesky of one n x n matrix over `world` GPUs (one process each).
 
@@ -57,8 +82,9 @@ class TiledCholesky:
     columns are still being updated (look-ahead of one panel).  Every rank ends up with the complete factor: the
     panels arrive in the broadcasts anyway, so there is no separate gather."""
 
-    def __init__(self, n, nb, device, rank, world):
+    def __init__(self, n, nb, device, rank, world, blas=None):
         self.n, self.nb, self.dev, self.rank, self.world = n, nb, device, rank, world
+        self.blas_factory = blas or LibBlas
         self.nblk = (n + nb - 1) // nb
         self.A = None
 
@@ -73,8 +99,7 @@ class TiledCholesky:
     def run(self):
         import libgpublas_b200 as g
         n, nb, A = self.n, self.nb, self.A
-        base = A.data_ptr()
-        at = lambda i, j: DevPtr(base + 8 * (i + j * n))
+        blas = self.blas_factory(A, n)
         cuda = self.dev.type == "cuda"
         main = torch.cuda.current_stream(self.dev) if cuda else None
         if cuda and not hasattr(self, "panel_stream"):
@@ -92,9 +117,9 @@ class TiledCholesky:
 
         def factor_panel(J):
             j = J * nb; jb = min(nb, n - j); rest = n - j - jb
-            r = potrf_lower(jb, at(j, j), n)
+            r = blas.potrf(j, jb)
             if rest > 0 and r == 0:
-                call("dtrsm_", "R", "L", "T", "N", rest, jb, 1.0, at(j, j), n, at(j + jb, j), n)
+                blas.trsm(j, jb, rest)
             return r + j if r else 0
 
         if cuda:
@@ -118,9 +143,9 @@ class TiledCholesky:
             mine = [K for K in range(J + 1, self.nblk) if self.owner(K) == self.rank]
             for K in mine:
                 kcol = K * nb; kb = min(nb, n - kcol); below = n - kcol - kb
-                call("dsyrk_", "L", "N", kb, jb, -1.0, at(kcol, j), n, 1.0, at(kcol, kcol), n)
+                blas.syrk(kcol, kb, j, jb)
                 if below > 0:
-                    call("dgemm_", "N", "T", below, kb, jb, -1.0, at(kcol + kb, j), n, at(kcol, j), n, 1.0, at(kcol + kb, kcol), n)
+                    blas.gemm(kcol, kb, below, j, jb)
                 if K == J + 1 and cuda:
                     ready = torch.cuda.Event(); ready.record(main)
                     self.panel_stream.wait_event(ready)

@@ -78,3 +78,72 @@ def test_tiled_gemm_gloo(world, shape):
     assert status == "ok", err
     assert err < 1e-10, err
     assert "2d-tile" in desc
+
+
+# ---------------------------------------------------------------------------------------------
+# Blocked Cholesky (BASELINE.json configs[3]) over ranks: ownership, broadcast order and look-ahead ordering of
+# libgpublas_b200/cholesky.py::TiledCholesky with the four block operations replaced by numpy on the shared buffer.
+class _NumpyBlas:
+    def __init__(self, A, n):
+        self.M = A.numpy().reshape((n, n), order="F")        # shares memory with the torch buffer
+
+    def potrf(self, j, jb):
+        blk = self.M[j:j + jb, j:j + jb]
+        try:
+            L = np.linalg.cholesky(np.tril(blk) + np.tril(blk, -1).T)
+        except np.linalg.LinAlgError:
+            return 1
+        blk[np.tril_indices(jb)] = L[np.tril_indices(jb)]
+        return 0
+
+    def trsm(self, j, jb, rest):
+        L = np.tril(self.M[j:j + jb, j:j + jb])
+        P = self.M[j + jb:j + jb + rest, j:j + jb]
+        P[:] = np.linalg.solve(L, P.T).T
+
+    def syrk(self, kcol, kb, j, jb):
+        P = self.M[kcol:kcol + kb, j:j + jb]
+        blk = self.M[kcol:kcol + kb, kcol:kcol + kb]
+        upd = P @ P.T
+        blk[np.tril_indices(kb)] -= upd[np.tril_indices(kb)]
+
+    def gemm(self, kcol, kb, below, j, jb):
+        self.M[kcol + kb:kcol + kb + below, kcol:kcol + kb] -= self.M[kcol + kb:kcol + kb + below, j:j + jb] @ self.M[kcol:kcol + kb, j:j + jb].T
+
+
+def _chol_worker(rank, world, port, n, nb, q):
+    from libgpublas_b200.cholesky import TiledCholesky
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        tc = TiledCholesky(n, nb, torch.device("cpu"), rank, world, blas=_NumpyBlas)
+        gen = torch.Generator().manual_seed(9)
+        G = torch.rand((n, n), dtype=torch.float64, generator=gen) * 2 - 1
+        S = torch.tril(G, -1); S = S + S.T + n * torch.eye(n, dtype=torch.float64)
+        A0 = S.numpy().copy()
+        buf = S.T.contiguous().view(-1) if rank == 0 else torch.zeros(n * n, dtype=torch.float64)   # only rank 0 holds the input
+        tc.set_matrix(buf)
+        info = tc.run()
+        L = np.tril(buf.numpy().reshape((n, n), order="F"))
+        err = np.linalg.norm(L @ L.T - A0) / np.linalg.norm(A0)
+        q.put(("ok", rank, info, float(err)))
+    except Exception as e:
+        q.put(("fail", rank, repr(e), 0.0))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,nb", [(2, 300, 64), (3, 257, 50), (2, 64, 100)])
+def test_tiled_cholesky_gloo(world, n, nb):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_chol_worker, args=(r, world, port, n, nb, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for status, rank, info, err in res:      # every rank ends with the complete factor
+        assert status == "ok", info
+        assert info == 0 and err < 1e-13, (rank, info, err)
