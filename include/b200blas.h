@@ -179,6 +179,7 @@ B200_API void* b200blas_malloc_managed(size_t bytes);            /* tracked mana
 B200_API void b200blas_free_managed(void* p);
 B200_API int b200blas_is_tracked(const void* p);
 B200_API int b200blas_device_count(void);
+B200_API int b200blas_residency(const void* p, size_t bytes);     /* device ordinal a managed range was last prefetched to; -1 host; -2 unknown */
 /* D := alpha*op(A)*op(B) + beta*C on device pointers with a separate output (may be peer-mapped) */
 B200_API void b200blas_dgemm_out(char transa, char transb, int m, int n, int k, double alpha, const double* a, long long lda, const double* b, long long ldb, double beta, const double* c, long long ldc, double* d, long long ldd);
 /* the same for a rank whose operand panels are still arriving over NVLink: a tile reads rows [g*a_group, ...) of op(A) only

@@ -27,7 +27,8 @@ static void print_help() {
         "   variant=<name>  -- force a kernel variant: generic_tile | dmma_tma | dmma_ldg | auto\n"
         "   devices=<n>     -- GPUs used for partitioned Level-3 calls (default 1)\n"
         "   sync=<0|1>      -- block until results are visible before returning (default 1)\n"
-        "   prefetch=<0|1>  -- cudaMemPrefetchAsync managed operands to the device (default 1)\n"
+        "   prefetch=<0|1|2> -- managed operands: 0 never prefetch, 1 bulk-migrate a tracked block to the device on its\n"
+        "                      first use (default), 2 prefetch on every call\n"
         "   pipeline_min=<n> -- host-resident GEMM operands of >= n bytes in total are staged in chunks\n"
         "                      overlapped with compute (default 64 MiB)\n");
 }
@@ -71,7 +72,7 @@ static void set_options(const char* env) {
         else if (!strncmp(opt, "variant=", 8)) force_variant = variant_from_name(opt + 8);
         else if (!strncmp(opt, "devices=", 8)) g_opts.devices = atoi(opt + 8);
         else if (!strncmp(opt, "sync=", 5)) g_opts.sync = atoi(opt + 5) != 0;
-        else if (!strncmp(opt, "prefetch=", 9)) g_opts.prefetch = atoi(opt + 9) != 0;
+        else if (!strncmp(opt, "prefetch=", 9)) g_opts.prefetch = atoi(opt + 9);
         else if (!strncmp(opt, "pipeline_min=", 13)) g_opts.pipeline_min_bytes = strtoull(opt + 13, nullptr, 0);
         else b200_writef(STDERR_FILENO, "b200blas: unknown option '%s'. Set BLAS2CUDA_OPTIONS=help.\n", opt);
     }
@@ -184,6 +185,15 @@ void* b200blas_ipc_open(const void* handle64) {
     return p;
 }
 void b200blas_ipc_close(void* p) { TrackerGuard g; cudaIpcCloseMemHandle(p); }
+
+// Where the driver last placed a managed range: device ordinal, -1 = host, -2 = not managed / unknown.
+int b200blas_residency(const void* p, size_t bytes) {
+    ensure_init();
+    TrackerGuard g;
+    int loc = -2;
+    if (cudaMemRangeGetAttribute(&loc, sizeof loc, cudaMemRangeAttributeLastPrefetchLocation, p, bytes) != cudaSuccess) { cudaGetLastError(); return -2; }
+    return loc;   // cudaCpuDeviceId == -1, cudaInvalidDeviceId == -2
+}
 
 // ---- building blocks of the copy-engine panel push (libgpublas_b200/multigpu.py) ----
 // 2-D strided device->device copy on a caller stream; dst may be a CUDA-IPC peer mapping (then the bytes

@@ -14,7 +14,7 @@ struct Options {
     bool debug_execfail = false;   // reference key: sync + check after every launch
     bool trace_copy = false;       // reference key: log host<->device copies
     bool sync = true;              // block until results are visible before returning (BLAS semantics)
-    bool prefetch = true;          // cudaMemPrefetchAsync managed operands to the device
+    int prefetch = 1;              // managed operands: 0 never prefetch, 1 bulk-migrate a tracked block on first use, 2 prefetch on every call
     size_t managed_threshold = 64 * 1024;   // tracker: allocations >= this go to managed memory
     int devices = 1;               // GPUs used by partitioned Level-3 calls
     size_t multi_gpu_min_dim = 8192;
@@ -53,6 +53,7 @@ void* device_scalar();              // 64 B of device memory for scalar results 
 enum Access { ACC_IN = 1, ACC_OUT = 2, ACC_INOUT = 3 };
 enum Residency { RES_DEVICE = 0, RES_MANAGED = 1, RES_HOST_PINNED = 2, RES_HOST_PAGEABLE = 3 };
 Residency classify(const void* p);
+void make_resident(const void* p, size_t bytes, cudaStream_t s);   // managed operand residency policy (runtime.cu)
 
 // A column-major matrix operand (vectors are 1 x n with ld = |inc|) made device-accessible.
 // Tracked-managed / device pointers are used in place (hit); host pointers are staged into the

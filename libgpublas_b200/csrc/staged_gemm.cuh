@@ -42,14 +42,7 @@ static inline StagedMat stage_matrix(const void* p, int64_t rows, int64_t cols, 
     } else {
         m.dld = ld; m.dev = (char*)p;
         __atomic_fetch_add(&g_stats.hits, 1ull, __ATOMIC_RELAXED);
-        if (r == RES_MANAGED && g_opts.prefetch) {
-            TrackerGuard guard;
-            int dev; cudaGetDevice(&dev);
-            const size_t bytes = (size_t)((cols - 1) * ld + rows) * es;
-            if (cudaMemPrefetchAsync(p, bytes, dev, s) == cudaSuccess)
-                __atomic_fetch_add(&g_stats.prefetch_bytes, (unsigned long long)bytes, __ATOMIC_RELAXED);
-            else cudaGetLastError();
-        }
+        if (r == RES_MANAGED) make_resident(p, (size_t)((cols - 1) * ld + rows) * es, s);
     }
     return m;
 }

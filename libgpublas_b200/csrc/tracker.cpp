@@ -29,7 +29,7 @@ void __libc_free(void*);
 
 namespace {
 
-struct Block { uintptr_t base; size_t size; };
+struct Block { uintptr_t base; size_t size; int resident; /* bulk-migrated to the device since it was allocated */ };
 
 pthread_rwlock_t g_lock = PTHREAD_RWLOCK_INITIALIZER;
 Block* g_blocks = nullptr;
@@ -94,7 +94,7 @@ bool registry_insert(uintptr_t base, size_t size) {
     }
     size_t pos = g_nblocks;
     while (pos > 0 && g_blocks[pos - 1].base > base) { g_blocks[pos] = g_blocks[pos - 1]; pos--; }
-    g_blocks[pos].base = base; g_blocks[pos].size = size;
+    g_blocks[pos].base = base; g_blocks[pos].size = size; g_blocks[pos].resident = 0;
     g_nblocks++;
     if (base < g_lo) g_lo = base;
     if (base + size > g_hi) g_hi = base + size;
@@ -177,6 +177,16 @@ int tracker_lookup(const void* ptr, void** base, size_t* size) {
     }
     pthread_rwlock_unlock(&g_lock);
     return found;
+}
+int tracker_test_and_set_resident(const void* ptr) {
+    uintptr_t p = (uintptr_t)ptr;
+    if (p < g_lo || p >= g_hi) return -1;
+    int prev = -1;
+    pthread_rwlock_rdlock(&g_lock);
+    long i = find_block(p);
+    if (i >= 0) prev = __sync_lock_test_and_set(&g_blocks[i].resident, 1);
+    pthread_rwlock_unlock(&g_lock);
+    return prev;
 }
 void tracker_enter(void) { t_inside++; }
 void tracker_leave(void) { t_inside--; }

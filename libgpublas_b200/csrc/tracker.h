@@ -16,6 +16,9 @@ enum b200_heuristic { B200_H_SIZE = 0, B200_H_TRUE, B200_H_FALSE, B200_H_RANDOM,
 // 1 if p lies inside a block handed out by the managed allocator (interior pointers included,
 // reference obj_tracker_objinfo_subptr, obj_tracker.c:602-637); base/size optional outputs.
 int tracker_lookup(const void* p, void** base, size_t* size);
+// Residency bookkeeping for a tracked block containing p: returns 1 if the block has already been bulk-migrated to
+// the device since it was allocated, 0 if not (and marks it), -1 if p is not in a tracked block.
+int tracker_test_and_set_resident(const void* p);
 // re-entrancy guard (reference obj_tracker_internal_enter/leave, obj_tracker.c:343-349): while a
 // thread is inside, its allocations go straight to glibc.
 void tracker_enter(void);

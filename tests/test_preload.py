@@ -127,6 +127,24 @@ def test_cg_chain_under_preload(tmp_path):
 
 
 @pytest.mark.gpu
+def test_l1_chain_under_preload(tmp_path):
+    """BASELINE config 3, Level-1 half (scaled): CPU-initialised calloc'd vectors, chained ddot/daxpy/dnrm2/idamax under
+    LD_PRELOAD agree with the CPU BLAS run, nothing is staged, and the vectors end up resident on the device."""
+    exe = build_driver("l1_chain")
+    gout, _ = run(exe, [1 << 22, 6], preload=True, cwd=str(tmp_path))
+    cout, _ = run(exe, [1 << 22, 6])
+    gr = fields([l for l in gout.splitlines() if l.startswith("RESULT")][0])
+    cr = fields([l for l in cout.splitlines() if l.startswith("RESULT")][0])
+    assert gr["imax"] == cr["imax"] == str((1 << 22) // 3 + 1)          # first of the planted tie, 1-based
+    assert abs(float(gr["acc"]) - float(cr["acc"])) <= 1e-9 * abs(float(cr["acc"])) + 1e-18
+    assert abs(float(gr["nrm"]) - float(cr["nrm"])) <= 1e-12 * float(cr["nrm"])
+    st = fields([l for l in gout.splitlines() if l.startswith("STATS")][0])
+    assert int(st["h2d"]) == 0 and int(st["d2h"]) == 0 and int(st["misses"]) == 0 and int(st["prefetch"]) > 0
+    res = [l for l in gout.splitlines() if l.startswith("RESIDENCY")][0].split()
+    assert res[1] == "x=0" and res[2] == "y=0"
+
+
+@pytest.mark.gpu
 def test_allocs_under_preload(tmp_path):
     exe = build_driver("allocs")
     out, _ = run(exe, preload=True, cwd=str(tmp_path), timeout=90)
