@@ -57,6 +57,23 @@ B200_API void ctrmm_(const char* side, const char* uplo, const char* transa, con
 B200_API void ztrsm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n, const b200_c64* alpha, const b200_c64* a, const int* lda, b200_c64* b, const int* ldb);
 B200_API void ztrmm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n, const b200_c64* alpha, const b200_c64* a, const int* lda, b200_c64* b, const int* ldb);
 
+/* the rest of the reference's Level-3 family -- blas.h:254-266 (symm), :217-227 (hemm), :276-288 (syr2k), :230-239 (herk: real
+ * alpha, beta), :242-252 (her2k: complex alpha, real beta) */
+B200_API void ssymm_(const char* side, const char* uplo, const int* m, const int* n, const float* alpha, const float* a, const int* lda, const float* b, const int* ldb, const float* beta, float* c, const int* ldc);
+B200_API void dsymm_(const char* side, const char* uplo, const int* m, const int* n, const double* alpha, const double* a, const int* lda, const double* b, const int* ldb, const double* beta, double* c, const int* ldc);
+B200_API void csymm_(const char* side, const char* uplo, const int* m, const int* n, const b200_c32* alpha, const b200_c32* a, const int* lda, const b200_c32* b, const int* ldb, const b200_c32* beta, b200_c32* c, const int* ldc);
+B200_API void zsymm_(const char* side, const char* uplo, const int* m, const int* n, const b200_c64* alpha, const b200_c64* a, const int* lda, const b200_c64* b, const int* ldb, const b200_c64* beta, b200_c64* c, const int* ldc);
+B200_API void chemm_(const char* side, const char* uplo, const int* m, const int* n, const b200_c32* alpha, const b200_c32* a, const int* lda, const b200_c32* b, const int* ldb, const b200_c32* beta, b200_c32* c, const int* ldc);
+B200_API void zhemm_(const char* side, const char* uplo, const int* m, const int* n, const b200_c64* alpha, const b200_c64* a, const int* lda, const b200_c64* b, const int* ldb, const b200_c64* beta, b200_c64* c, const int* ldc);
+B200_API void ssyr2k_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha, const float* a, const int* lda, const float* b, const int* ldb, const float* beta, float* c, const int* ldc);
+B200_API void dsyr2k_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const double* a, const int* lda, const double* b, const int* ldb, const double* beta, double* c, const int* ldc);
+B200_API void csyr2k_(const char* uplo, const char* trans, const int* n, const int* k, const b200_c32* alpha, const b200_c32* a, const int* lda, const b200_c32* b, const int* ldb, const b200_c32* beta, b200_c32* c, const int* ldc);
+B200_API void zsyr2k_(const char* uplo, const char* trans, const int* n, const int* k, const b200_c64* alpha, const b200_c64* a, const int* lda, const b200_c64* b, const int* ldb, const b200_c64* beta, b200_c64* c, const int* ldc);
+B200_API void cherk_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha, const b200_c32* a, const int* lda, const float* beta, b200_c32* c, const int* ldc);
+B200_API void zherk_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const b200_c64* a, const int* lda, const double* beta, b200_c64* c, const int* ldc);
+B200_API void cher2k_(const char* uplo, const char* trans, const int* n, const int* k, const b200_c32* alpha, const b200_c32* a, const int* lda, const b200_c32* b, const int* ldb, const float* beta, b200_c32* c, const int* ldc);
+B200_API void zher2k_(const char* uplo, const char* trans, const int* n, const int* k, const b200_c64* alpha, const b200_c64* a, const int* lda, const b200_c64* b, const int* ldb, const double* beta, b200_c64* c, const int* ldc);
+
 /* Level 1 -- gfortran ABI of the CPU BLAS (functions return their result; complex results by value):
  * reference blas_level1/dot.cc:38-48, dotc.cc, dotu.cc, nrm2.cc:31-54, asum.cc, amax.cc:32-56, axpy.cc:44-59,
  * scal.cc, copy.cc, swap.cc (dead wrappers naming the routines).  i?amax_ is 1-based, 0 if n<1 or incx<=0.
@@ -120,6 +137,22 @@ B200_API void cblas_sgemm(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE transa, e
 B200_API void cblas_dgemm(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE transa, enum CBLAS_TRANSPOSE transb, int m, int n, int k, double alpha, const double* a, int lda, const double* b, int ldb, double beta, double* c, int ldc);
 B200_API void cblas_cgemm(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE transa, enum CBLAS_TRANSPOSE transb, int m, int n, int k, const void* alpha, const void* a, int lda, const void* b, int ldb, const void* beta, void* c, int ldc);
 B200_API void cblas_zgemm(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE transa, enum CBLAS_TRANSPOSE transb, int m, int n, int k, const void* alpha, const void* a, int lda, const void* b, int ldb, const void* beta, void* c, int ldc);
+
+/* CBLAS Level 3 beyond gemm -- reference cblas.h:693-824 */
+#define B200_DECL_CBLAS_REAL(P, T) \
+    B200_API void cblas_##P##syrk(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, T alpha, const T* a, int lda, T beta, T* c, int ldc); \
+    B200_API void cblas_##P##syr2k(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, T alpha, const T* a, int lda, const T* b, int ldb, T beta, T* c, int ldc); \
+    B200_API void cblas_##P##symm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, int m, int n, T alpha, const T* a, int lda, const T* b, int ldb, T beta, T* c, int ldc); \
+    B200_API void cblas_##P##trsm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa, enum CBLAS_DIAG diag, int m, int n, T alpha, const T* a, int lda, T* b, int ldb); \
+    B200_API void cblas_##P##trmm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa, enum CBLAS_DIAG diag, int m, int n, T alpha, const T* a, int lda, T* b, int ldb);
+B200_DECL_CBLAS_REAL(s, float)
+B200_DECL_CBLAS_REAL(d, double)
+#define B200_DECL_CBLAS_CPLX(P) \
+    B200_API void cblas_##P##syrk(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, const void* alpha, const void* a, int lda, const void* beta, void* c, int ldc); \
+    B200_API void cblas_##P##trsm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa, enum CBLAS_DIAG diag, int m, int n, const void* alpha, const void* a, int lda, void* b, int ldb); \
+    B200_API void cblas_##P##trmm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa, enum CBLAS_DIAG diag, int m, int n, const void* alpha, const void* a, int lda, void* b, int ldb);
+B200_DECL_CBLAS_CPLX(c)
+B200_DECL_CBLAS_CPLX(z)
 
 /* CBLAS Level 1 / 2 -- reference cblas.h:46-656; cblas_i?amax is 0-based */
 B200_API float cblas_sdot(int n, const float* x, int incx, const float* y, int incy);

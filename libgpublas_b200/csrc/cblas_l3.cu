@@ -38,4 +38,69 @@ void cblas_zgemm(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE transa, enum CBLAS
     else
         zgemm_(&tb, &ta, &n, &m, &k, (const b200_c64*)alpha, (const b200_c64*)b, &ldb, (const b200_c64*)a, &lda, (const b200_c64*)beta, (b200_c64*)c, &ldc);
 }
+// ---- CBLAS SYRK / TRSM / TRMM / SYMM / SYR2K (reference cblas.h:693-824).  Row-major C is the column-major C^T:
+//   syrk/syr2k: the other triangle of C^T and the other transpose of A;  trsm/trmm/symm: the other side and triangle.
+static inline char up(enum CBLAS_UPLO u) { return u == CblasUpper ? 'U' : (u == CblasLower ? 'L' : '?'); }
+static inline char sd(enum CBLAS_SIDE x) { return x == CblasLeft ? 'L' : (x == CblasRight ? 'R' : '?'); }
+static inline char dg(enum CBLAS_DIAG d) { return d == CblasUnit ? 'U' : (d == CblasNonUnit ? 'N' : '?'); }
+static inline char flip_up(char u) { return u == 'U' ? 'L' : (u == 'L' ? 'U' : u); }
+static inline char flip_sd(char x) { return x == 'L' ? 'R' : (x == 'R' ? 'L' : x); }
+static inline char flip_tr(char t) { return t == 'N' ? 'T' : (t == 'T' || t == 'C' ? 'N' : t); }
+
+#define B200_CBLAS_REAL(P, T)                                                                                                     \
+    void cblas_##P##syrk(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, T alpha,         \
+                         const T* a, int lda, T beta, T* c, int ldc) {                                                            \
+        char u = up(uplo), t = tr(trans);                                                                                         \
+        if (order == CblasRowMajor) { u = flip_up(u); t = flip_tr(t); }                                                           \
+        P##syrk_(&u, &t, &n, &k, &alpha, a, &lda, &beta, c, &ldc);                                                                \
+    }                                                                                                                             \
+    void cblas_##P##syr2k(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, T alpha,        \
+                          const T* a, int lda, const T* b, int ldb, T beta, T* c, int ldc) {                                      \
+        char u = up(uplo), t = tr(trans);                                                                                         \
+        if (order == CblasRowMajor) { u = flip_up(u); t = flip_tr(t); }                                                           \
+        P##syr2k_(&u, &t, &n, &k, &alpha, a, &lda, b, &ldb, &beta, c, &ldc);                                                      \
+    }                                                                                                                             \
+    void cblas_##P##symm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, int m, int n, T alpha, const T* a,   \
+                         int lda, const T* b, int ldb, T beta, T* c, int ldc) {                                                   \
+        char s = sd(side), u = up(uplo);                                                                                          \
+        if (order == CblasRowMajor) { s = flip_sd(s); u = flip_up(u); P##symm_(&s, &u, &n, &m, &alpha, a, &lda, b, &ldb, &beta, c, &ldc); } \
+        else P##symm_(&s, &u, &m, &n, &alpha, a, &lda, b, &ldb, &beta, c, &ldc);                                                  \
+    }                                                                                                                             \
+    void cblas_##P##trsm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa,         \
+                         enum CBLAS_DIAG diag, int m, int n, T alpha, const T* a, int lda, T* b, int ldb) {                       \
+        char s = sd(side), u = up(uplo), t = tr(transa), d = dg(diag);                                                            \
+        if (order == CblasRowMajor) { s = flip_sd(s); u = flip_up(u); P##trsm_(&s, &u, &t, &d, &n, &m, &alpha, a, &lda, b, &ldb); } \
+        else P##trsm_(&s, &u, &t, &d, &m, &n, &alpha, a, &lda, b, &ldb);                                                          \
+    }                                                                                                                             \
+    void cblas_##P##trmm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa,         \
+                         enum CBLAS_DIAG diag, int m, int n, T alpha, const T* a, int lda, T* b, int ldb) {                       \
+        char s = sd(side), u = up(uplo), t = tr(transa), d = dg(diag);                                                            \
+        if (order == CblasRowMajor) { s = flip_sd(s); u = flip_up(u); P##trmm_(&s, &u, &t, &d, &n, &m, &alpha, a, &lda, b, &ldb); } \
+        else P##trmm_(&s, &u, &t, &d, &m, &n, &alpha, a, &lda, b, &ldb);                                                          \
+    }
+B200_CBLAS_REAL(s, float)
+B200_CBLAS_REAL(d, double)
+
+// complex: scalars by pointer (standard CBLAS; the reference header declares them by value, cblas.h:662-677)
+#define B200_CBLAS_CPLX(P, CT)                                                                                                    \
+    void cblas_##P##syrk(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, const void* alpha, \
+                         const void* a, int lda, const void* beta, void* c, int ldc) {                                            \
+        char u = up(uplo), t = tr(trans);                                                                                         \
+        if (order == CblasRowMajor) { u = flip_up(u); t = flip_tr(t); }                                                           \
+        P##syrk_(&u, &t, &n, &k, (const CT*)alpha, (const CT*)a, &lda, (const CT*)beta, (CT*)c, &ldc);                            \
+    }                                                                                                                             \
+    void cblas_##P##trsm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa,         \
+                         enum CBLAS_DIAG diag, int m, int n, const void* alpha, const void* a, int lda, void* b, int ldb) {       \
+        char s = sd(side), u = up(uplo), t = tr(transa), d = dg(diag);                                                            \
+        if (order == CblasRowMajor) { s = flip_sd(s); u = flip_up(u); P##trsm_(&s, &u, &t, &d, &n, &m, (const CT*)alpha, (const CT*)a, &lda, (CT*)b, &ldb); } \
+        else P##trsm_(&s, &u, &t, &d, &m, &n, (const CT*)alpha, (const CT*)a, &lda, (CT*)b, &ldb);                                \
+    }                                                                                                                             \
+    void cblas_##P##trmm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa,         \
+                         enum CBLAS_DIAG diag, int m, int n, const void* alpha, const void* a, int lda, void* b, int ldb) {       \
+        char s = sd(side), u = up(uplo), t = tr(transa), d = dg(diag);                                                            \
+        if (order == CblasRowMajor) { s = flip_sd(s); u = flip_up(u); P##trmm_(&s, &u, &t, &d, &n, &m, (const CT*)alpha, (const CT*)a, &lda, (CT*)b, &ldb); } \
+        else P##trmm_(&s, &u, &t, &d, &m, &n, (const CT*)alpha, (const CT*)a, &lda, (CT*)b, &ldb);                                \
+    }
+B200_CBLAS_CPLX(c, b200_c32)
+B200_CBLAS_CPLX(z, b200_c64)
 }

@@ -18,13 +18,15 @@ struct VecOperand : Operand {
         : Operand(p, n > 0 ? 1 + (n - 1) * (inc < 0 ? -inc : inc) : 0, 1, n > 0 ? 1 + (n - 1) * (inc < 0 ? -inc : inc) : 1, elem, access) {}
 };
 
-// scalar results: device -> pinned host, then wait (these routines are synchronous by nature)
-template <typename R> R fetch_scalar(const void* dev) {
-    void* pin = pinned_scalar();
-    cudaStream_t s = current_stream();
-    B200_CUDA(cudaMemcpyAsync(pin, dev, sizeof(R), cudaMemcpyDeviceToHost, s));
-    B200_CUDA(cudaStreamSynchronize(s));
-    return *(const R*)pin;
+// Scalar results: the reduction kernel's finishing block stores the value straight into pinned, device-mapped host
+// memory (zero-copy), so returning it costs one stream synchronisation and no separate copy (these routines are
+// synchronous by nature: they return a value).
+template <typename R> R* scalar_slot() { return (R*)pinned_scalar(); }
+template <typename R> R fetch_scalar(const void* slot) {
+    B200_CUDA(cudaStreamSynchronize(current_stream()));
+    R r;
+    memcpy(&r, slot, sizeof(R));     // pinned host memory, written by the kernel before the synchronise returned
+    return r;
 }
 
 template <typename T> T dot_entry(const char* name, const int* n, const T* x, const int* incx, const T* y, const int* incy, bool conj) {
@@ -32,7 +34,7 @@ template <typename T> T dot_entry(const char* name, const int* n, const T* x, co
     if (*n <= 0) return zero;
     CallScope scope;
     VecOperand ox(x, *n, *incx, sizeof(T), ACC_IN), oy(y, *n, *incy, sizeof(T), ACC_IN);
-    T* out = (T*)device_scalar();
+    T* out = scalar_slot<T>();
     dot_dev<T>(current_stream(), *n, (const T*)ox.dev(), *incx, (const T*)oy.dev(), *incy, out, conj);
     T r = fetch_scalar<T>(out);
     log_exec(name, "n=%d incx=%d incy=%d", *n, *incx, *incy);
@@ -42,7 +44,7 @@ template <typename T, typename R> R nrm2_entry(const char* name, const int* n, c
     if (*n < 1 || *incx < 1) return R(0);
     CallScope scope;
     VecOperand ox(x, *n, *incx, sizeof(T), ACC_IN);
-    R* out = (R*)device_scalar();
+    R* out = scalar_slot<R>();
     if (asum) asum_dev<T, R>(current_stream(), *n, (const T*)ox.dev(), *incx, out);
     else nrm2_dev<T, R>(current_stream(), *n, (const T*)ox.dev(), *incx, out);
     R r = fetch_scalar<R>(out);
@@ -53,7 +55,7 @@ template <typename T> int iamax_entry(const char* name, const int* n, const T* x
     if (*n < 1 || *incx <= 0) return 0;
     CallScope scope;
     VecOperand ox(x, *n, *incx, sizeof(T), ACC_IN);
-    long long* out = (long long*)device_scalar();
+    long long* out = scalar_slot<long long>();
     iamax_dev<T>(current_stream(), *n, (const T*)ox.dev(), *incx, out);
     long long r = fetch_scalar<long long>(out);
     log_exec(name, "n=%d incx=%d", *n, *incx);

@@ -4,6 +4,7 @@
 // problems pick a small-tile GPU variant instead.
 #include "abi_common.h"
 #include "staged_gemm.cuh"
+#include <type_traits>
 #include "../../include/b200blas.h"
 
 using namespace b200;
@@ -109,6 +110,89 @@ void tr_entry(const char* name, bool solve, const char* side, const char* uplo, 
     log_exec(name, "%c%c%c%c m=%d n=%d lda=%d ldb=%d", lside ? 'L' : 'R', upper ? 'U' : 'L', t, lsame(diag, 'U') ? 'U' : 'N', *m, *n, *lda, *ldb);
 }
 
+// reference symm.cc:70-112 / hemm.cc:68-110 (info 1,2,3,4,7,9,12)
+template <typename T>
+void symm_entry(const char* name, bool herm, const char* side, const char* uplo, const int* m, const int* n, const T* alpha, const T* a,
+                const int* lda, const T* b, const int* ldb, const T* beta, T* c, const int* ldc) {
+    const bool lside = lsame(side, 'L'), upper = lsame(uplo, 'U');
+    const int nrowa = lside ? *m : *n;
+    int info = 0;
+    if (!lside && !lsame(side, 'R')) info = 1;
+    else if (!upper && !lsame(uplo, 'L')) info = 2;
+    else if (*m < 0) info = 3;
+    else if (*n < 0) info = 4;
+    else if (*lda < imax(1, nrowa)) info = 7;
+    else if (*ldb < imax(1, *m)) info = 9;
+    else if (*ldc < imax(1, *m)) info = 12;
+    if (info) { call_xerbla(name, info); return; }
+    if (*m == 0 || *n == 0 || (is0(*alpha) && is1(*beta))) return;
+    CallScope scope;
+    const bool scale_only = is0(*alpha);
+    Operand oa(scale_only ? nullptr : a, nrowa, nrowa, *lda, sizeof(T), ACC_IN);
+    Operand ob(scale_only ? nullptr : b, *m, *n, *ldb, sizeof(T), ACC_IN);
+    Operand oc(c, *m, *n, *ldc, sizeof(T), is0(*beta) ? ACC_OUT : ACC_INOUT);
+    symm_dev<T>(current_stream(), herm, lside ? 'L' : 'R', upper ? 'U' : 'L', *m, *n, *alpha, (const T*)oa.dev(), oa.ld(), (const T*)ob.dev(), ob.ld(),
+                *beta, (T*)oc.dev(), oc.ld());
+    oc.release();
+    log_exec(name, "%c%c m=%d n=%d lda=%d ldb=%d ldc=%d", lside ? 'L' : 'R', upper ? 'U' : 'L', *m, *n, *lda, *ldb, *ldc);
+}
+
+// reference syr2k.cc:67-118 / her2k.cc:72-124 (info 1,2,3,4,7,9,12).  herm: trans in {N,C}, real beta (RB = real type).
+template <typename T, typename RB>
+void r2k_entry(const char* name, bool herm, bool cplx, const char* uplo, const char* trans, const int* n, const int* k, const T* alpha, const T* a,
+               const int* lda, const T* b, const int* ldb, const RB* beta, T* c, const int* ldc) {
+    const bool upper = lsame(uplo, 'U'), nota = lsame(trans, 'N');
+    const int nrowa = nota ? *n : *k;
+    int info = 0;
+    const bool trans_ok = nota || (herm ? lsame(trans, 'C') : (lsame(trans, 'T') || (!cplx && lsame(trans, 'C'))));
+    if (!upper && !lsame(uplo, 'L')) info = 1;
+    else if (!trans_ok) info = 2;
+    else if (*n < 0) info = 3;
+    else if (*k < 0) info = 4;
+    else if (*lda < imax(1, nrowa)) info = 7;
+    else if (*ldb < imax(1, nrowa)) info = 9;
+    else if (*ldc < imax(1, *n)) info = 12;
+    if (info) { call_xerbla(name, info); return; }
+    if (*n == 0 || ((is0(*alpha) || *k == 0) && is1(*beta))) return;
+    CallScope scope;
+    const bool scale_only = is0(*alpha) || *k == 0;
+    Operand oa(scale_only ? nullptr : a, nrowa, nota ? *k : *n, *lda, sizeof(T), ACC_IN);
+    Operand ob(scale_only ? nullptr : b, nrowa, nota ? *k : *n, *ldb, sizeof(T), ACC_IN);
+    Operand oc(c, *n, *n, *ldc, sizeof(T), ACC_INOUT);      // the unreferenced triangle must survive a staged round trip
+    if constexpr (std::is_same<T, RB>::value)
+        syr2k_dev<T>(current_stream(), upper ? 'U' : 'L', nota ? 'N' : 'T', *n, *k, *alpha, (const T*)oa.dev(), oa.ld(), (const T*)ob.dev(), ob.ld(), *beta,
+                     (T*)oc.dev(), oc.ld());
+    else
+        her2k_dev<T, RB>(current_stream(), upper ? 'U' : 'L', nota ? 'N' : 'C', *n, *k, *alpha, (const T*)oa.dev(), oa.ld(), (const T*)ob.dev(), ob.ld(),
+                         *beta, (T*)oc.dev(), oc.ld());
+    oc.release();
+    log_exec(name, "%c%c n=%d k=%d lda=%d ldb=%d ldc=%d", upper ? 'U' : 'L', nota ? 'N' : 'T', *n, *k, *lda, *ldb, *ldc);
+}
+
+// reference herk.cc:64-121 (info 1,2,3,4,7,10; real alpha and beta; trans in {N,C})
+template <typename T, typename RB>
+void herk_entry(const char* name, const char* uplo, const char* trans, const int* n, const int* k, const RB* alpha, const T* a, const int* lda,
+                const RB* beta, T* c, const int* ldc) {
+    const bool upper = lsame(uplo, 'U'), nota = lsame(trans, 'N');
+    const int nrowa = nota ? *n : *k;
+    int info = 0;
+    if (!upper && !lsame(uplo, 'L')) info = 1;
+    else if (!nota && !lsame(trans, 'C')) info = 2;
+    else if (*n < 0) info = 3;
+    else if (*k < 0) info = 4;
+    else if (*lda < imax(1, nrowa)) info = 7;
+    else if (*ldc < imax(1, *n)) info = 10;
+    if (info) { call_xerbla(name, info); return; }
+    if (*n == 0 || ((*alpha == RB(0) || *k == 0) && *beta == RB(1))) return;
+    CallScope scope;
+    const bool scale_only = *alpha == RB(0) || *k == 0;
+    Operand oa(scale_only ? nullptr : a, nrowa, nota ? *k : *n, *lda, sizeof(T), ACC_IN);
+    Operand oc(c, *n, *n, *ldc, sizeof(T), ACC_INOUT);
+    herk_dev<T, RB>(current_stream(), upper ? 'U' : 'L', nota ? 'N' : 'C', *n, *k, *alpha, (const T*)oa.dev(), oa.ld(), *beta, (T*)oc.dev(), oc.ld());
+    oc.release();
+    log_exec(name, "%c%c n=%d k=%d lda=%d ldc=%d", upper ? 'U' : 'L', nota ? 'N' : 'C', *n, *k, *lda, *ldc);
+}
+
 }  // namespace
 
 extern "C" {
@@ -175,5 +259,42 @@ B200_TR(s, float, float)
 B200_TR(d, double, double)
 B200_TR(c, b200_c32, cuFloatComplex)
 B200_TR(z, b200_c64, cuDoubleComplex)
+
+#define B200_SYMM(P, NAME, T, CT, HERM)                                                                                 \
+    void P##NAME##_(const char* side, const char* uplo, const int* m, const int* n, const T* alpha, const T* a, const int* lda, \
+                    const T* b, const int* ldb, const T* beta, T* c, const int* ldc) {                                  \
+        symm_entry<CT>(#P #NAME "_", HERM, side, uplo, m, n, (const CT*)alpha, (const CT*)a, lda, (const CT*)b, ldb, (const CT*)beta, (CT*)c, ldc); \
+    }
+B200_SYMM(s, symm, float, float, false)
+B200_SYMM(d, symm, double, double, false)
+B200_SYMM(c, symm, b200_c32, cuFloatComplex, false)
+B200_SYMM(z, symm, b200_c64, cuDoubleComplex, false)
+B200_SYMM(c, hemm, b200_c32, cuFloatComplex, true)
+B200_SYMM(z, hemm, b200_c64, cuDoubleComplex, true)
+#define B200_SYR2K(P, T, CT, CPLX)                                                                                      \
+    void P##syr2k_(const char* uplo, const char* trans, const int* n, const int* k, const T* alpha, const T* a, const int* lda, \
+                   const T* b, const int* ldb, const T* beta, T* c, const int* ldc) {                                   \
+        r2k_entry<CT, CT>(#P "syr2k_", false, CPLX, uplo, trans, n, k, (const CT*)alpha, (const CT*)a, lda, (const CT*)b, ldb, (const CT*)beta, (CT*)c, ldc); \
+    }
+B200_SYR2K(s, float, float, false)
+B200_SYR2K(d, double, double, false)
+B200_SYR2K(c, b200_c32, cuFloatComplex, true)
+B200_SYR2K(z, b200_c64, cuDoubleComplex, true)
+void cher2k_(const char* uplo, const char* trans, const int* n, const int* k, const b200_c32* alpha, const b200_c32* a, const int* lda,
+             const b200_c32* b, const int* ldb, const float* beta, b200_c32* c, const int* ldc) {
+    r2k_entry<cuFloatComplex, float>("cher2k_", true, true, uplo, trans, n, k, (const cuFloatComplex*)alpha, (const cuFloatComplex*)a, lda, (const cuFloatComplex*)b, ldb, beta, (cuFloatComplex*)c, ldc);
+}
+void zher2k_(const char* uplo, const char* trans, const int* n, const int* k, const b200_c64* alpha, const b200_c64* a, const int* lda,
+             const b200_c64* b, const int* ldb, const double* beta, b200_c64* c, const int* ldc) {
+    r2k_entry<cuDoubleComplex, double>("zher2k_", true, true, uplo, trans, n, k, (const cuDoubleComplex*)alpha, (const cuDoubleComplex*)a, lda, (const cuDoubleComplex*)b, ldb, beta, (cuDoubleComplex*)c, ldc);
+}
+void cherk_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha, const b200_c32* a, const int* lda, const float* beta,
+            b200_c32* c, const int* ldc) {
+    herk_entry<cuFloatComplex, float>("cherk_", uplo, trans, n, k, alpha, (const cuFloatComplex*)a, lda, beta, (cuFloatComplex*)c, ldc);
+}
+void zherk_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const b200_c64* a, const int* lda, const double* beta,
+            b200_c64* c, const int* ldc) {
+    herk_entry<cuDoubleComplex, double>("zherk_", uplo, trans, n, k, alpha, (const cuDoubleComplex*)a, lda, beta, (cuDoubleComplex*)c, ldc);
+}
 
 }  // extern "C"

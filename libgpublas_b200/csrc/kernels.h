@@ -46,6 +46,15 @@ template <typename T> void gemm_dev(cudaStream_t s, char ta, char tb, int m, int
 // C := alpha*op(A)*op(A)^T + beta*C on one triangle (trans 'N': A n x k; 'T': A k x n).  herm: C/A^H variant.
 template <typename T> void syrk_dev(cudaStream_t s, char uplo, char trans, int n, int k, T alpha, const T* A, int64_t lda, T beta, T* C,
                                     int64_t ldc);
+// C := alpha*A*B + beta*C ('L') or alpha*B*A + beta*C ('R'), A symmetric (herm: Hermitian) with one triangle stored
+template <typename T> void symm_dev(cudaStream_t s, bool herm, char side, char uplo, int m, int n, T alpha, const T* A, int64_t lda, const T* B,
+                                    int64_t ldb, T beta, T* C, int64_t ldc);
+template <typename T> void syr2k_dev(cudaStream_t s, char uplo, char trans, int n, int k, T alpha, const T* A, int64_t lda, const T* B, int64_t ldb,
+                                     T beta, T* C, int64_t ldc);
+template <typename T, typename R> void herk_dev(cudaStream_t s, char uplo, char trans, int n, int k, R alpha, const T* A, int64_t lda, R beta, T* C,
+                                                int64_t ldc);
+template <typename T, typename R> void her2k_dev(cudaStream_t s, char uplo, char trans, int n, int k, T alpha, const T* A, int64_t lda, const T* B,
+                                                 int64_t ldb, R beta, T* C, int64_t ldc);
 // B := alpha*op(A)*B (side 'L') or alpha*B*op(A) ('R'), A triangular; in place, blocked on the GEMM tiles
 template <typename T> void trmm_dev(cudaStream_t s, char side, char uplo, char trans, char diag, int m, int n, T alpha, const T* A,
                                     int64_t lda, T* B, int64_t ldb);

@@ -246,6 +246,133 @@ def chk_syrk(p, call):
     return nc, errmax
 
 
+def chk_symm(p, call, which="symm"):
+    """DCHK2 (dblat3.f:637-906) / ZCHK2: SYMM and, for complex types, HEMM."""
+    beg = Beg(p in "cz"); nc, errmax = 0, 0.0
+    typ = "HE" if which == "hemm" else "SY"
+    for m in IDIM:
+        for n in IDIM:
+            ldc = _ld(m); ldb = _ld(m); null = n <= 0 or m <= 0
+            B, BB = make(p, beg, "GE", " ", " ", m, n, ldb)
+            for side in "LR":
+                na = m if side == "L" else n
+                lda = _ld(na)
+                for uplo in "UL":
+                    A, AA = make(p, beg, typ, uplo, " ", na, na, lda)
+                    for alpha in alphas(p):
+                        for beta in betas(p):
+                            C, CC = make(p, beg, "GE", " ", " ", m, n, ldc)
+                            nc += 1
+                            AS, BS, CS = AA.copy(order="F"), BB.copy(order="F"), CC.copy(order="F")
+                            call(p + which + "_", side, uplo, m, n, alpha, AA, lda, BB, ldb, beta, CC, ldc)
+                            assert np.array_equal(AS, AA) and np.array_equal(BS, BB), "input operand changed"
+                            if null:
+                                assert np.array_equal(CS, CC)
+                                continue
+                            assert same_outside("GE", " ", m, n, CS, CC), "rogue padding of C touched"
+                            err = mmch(p, "N", "N", alpha, A, B, beta, C, CC[:m, :n]) if side == "L" else \
+                                mmch(p, "N", "N", alpha, B, A, beta, C, CC[:m, :n])
+                            errmax = max(errmax, err)
+                            assert err < THRESH, (p, which, side, uplo, m, n, alpha, beta, err)
+    return nc, errmax
+
+
+def _rk_scalars(p, herm):
+    """alpha/beta sets of DCHK4/DCHK5; the Hermitian routines take real beta (and HERK a real alpha): the real parts
+    of the complex input values, as ZCHK4/ZCHK5 do (RALPHA = DBLE(ALPHA), RBETA = DBLE(BETA))."""
+    return alphas(p), betas(p)
+
+
+def chk_herk(p, call):
+    """ZCHK4 (zblat3.f), HERK part: real alpha/beta, trans in {N,C}, imaginary diagonal of the result is zero."""
+    assert p in "cz"
+    beg = Beg(True); nc, errmax = 0, 0.0
+    rt = np.float32 if p == "c" else np.float64
+    for n in IDIM:
+        ldc = _ld(n)
+        for k in IDIM:
+            for trans in "NC":
+                ma, na = (k, n) if trans != "N" else (n, k)
+                lda = _ld(ma)
+                A, AA = make(p, beg, "GE", " ", " ", ma, na, lda)
+                for uplo in "UL":
+                    for alpha in alphas(p):
+                        ralpha = rt(alpha.real)
+                        for beta in betas(p):
+                            rbeta = rt(beta.real)
+                            C, CC = make(p, beg, "HE", uplo, " ", n, n, ldc)
+                            nc += 1
+                            AS, CS = AA.copy(order="F"), CC.copy(order="F")
+                            call(p + "herk_", uplo, trans, n, k, ralpha, AA, lda, rbeta, CC, ldc)
+                            assert np.array_equal(AS, AA)
+                            if n <= 0:
+                                assert np.array_equal(CS, CC)
+                                continue
+                            null = (ralpha == 0 or k <= 0) and rbeta == 1
+                            assert same_outside("SY", uplo, n, n, CS, CC), "unreferenced triangle / padding of C touched"
+                            if null:
+                                assert np.array_equal(CS, CC)
+                                continue
+                            a = A if trans == "N" else A.conj().T            # n x k
+                            for j in range(n):
+                                rows = slice(0, j + 1) if uplo == "U" else slice(j, n)
+                                err = mmch(p, "N", "C", complex(ralpha), a[rows, :], a[j:j + 1, :], complex(rbeta), C[rows, j:j + 1], CC[rows, j:j + 1])
+                                errmax = max(errmax, err)
+                                assert err < THRESH, (p, "herk", uplo, trans, n, k, ralpha, rbeta, j, err)
+                                assert CC[j, j].imag == 0
+    return nc, errmax
+
+
+def chk_r2k(p, call, which="syr2k"):
+    """DCHK5 (dblat3.f:1487-1800) / ZCHK5: SYR2K and, for complex types, HER2K (real beta, conj(alpha) on the second term)."""
+    herm = which == "her2k"
+    beg = Beg(p in "cz"); nc, errmax = 0, 0.0
+    hi = np.complex128 if p in "cz" else np.float64
+    rt = np.float32 if p in "sc" else np.float64
+    transes = "NC" if herm else ("NTC" if p in "sd" else "NT")
+    for n in IDIM:
+        ldc = _ld(n)
+        for k in IDIM:
+            for trans in transes:
+                ma, na = (k, n) if trans != "N" else (n, k)
+                lda = _ld(ma)
+                A, AA = make(p, beg, "GE", " ", " ", ma, na, lda)
+                B, BB = make(p, beg, "GE", " ", " ", ma, na, lda)
+                for uplo in "UL":
+                    for alpha in alphas(p):
+                        for beta in betas(p):
+                            bet = rt(beta.real) if herm else beta
+                            C, CC = make(p, beg, "HE" if herm else "SY", uplo, " ", n, n, ldc)
+                            nc += 1
+                            AS, BS, CS = AA.copy(order="F"), BB.copy(order="F"), CC.copy(order="F")
+                            call(p + which + "_", uplo, trans, n, k, alpha, AA, lda, BB, lda, bet, CC, ldc)
+                            assert np.array_equal(AS, AA) and np.array_equal(BS, BB)
+                            if n <= 0:
+                                assert np.array_equal(CS, CC)
+                                continue
+                            assert same_outside("SY", uplo, n, n, CS, CC), "unreferenced triangle / padding of C touched"
+                            null = (alpha == 0 or k <= 0) and bet == 1
+                            if null:
+                                assert np.array_equal(CS, CC)
+                                continue
+                            # C = alpha a b^X + alpha' b a^X + beta C  ==  [alpha a | alpha' b] [b | a]^X   (X = T or H), the DCHK5 trick
+                            a = (A if trans == "N" else (A.conj().T if herm else A.T)).astype(hi)      # n x k
+                            b = (B if trans == "N" else (B.conj().T if herm else B.T)).astype(hi)
+                            al2 = np.conj(alpha) if herm else alpha
+                            W = np.concatenate([alpha * a, al2 * b], axis=1)                           # n x 2k
+                            Z = np.concatenate([b, a], axis=1)
+                            one = 1.0 + 0j if p in "cz" else 1.0
+                            for j in range(n):
+                                rows = slice(0, j + 1) if uplo == "U" else slice(j, n)
+                                err = mmch(p, "N", "C" if herm else "T", one, W[rows, :], Z[j:j + 1, :], complex(bet) if p in "cz" else bet,
+                                           C[rows, j:j + 1], CC[rows, j:j + 1])
+                                errmax = max(errmax, err)
+                                assert err < THRESH, (p, which, uplo, trans, n, k, alpha, beta, j, err)
+                                if herm:
+                                    assert CC[j, j].imag == 0
+    return nc, errmax
+
+
 def chke(p, call_capture):
     """DCHKE restated for the routines built: every illegal argument must report its INFO through
     XERBLA under the routine's SRNAME and touch nothing.  `call_capture(name, *args)` performs the call
@@ -313,5 +440,50 @@ def chke(p, call_capture):
         expect(s, 7, uplo, "T", 0, 2, one, A, 1, one, C, 1)
         expect(s, 10, uplo, "N", 2, 0, one, A, 2, one, C, 1)
         expect(s, 10, uplo, "T", 2, 0, one, A, 1, one, C, 1)
+    # ---- DCHKE/ZCHKE blocks for SYMM/HEMM, SYR2K/HER2K, HERK ----
+    rt = np.float32 if p in "sc" else np.float64
+    for r in (("symm_", "hemm_") if p in "cz" else ("symm_",)):
+        t = p + r
+        expect(t, 1, "/", "U", 0, 0, one, A, 1, B, 1, one, C, 1)
+        expect(t, 2, "L", "/", 0, 0, one, A, 1, B, 1, one, C, 1)
+        for side in "LR":
+            for uplo in "UL":
+                expect(t, 3, side, uplo, -1, 0, one, A, 1, B, 1, one, C, 1)
+                expect(t, 4, side, uplo, 0, -1, one, A, 1, B, 1, one, C, 1)
+        for uplo in "UL":
+            expect(t, 7, "L", uplo, 2, 0, one, A, 1, B, 2, one, C, 2)
+            expect(t, 7, "R", uplo, 0, 2, one, A, 1, B, 1, one, C, 1)
+            expect(t, 9, "L", uplo, 2, 0, one, A, 2, B, 1, one, C, 2)
+            expect(t, 9, "R", uplo, 2, 0, one, A, 1, B, 1, one, C, 2)
+            expect(t, 12, "L", uplo, 2, 0, one, A, 2, B, 2, one, C, 1)
+            expect(t, 12, "R", uplo, 2, 0, one, A, 1, B, 2, one, C, 1)
+    for r, tr2, bet in ((("syr2k_", "T", one),) + ((("her2k_", "C", rt(1)),) if p in "cz" else ())):
+        t = p + r
+        expect(t, 1, "/", "N", 0, 0, one, A, 1, B, 1, bet, C, 1)
+        expect(t, 2, "U", "/", 0, 0, one, A, 1, B, 1, bet, C, 1)
+        if p in "cz":
+            expect(t, 2, "U", "C" if r == "syr2k_" else "T", 0, 0, one, A, 1, B, 1, bet, C, 1)
+        for uplo in "UL":
+            for tr in ("N", tr2):
+                expect(t, 3, uplo, tr, -1, 0, one, A, 1, B, 1, bet, C, 1)
+                expect(t, 4, uplo, tr, 0, -1, one, A, 1, B, 1, bet, C, 1)
+            expect(t, 7, uplo, "N", 2, 0, one, A, 1, B, 1, bet, C, 2)
+            expect(t, 7, uplo, tr2, 0, 2, one, A, 1, B, 1, bet, C, 1)
+            expect(t, 9, uplo, "N", 2, 0, one, A, 2, B, 1, bet, C, 2)
+            expect(t, 9, uplo, tr2, 0, 2, one, A, 2, B, 1, bet, C, 1)
+            expect(t, 12, uplo, "N", 2, 0, one, A, 2, B, 2, bet, C, 1)
+            expect(t, 12, uplo, tr2, 2, 0, one, A, 1, B, 1, bet, C, 1)
+    if p in "cz":
+        t = p + "herk_"
+        expect(t, 1, "/", "N", 0, 0, rt(1), A, 1, rt(1), C, 1)
+        expect(t, 2, "U", "T", 0, 0, rt(1), A, 1, rt(1), C, 1)
+        for uplo in "UL":
+            for tr in "NC":
+                expect(t, 3, uplo, tr, -1, 0, rt(1), A, 1, rt(1), C, 1)
+                expect(t, 4, uplo, tr, 0, -1, rt(1), A, 1, rt(1), C, 1)
+            expect(t, 7, uplo, "N", 2, 0, rt(1), A, 1, rt(1), C, 2)
+            expect(t, 7, uplo, "C", 0, 2, rt(1), A, 1, rt(1), C, 1)
+            expect(t, 10, uplo, "N", 2, 0, rt(1), A, 2, rt(1), C, 1)
+            expect(t, 10, uplo, "C", 2, 0, rt(1), A, 1, rt(1), C, 1)
     assert not A.any() and not B.any() and not C.any()
     return n_checked

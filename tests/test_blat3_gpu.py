@@ -51,3 +51,20 @@ def test_blat3_error_exits(p):
         assert blat3.chke(p, cap) > 100
     finally:
         lib.b200blas_set_xerbla(CB(0))
+
+
+@pytest.mark.parametrize("p", ["s", "d", "c", "z"])
+def test_blat3_symm_syr2k(p):
+    """SURVEY 8(f) rank 1 on the GPU: DCHK2 (SYMM) and DCHK5 (SYR2K)."""
+    nc, err = blat3.chk_symm(p, call, "symm")
+    assert nc == 1296 and err < blat3.THRESH
+    nc, err = blat3.chk_r2k(p, call, "syr2k")
+    assert nc > 0 and err < blat3.THRESH
+
+
+@pytest.mark.parametrize("p", ["c", "z"])
+def test_blat3_hermitian_family(p):
+    """ZCHK2 (HEMM), ZCHK4 (HERK), ZCHK5 (HER2K)."""
+    assert blat3.chk_symm(p, call, "hemm")[1] < blat3.THRESH
+    assert blat3.chk_herk(p, call)[1] < blat3.THRESH
+    assert blat3.chk_r2k(p, call, "her2k")[1] < blat3.THRESH

@@ -95,3 +95,82 @@ def test_dsyrk_dtrsm_large_device_property():
     X = B.T                                        # n x k
     back = X @ L.T
     assert (back - B0.T).abs().max().item() <= 64 * 2.0 ** -53 * k * X.abs().max().item() * k
+
+
+def test_cblas_level3_row_major_wrappers():
+    """cblas_dsyrk / cblas_dsymm / cblas_dtrsm / cblas_dtrmm / cblas_dsyr2k in row-major order map onto the column-major
+    core by flipping uplo/side/trans (reference cblas.h:693-824); checked against numpy on row-major arrays."""
+    import ctypes
+    lib = g.load()
+    RowMajor, NoTrans, Trans, Upper, Lower, NonUnit, Left, Right = 101, 111, 112, 121, 122, 131, 141, 142
+    d = ctypes.c_double; P = ctypes.c_void_p
+    n, k, m = 70, 33, 45
+    rng = np.random.default_rng(3)
+    A = rng.uniform(-1, 1, (n, k)); C0 = rng.uniform(-1, 1, (n, n)); C = C0.copy()      # C-order (row-major) numpy arrays
+    lib.cblas_dsyrk(RowMajor, Upper, NoTrans, n, k, d(0.7), P(A.ctypes.data), k, d(1.3), P(C.ctypes.data), n)
+    ref = 0.7 * A @ A.T + 1.3 * C0
+    iu = np.triu_indices(n); il = np.tril_indices(n, -1)
+    assert np.allclose(C[iu], ref[iu], rtol=1e-13, atol=1e-13) and np.array_equal(C[il], C0[il])
+    B = rng.uniform(-1, 1, (n, k)); C = C0.copy()
+    lib.cblas_dsyr2k(RowMajor, Lower, NoTrans, n, k, d(0.7), P(A.ctypes.data), k, P(B.ctypes.data), k, d(1.3), P(C.ctypes.data), n)
+    ref = 0.7 * (A @ B.T + B @ A.T) + 1.3 * C0
+    il0 = np.tril_indices(n); iu1 = np.triu_indices(n, 1)
+    assert np.allclose(C[il0], ref[il0], rtol=1e-13, atol=1e-13) and np.array_equal(C[iu1], C0[iu1])
+    S = rng.uniform(-1, 1, (m, m)); S = S + S.T; Bm = rng.uniform(-1, 1, (m, n)); Cm0 = rng.uniform(-1, 1, (m, n)); Cm = Cm0.copy()
+    Sl = np.tril(S) + np.triu(np.full((m, m), 1e10), 1)                                   # upper part poisoned: must not be read
+    lib.cblas_dsymm(RowMajor, Left, Lower, m, n, d(0.7), P(Sl.ctypes.data), m, P(Bm.ctypes.data), n, d(1.3), P(Cm.ctypes.data), n)
+    assert np.allclose(Cm, 0.7 * S @ Bm + 1.3 * Cm0, rtol=1e-12, atol=1e-12)
+    T = np.triu(rng.uniform(-1, 1, (m, m))) + m * np.eye(m); X = Bm.copy()
+    lib.cblas_dtrsm(RowMajor, Left, Upper, NoTrans, NonUnit, m, n, d(2.0), P(T.ctypes.data), m, P(X.ctypes.data), n)
+    assert np.allclose(T @ X, 2.0 * Bm, rtol=1e-11, atol=1e-11)
+    X = Bm.copy()
+    lib.cblas_dtrmm(RowMajor, Right, Upper, Trans, NonUnit, m, n, d(2.0), P(np.ascontiguousarray(np.triu(rng.uniform(-1, 1, (n, n)))).ctypes.data), n, P(X.ctypes.data), n)
+    # recompute with the same triangular factor
+    rng2 = np.random.default_rng(3); _ = rng2.uniform(-1, 1, (n, k)); _ = rng2.uniform(-1, 1, (n, n)); _ = rng2.uniform(-1, 1, (n, k))
+    _ = rng2.uniform(-1, 1, (m, m)); _ = rng2.uniform(-1, 1, (m, n)); _ = rng2.uniform(-1, 1, (m, n)); _ = rng2.uniform(-1, 1, (m, m))
+    U = np.triu(rng2.uniform(-1, 1, (n, n)))
+    assert np.allclose(X, 2.0 * Bm @ U.T, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("p", ["d", "z", "s"])
+def test_next_family_larger_shapes_vs_oracle(p):
+    """SYMM/SYR2K (+ HEMM/HERK/HER2K for z) at sizes that run on the tensor-pipe tiles (masked DMMA / tcgen05 launches,
+    ragged edges, odd leading dimensions), against the oracle; untouched triangle / padding verified."""
+    lib = g.load(); dt = DT[p]
+    al, be = ((0.7 - 0.9j), (1.3 - 1.1j)) if p == "z" else (0.7, 1.3)
+    n, k, m = 330, 270, 290
+    tol = lambda kk, *mats: 8 * (kk + 2) * EPS[p] * np.prod([fro(x) for x in mats])
+    for uplo in "UL":
+        tri = np.triu(np.ones((n, n), bool)) if uplo == "U" else np.tril(np.ones((n, n), bool))
+        full = np.zeros((n + 3, n), bool); full[:n] = tri
+        for tr in "NT":
+            ra, ca = (n, k) if tr == "N" else (k, n)
+            A = splitmix_uniform(1, (ra + 1, ca), dt); B = splitmix_uniform(2, (ra + 1, ca), dt); C0 = splitmix_uniform(3, (n + 3, n), dt)
+            C, R = F(C0), F(C0)
+            f77(lib, p + "syr2k_", uplo, tr, n, k, al, A, ra + 1, B, ra + 1, be, C, n + 3)
+            assert oracle_call(p + "syr2k", uplo, tr, n, k, al, A, ra + 1, B, ra + 1, be, R, n + 3) == 0
+            assert np.array_equal(C[~full], C0[~full])
+            assert fro((C - R)[full]) <= 2 * abs(al) * tol(k, A, B) + 8 * EPS[p] * abs(be) * fro(C0)
+        if p == "z":
+            for tr in "NC":
+                ra, ca = (n, k) if tr == "N" else (k, n)
+                A = splitmix_uniform(4, (ra + 1, ca), dt); B = splitmix_uniform(5, (ra + 1, ca), dt); C0 = splitmix_uniform(6, (n + 3, n), dt)
+                C, R = F(C0), F(C0)
+                f77(lib, "zherk_", uplo, tr, n, k, np.float64(0.7), A, ra + 1, np.float64(1.3), C, n + 3)
+                assert oracle_call("zherk", uplo, tr, n, k, np.float64(0.7), A, ra + 1, np.float64(1.3), R, n + 3) == 0
+                assert np.array_equal(C[~full], C0[~full]) and np.all(np.diag(C[:n]).imag == 0)
+                assert fro((C - R)[full]) <= tol(k, A, A) + 8 * EPS[p] * 1.3 * fro(C0)
+                C, R = F(C0), F(C0)
+                f77(lib, "zher2k_", uplo, tr, n, k, al, A, ra + 1, B, ra + 1, np.float64(1.3), C, n + 3)
+                assert oracle_call("zher2k", uplo, tr, n, k, al, A, ra + 1, B, ra + 1, np.float64(1.3), R, n + 3) == 0
+                assert np.array_equal(C[~full], C0[~full]) and np.all(np.diag(C[:n]).imag == 0)
+                assert fro((C - R)[full]) <= 2 * abs(al) * tol(k, A, B) + 8 * EPS[p] * 1.3 * fro(C0)
+        for side in "LR":
+            na = m if side == "L" else n
+            S = splitmix_uniform(7, (na + 1, na), dt); Bm = splitmix_uniform(8, (m + 2, n), dt); C0 = splitmix_uniform(9, (m + 1, n), dt)
+            for r in (("symm", "hemm") if p == "z" else ("symm",)):
+                C, R = F(C0), F(C0)
+                f77(lib, p + r + "_", side, uplo, m, n, al, S, na + 1, Bm, m + 2, be, C, m + 1)
+                assert oracle_call(p + r, side, uplo, m, n, al, S, na + 1, Bm, m + 2, be, R, m + 1) == 0
+                assert np.array_equal(C[m:], C0[m:])
+                assert fro(C[:m] - R[:m]) <= abs(al) * tol(na, S, Bm) + 8 * EPS[p] * abs(be) * fro(C0)
