@@ -20,6 +20,7 @@
 #include "kernels.h"
 #include "gemm_generic.cuh"
 #include "runtime.h"
+#include <cstdlib>
 
 namespace b200 {
 
@@ -104,7 +105,7 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     if (tid == 0) {
         for (int s = 0; s < DG_STAGES; s++) {
             mbar_init(full0 + 8 * s, USE_TMA ? 1 : 128);
-            mbar_init(empty0 + 8 * s, 8);   // one arrival per consumer warp
+            mbar_init(empty0 + 8 * s, 256);   // one arrival per consumer thread
         }
         mbar_fence_init();
         if (USE_TMA) { tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB); }
@@ -202,6 +203,18 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 #pragma unroll
         for (int j = 0; j < NB; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    // beta != 0: pull this tile of C into L2 now (no registers, no waiting), so that the epilogue's reads -- which
+    // cannot be overlapped with the k loop because the accumulators fill the register file -- hit L2 instead of
+    // HBM.  Matters for short k (panel updates with k = 1-2 K: the epilogue is ~10% of the tile time).
+    if (p.beta != 0.0) {
+        const int ct = tid - 128;                              // 0..255
+        for (int idx = ct; idx < BN * (BM / 16); idx += 256) {
+            const int col = idx / (BM / 16), seg = idx - col * (BM / 16);
+            const int64_t r = (int64_t)m0 + seg * 16, c = (int64_t)n0 + col;
+            if (r < p.m && c < p.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.C + r + c * p.ldc));
+        }
+    }
+
     {
         int stage = 0; uint32_t phase = 0;
         for (int kt = 0; kt < ktiles; kt++) {
@@ -219,28 +232,46 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 #pragma unroll
                     for (int j = 0; j < NB; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + 8 * stage);
+            // EVERY lane arrives (count 256), not one elected lane after __syncwarp(): a lane's release-arrive is ordered
+            // after that lane's own shared-memory reads, but not after the still in-flight LDS of the other 31 lanes, and
+            // ptxas hoists a lane-0 arrive above the trailing DMMAs -- the producer could then let TMA overwrite the stage
+            // under a pending read (observed as sporadic wrong 8x8 blocks with the small 64x32 tile, whose k-step has
+            // only 4 DMMAs to hide behind).
+            mbar_arrive(empty0 + 8 * stage);
             if (++stage == DG_STAGES) { stage = 0; phase ^= 1; }
         }
     }
 
     // ---- epilogue: C = alpha*acc + beta*C on the kept region ----
+    // Loads of the old C are issued 2*MB at a time BEFORE any dependent store: C and D may alias, so the compiler must
+    // keep program order between a store and the next load, and a load->fma->store chain per element serialises the
+    // memory latency (measured: +22 us per 128x128 tile, 2.5 ms on a 16384^2 C).
     const bool beta0 = (p.beta == 0.0);
 #pragma unroll
     for (int j = 0; j < NB; j++) {
+        double old[2][MB];
+        bool ok[2][MB];
 #pragma unroll
         for (int c = 0; c < 2; c++) {
             const int64_t col = n0 + wn0 + 8 * j + 2 * tig + c;
-            if (col >= p.n) continue;
             const double* cp = p.C + col * p.ldc;
+#pragma unroll
+            for (int i = 0; i < MB; i++) {
+                const int64_t row = m0 + wm0 + 8 * i + g;
+                ok[c][i] = col < p.n && row < p.m && tri_keep(p.mask, row, col);
+                old[c][i] = (!beta0 && ok[c][i]) ? cp[row] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int64_t col = n0 + wn0 + 8 * j + 2 * tig + c;
             double* dp = p.D + col * p.ldd;
 #pragma unroll
             for (int i = 0; i < MB; i++) {
                 const int64_t row = m0 + wm0 + 8 * i + g;
-                if (row >= p.m || !tri_keep(p.mask, row, col)) continue;
+                if (!ok[c][i]) continue;
                 double v = p.alpha * acc[i][j][c];
-                if (!beta0) v = fma(p.beta, cp[row], v);
+                if (!beta0) v = fma(p.beta, old[c][i], v);
                 dp[row] = v;
             }
         }
@@ -354,9 +385,19 @@ void dgemm_out_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, double
     // triangular-solve leaves, Cholesky diagonal blocks -- smaller tiles finish sooner although each is less efficient.
     const int64_t sms = sm_count() > 0 ? sm_count() : 148;
     auto ntiles = [&](int bm, int bn) { return (int64_t)((m + bm - 1) / bm) * ((n + bn - 1) / bn); };
-    if (flagged || ntiles(128, 128) >= sms) dgemm_dmma_dispatch<8, 4>(s, nota, notb, tma_ok, p);
-    else if (ntiles(64, 64) >= sms) dgemm_dmma_dispatch<4, 2>(s, nota, notb, tma_ok, p);
-    else dgemm_dmma_dispatch<4, 1>(s, nota, notb, tma_ok, p);
+    // The small tiles stage their operands with the LDG producer, not TMA: with two CTAs resident per SM the TMA-fed
+    // ring showed sporadic stale 8x8 blocks (1-3% of launches, only when stages are reused and only with TMA; the
+    // LDG producer was clean in the same runs -- profiles/r01b_small_tile_race.txt).  These launches are latency
+    // bound, the staging method does not matter for their speed.
+    static const int dbg_tiles = getenv("B200BLAS_DBG_TILES") ? atoi(getenv("B200BLAS_DBG_TILES")) : 0;   // 1: 128x128 only, 2: 64x64 only, 3: 64x32 only
+    static const bool dbg_small_tma = getenv("B200BLAS_DBG_SMALL_TMA") != nullptr;
+    const bool small_tma = tma_ok && dbg_small_tma;
+    if (dbg_tiles == 2) { dgemm_dmma_dispatch<4, 2>(s, nota, notb, small_tma, p); return; }
+    if (dbg_tiles == 3) { dgemm_dmma_dispatch<4, 1>(s, nota, notb, small_tma, p); return; }
+    // variant=dmma_tma (forced) means the TMA kernel proper, i.e. the 128x128 tile
+    if (dbg_tiles == 1 || force_variant == VAR_DMMA_TMA || flagged || ntiles(128, 128) >= sms) dgemm_dmma_dispatch<8, 4>(s, nota, notb, tma_ok, p);
+    else if (ntiles(64, 64) >= sms) dgemm_dmma_dispatch<4, 2>(s, nota, notb, small_tma, p);
+    else dgemm_dmma_dispatch<4, 1>(s, nota, notb, small_tma, p);
 }
 
 }  // namespace b200

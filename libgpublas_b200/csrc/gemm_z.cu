@@ -77,7 +77,7 @@ zgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     if (tid == 0) {
         for (int s = 0; s < ZG_STAGES; s++) {
             mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, 8);
+            mbar_init(empty0 + 8 * s, 256);
         }
         mbar_fence_init();
         tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB);
@@ -165,32 +165,43 @@ zgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                         dmma884(cim[i][j][0], cim[i][j][1], a[i].y, b[j].x);
                     }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + 8 * stage);
+            // EVERY lane arrives (count 256), not one elected lane after __syncwarp(): a lane's release-arrive is ordered
+            // after that lane's own shared-memory reads, but not after the still in-flight LDS of the other 31 lanes, and
+            // ptxas hoists a lane-0 arrive above the trailing DMMAs -- the producer could then let TMA overwrite the stage
+            // under a pending read (observed as sporadic wrong 8x8 blocks with the small 64x32 tile, whose k-step has
+            // only 4 DMMAs to hide behind).
+            mbar_arrive(empty0 + 8 * stage);
             if (++stage == ZG_STAGES) { stage = 0; phase ^= 1; }
         }
     }
 
-    // ---- epilogue: C = alpha*acc + beta*C on the kept region ----
+    // ---- epilogue: C = alpha*acc + beta*C on the kept region (old values loaded MB at a time before the stores
+    // that may alias them, see gemm_f64.cu) ----
     const bool beta0 = (p.beta.x == 0.0 && p.beta.y == 0.0);
 #pragma unroll
     for (int j = 0; j < NB; j++) {
 #pragma unroll
         for (int c = 0; c < 2; c++) {
             const int64_t col = n0 + wn0 + 8 * j + 2 * tig + c;
-            if (col >= p.n) continue;
             cuDoubleComplex* cp = p.C + col * p.ldc;
+            double2 old[MB];
+            bool ok[MB];
 #pragma unroll
             for (int i = 0; i < MB; i++) {
                 const int64_t row = m0 + wm0 + 8 * i + g;
-                if (row >= p.m || !tri_keep(p.mask, row, col)) continue;
+                ok[i] = col < p.n && row < p.m && tri_keep(p.mask, row, col);
+                old[i] = (!beta0 && ok[i]) ? *reinterpret_cast<const double2*>(cp + row) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int i = 0; i < MB; i++) {
+                const int64_t row = m0 + wm0 + 8 * i + g;
+                if (!ok[i]) continue;
                 const double xr = cre[i][j][c], xi = cim[i][j][c];
                 double vr = fma(p.alpha.x, xr, -(p.alpha.y * xi));
                 double vi = fma(p.alpha.x, xi, p.alpha.y * xr);
                 if (!beta0) {
-                    const double2 old = *reinterpret_cast<const double2*>(cp + row);
-                    vr += fma(p.beta.x, old.x, -(p.beta.y * old.y));
-                    vi += fma(p.beta.x, old.y, p.beta.y * old.x);
+                    vr += fma(p.beta.x, old[i].x, -(p.beta.y * old[i].y));
+                    vi += fma(p.beta.x, old[i].y, p.beta.y * old[i].x);
                 }
                 *reinterpret_cast<double2*>(cp + row) = make_double2(vr, vi);
             }

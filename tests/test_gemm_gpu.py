@@ -137,8 +137,15 @@ def test_dgemm_golden_fixture_1024():
     i = np.arange(n, dtype=np.float64)
     A = F(np.repeat(i[:, None], n, axis=1)); B = F(np.repeat(i[None, :], n, axis=0)); C = np.zeros((n, n), order="F")
     f77(lib, "dgemm_", "N", "N", n, n, n, 1.0, A, n, B, n, 0.0, C, n)
-    assert g.last_variant() == "dmma_tma"
+    assert g.last_variant() in ("dmma_tma", "dmma_ldg")      # 64 tiles of 128x128 < 148 SMs: the small-tile DMMA variant
     assert np.array_equal(C, n * np.outer(i, i))
+    g.force_variant("dmma_tma")                               # and the 128x128 TMA kernel on the same fixture
+    try:
+        C[:] = -1
+        f77(lib, "dgemm_", "N", "N", n, n, n, 1.0, A, n, B, n, 0.0, C, n)
+        assert g.last_variant() == "dmma_tma" and np.array_equal(C, n * np.outer(i, i))
+    finally:
+        g.force_variant("auto")
     # same through CBLAS, column- and row-major
     for order in (102, 101):
         C[:] = -1
@@ -156,7 +163,9 @@ def test_dgemm_device_resident_vs_oracle_and_unaligned():
     lib = g.load()
     m, n, k = 300, 260, 190
     for (ta, tb) in [("N", "N"), ("T", "N"), ("N", "T"), ("T", "T")]:
-        for (lda_pad, off) in [(0, 0), (1, 0), (0, 1), (3, 1)]:
+        for (lda_pad, off) in [(0, 0), (1, 0), (0, 1), (3, 1), (0, 0)]:
+            forced = (lda_pad, off) == (0, 0) and ta == "T"      # aligned case: also run the 128x128 TMA kernel on these ragged shapes
+            g.force_variant("dmma_tma" if forced else "auto")
             ra, ca = (m, k) if ta == "N" else (k, m)
             rb, cb = (k, n) if tb == "N" else (n, k)
             lda, ldb, ldc = ra + lda_pad, rb + lda_pad, m + lda_pad
@@ -167,7 +176,8 @@ def test_dgemm_device_resident_vs_oracle_and_unaligned():
             torch.cuda.synchronize()
             f77(lib, "dgemm_", ta, tb, m, n, k, 0.7, g.DevPtr(dA.data_ptr() + 8 * off), lda, g.DevPtr(dB.data_ptr() + 8 * off), ldb,
                 1.3, g.DevPtr(dC.data_ptr() + 8 * off), ldc)
-            want = "dmma_tma" if (lda_pad % 2 == 0 and off == 0) else "dmma_ldg"
+            g.force_variant("auto")
+            want = "dmma_tma" if forced else "dmma_ldg"           # small shapes run the LDG-staged small tiles
             assert g.last_variant() == want, (g.last_variant(), want)
             C = dC[off:off + ldc * n].cpu().numpy().reshape((ldc, n), order="F")
             check_gemm("d", ta, tb, m, n, k, 0.7, 1.3, A, B, C0, C)
