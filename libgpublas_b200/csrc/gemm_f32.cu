@@ -6,7 +6,8 @@
 //  1. split pass (HBM-bound, ~1 ms at n=16384):  a = hi + lo with hi = RN_tf32(a), lo = RN_tf32(a - hi)
 //     (a - hi is exact in fp32).  Both operands are written k-contiguous ("K-major"), so the
 //     transpose/no-transpose cases collapse into one GEMM kernel: Asplit[2][m][kpad], Bsplit[2][n][kpad].
-//  2. GEMM: CTA tile 128 x BN, BK = 32 floats (one 128-byte swizzle row).  Warp 0 = TMA producer
+//  2. GEMM: CTA tile 128 x BN (BN = 256 with BK = 16 and four 48 KiB stages when the grid still fills the SMs, else
+//     BN = 128 with BK = 32 and three 64 KiB stages; one swizzle row of 64 or 128 bytes per operand row).  Warp 0 = TMA producer
 //     (one 3-D box per operand per stage brings hi and lo planes together), warp 1 = MMA issuer
 //     (one thread; per 8-wide k step three tcgen05.mma into the same TMEM accumulator:
 //     lo*hi, hi*lo, hi*hi -- small terms first), warps 2..9 = epilogue (tcgen05.ld 32x32b.x64: lane
@@ -20,12 +21,18 @@
 #include "gemm_generic.cuh"
 #include "runtime.h"
 #include <cstdio>
+#include <cstdlib>
 
 namespace b200 {
 
-constexpr int SG_BM = 128, SG_BK = 32, SG_STAGES = 3;
+constexpr int SG_BM = 128;
 constexpr int SG_THREADS = 64 + 256;      // TMA warp, MMA warp, 8 epilogue warps (lane quarter x column half)
-constexpr int SG_CHUNK_STAGES = 4;      // k per TMEM accumulation chunk = 4 * 32 = 128 (see the epilogue comment)
+constexpr int SG_CHUNK_K = 128;
+constexpr int SG_DEFAULT_WIDE_CFG = 2;     // large problems: 128x256, BK=16, 4 stages (232 TFLOP/s at n=16384 vs 203 for 128x128)           // k per TMEM accumulation chunk (see the epilogue comment)
+// Tile configurations <BN, BK, STAGES>: BK = 32 floats is one 128-byte swizzle row, BK = 16 one 64-byte swizzle row.
+//   <128, 32, 3>  64 KiB stages; the 128-wide N keeps the MMA shared-memory read rate at ~120 B/clk (the limit is 128)
+//   <256, 16, 4>  48 KiB stages; N = 256 halves the A re-reads per flop (88 B/clk) and raises flop/byte of L2 traffic
+//   <256, 32, 2>  96 KiB stages (two only)
 
 struct SgemmParams {
     int m, n, k;
@@ -75,11 +82,12 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(int rows, int k, c
 }
 
 // ------------------------------------------------------------------ tcgen05 helpers
-__device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t saddr) {
-    // K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1),
-    // descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
+template <int ROW_BYTES> __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr) {
+    // K-major operand tile whose rows are ROW_BYTES long (= the TMA swizzle span): 8-row groups ROW_BYTES*8 apart (SBO),
+    // LBO unused (=1), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B / 4 = SWIZZLE_64B
+    static_assert(ROW_BYTES == 128 || ROW_BYTES == 64, "swizzle span");
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)((ROW_BYTES * 8) >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -131,12 +139,15 @@ template <int BN> __host__ __device__ constexpr uint32_t sg_idesc() {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(SG_BM >> 4) << 24);
 }
 
-template <int BN>
+template <int BN, int SG_BK, int SG_STAGES>
 __global__ void __launch_bounds__(SG_THREADS, 1)
 sgemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const SgemmParams p) {
     constexpr int A_PLANE = SG_BM * SG_BK * 4, B_PLANE = BN * SG_BK * 4;     // one (hi or lo) tile
     constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;
     constexpr uint32_t TMEM_COLS = 2 * BN;                                   // two ping-pong accumulators
+    constexpr int SG_CHUNK_STAGES = SG_CHUNK_K / SG_BK;
+    constexpr int ROW_BYTES = SG_BK * 4;
+    constexpr int HALF = BN / 2;                                             // columns per epilogue warp
 
     int tile_m, tile_n;
     {
@@ -209,8 +220,8 @@ sgemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     mbar_wait(full0 + 8 * stage, phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t sA = smem_base + stage * STAGE_BYTES, sB = sA + 2 * A_PLANE;
-                    const uint64_t ahi = umma_desc_sw128_kmajor(sA), alo = umma_desc_sw128_kmajor(sA + A_PLANE);
-                    const uint64_t bhi = umma_desc_sw128_kmajor(sB), blo = umma_desc_sw128_kmajor(sB + B_PLANE);
+                    const uint64_t ahi = umma_desc_kmajor<ROW_BYTES>(sA), alo = umma_desc_kmajor<ROW_BYTES>(sA + A_PLANE);
+                    const uint64_t bhi = umma_desc_kmajor<ROW_BYTES>(sB), blo = umma_desc_kmajor<ROW_BYTES>(sB + B_PLANE);
 #pragma unroll
                     for (int ks = 0; ks < SG_BK / 8; ks++) {
                         const uint64_t adv = (uint64_t)((ks * 32) >> 4);   // 8 tf32 = 32 bytes along k inside the swizzle row
@@ -231,30 +242,43 @@ sgemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         // accumulation steps.  So the k loop is cut into chunks of SG_CHUNK_STAGES*32; each chunk is summed in
         // TMEM from zero and folded into per-thread register accumulators here with round-to-nearest FADDs,
         // while the MMA warp is already filling the other TMEM accumulator.
-        static_assert(BN == 128, "epilogue: two column halves of 64");
         const int q = warp & 3;                       // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2;             // which 64 columns of the tile
-        float acc[64];
+        const int half = (warp - 2) >> 2;             // which HALF columns of the tile
+        float acc[HALF];
 #pragma unroll
-        for (int j = 0; j < 64; j++) acc[j] = 0.f;
+        for (int j = 0; j < HALF; j++) acc[j] = 0.f;
         for (int c = 0; c < nchunks; c++) {
             const int buf = c & 1;
             mbar_wait(accfull0 + 8 * buf, (c >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t v[64];
-            tmem_ld64(tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * BN + half * 64), v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(accempty0 + 8 * buf);         // values are in registers: the MMA warp may overwrite the buffer
+            const uint32_t tsrc = tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * BN + half * HALF);
+            if constexpr (HALF == 64) {
+                uint32_t v[64];
+                tmem_ld64(tsrc, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(accempty0 + 8 * buf);     // values are in registers: the MMA warp may overwrite the buffer
 #pragma unroll
-            for (int j = 0; j < 64; j++) acc[j] += __uint_as_float(v[j]);
+                for (int j = 0; j < 64; j++) acc[j] += __uint_as_float(v[j]);
+            } else {                                  // 128 columns per warp: 32 at a time keeps the staging registers low
+#pragma unroll
+                for (int c0 = 0; c0 < HALF; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tsrc + (uint32_t)c0, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; j++) acc[c0 + j] += __uint_as_float(v[j]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(accempty0 + 8 * buf);
+            }
         }
         const int64_t row = (int64_t)m0 + 32 * q + lane;
         const bool beta0 = p.beta == 0.f;
         if (row < p.m) {
 #pragma unroll
-            for (int j = 0; j < 64; j++) {
-                const int64_t col = (int64_t)n0 + half * 64 + j;
+            for (int j = 0; j < HALF; j++) {
+                const int64_t col = (int64_t)n0 + half * HALF + j;
                 if (col < p.n && tri_keep(p.mask, row, col)) {
                     float* cp = p.C + row + col * p.ldc;
                     float r = p.alpha * acc[j];
@@ -272,29 +296,35 @@ sgemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------
-static bool make_map_split(CUtensorMap* map, const float* base, int64_t rows, int64_t k, int64_t kpad, int box_rows) {
+static bool make_map_split(CUtensorMap* map, const float* base, int64_t rows, int64_t k, int64_t kpad, int box_rows, int bk) {
     cuuint64_t gdim[3] = {(cuuint64_t)k, (cuuint64_t)rows, 2};
     cuuint64_t gstride[2] = {(cuuint64_t)kpad * 4, (cuuint64_t)rows * (cuuint64_t)kpad * 4};
-    cuuint32_t box[3] = {SG_BK, (cuuint32_t)box_rows, 2}, estr[3] = {1, 1, 1};
-    return encode_tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
+    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)box_rows, 2}, estr[3] = {1, 1, 1};
+    return encode_tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstride, box, estr,
+                             bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
-template <int BN> static void launch_sg(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, SgemmParams p) {
-    constexpr int SMEM = SG_STAGES * (2 * SG_BM + 2 * BN) * SG_BK * 4 + (2 * SG_STAGES + 6) * 8 + 1024;
+template <int BN, int BK, int STAGES>
+static bool launch_sg(cudaStream_t s, const float* as, const float* bs, int64_t kpad, SgemmParams p) {
+    constexpr int SMEM = STAGES * (2 * SG_BM + 2 * BN) * BK * 4 + (2 * STAGES + 6) * 8 + 1024;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    CUtensorMap ma, mb;
+    memset(&ma, 0, sizeof ma); memset(&mb, 0, sizeof mb);
+    if (!make_map_split(&ma, as, p.m, p.k, kpad, SG_BM, BK) || !make_map_split(&mb, bs, p.n, p.k, kpad, BN, BK)) return false;
     static bool attr_set = false;
     if (!attr_set) {
-        B200_CUDA(cudaFuncSetAttribute(sgemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        B200_CUDA(cudaFuncSetAttribute(sgemm_tf32x3_kernel<BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_set = true;
     }
     p.tiles_m = (p.m + SG_BM - 1) / SG_BM;
     p.tiles_n = (p.n + BN - 1) / BN;
-    sgemm_tf32x3_kernel<BN><<<p.tiles_m * p.tiles_n, SG_THREADS, SMEM, s>>>(ma, mb, p);
+    sgemm_tf32x3_kernel<BN, BK, STAGES><<<p.tiles_m * p.tiles_n, SG_THREADS, SMEM, s>>>(ma, mb, p);
+    return true;
 }
 
 static bool sgemm_tf32x3(cudaStream_t s, int oa, int ob, int m, int n, int k, float alpha, const float* A, int64_t lda,
                          const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int mask) {
     if (!tma_available()) return false;
-    constexpr int BN = 128;
     const int64_t kpad = ((int64_t)k + 3) / 4 * 4;          // 16-byte row pitch for TMA
     float* as = (float*)ws_alloc((size_t)2 * m * kpad * 4);
     float* bs = (float*)ws_alloc((size_t)2 * n * kpad * 4);
@@ -304,12 +334,18 @@ static bool sgemm_tf32x3(cudaStream_t s, int oa, int ob, int m, int n, int k, fl
     // op(B) is k x n: 'N' stores it k-contiguous per column, 'T'/'C' n-contiguous
     if (ob == 0) split_kmajor_kernel<<<dim3((k + 255) / 256, n < 65535 ? n : 65535), 256, 0, s>>>(n, k, B, ldb, bs, bs + (int64_t)n * kpad, kpad);
     else split_transpose_kernel<<<dim3((n + 31) / 32, (k + 31) / 32), 256, 0, s>>>(n, k, B, ldb, bs, bs + (int64_t)n * kpad, kpad);
-    CUtensorMap ma, mb;
-    memset(&ma, 0, sizeof ma); memset(&mb, 0, sizeof mb);
-    if (!make_map_split(&ma, as, m, k, kpad, SG_BM) || !make_map_split(&mb, bs, n, k, kpad, BN)) return false;
     SgemmParams p;
     p.m = m; p.n = n; p.k = k; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.mask = mask; p.tiles_m = p.tiles_n = 0;
-    launch_sg<BN>(s, ma, mb, p);
+    // tile configuration: B200BLAS_SGEMM_CFG overrides (0: 128x128 BK32 x3, 1: 128x256 BK32 x2, 2: 128x256 BK16 x4)
+    static const int cfg_env = getenv("B200BLAS_SGEMM_CFG") ? atoi(getenv("B200BLAS_SGEMM_CFG")) : -1;
+    const int64_t sms = sm_count() > 0 ? sm_count() : 148;
+    int cfg = cfg_env;
+    if (cfg < 0) cfg = ((int64_t)((m + 127) / 128) * ((n + 255) / 256) >= sms) ? SG_DEFAULT_WIDE_CFG : 0;
+    bool ok;
+    if (cfg == 1) ok = launch_sg<256, 32, 2>(s, as, bs, kpad, p);
+    else if (cfg == 2) ok = launch_sg<256, 16, 4>(s, as, bs, kpad, p);
+    else ok = launch_sg<128, 32, 3>(s, as, bs, kpad, p);
+    if (!ok) return false;
     last_variant = VAR_TF32X3_TCGEN05;
     return true;
 }
