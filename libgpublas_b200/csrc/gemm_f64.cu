@@ -295,8 +295,10 @@ static bool make_map_f64(CUtensorMap* map, const double* base, int layout, int64
 template <int MB, int NB, int LAYA, int LAYB, bool USE_TMA>
 static void launch_dmma(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const DgemmParams& p) {
     constexpr int BM = 16 * MB, BN = 32 * NB;
-    constexpr int SMEM = DG_STAGES * (BM + BN) * DG_BK * 8 + 2 * DG_STAGES * 8 + 1024;
+    constexpr int SMEM0 = DG_STAGES * (BM + BN) * DG_BK * 8 + 2 * DG_STAGES * 8 + 1024;
     auto kern = dgemm_dmma_kernel<MB, NB, LAYA, LAYB, USE_TMA>;
+    static const int extra = getenv("B200BLAS_DBG_EXTRA_SMEM") ? atoi(getenv("B200BLAS_DBG_EXTRA_SMEM")) : 0;   // experiment: force 1 CTA/SM
+    const int SMEM = SMEM0 + (MB * NB < 32 ? extra : 0);
     static bool attr_set = false;
     if (!attr_set) {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
