@@ -109,7 +109,7 @@ def other_routines(g, torch, dev, peaks):
     tf32_peak = peaks.get("bf16_tflops", 1667.5) / 2.0     # tf32 dense = half the bf16 rate; 3 MMAs per product
     out["sgemm_16384"] = {"tflops": tf, "ms": ms, "variant": g.last_variant(), "frac_of_fp32_ffma_peak_74.4": tf / 74.4,
                           "frac_of_tf32_pipe_div3": tf / (tf32_peak / 3.0),
-                          "note": "3xTF32 on tcgen05 incl. the split pass; tensor denominator = measured bf16 burst / 2 / 3"}
+                          "note": "3xTF32 on tcgen05 incl. the split pass; tensor denominator = measured bf16 burst / 2 / 3; cuBLAS SGEMM (FFMA) on this part: 67 TFLOP/s"}
     del A, B, C
     n = 8192
     A = torch.rand((n, n), dtype=torch.complex128, device=dev); B = torch.rand((n, n), dtype=torch.complex128, device=dev)
@@ -137,6 +137,21 @@ def other_routines(g, torch, dev, peaks):
     ms = timed(lambda: g.call("idamax_", n, z, 1, restype=ctypes.c_int), reps=9)
     out["idamax_2^28"] = {"gbs": 8.0 * n / ms / 1e6, "ms": ms, "frac_of_measured_hbm": 8.0 * n / ms / 1e6 / hbm}
     del z
+    # blocked Cholesky workload (BASELINE.json configs[3]) on one GPU: wall clock, the driver synchronises per panel
+    from libgpublas_b200.cholesky import blocked_cholesky
+    n = 32768
+    M = torch.rand((n, n), dtype=torch.float64, device=dev) * 2 - 1
+    M = torch.tril(M, -1); M = M + M.T; M.diagonal().fill_(float(n))
+    W = torch.empty_like(M)
+    best = None
+    for _ in range(3):
+        W.copy_(M); torch.cuda.synchronize()
+        t0 = time.perf_counter(); info = blocked_cholesky(n, W, n, 2048); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    out["cholesky_32768"] = {"tflops": n ** 3 / 3.0 / best / 1e12, "ms": best * 1e3, "info": info, "nb": 2048,
+                             "frac_of_fp64_peak": n ** 3 / 3.0 / best / 1e12 / FP64_PEAK_NOMINAL,
+                             "note": "device potrf + dtrsm_ + dsyrk_ through the Fortran symbols; flops n^3/3"}
+    del M, W
     return out
 
 
