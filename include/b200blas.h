@@ -223,6 +223,7 @@ B200_API void b200blas_dgemm_out_flagged(char transa, char transb, int m, int n,
 B200_API void b200blas_copy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t height, void* cuda_stream);
 B200_API void b200blas_write_flag_async(void* dst_flag, unsigned value, void* cuda_stream);
 B200_API void b200blas_memset_async(void* dst, int byte, size_t bytes, void* cuda_stream);
+B200_API void b200blas_wait_flag_async(const void* flag, unsigned value, void* cuda_stream);   /* stream waits until *flag >= value */
 /* Lower Cholesky factor in place on the library's own Level-3 kernels (the diagonal-block step of the blocked Cholesky
  * workload, BASELINE.json configs[3]); a may be host, managed or device memory.  Returns LAPACK-style info. */
 B200_API int b200blas_dpotrf_lower(int n, double* a, long long lda);

@@ -219,6 +219,23 @@ void b200blas_write_flag_async(void* dst_flag, unsigned value, void* stream) {
     });
     B200_CUDA(cudaMemcpyAsync(dst_flag, table + (value & 0xffffu), sizeof(unsigned), cudaMemcpyDefault, (cudaStream_t)stream));
 }
+// Stream-ordered wait until *flag >= value (flag in this device's memory, written remotely by a peer's copy engine):
+// a one-thread kernel that polls with system-scope acquire loads, so everything queued behind it on `stream` sees the
+// data that was pushed before the flag.
+__global__ void b200_wait_flag_kernel(const unsigned* flag, unsigned value) {
+    unsigned v;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= value) break;
+        __nanosleep(500);
+    }
+}
+void b200blas_wait_flag_async(const void* flag, unsigned value, void* stream) {
+    ensure_init();
+    TrackerGuard g;
+    b200_wait_flag_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const unsigned*)flag, value);
+    B200_CUDA(cudaGetLastError());
+}
 void b200blas_memset_async(void* dst, int byte, size_t bytes, void* stream) {
     ensure_init();
     TrackerGuard g;
