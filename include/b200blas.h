@@ -211,6 +211,7 @@ B200_API void b200blas_get_stats(struct b200blas_stats* out);
 B200_API void* b200blas_malloc_managed(size_t bytes);            /* tracked managed block (what malloc() hands out) */
 B200_API void b200blas_free_managed(void* p);
 B200_API int b200blas_is_tracked(const void* p);
+B200_API int b200blas_tracker_decision(unsigned long long nth, size_t request);   /* would the nth allocation of `request` bytes be managed (current heuristic)? */
 B200_API int b200blas_device_count(void);
 B200_API int b200blas_residency(const void* p, size_t bytes);     /* device ordinal a managed range was last prefetched to; -1 host; -2 unknown */
 /* D := alpha*op(A)*op(B) + beta*C on device pointers with a separate output (may be peer-mapped) */

@@ -36,7 +36,8 @@ static inline bool is1(cuDoubleComplex a) { return a.x == 1.0 && a.y == 0.0; }
 // obj_tracker_internal_enter/leave), workspace reset on entry, synchronous return on exit.
 struct CallScope {
     TrackerGuard guard;
-    CallScope() { ensure_init(); ws_reset(); }
+    CallScope() { ensure_init(); ws_reset(); t_call_name = "blas"; }
+    explicit CallScope(const char* routine) { ensure_init(); ws_reset(); t_call_name = routine; }
     ~CallScope() { finish_call(); }
 };
 

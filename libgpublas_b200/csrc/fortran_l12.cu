@@ -32,7 +32,7 @@ template <typename R> R fetch_scalar(const void* slot) {
 template <typename T> T dot_entry(const char* name, const int* n, const T* x, const int* incx, const T* y, const int* incy, bool conj) {
     T zero; memset(&zero, 0, sizeof zero);
     if (*n <= 0) return zero;
-    CallScope scope;
+    CallScope scope(name);
     VecOperand ox(x, *n, *incx, sizeof(T), ACC_IN), oy(y, *n, *incy, sizeof(T), ACC_IN);
     T* out = scalar_slot<T>();
     dot_dev<T>(current_stream(), *n, (const T*)ox.dev(), *incx, (const T*)oy.dev(), *incy, out, conj);
@@ -42,7 +42,7 @@ template <typename T> T dot_entry(const char* name, const int* n, const T* x, co
 }
 template <typename T, typename R> R nrm2_entry(const char* name, const int* n, const T* x, const int* incx, bool asum) {
     if (*n < 1 || *incx < 1) return R(0);
-    CallScope scope;
+    CallScope scope(name);
     VecOperand ox(x, *n, *incx, sizeof(T), ACC_IN);
     R* out = scalar_slot<R>();
     if (asum) asum_dev<T, R>(current_stream(), *n, (const T*)ox.dev(), *incx, out);
@@ -53,7 +53,7 @@ template <typename T, typename R> R nrm2_entry(const char* name, const int* n, c
 }
 template <typename T> int iamax_entry(const char* name, const int* n, const T* x, const int* incx) {
     if (*n < 1 || *incx <= 0) return 0;
-    CallScope scope;
+    CallScope scope(name);
     VecOperand ox(x, *n, *incx, sizeof(T), ACC_IN);
     long long* out = scalar_slot<long long>();
     iamax_dev<T>(current_stream(), *n, (const T*)ox.dev(), *incx, out);
@@ -63,7 +63,7 @@ template <typename T> int iamax_entry(const char* name, const int* n, const T* x
 }
 template <typename T> void axpy_entry(const char* name, const int* n, const T* alpha, const T* x, const int* incx, T* y, const int* incy) {
     if (*n <= 0 || is0(*alpha)) return;
-    CallScope scope;
+    CallScope scope(name);
     VecOperand ox(x, *n, *incx, sizeof(T), ACC_IN), oy(y, *n, *incy, sizeof(T), ACC_INOUT);
     axpy_dev<T>(current_stream(), *n, *alpha, (const T*)ox.dev(), *incx, (T*)oy.dev(), *incy);
     oy.release();
@@ -71,7 +71,7 @@ template <typename T> void axpy_entry(const char* name, const int* n, const T* a
 }
 template <typename T, typename S> void scal_entry(const char* name, const int* n, const S* alpha, T* x, const int* incx) {
     if (*n <= 0 || *incx <= 0) return;
-    CallScope scope;
+    CallScope scope(name);
     VecOperand ox(x, *n, *incx, sizeof(T), ACC_INOUT);
     scal_dev<T, S>(current_stream(), *n, *alpha, (T*)ox.dev(), *incx);
     ox.release();
@@ -79,7 +79,7 @@ template <typename T, typename S> void scal_entry(const char* name, const int* n
 }
 template <typename T> void copy_entry(const char* name, const int* n, const T* x, const int* incx, T* y, const int* incy, bool swap) {
     if (*n <= 0) return;
-    CallScope scope;
+    CallScope scope(name);
     VecOperand ox(x, *n, *incx, sizeof(T), swap ? ACC_INOUT : ACC_IN);
     // strided copy targets keep their gaps: read-modify-write staging unless contiguous
     VecOperand oy(y, *n, *incy, sizeof(T), (swap || (*incy != 1 && *incy != -1)) ? ACC_INOUT : ACC_OUT);
@@ -106,7 +106,7 @@ void gemv_entry(const char* name, const char* trans, const int* m, const int* n,
     if (*m == 0 || *n == 0 || (is0(*alpha) && is1(*beta))) return;
     const int lenx = nota ? *n : *m, leny = nota ? *m : *n;
     const char t = nota ? 'N' : (lsame(trans, 'T') ? 'T' : 'C');
-    CallScope scope;
+    CallScope scope(name);
     Operand oa(is0(*alpha) ? nullptr : a, *m, *n, *lda, sizeof(T), ACC_IN);
     VecOperand ox(is0(*alpha) ? nullptr : x, lenx, *incx, sizeof(T), ACC_IN);
     const bool strided_y = (*incy != 1 && *incy != -1);
@@ -128,7 +128,7 @@ void trsv_entry(const char* name, const char* uplo, const char* trans, const cha
     else if (*incx == 0) info = 8;
     if (info) { call_xerbla(name, info); return; }
     if (*n == 0) return;
-    CallScope scope;
+    CallScope scope(name);
     Operand oa(a, *n, *n, *lda, sizeof(T), ACC_IN);
     VecOperand ox(x, *n, *incx, sizeof(T), ACC_INOUT);
     const char u = lsame(uplo, 'U') ? 'U' : 'L', t = lsame(trans, 'N') ? 'N' : (lsame(trans, 'T') ? 'T' : 'C'), d = lsame(diag, 'U') ? 'U' : 'N';

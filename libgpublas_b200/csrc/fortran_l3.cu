@@ -36,7 +36,7 @@ void gemm_entry(const char* name, const char* transa, const char* transb, const 
     if (info) { call_xerbla(name, info); return; }
     if (*m == 0 || *n == 0 || ((is0(*alpha) || *k == 0) && is1(*beta))) return;
 
-    CallScope scope;
+    CallScope scope(name);
     const bool scale_only = is0(*alpha) || *k == 0;
     const char ta = nota ? 'N' : (lsame(transa, 'T') ? 'T' : 'C');
     const char tb = notb ? 'N' : (lsame(transb, 'T') ? 'T' : 'C');
@@ -73,7 +73,7 @@ void syrk_entry(const char* name, bool cplx, const char* uplo, const char* trans
     else if (*ldc < imax(1, *n)) info = 10;
     if (info) { call_xerbla(name, info); return; }
     if (*n == 0 || ((is0(*alpha) || *k == 0) && is1(*beta))) return;
-    CallScope scope;
+    CallScope scope(name);
     const bool scale_only = is0(*alpha) || *k == 0;
     Operand oa(scale_only ? nullptr : a, nrowa, nota ? *k : *n, *lda, sizeof(T), ACC_IN);
     // C is read even when beta == 0: the unreferenced triangle must survive a staged round trip
@@ -100,7 +100,7 @@ void tr_entry(const char* name, bool solve, const char* side, const char* uplo, 
     else if (*ldb < imax(1, *m)) info = 11;
     if (info) { call_xerbla(name, info); return; }
     if (*m == 0 || *n == 0) return;
-    CallScope scope;
+    CallScope scope(name);
     const char t = lsame(transa, 'N') ? 'N' : (lsame(transa, 'T') ? 'T' : 'C');
     Operand oa(is0(*alpha) ? nullptr : a, nrowa, nrowa, *lda, sizeof(T), ACC_IN);
     Operand ob(b, *m, *n, *ldb, sizeof(T), is0(*alpha) ? ACC_OUT : ACC_INOUT);
@@ -126,7 +126,7 @@ void symm_entry(const char* name, bool herm, const char* side, const char* uplo,
     else if (*ldc < imax(1, *m)) info = 12;
     if (info) { call_xerbla(name, info); return; }
     if (*m == 0 || *n == 0 || (is0(*alpha) && is1(*beta))) return;
-    CallScope scope;
+    CallScope scope(name);
     const bool scale_only = is0(*alpha);
     Operand oa(scale_only ? nullptr : a, nrowa, nrowa, *lda, sizeof(T), ACC_IN);
     Operand ob(scale_only ? nullptr : b, *m, *n, *ldb, sizeof(T), ACC_IN);
@@ -154,7 +154,7 @@ void r2k_entry(const char* name, bool herm, bool cplx, const char* uplo, const c
     else if (*ldc < imax(1, *n)) info = 12;
     if (info) { call_xerbla(name, info); return; }
     if (*n == 0 || ((is0(*alpha) || *k == 0) && is1(*beta))) return;
-    CallScope scope;
+    CallScope scope(name);
     const bool scale_only = is0(*alpha) || *k == 0;
     Operand oa(scale_only ? nullptr : a, nrowa, nota ? *k : *n, *lda, sizeof(T), ACC_IN);
     Operand ob(scale_only ? nullptr : b, nrowa, nota ? *k : *n, *ldb, sizeof(T), ACC_IN);
@@ -184,7 +184,7 @@ void herk_entry(const char* name, const char* uplo, const char* trans, const int
     else if (*ldc < imax(1, *n)) info = 10;
     if (info) { call_xerbla(name, info); return; }
     if (*n == 0 || ((*alpha == RB(0) || *k == 0) && *beta == RB(1))) return;
-    CallScope scope;
+    CallScope scope(name);
     const bool scale_only = *alpha == RB(0) || *k == 0;
     Operand oa(scale_only ? nullptr : a, nrowa, nota ? *k : *n, *lda, sizeof(T), ACC_IN);
     Operand oc(c, *n, *n, *ldc, sizeof(T), ACC_INOUT);

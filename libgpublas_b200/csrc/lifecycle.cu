@@ -21,6 +21,8 @@ static void print_help() {
         "   debug_execfail  -- debug kernel failures (synchronise and check after every call)\n"
         "   debug_exec      -- debug kernel invocations (one line per BLAS call: shapes, variant)\n"
         "   trace_copy      -- trace copies between CPU and GPU\n"
+        "   trace           -- object trace on stdout (T/U/C lines, the reference's TRACE_OUTPUT format; input of\n"
+        "                      scripts/analyze_trace.py and of heuristic=oracle:<file>)\n"
         "   heuristic=<val> -- one of: 'size' (default), 'random', 'true', 'false', or:\n"
         "                      'oracle:<filename>', where <filename> is the name of an object trace\n"
         "   threshold=<n>   -- heuristic=size: allocations of >= n bytes become managed (default 65536)\n"
@@ -50,6 +52,7 @@ static void set_options(const char* env) {
         else if (!strcmp(opt, "debug_execfail")) g_opts.debug_execfail = true;
         else if (!strcmp(opt, "debug_exec")) g_opts.debug_exec = true;
         else if (!strcmp(opt, "trace_copy")) g_opts.trace_copy = true;
+        else if (!strcmp(opt, "trace")) tracker_set_trace(1);
         else if (!strncmp(opt, "heuristic=", 10)) {
             const char* h = opt + 10;
             if (!strncmp(h, "random", 6)) tracker_set_heuristic(B200_H_RANDOM);
@@ -187,6 +190,7 @@ void* b200blas_ipc_open(const void* handle64) {
 void b200blas_ipc_close(void* p) { TrackerGuard g; cudaIpcCloseMemHandle(p); }
 
 // Where the driver last placed a managed range: device ordinal, -1 = host, -2 = not managed / unknown.
+int b200blas_tracker_decision(unsigned long long nth, size_t request) { return tracker_decision(nth, request); }
 int b200blas_residency(const void* p, size_t bytes) {
     ensure_init();
     TrackerGuard g;

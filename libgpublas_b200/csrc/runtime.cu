@@ -27,6 +27,7 @@ namespace b200 {
 Options g_opts;
 Stats g_stats = {0, 0, 0, 0, 0, 0};
 thread_local int last_variant = VAR_NONE;
+thread_local const char* t_call_name = "blas";
 int force_variant = VAR_NONE;
 
 const char* variant_name(int v) {
@@ -285,6 +286,7 @@ Operand::Operand(const void* host, int64_t rows, int64_t cols, int64_t ld, size_
     if (r == RES_DEVICE || r == RES_MANAGED) {
         dev_ = (void*)host;
         __atomic_fetch_add(&g_stats.hits, 1ull, __ATOMIC_RELAXED);
+        if (r == RES_MANAGED) tracker_trace_call(host, t_call_name);
         if (r == RES_MANAGED) make_resident(host, (size_t)((cols - 1) * ld + rows) * elem, s);
         done_ = true;   // nothing to write back
         return;

@@ -71,6 +71,7 @@ private:
 };
 
 void log_exec(const char* routine, const char* fmt, ...);
+extern thread_local const char* t_call_name;   // routine name of the call in progress (for the trace's C lines)
 
 }  // namespace b200
 

@@ -19,6 +19,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
+#include <sys/syscall.h>
+#include <time.h>
 
 extern "C" {
 void* __libc_malloc(size_t);
@@ -29,7 +31,7 @@ void __libc_free(void*);
 
 namespace {
 
-struct Block { uintptr_t base; size_t size; int resident; /* bulk-migrated to the device since it was allocated */ };
+struct Block { uintptr_t base; size_t size; int resident; /* bulk-migrated to the device since it was allocated */ uint64_t nth, uid; };
 
 pthread_rwlock_t g_lock = PTHREAD_RWLOCK_INITIALIZER;
 Block* g_blocks = nullptr;
@@ -84,7 +86,18 @@ long find_block(uintptr_t p) {
     return -1;
 }
 
-bool registry_insert(uintptr_t base, size_t size) {
+volatile int g_trace = 0;          // BLAS2CUDA_OPTIONS=trace: T/U/C lines in the reference's TRACE_OUTPUT format
+uint64_t g_uid = 0;
+
+// reference obj_tracker_print_info (lib/obj_tracker.c:426-483): "<T|U|C> #nth [ptr] fun=[..] reqsize=[..] tid=[..] time=[..s+..ns] uid=[..]"
+void trace_line(char kind, uint64_t nth, const void* ptr, const char* fun, size_t reqsize, uint64_t uid) {
+    struct timespec tm;
+    clock_gettime(CLOCK_MONOTONIC_RAW, &tm);
+    b200_writef(STDOUT_FILENO, "%c #%lu [%p] fun=[%s] reqsize=[%zu] tid=[%d] time=[%lds+%ldns] uid=[%lu]\n", kind, (unsigned long)nth, ptr, fun,
+                reqsize, (int)syscall(SYS_gettid), (long)tm.tv_sec, (long)tm.tv_nsec, (unsigned long)uid);
+}
+
+bool registry_insert(uintptr_t base, size_t size, uint64_t nth, const char* fun) {
     pthread_rwlock_wrlock(&g_lock);
     if (g_nblocks == g_cap) {
         size_t ncap = g_cap ? g_cap * 2 : 256;
@@ -95,6 +108,8 @@ bool registry_insert(uintptr_t base, size_t size) {
     size_t pos = g_nblocks;
     while (pos > 0 && g_blocks[pos - 1].base > base) { g_blocks[pos] = g_blocks[pos - 1]; pos--; }
     g_blocks[pos].base = base; g_blocks[pos].size = size; g_blocks[pos].resident = 0;
+    g_blocks[pos].nth = nth; g_blocks[pos].uid = ++g_uid;
+    const uint64_t uid = g_blocks[pos].uid;
     g_nblocks++;
     if (base < g_lo) g_lo = base;
     if (base + size > g_hi) g_hi = base + size;
@@ -102,6 +117,7 @@ bool registry_insert(uintptr_t base, size_t size) {
     g_tstats.managed_bytes_live += size;
     if (g_tstats.managed_bytes_live > g_tstats.managed_bytes_peak) g_tstats.managed_bytes_peak = g_tstats.managed_bytes_live;
     pthread_rwlock_unlock(&g_lock);
+    if (g_trace) trace_line('T', nth, (void*)base, fun, size, uid);
     return true;
 }
 
@@ -112,6 +128,7 @@ size_t registry_remove(uintptr_t p) {
     long i = find_block(p);
     if (i >= 0 && g_blocks[i].base == p) {
         sz = g_blocks[i].size;
+        if (g_trace) trace_line('U', g_blocks[i].nth, (void*)p, "free", sz, g_blocks[i].uid);
         memmove(&g_blocks[i], &g_blocks[i + 1], (g_nblocks - i - 1) * sizeof(Block));
         g_nblocks--;
         g_tstats.managed_frees++;
@@ -131,7 +148,7 @@ bool should_manage(size_t request, uint64_t nth) {
     }
 }
 
-void* managed_new(size_t request) {
+void* managed_new(size_t request, uint64_t nth = 0, const char* fun = "malloc") {
     // first qualifying allocation brings the device up; allocations made meanwhile (by CUDA itself,
     // on this or on helper threads) see t_inside / g_initialising and go to glibc
     if (!b200::device_ready()) {
@@ -151,7 +168,7 @@ void* managed_new(size_t request) {
                     cudaGetErrorString(e));
         return nullptr;
     }
-    if (!registry_insert((uintptr_t)p, request ? request : 1)) {
+    if (!registry_insert((uintptr_t)p, request ? request : 1, nth, fun)) {
         t_inside++; cudaFree(p); t_inside--;
         return nullptr;
     }
@@ -188,6 +205,21 @@ int tracker_test_and_set_resident(const void* ptr) {
     pthread_rwlock_unlock(&g_lock);
     return prev;
 }
+void tracker_set_trace(int on) { g_trace = on; }
+// "C" line for a tracked operand of a BLAS call (reference OBJPRINT_CALL): which allocation the routine `fun` used
+void tracker_trace_call(const void* ptr, const char* fun) {
+    if (!g_trace) return;
+    uintptr_t p = (uintptr_t)ptr;
+    if (p < g_lo || p >= g_hi) return;
+    pthread_rwlock_rdlock(&g_lock);
+    long i = find_block(p);
+    uint64_t nth = 0, uid = 0; size_t sz = 0; uintptr_t base = 0;
+    if (i >= 0) { nth = g_blocks[i].nth; uid = g_blocks[i].uid; sz = g_blocks[i].size; base = g_blocks[i].base; }
+    pthread_rwlock_unlock(&g_lock);
+    if (i >= 0) trace_line('C', nth, (void*)base, fun, sz, uid);
+}
+// what the allocator would decide for the nth allocation of `request` bytes (tests; CPU-only, touches no device)
+int tracker_decision(uint64_t nth, size_t request) { return should_manage(request, nth) ? 1 : 0; }
 void tracker_enter(void) { t_inside++; }
 void tracker_leave(void) { t_inside--; }
 void tracker_set_tracking(int on) { g_tracking = on; }
@@ -281,7 +313,7 @@ void* malloc(size_t request) noexcept {
     if (bypass()) return __libc_malloc(request);
     uint64_t nth = __sync_fetch_and_add(&g_nth, 1);
     if (request && should_manage(request, nth)) {
-        void* p = managed_new(request);
+        void* p = managed_new(request, nth, "malloc");
         if (p) return p;
     }
     return __libc_malloc(request);
@@ -293,7 +325,7 @@ void* calloc(size_t nmemb, size_t size) noexcept {
     size_t total;
     if (__builtin_mul_overflow(nmemb, size, &total)) { errno = ENOMEM; return nullptr; }
     if (total && should_manage(total, nth)) {
-        void* p = managed_new(total);
+        void* p = managed_new(total, nth, "calloc");
         if (p) { memset(p, 0, total); return p; }   // reference calloc_managed, blas2cuda.c:150-154
     }
     return __libc_calloc(nmemb, size);
@@ -305,7 +337,7 @@ void* realloc(void* ptr, size_t request) noexcept {
     if (!tracker_lookup(ptr, &base, &old) || base != ptr) return __libc_realloc(ptr, request);
     if (request == 0) { tracker_free_managed(ptr); return nullptr; }
     // reference realloc_managed (blas2cuda.c:156-166): new block, copy, free -- stays managed
-    void* np = managed_new(request);
+    void* np = managed_new(request, __sync_fetch_and_add(&g_nth, 1), "realloc");
     if (!np) np = __libc_malloc(request);
     if (!np) return nullptr;
     memcpy(np, ptr, old < request ? old : request);

@@ -28,7 +28,10 @@ int tracker_get_tracking(void);
 void tracker_set_shutdown(void);             // process is exiting: stop tracking, never call into CUDA from free() again
 void tracker_set_heuristic(int h);
 void tracker_set_threshold(size_t bytes);
-int tracker_load_oracle_file(const char* filename);   // reference oracle_load_file, oracle.c:26-72
+int tracker_load_oracle_file(const char* filename);
+void tracker_set_trace(int on);                        // T/U/C lines in the reference TRACE_OUTPUT format (obj_tracker.c:426-483)
+void tracker_trace_call(const void* ptr, const char* fun);
+int tracker_decision(uint64_t nth, size_t request);    // managed-or-not for the nth allocation under the current heuristic   // reference oracle_load_file, oracle.c:26-72
 // direct entry points to the managed allocator (reference blas2cuda_manager ctor/dtor); used by
 // the C-ABI b200blas_malloc_managed / tests.  NULL on failure.
 void* tracker_alloc_managed(size_t bytes);

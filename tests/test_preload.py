@@ -166,3 +166,54 @@ def test_preload_untracked_operands_are_staged(tmp_path):
     assert all(float(r["max_abs_err"]) == 0.0 for r in res)
     st = fields([l for l in out.splitlines() if l.startswith("STATS")][0])
     assert int(st["hits"]) == 0 and int(st["misses"]) == 2 * 2 * 3 and int(st["h2d"]) > 0 and int(st["d2h"]) > 0
+
+
+def test_allocation_heuristics_and_oracle_file(tmp_path):
+    """north_star (3): the size-based selector and the reference's other heuristics (obj_tracker.c:226-243), including the
+    per-allocation oracle file of lib/oracle.c:26-72 ("H #<nth> ..." host, "D #<nth> ..." device lines).  CPU-only: asks
+    the tracker what it WOULD decide, touches no device."""
+    import ctypes
+    import libgpublas_b200 as g
+    lib = g.load()
+    lib.b200blas_tracker_decision.argtypes = [ctypes.c_ulonglong, ctypes.c_size_t]
+    try:
+        lib.b200blas_set_options(b"heuristic=size;threshold=65536")
+        assert [lib.b200blas_tracker_decision(7, s) for s in (1, 65535, 65536, 1 << 30)] == [0, 0, 1, 1]
+        lib.b200blas_set_options(b"threshold=4096")
+        assert lib.b200blas_tracker_decision(0, 4096) == 1 and lib.b200blas_tracker_decision(0, 4095) == 0
+        lib.b200blas_set_options(b"heuristic=true")
+        assert lib.b200blas_tracker_decision(3, 1) == 1
+        lib.b200blas_set_options(b"heuristic=false")
+        assert lib.b200blas_tracker_decision(3, 1 << 30) == 0
+        trace = tmp_path / "objtrace.txt"
+        trace.write_text("H #0 [0x1] fun=[malloc]\nD #1 [0x2] fun=[calloc]\nD #5 [0x3] fun=[malloc]\nH #6 x\ngarbage line\nD #70 y\n")
+        lib.b200blas_set_options(("heuristic=oracle:%s" % trace).encode())
+        got = [lib.b200blas_tracker_decision(n, 8) for n in (0, 1, 2, 5, 6, 69, 70, 71, 10 ** 6)]
+        assert got == [0, 1, 0, 1, 0, 0, 1, 0, 0]
+    finally:
+        lib.b200blas_set_options(b"heuristic=size;threshold=65536")
+
+
+@pytest.mark.gpu
+def test_object_trace_feeds_the_oracle_heuristic(tmp_path):
+    """BLAS2CUDA_OPTIONS=trace prints the reference's TRACE_OUTPUT lines (obj_tracker.c:426-483); turned into an oracle file
+    (what scripts/analyze_trace.py does) they reproduce the placement under heuristic=oracle:<file>."""
+    exe = build_driver("cg_chain")
+    out, _ = run(exe, [512, 3], preload=True, env_extra={"BLAS2CUDA_OPTIONS": "trace;threshold=2048"}, cwd=str(tmp_path))
+    pat = re.compile(r"^([TUC]) #(\d+) \[(0x[0-9a-f]+)\] fun=\[(\w+)\] reqsize=\[(\d+)\] tid=\[\d+\] time=\[\d+s\+\d+ns\] uid=\[(\d+)\]$")
+    ev = [pat.match(l).groups() for l in out.splitlines() if l[:2] in ("T ", "U ", "C ")]
+    tracked = [e for e in ev if e[0] == "T"]
+    assert len(tracked) == 5 and {e[3] for e in tracked} == {"calloc"}            # A, x, r, p, q
+    assert len([e for e in ev if e[0] == "U"]) == 5
+    calls = [e for e in ev if e[0] == "C"]
+    assert {"dgemv_", "ddot_", "daxpy_", "dscal_"} <= {e[3] for e in calls}
+    assert {e[2] for e in calls} <= {e[2] for e in tracked}                        # every C line names a tracked block
+    oracle = tmp_path / "oracle.txt"
+    big = max(int(e[4]) for e in tracked)
+    oracle.write_text("".join("%s #%s\n" % ("D" if int(e[4]) == big else "H", e[1]) for e in tracked))
+    out2, _ = run(exe, [512, 3], preload=True, env_extra={"BLAS2CUDA_OPTIONS": "trace;heuristic=oracle:%s" % oracle}, cwd=str(tmp_path))
+    t2 = [l for l in out2.splitlines() if l.startswith("T ")]
+    assert len(t2) == 1 and ("reqsize=[%d]" % big) in t2[0]                        # only the matrix was placed on the device
+    r1 = [l for l in out.splitlines() if l.startswith("RESULT")][0].split()[:6]
+    r2 = [l for l in out2.splitlines() if l.startswith("RESULT")][0].split()[:6]
+    assert r1 == r2                                                                # same numbers either way
