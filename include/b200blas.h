@@ -123,6 +123,21 @@ B200_API void dtrsv_(const char* uplo, const char* trans, const char* diag, cons
 B200_API void ctrsv_(const char* uplo, const char* trans, const char* diag, const int* n, const b200_c32* a, const int* lda, b200_c32* x, const int* incx);
 B200_API void ztrsv_(const char* uplo, const char* trans, const char* diag, const int* n, const b200_c64* a, const int* lda, b200_c64* x, const int* incx);
 
+/* more Level 1/2 (reference blas_level2/ger.cc, syr.cc, symv.cc, trmv.cc, blas_level1/rot.cc, rotg.cc): real types.
+ * The Fortran declarations must precede the CBLAS enums they do not use; the cblas_ ones follow the enums below. */
+B200_API void sger_(const int* m, const int* n, const float* alpha, const float* x, const int* incx, const float* y, const int* incy, float* a, const int* lda);
+B200_API void ssyr_(const char* uplo, const int* n, const float* alpha, const float* x, const int* incx, float* a, const int* lda);
+B200_API void ssymv_(const char* uplo, const int* n, const float* alpha, const float* a, const int* lda, const float* x, const int* incx, const float* beta, float* y, const int* incy);
+B200_API void strmv_(const char* uplo, const char* trans, const char* diag, const int* n, const float* a, const int* lda, float* x, const int* incx);
+B200_API void srot_(const int* n, float* x, const int* incx, float* y, const int* incy, const float* c, const float* s);
+B200_API void srotg_(float* a, float* b, float* c, float* s);
+B200_API void dger_(const int* m, const int* n, const double* alpha, const double* x, const int* incx, const double* y, const int* incy, double* a, const int* lda);
+B200_API void dsyr_(const char* uplo, const int* n, const double* alpha, const double* x, const int* incx, double* a, const int* lda);
+B200_API void dsymv_(const char* uplo, const int* n, const double* alpha, const double* a, const int* lda, const double* x, const int* incx, const double* beta, double* y, const int* incy);
+B200_API void dtrmv_(const char* uplo, const char* trans, const char* diag, const int* n, const double* a, const int* lda, double* x, const int* incx);
+B200_API void drot_(const int* n, double* x, const int* incx, double* y, const int* incy, const double* c, const double* s);
+B200_API void drotg_(double* a, double* b, double* c, double* s);
+
 /* ------------------------------ 2. CBLAS ABI ------------------------------ */
 /* enums: reference cblas.h:21-25 */
 enum CBLAS_ORDER { CblasRowMajor = 101, CblasColMajor = 102 };
@@ -139,20 +154,22 @@ B200_API void cblas_cgemm(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE transa, e
 B200_API void cblas_zgemm(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE transa, enum CBLAS_TRANSPOSE transb, int m, int n, int k, const void* alpha, const void* a, int lda, const void* b, int ldb, const void* beta, void* c, int ldc);
 
 /* CBLAS Level 3 beyond gemm -- reference cblas.h:693-824 */
-#define B200_DECL_CBLAS_REAL(P, T) \
-    B200_API void cblas_##P##syrk(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, T alpha, const T* a, int lda, T beta, T* c, int ldc); \
-    B200_API void cblas_##P##syr2k(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, T alpha, const T* a, int lda, const T* b, int ldb, T beta, T* c, int ldc); \
-    B200_API void cblas_##P##symm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, int m, int n, T alpha, const T* a, int lda, const T* b, int ldb, T beta, T* c, int ldc); \
-    B200_API void cblas_##P##trsm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa, enum CBLAS_DIAG diag, int m, int n, T alpha, const T* a, int lda, T* b, int ldb); \
-    B200_API void cblas_##P##trmm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa, enum CBLAS_DIAG diag, int m, int n, T alpha, const T* a, int lda, T* b, int ldb);
-B200_DECL_CBLAS_REAL(s, float)
-B200_DECL_CBLAS_REAL(d, double)
-#define B200_DECL_CBLAS_CPLX(P) \
-    B200_API void cblas_##P##syrk(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, const void* alpha, const void* a, int lda, const void* beta, void* c, int ldc); \
-    B200_API void cblas_##P##trsm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa, enum CBLAS_DIAG diag, int m, int n, const void* alpha, const void* a, int lda, void* b, int ldb); \
-    B200_API void cblas_##P##trmm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa, enum CBLAS_DIAG diag, int m, int n, const void* alpha, const void* a, int lda, void* b, int ldb);
-B200_DECL_CBLAS_CPLX(c)
-B200_DECL_CBLAS_CPLX(z)
+B200_API void cblas_ssyrk(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, float alpha, const float* a, int lda, float beta, float* c, int ldc);
+B200_API void cblas_ssyr2k(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, float alpha, const float* a, int lda, const float* b, int ldb, float beta, float* c, int ldc);
+B200_API void cblas_ssymm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, int m, int n, float alpha, const float* a, int lda, const float* b, int ldb, float beta, float* c, int ldc);
+B200_API void cblas_strsm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa, enum CBLAS_DIAG diag, int m, int n, float alpha, const float* a, int lda, float* b, int ldb);
+B200_API void cblas_strmm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa, enum CBLAS_DIAG diag, int m, int n, float alpha, const float* a, int lda, float* b, int ldb);
+B200_API void cblas_dsyrk(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, double alpha, const double* a, int lda, double beta, double* c, int ldc);
+B200_API void cblas_dsyr2k(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, double alpha, const double* a, int lda, const double* b, int ldb, double beta, double* c, int ldc);
+B200_API void cblas_dsymm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, int m, int n, double alpha, const double* a, int lda, const double* b, int ldb, double beta, double* c, int ldc);
+B200_API void cblas_dtrsm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa, enum CBLAS_DIAG diag, int m, int n, double alpha, const double* a, int lda, double* b, int ldb);
+B200_API void cblas_dtrmm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa, enum CBLAS_DIAG diag, int m, int n, double alpha, const double* a, int lda, double* b, int ldb);
+B200_API void cblas_csyrk(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, const void* alpha, const void* a, int lda, const void* beta, void* c, int ldc);
+B200_API void cblas_ctrsm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa, enum CBLAS_DIAG diag, int m, int n, const void* alpha, const void* a, int lda, void* b, int ldb);
+B200_API void cblas_ctrmm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa, enum CBLAS_DIAG diag, int m, int n, const void* alpha, const void* a, int lda, void* b, int ldb);
+B200_API void cblas_zsyrk(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, const void* alpha, const void* a, int lda, const void* beta, void* c, int ldc);
+B200_API void cblas_ztrsm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa, enum CBLAS_DIAG diag, int m, int n, const void* alpha, const void* a, int lda, void* b, int ldb);
+B200_API void cblas_ztrmm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE transa, enum CBLAS_DIAG diag, int m, int n, const void* alpha, const void* a, int lda, void* b, int ldb);
 
 /* CBLAS Level 1 / 2 -- reference cblas.h:46-656; cblas_i?amax is 0-based */
 B200_API float cblas_sdot(int n, const float* x, int incx, const float* y, int incy);
@@ -185,6 +202,19 @@ B200_API void cblas_sgemv(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE trans, in
 B200_API void cblas_dgemv(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE trans, int m, int n, double alpha, const double* a, int lda, const double* x, int incx, double beta, double* y, int incy);
 B200_API void cblas_strsv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const float* a, int lda, float* x, int incx);
 B200_API void cblas_dtrsv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const double* a, int lda, double* x, int incx);
+
+B200_API void cblas_sger(enum CBLAS_ORDER order, int m, int n, float alpha, const float* x, int incx, const float* y, int incy, float* a, int lda);
+B200_API void cblas_ssyr(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, float alpha, const float* x, int incx, float* a, int lda);
+B200_API void cblas_ssymv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, float alpha, const float* a, int lda, const float* x, int incx, float beta, float* y, int incy);
+B200_API void cblas_strmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const float* a, int lda, float* x, int incx);
+B200_API void cblas_srot(int n, float* x, int incx, float* y, int incy, float c, float s);
+B200_API void cblas_srotg(float* a, float* b, float* c, float* s);
+B200_API void cblas_dger(enum CBLAS_ORDER order, int m, int n, double alpha, const double* x, int incx, const double* y, int incy, double* a, int lda);
+B200_API void cblas_dsyr(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, double alpha, const double* x, int incx, double* a, int lda);
+B200_API void cblas_dsymv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, double alpha, const double* a, int lda, const double* x, int incx, double beta, double* y, int incy);
+B200_API void cblas_dtrmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const double* a, int lda, double* x, int incx);
+B200_API void cblas_drot(int n, double* x, int incx, double* y, int incy, double c, double s);
+B200_API void cblas_drotg(double* a, double* b, double* c, double* s);
 
 /* ------------------------------ 3. allocator symbols ------------------------------ */
 /* malloc / calloc / realloc / free are exported with their libc prototypes (<stdlib.h>);

@@ -257,3 +257,47 @@ def test_dgemv_large_device_resident():
         f77(lib, "dgemv_", trans, n, n, 1.0, A, n, x, 1, 0.0, y, 1)
         gb = (A.abs().T if trans == "N" else A.abs()) @ x.abs()
         assert ((y - ref).abs() / (2.0 ** -53 * gb)).max().item() < 16
+
+
+@pytest.mark.parametrize("p", ["s", "d"])
+def test_level2_more_vs_oracle(p):
+    """GER / SYR / SYMV / TRMV / ROT / ROTG through the Fortran symbols against the oracle: ragged
+    sizes spanning several column chunks, odd leading dimensions, positive and negative increments, untouched padding."""
+    lib = g.load(); dt = DT[p]
+    tol = 64 * EPS[p]
+    for (m, n) in [(1, 1), (7, 5), (300, 129), (1030, 700)]:
+        for (ix, iy) in [(1, 1), (2, -3)]:
+            x = strided(41, m, ix, dt); y = strided(42, n, iy, dt)
+            A0 = splitmix_uniform(43, (m + 1, n), dt); A, R = A0.copy(order="F"), A0.copy(order="F")
+            f77(lib, p + "ger_", m, n, 0.7, x, ix, y, iy, A, m + 1)
+            assert oracle_call(p + "ger", m, n, 0.7, x, ix, y, iy, R, m + 1) == 0
+            assert np.array_equal(A[m:], A0[m:]) and np.allclose(A, R, rtol=tol, atol=tol)
+    for n in [1, 5, 130, 777]:
+        S0 = splitmix_uniform(44, (n + 2, n), dt)
+        for uplo in "UL":
+            tri = np.triu(np.ones((n, n), bool)) if uplo == "U" else np.tril(np.ones((n, n), bool))
+            for (ix, iy) in [(1, 1), (-2, 3)]:
+                x = strided(45, n, ix, dt); y0 = strided(46, n, iy, dt)
+                y, r = y0.copy(), y0.copy()
+                f77(lib, p + "symv_", uplo, n, 0.7, S0, n + 2, x, ix, 1.3, y, iy)
+                assert oracle_call(p + "symv", uplo, n, 0.7, S0, n + 2, x, ix, 1.3, r, iy) == 0
+                assert np.allclose(y, r, rtol=tol * n, atol=tol * n)
+                S, R = S0.copy(order="F"), S0.copy(order="F")
+                f77(lib, p + "syr_", uplo, n, 0.7, x, ix, S, n + 2)
+                assert oracle_call(p + "syr", uplo, n, 0.7, x, ix, R, n + 2) == 0
+                full = np.zeros((n + 2, n), bool); full[:n] = tri
+                assert np.array_equal(S[~full], S0[~full]) and np.allclose(S, R, rtol=tol, atol=tol)
+                for tr in "NTC":
+                    for diag in "NU":
+                        xv, rv = x.copy(), x.copy()
+                        f77(lib, p + "trmv_", uplo, tr, diag, n, S0, n + 2, xv, ix)
+                        assert oracle_call(p + "trmv", uplo, tr, diag, n, S0, n + 2, rv, ix) == 0
+                        assert np.allclose(xv, rv, rtol=tol * n, atol=tol * n), (p, n, uplo, tr, diag, ix)
+        x0 = strided(47, n, 2, dt); y0 = strided(48, n, -1, dt)
+        x, y, xr, yr = x0.copy(), y0.copy(), x0.copy(), y0.copy()
+        f77(lib, p + "rot_", n, x, 2, y, -1, dt(0.6), dt(0.8)); oracle_call(p + "rot", n, xr, 2, yr, -1, dt(0.6), dt(0.8), restype=None)
+        assert np.allclose(x, xr, rtol=tol, atol=tol) and np.allclose(y, yr, rtol=tol, atol=tol)
+    for (a, b) in [(3.0, 4.0), (-3.0, 4.0), (4.0, -3.0), (0.0, 2.0), (0.0, 0.0)]:
+        v1 = [np.array([v], dtype=dt) for v in (a, b, 0, 0)]; v2 = [np.array([v], dtype=dt) for v in (a, b, 0, 0)]
+        f77(lib, p + "rotg_", *v1); oracle_call(p + "rotg", *v2, restype=None)
+        assert np.allclose([v[0] for v in v1], [v[0] for v in v2], rtol=4 * EPS[p])

@@ -199,7 +199,8 @@ def test_object_trace_feeds_the_oracle_heuristic(tmp_path):
     """BLAS2CUDA_OPTIONS=trace prints the reference's TRACE_OUTPUT lines (obj_tracker.c:426-483); turned into an oracle file
     (what scripts/analyze_trace.py does) they reproduce the placement under heuristic=oracle:<file>."""
     exe = build_driver("cg_chain")
-    out, _ = run(exe, [512, 3], preload=True, env_extra={"BLAS2CUDA_OPTIONS": "trace;threshold=2048"}, cwd=str(tmp_path))
+    # 1024 doubles = 8 KiB per vector: above stdio's own 4 KiB buffer malloc, which must stay on the heap
+    out, _ = run(exe, [1024, 3], preload=True, env_extra={"BLAS2CUDA_OPTIONS": "trace;threshold=8192"}, cwd=str(tmp_path))
     pat = re.compile(r"^([TUC]) #(\d+) \[(0x[0-9a-f]+)\] fun=\[(\w+)\] reqsize=\[(\d+)\] tid=\[\d+\] time=\[\d+s\+\d+ns\] uid=\[(\d+)\]$")
     ev = [pat.match(l).groups() for l in out.splitlines() if l[:2] in ("T ", "U ", "C ")]
     tracked = [e for e in ev if e[0] == "T"]
@@ -211,7 +212,7 @@ def test_object_trace_feeds_the_oracle_heuristic(tmp_path):
     oracle = tmp_path / "oracle.txt"
     big = max(int(e[4]) for e in tracked)
     oracle.write_text("".join("%s #%s\n" % ("D" if int(e[4]) == big else "H", e[1]) for e in tracked))
-    out2, _ = run(exe, [512, 3], preload=True, env_extra={"BLAS2CUDA_OPTIONS": "trace;heuristic=oracle:%s" % oracle}, cwd=str(tmp_path))
+    out2, _ = run(exe, [1024, 3], preload=True, env_extra={"BLAS2CUDA_OPTIONS": "trace;heuristic=oracle:%s" % oracle}, cwd=str(tmp_path))
     t2 = [l for l in out2.splitlines() if l.startswith("T ")]
     assert len(t2) == 1 and ("reqsize=[%d]" % big) in t2[0]                        # only the matrix was placed on the device
     r1 = [l for l in out.splitlines() if l.startswith("RESULT")][0].split()[:6]
