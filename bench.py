@@ -326,16 +326,16 @@ def main():
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / args.steps
         s2 = g.stats()
-        # the result read back must agree with the device-resident one.  torch (n,n) tensors are the column-major
-        # matrix transposed, so rows of hC are columns of C.  Column panel 0 is accumulated in k-chunks by the staging
-        # pipeline (a different summation order: equal to rounding, |diff| <= 16*eps*k for U(-1,1) data); later panels
-        # run the same single-k-loop kernel as the resident path and must be bit-identical.
+        # the result read back must agree with the device-resident one.  The staging pipeline accumulates C over k-chunks
+        # (a different summation order than the single k loop of the resident path): equal to rounding,
+        # |diff| <= 16*eps*k for U(-1,1) data; checked on two corners (first and last column panel).
         d0 = float((hC[:256, :256].double() - C[:256, :256].cpu().double()).abs().max())
-        same = bool(d0 <= 16 * 2.0 ** -53 * n) and bool(torch.equal(hC[n - 256:, :256], C[n - 256:, :256].cpu()))
+        d1 = float((hC[n - 256:, n - 256:].double() - C[n - 256:, n - 256:].cpu().double()).abs().max())
+        same = bool(max(d0, d1) <= 16 * 2.0 ** -53 * n) and bool(d0 > 0 or n < 4096)
         e2e = {"value": flops / dt / 1e12, "unit": "TFLOP/s", "ms_per_step": dt * 1e3,
                "h2d_bytes_per_step": (s2["h2d_bytes"] - s1["h2d_bytes"]) // args.steps,
                "d2h_bytes_per_step": (s2["d2h_bytes"] - s1["d2h_bytes"]) // args.steps,
-               "host_memory": "pinned", "matches_device_result": same, "max_abs_diff_chunked_panel": d0,
+               "host_memory": "pinned", "matches_device_result": same, "max_abs_diff_vs_resident": max(d0, d1),
                "path": "dgemm_ on host pointers: chunked H2D of A/B and D2H of C panels overlapped with the DMMA kernel (csrc/staged_gemm.cuh)"}
         g.set_sync(False)
 

@@ -7,14 +7,10 @@
 // At BASELINE config 2 (16384^3 f64) that serialisation costs as much as the GEMM itself
 // (6.4 GB over PCIe vs 245 ms of DMMA work).
 //
-// Schedule (three streams, events only, no host synchronisation until the end):
-//   * C is cut into column panels; A stays on the device once it has arrived.
-//   * panel 0 is computed in k-chunks: chunk i of A (and of B's panel-0 slice) is copied on the H2D
-//     stream while chunk i-1 is being multiplied (C_panel += A_chunk * B_chunk), so only the first
-//     chunk's copy is exposed;
-//   * panel p >= 1 needs only B's panel-p slice (and C's, when beta != 0): copied during panel p-1;
-//   * the finished panel p-1 of C goes back on the D2H stream while panel p is computed (PCIe is
-//     full duplex), so only the last panel's return is exposed.
+// Schedule (three streams, events only, no host synchronisation until the end; details at the boundaries below):
+//   * the first ~3/4 of k in full-width k-chunks, chunk i+1's slices of A and B copied while chunk i is multiplied;
+//   * the last ~1/4 of k column panel by column panel, each finished panel of C returning on the D2H stream under
+//     the next panel's multiply (PCIe is full duplex).
 // Operands that are already device-accessible (tracked managed blocks, device pointers) take part
 // without copies, so any mix of resident and host operands uses the same code.
 #pragma once
@@ -88,10 +84,34 @@ bool gemm_pipelined(GEMM gemm, char ta, char tb, int m, int n, int k, T alpha, c
     const bool beta0 = is0(beta);
     const T one = num<T>::real(1.0);
 
-    const int np = (int)std::max<int64_t>(512, round_up((n + 7) / 8, 128));      // <= 8 panels
-    const int kc = (int)std::max<int64_t>(512, round_up((k + 7) / 8, 256));      // <= 8 chunks
-    const int P = (n + np - 1) / np, NCH = (k + kc - 1) / kc;
-    enum { EV_START = 0, EV_CHUNK = 1, EV_READY = 16, EV_DONE = 32, EV_END = 48 };
+    // Schedule.  The first ~3/4 of k is consumed in full-width k-chunks: C += A[:, chunk] * B[chunk, :], each chunk's
+    // operand slices (m*kc + kc*n elements) copied on the H2D stream while the previous chunk is multiplied -- per chunk
+    // the copy is ~1/3 of the multiply, so after the first chunk (split 1/4 + 1/4 + 1/2 to shrink the exposed head) the
+    // tensor pipe never waits for PCIe.  The last ~1/4 of k is consumed column panel by column panel, each finished panel
+    // of C returning on the D2H stream under the next panel's multiply (last panel split 1/2 + 1/4 + 1/4 to shrink the
+    // exposed tail).  (An earlier schedule -- column panels outermost, A resident after panel 0 -- made panel 0 wait for
+    // all of A: 44 ms of copies against 31 ms of work.)
+    const int np = (int)std::max<int64_t>(512, round_up((n + 7) / 8, 128));
+    const int kc = (int)std::max<int64_t>(512, round_up((k + 7) / 8, 256));
+    const int64_t kL = k >= 4 * kc ? (int64_t)(3 * (int64_t)k / 4) / kc * kc : 0;      // [0, kL) by chunks, [kL, k) by panels
+    int pb[24], kb[24], P = 0, NCH = 0;          // boundaries: panel p = [pb[p], pb[p+1]), chunk i = [kb[i], kb[i+1])
+    pb[0] = 0;
+    for (int64_t c = 0; c < n; c += np) {
+        const int64_t w = std::min<int64_t>(np, n - c);
+        if (c + np >= n && w >= 512) {           // last panel
+            const int64_t h = round_up(w / 2, 128), q = round_up(w / 4, 128);
+            pb[++P] = (int)(c + h); if (c + h + q < c + w) pb[++P] = (int)(c + h + q); pb[++P] = (int)(c + w);
+        } else pb[++P] = (int)(c + w);
+    }
+    kb[0] = 0;
+    for (int64_t c = 0; c < kL; c += kc) {
+        const int64_t d = std::min<int64_t>(kc, kL - c);
+        if (c == 0 && d >= 1024) {               // first chunk
+            const int64_t q = round_up(d / 4, 128);
+            kb[++NCH] = (int)q; kb[++NCH] = (int)(2 * q); kb[++NCH] = (int)d;
+        } else kb[++NCH] = (int)(c + d);
+    }
+    enum { EV_START = 0, EV_CHUNK = 1, EV_TAIL = 15, EV_DONE = 32, EV_END = 60 };
 
     {   // the copy streams must not overwrite workspace a previous (asynchronous) call may still be reading
         TrackerGuard guard;
@@ -108,34 +128,29 @@ bool gemm_pipelined(GEMM gemm, char ta, char tb, int m, int n, int k, T alpha, c
     auto record = [&](int ev, cudaStream_t on) { TrackerGuard guard; B200_CUDA(cudaEventRecord(pooled_event(ev), on)); };
     auto wait = [&](cudaStream_t who, int ev) { TrackerGuard guard; B200_CUDA(cudaStreamWaitEvent(who, pooled_event(ev), 0)); };
 
-    // ---- panel 0: k-chunked so that the multiply starts after the first chunk has landed ----
-    const int nn0 = std::min(np, n);
+    // ---- H2D stream: every copy is queued up front (asynchronous for pinned memory; for pageable memory the calls
+    // block the host, which is why they are interleaved with the launches below instead) ----
+    if (!beta0) copy_region(C, 0, 0, m, n, h2d, true);
+    // ---- full-width k-chunks ----
     for (int i = 0; i < NCH; i++) {
-        const int64_t k0 = (int64_t)i * kc; const int kk = (int)std::min<int64_t>(kc, k - k0);
-        if (i == 0 && !beta0) copy_region(C, 0, 0, m, nn0, h2d, true);
+        const int64_t k0 = kb[i]; const int kk = kb[i + 1] - kb[i];
         copy_a(k0, kk);
-        copy_b(k0, kk, 0, nn0);
+        copy_b(k0, kk, 0, n);
         record(EV_CHUNK + i, h2d);
         wait(s, EV_CHUNK + i);
-        gemm(s, ta, tb, m, nn0, kk, alpha, a_chunk(k0), A.dld, b_block(k0, 0), B.dld, i == 0 ? beta : one, c_panel(0), C.dld, MASK_FULL);
+        gemm(s, ta, tb, m, n, kk, alpha, a_chunk(k0), A.dld, b_block(k0, 0), B.dld, i == 0 ? beta : one, (T*)C.dev, C.dld, MASK_FULL);
     }
-    record(EV_DONE + 0, s);
-    // ---- panels 1..P-1: B slice in, previous C panel out, both under the multiply ----
-    for (int p = 1; p < P; p++) {
-        const int64_t n0 = (int64_t)p * np; const int nn = (int)std::min<int64_t>(np, n - n0);
-        if (!beta0) copy_region(C, 0, n0, m, nn, h2d, true);
-        copy_b(0, k, n0, nn);
-        record(EV_READY + p, h2d);
-        wait(s, EV_READY + p);
-        gemm(s, ta, tb, m, nn, k, alpha, a_chunk(0), A.dld, b_block(0, n0), B.dld, beta, c_panel(n0), C.dld, MASK_FULL);
+    // ---- the rest of k, panel by panel, with C flowing back ----
+    copy_a(kL, k - kL);
+    copy_b(kL, k - kL, 0, n);
+    record(EV_TAIL, h2d);
+    wait(s, EV_TAIL);
+    for (int p = 0; p < P; p++) {
+        const int64_t n0 = pb[p]; const int nn = pb[p + 1] - pb[p];
+        gemm(s, ta, tb, m, nn, (int)(k - kL), alpha, a_chunk(kL), A.dld, b_block(kL, n0), B.dld, NCH ? one : beta, c_panel(n0), C.dld, MASK_FULL);
         record(EV_DONE + p, s);
-        wait(d2h, EV_DONE + p - 1);
-        copy_region(C, 0, n0 - np, m, np, d2h, false);
-    }
-    wait(d2h, EV_DONE + P - 1);
-    {
-        const int64_t n0 = (int64_t)(P - 1) * np;
-        copy_region(C, 0, n0, m, n - n0, d2h, false);
+        wait(d2h, EV_DONE + p);
+        copy_region(C, 0, n0, m, nn, d2h, false);
     }
     record(EV_END, d2h);
     wait(s, EV_END);      // the call's own stream completes only when C is back: finish_call() then covers everything
