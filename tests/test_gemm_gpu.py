@@ -321,3 +321,41 @@ def test_dgemm_pipelined_mixed_residency():
         assert s1["h2d_bytes"] - s0["h2d_bytes"] == (k * n + m * n) * 8 and s1["hits"] - s0["hits"] == 1
     finally:
         lib.b200blas_set_options(b"pipeline_min=67108864")
+
+
+def test_entry_points_are_thread_safe():
+    """SURVEY 8(b) "Threading": entry points may be called from any thread.  Each thread gets its own stream and workspace
+    (csrc/runtime.cu ThreadCtx); eight threads issue different staged GEMMs / reductions concurrently and every result
+    must equal the single-threaded one."""
+    import threading
+    lib = g.load()
+    rng = np.random.default_rng(11)
+    jobs = []
+    for t in range(8):
+        m, n, k = 200 + 17 * t, 150 + 9 * t, 300 + 31 * t
+        A = F(rng.uniform(-1, 1, (m, k))); B = F(rng.uniform(-1, 1, (k, n))); x = rng.uniform(-1, 1, 50000 + 1000 * t)
+        jobs.append((m, n, k, A, B, x))
+    want = [(A @ B, float(x @ x)) for (m, n, k, A, B, x) in jobs]
+    got = [None] * 8
+    errs = []
+
+    def work(t):
+        try:
+            m, n, k, A, B, x = jobs[t]
+            for _ in range(5):
+                C = np.zeros((m, n), order="F")
+                f77(lib, "dgemm_", "N", "N", m, n, k, 1.0, A, m, B, k, 0.0, C, m)
+                d = f77(lib, "ddot_", x.size, x, 1, x, 1, restype=ctypes.c_double)
+                got[t] = (C, d)
+        except Exception as e:      # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    for t_ in th:
+        t_.start()
+    for t_ in th:
+        t_.join()
+    assert not errs, errs
+    for t in range(8):
+        assert np.abs(got[t][0] - want[t][0]).max() <= 16 * 2.0 ** -53 * jobs[t][2]
+        assert abs(got[t][1] - want[t][1]) <= 1e-12 * want[t][1]
