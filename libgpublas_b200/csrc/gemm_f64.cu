@@ -232,11 +232,12 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 #pragma unroll
                     for (int j = 0; j < NB; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
-            // EVERY lane arrives (count 256), not one elected lane after __syncwarp(): a lane's release-arrive is ordered
-            // after that lane's own shared-memory reads, but not after the still in-flight LDS of the other 31 lanes, and
-            // ptxas hoists a lane-0 arrive above the trailing DMMAs -- the producer could then let TMA overwrite the stage
-            // under a pending read (observed as sporadic wrong 8x8 blocks with the small 64x32 tile, whose k-step has
-            // only 4 DMMAs to hide behind).
+            // Releasing a stage to the TMA producer: the consumer's shared-memory reads are generic-proxy accesses, the
+            // refill is an async-proxy write, and the PTX memory model orders the two only through a proxy fence --
+            // an mbarrier arrive alone is NOT enough.  Without this fence two CTAs sharing an SM (the small tiles)
+            // produced sporadic stale 8x8 blocks in 12-60% of launches (profiles/r01b_small_tile_race.txt); with one
+            // CTA per SM it never showed, but the hazard is the same.  Every lane fences and arrives for its own reads.
+            if (USE_TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(empty0 + 8 * stage);
             if (++stage == DG_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -387,13 +388,8 @@ void dgemm_out_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, double
     // triangular-solve leaves, Cholesky diagonal blocks -- smaller tiles finish sooner although each is less efficient.
     const int64_t sms = sm_count() > 0 ? sm_count() : 148;
     auto ntiles = [&](int bm, int bn) { return (int64_t)((m + bm - 1) / bm) * ((n + bn - 1) / bn); };
-    // The small tiles stage their operands with the LDG producer, not TMA: with two CTAs resident per SM the TMA-fed
-    // ring showed sporadic stale 8x8 blocks (1-3% of launches, only when stages are reused and only with TMA; the
-    // LDG producer was clean in the same runs -- profiles/r01b_small_tile_race.txt).  These launches are latency
-    // bound, the staging method does not matter for their speed.
     static const int dbg_tiles = getenv("B200BLAS_DBG_TILES") ? atoi(getenv("B200BLAS_DBG_TILES")) : 0;   // 1: 128x128 only, 2: 64x64 only, 3: 64x32 only
-    static const bool dbg_small_tma = getenv("B200BLAS_DBG_SMALL_TMA") != nullptr;
-    const bool small_tma = tma_ok && dbg_small_tma;
+    const bool small_tma = tma_ok;
     if (dbg_tiles == 2) { dgemm_dmma_dispatch<4, 2>(s, nota, notb, small_tma, p); return; }
     if (dbg_tiles == 3) { dgemm_dmma_dispatch<4, 1>(s, nota, notb, small_tma, p); return; }
     // variant=dmma_tma (forced) means the TMA kernel proper, i.e. the 128x128 tile

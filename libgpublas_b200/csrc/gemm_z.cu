@@ -165,11 +165,9 @@ zgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                         dmma884(cim[i][j][0], cim[i][j][1], a[i].y, b[j].x);
                     }
             }
-            // EVERY lane arrives (count 256), not one elected lane after __syncwarp(): a lane's release-arrive is ordered
-            // after that lane's own shared-memory reads, but not after the still in-flight LDS of the other 31 lanes, and
-            // ptxas hoists a lane-0 arrive above the trailing DMMAs -- the producer could then let TMA overwrite the stage
-            // under a pending read (observed as sporadic wrong 8x8 blocks with the small 64x32 tile, whose k-step has
-            // only 4 DMMAs to hide behind).
+            // generic-proxy reads of this stage must be fenced against the async-proxy (TMA) refill before the stage is
+            // released (see gemm_f64.cu); every lane fences and arrives for its own reads
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(empty0 + 8 * stage);
             if (++stage == ZG_STAGES) { stage = 0; phase ^= 1; }
         }

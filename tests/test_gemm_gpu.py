@@ -137,7 +137,7 @@ def test_dgemm_golden_fixture_1024():
     i = np.arange(n, dtype=np.float64)
     A = F(np.repeat(i[:, None], n, axis=1)); B = F(np.repeat(i[None, :], n, axis=0)); C = np.zeros((n, n), order="F")
     f77(lib, "dgemm_", "N", "N", n, n, n, 1.0, A, n, B, n, 0.0, C, n)
-    assert g.last_variant() in ("dmma_tma", "dmma_ldg")      # 64 tiles of 128x128 < 148 SMs: the small-tile DMMA variant
+    assert g.last_variant() == "dmma_tma"                     # 64 tiles of 128x128 < 148 SMs: the small-tile DMMA variant
     assert np.array_equal(C, n * np.outer(i, i))
     g.force_variant("dmma_tma")                               # and the 128x128 TMA kernel on the same fixture
     try:
@@ -177,7 +177,7 @@ def test_dgemm_device_resident_vs_oracle_and_unaligned():
             f77(lib, "dgemm_", ta, tb, m, n, k, 0.7, g.DevPtr(dA.data_ptr() + 8 * off), lda, g.DevPtr(dB.data_ptr() + 8 * off), ldb,
                 1.3, g.DevPtr(dC.data_ptr() + 8 * off), ldc)
             g.force_variant("auto")
-            want = "dmma_tma" if forced else "dmma_ldg"           # small shapes run the LDG-staged small tiles
+            want = "dmma_tma" if (lda_pad % 2 == 0 and off == 0) else "dmma_ldg"   # TMA needs 16-byte aligned base and pitch
             assert g.last_variant() == want, (g.last_variant(), want)
             C = dC[off:off + ldc * n].cpu().numpy().reshape((ldc, n), order="F")
             check_gemm("d", ta, tb, m, n, k, 0.7, 1.3, A, B, C0, C)
