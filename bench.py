@@ -186,7 +186,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--n", type=int, default=16384)
+    ap.add_argument("--n", "--size", dest="n", type=int, default=16384)   # --size: torchrun's own parser finds a bare --n ambiguous
     ap.add_argument("--ksample", type=int, default=1024)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -28,7 +28,7 @@ def _torchrun(n, script, *args, timeout=900):
 def test_tiled_dgemm_p2p_push_two_gpus():
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
-    lines = _torchrun(2, "bench.py", "--gpus", "2", "--steps", "2", "--warmup", "1", "--n", "4096", "--verify")
+    lines = _torchrun(2, "bench.py", "--gpus", "2", "--steps", "2", "--warmup", "1", "--size", "4096", "--verify")
     assert lines and lines[-1]["n_gpus"] == 2 and lines[-1]["verified"]["max_abs_diff_vs_1gpu"] == 0.0
     assert "copy engines" in lines[-1]["config"]["parallelism"]
 
