@@ -31,20 +31,73 @@ def potrf_lower(n, A, lda):
     return lib.b200blas_dpotrf_lower(n, ctypes.c_void_p(_ptr(A)), lda)
 
 
-def blocked_cholesky(n, A, lda, nb=2048):
-    """A := L (lower triangle) with A = L L^T, column-major, leading dimension lda.  Returns LAPACK info."""
+def blocked_cholesky(n, A, lda, nb=2048, lookahead=True):
+    """A := L (lower triangle) with A = L L^T, column-major, leading dimension lda.  Returns LAPACK info.
+
+    lookahead (device-resident A, library in asynchronous mode `set_sync(False)`): the trailing update of step J is split
+    into the next block column and the rest; as soon as the next block column is up to date its diagonal-block
+    factorisation and panel solve (latency-bound, a few SMs) run on a second stream underneath the rest of step J's
+    rank-nb update (compute-bound), so the tensor pipe does not idle during the panel work.  Only the update kernels
+    (DSYRK/DGEMM, no workspace) run concurrently with the panel kernels (which use the per-thread workspace)."""
     base = _ptr(A)
     at = lambda i, j: DevPtr(base + 8 * (i + j * lda))
-    for j in range(0, n, nb):
-        jb = min(nb, n - j)
-        info = potrf_lower(jb, at(j, j), lda)
-        if info:
-            return info + j
-        rest = n - j - jb
-        if rest > 0:
+    dev = getattr(A, "device", None)
+    use_la = bool(lookahead) and dev is not None and getattr(dev, "type", "") == "cuda" and n > 2 * nb
+    if not use_la:
+        for j in range(0, n, nb):
+            jb = min(nb, n - j)
+            info = potrf_lower(jb, at(j, j), lda)
+            if info:
+                return info + j
+            rest = n - j - jb
+            if rest > 0:
+                call("dtrsm_", "R", "L", "T", "N", rest, jb, 1.0, at(j, j), lda, at(j + jb, j), lda)
+                call("dsyrk_", "L", "N", rest, jb, -1.0, at(j + jb, j), lda, 1.0, at(j + jb, j + jb), lda)
+        return 0
+
+    from . import use_torch_stream
+    use_torch_stream()              # the library's calls follow torch's current stream from here on (main, then panel)
+    main = torch.cuda.current_stream(dev)
+    # high priority: the update kernels keep every SM occupied, and the block scheduler hands freed SMs to the running
+    # kernel's own pending CTAs first -- only a higher-priority stream gets its (small) panel kernels in between
+    panel = torch.cuda.Stream(device=dev, priority=-1)
+
+    class on:                       # issue the enclosed BLAS calls on `stream`
+        def __init__(s, stream): s.stream = stream
+        def __enter__(s): s.ctx = torch.cuda.stream(s.stream); s.ctx.__enter__(); use_torch_stream()
+        def __exit__(s, *a): s.ctx.__exit__(*a); use_torch_stream()
+
+    def factor(j, jb, rest):        # diagonal block + panel solve of block column j
+        r = potrf_lower(jb, at(j, j), lda)
+        if r == 0 and rest > 0:
             call("dtrsm_", "R", "L", "T", "N", rest, jb, 1.0, at(j, j), lda, at(j + jb, j), lda)
-            call("dsyrk_", "L", "N", rest, jb, -1.0, at(j + jb, j), lda, 1.0, at(j + jb, j + jb), lda)
-    return 0
+        return r + j if r else 0
+
+    info = factor(0, min(nb, n), n - min(nb, n))
+    panel_done = None
+    for j in range(0, n, nb):
+        if info:
+            break
+        jb = min(nb, n - j); rest = n - j - jb
+        if rest <= 0:
+            break
+        if panel_done is not None:
+            main.wait_event(panel_done)                     # panel j was factored on the panel stream
+        t0 = j + jb; nb2 = min(nb, rest); below = rest - nb2
+        # next block column first
+        call("dsyrk_", "L", "N", nb2, jb, -1.0, at(t0, j), lda, 1.0, at(t0, t0), lda)
+        if below > 0:
+            call("dgemm_", "N", "T", below, nb2, jb, -1.0, at(t0 + nb2, j), lda, at(t0, j), lda, 1.0, at(t0 + nb2, t0), lda)
+        col_ready = torch.cuda.Event(); col_ready.record(main)
+        # the rest of the trailing matrix (queued BEFORE the panel work, whose info read-back blocks the host)
+        if below > 0:
+            call("dsyrk_", "L", "N", below, jb, -1.0, at(t0 + nb2, j), lda, 1.0, at(t0 + nb2, t0 + nb2), lda)
+        panel.wait_event(col_ready)
+        with on(panel):
+            info = factor(t0, nb2, below)
+            panel_done = torch.cuda.Event(); panel_done.record(panel)
+    main.wait_stream(panel)
+    return info
 
 
 class LibBlas:
@@ -103,7 +156,7 @@ class TiledCholesky:
         cuda = self.dev.type == "cuda"
         main = torch.cuda.current_stream(self.dev) if cuda else None
         if cuda and not hasattr(self, "panel_stream"):
-            self.panel_stream = torch.cuda.Stream(device=self.dev)
+            self.panel_stream = torch.cuda.Stream(device=self.dev, priority=-1)    # see blocked_cholesky: panel kernels must get SMs in between
         info = 0
 
         class on:                       # run the enclosed BLAS calls / collectives on the given stream
