@@ -147,3 +147,15 @@ def test_tiled_cholesky_gloo(world, n, nb):
     for status, rank, info, err in res:      # every rank ends with the complete factor
         assert status == "ok", info
         assert info == 0 and err < 1e-13, (rank, info, err)
+
+
+def test_syrk_strip_bounds_equal_area():
+    """partitioned.PartitionedSyrk: column strips of the lower triangle with (nearly) equal areas, 128-aligned, covering n."""
+    from libgpublas_b200.partitioned import strip_bounds
+    for n, parts in [(32768, 8), (32768, 2), (16384, 4), (1000, 3), (128, 8)]:
+        b = strip_bounds(n, parts)
+        assert b[0] == 0 and b[-1] == n and len(b) == parts + 1 and all(b[i] <= b[i + 1] for i in range(parts))
+        assert all(x % 128 == 0 for x in b[1:-1])
+        if n >= 128 * parts * 4:
+            areas = [(n - b[i]) ** 2 - (n - b[i + 1]) ** 2 for i in range(parts)]
+            assert max(areas) <= 1.25 * (n * n / parts), (n, parts, b, areas)
