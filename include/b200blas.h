@@ -138,6 +138,75 @@ B200_API void dtrmv_(const char* uplo, const char* trans, const char* diag, cons
 B200_API void drot_(const int* n, double* x, const int* incx, double* y, const int* incy, const double* c, const double* s);
 B200_API void drotg_(double* a, double* b, double* c, double* s);
 
+/* banded, packed, Hermitian and complex Level 2 (reference blas_level2/gbmv.cc, bmv.cc (sbmv/hbmv), pmv.cc (spmv/hpmv),
+ * hemv.cc, her.cc, her2.cc, hpr.cc, hpr2.cc, spr.cc, spr2.cc, syr2.cc, tbmv.cc, tbsv.cc, tpmv.cc, tpsv.cc, ger.cc (geru/gerc), trmv.cc):
+ * netlib signatures and INFO numbering; band storage AB(ku+1+i-j, j), packed storage by columns. */
+B200_API void sgbmv_(const char* trans, const int* m, const int* n, const int* kl, const int* ku, const float* alpha, const float* a, const int* lda, const float* x, const int* incx, const float* beta, float* y, const int* incy);
+B200_API void stbmv_(const char* uplo, const char* trans, const char* diag, const int* n, const int* k, const float* a, const int* lda, float* x, const int* incx);
+B200_API void stbsv_(const char* uplo, const char* trans, const char* diag, const int* n, const int* k, const float* a, const int* lda, float* x, const int* incx);
+B200_API void stpmv_(const char* uplo, const char* trans, const char* diag, const int* n, const float* ap, float* x, const int* incx);
+B200_API void stpsv_(const char* uplo, const char* trans, const char* diag, const int* n, const float* ap, float* x, const int* incx);
+B200_API void ssbmv_(const char* uplo, const int* n, const int* k, const float* alpha, const float* a, const int* lda, const float* x, const int* incx, const float* beta, float* y, const int* incy);
+B200_API void sspmv_(const char* uplo, const int* n, const float* alpha, const float* ap, const float* x, const int* incx, const float* beta, float* y, const int* incy);
+B200_API void ssyr2_(const char* uplo, const int* n, const float* alpha, const float* x, const int* incx, const float* y, const int* incy, float* a, const int* lda);
+B200_API void sspr_(const char* uplo, const int* n, const float* alpha, const float* x, const int* incx, float* ap);
+B200_API void sspr2_(const char* uplo, const int* n, const float* alpha, const float* x, const int* incx, const float* y, const int* incy, float* ap);
+B200_API void dgbmv_(const char* trans, const int* m, const int* n, const int* kl, const int* ku, const double* alpha, const double* a, const int* lda, const double* x, const int* incx, const double* beta, double* y, const int* incy);
+B200_API void dtbmv_(const char* uplo, const char* trans, const char* diag, const int* n, const int* k, const double* a, const int* lda, double* x, const int* incx);
+B200_API void dtbsv_(const char* uplo, const char* trans, const char* diag, const int* n, const int* k, const double* a, const int* lda, double* x, const int* incx);
+B200_API void dtpmv_(const char* uplo, const char* trans, const char* diag, const int* n, const double* ap, double* x, const int* incx);
+B200_API void dtpsv_(const char* uplo, const char* trans, const char* diag, const int* n, const double* ap, double* x, const int* incx);
+B200_API void dsbmv_(const char* uplo, const int* n, const int* k, const double* alpha, const double* a, const int* lda, const double* x, const int* incx, const double* beta, double* y, const int* incy);
+B200_API void dspmv_(const char* uplo, const int* n, const double* alpha, const double* ap, const double* x, const int* incx, const double* beta, double* y, const int* incy);
+B200_API void dsyr2_(const char* uplo, const int* n, const double* alpha, const double* x, const int* incx, const double* y, const int* incy, double* a, const int* lda);
+B200_API void dspr_(const char* uplo, const int* n, const double* alpha, const double* x, const int* incx, double* ap);
+B200_API void dspr2_(const char* uplo, const int* n, const double* alpha, const double* x, const int* incx, const double* y, const int* incy, double* ap);
+B200_API void cgbmv_(const char* trans, const int* m, const int* n, const int* kl, const int* ku, const b200_c32* alpha, const b200_c32* a, const int* lda, const b200_c32* x, const int* incx, const b200_c32* beta, b200_c32* y, const int* incy);
+B200_API void ctbmv_(const char* uplo, const char* trans, const char* diag, const int* n, const int* k, const b200_c32* a, const int* lda, b200_c32* x, const int* incx);
+B200_API void ctbsv_(const char* uplo, const char* trans, const char* diag, const int* n, const int* k, const b200_c32* a, const int* lda, b200_c32* x, const int* incx);
+B200_API void ctpmv_(const char* uplo, const char* trans, const char* diag, const int* n, const b200_c32* ap, b200_c32* x, const int* incx);
+B200_API void ctpsv_(const char* uplo, const char* trans, const char* diag, const int* n, const b200_c32* ap, b200_c32* x, const int* incx);
+B200_API void chbmv_(const char* uplo, const int* n, const int* k, const b200_c32* alpha, const b200_c32* a, const int* lda, const b200_c32* x, const int* incx, const b200_c32* beta, b200_c32* y, const int* incy);
+B200_API void chpmv_(const char* uplo, const int* n, const b200_c32* alpha, const b200_c32* ap, const b200_c32* x, const int* incx, const b200_c32* beta, b200_c32* y, const int* incy);
+B200_API void chemv_(const char* uplo, const int* n, const b200_c32* alpha, const b200_c32* a, const int* lda, const b200_c32* x, const int* incx, const b200_c32* beta, b200_c32* y, const int* incy);
+B200_API void cgeru_(const int* m, const int* n, const b200_c32* alpha, const b200_c32* x, const int* incx, const b200_c32* y, const int* incy, b200_c32* a, const int* lda);
+B200_API void cgerc_(const int* m, const int* n, const b200_c32* alpha, const b200_c32* x, const int* incx, const b200_c32* y, const int* incy, b200_c32* a, const int* lda);
+B200_API void cher_(const char* uplo, const int* n, const float* alpha, const b200_c32* x, const int* incx, b200_c32* a, const int* lda);
+B200_API void cher2_(const char* uplo, const int* n, const b200_c32* alpha, const b200_c32* x, const int* incx, const b200_c32* y, const int* incy, b200_c32* a, const int* lda);
+B200_API void chpr_(const char* uplo, const int* n, const float* alpha, const b200_c32* x, const int* incx, b200_c32* ap);
+B200_API void chpr2_(const char* uplo, const int* n, const b200_c32* alpha, const b200_c32* x, const int* incx, const b200_c32* y, const int* incy, b200_c32* ap);
+B200_API void ctrmv_(const char* uplo, const char* trans, const char* diag, const int* n, const b200_c32* a, const int* lda, b200_c32* x, const int* incx);
+B200_API void zgbmv_(const char* trans, const int* m, const int* n, const int* kl, const int* ku, const b200_c64* alpha, const b200_c64* a, const int* lda, const b200_c64* x, const int* incx, const b200_c64* beta, b200_c64* y, const int* incy);
+B200_API void ztbmv_(const char* uplo, const char* trans, const char* diag, const int* n, const int* k, const b200_c64* a, const int* lda, b200_c64* x, const int* incx);
+B200_API void ztbsv_(const char* uplo, const char* trans, const char* diag, const int* n, const int* k, const b200_c64* a, const int* lda, b200_c64* x, const int* incx);
+B200_API void ztpmv_(const char* uplo, const char* trans, const char* diag, const int* n, const b200_c64* ap, b200_c64* x, const int* incx);
+B200_API void ztpsv_(const char* uplo, const char* trans, const char* diag, const int* n, const b200_c64* ap, b200_c64* x, const int* incx);
+B200_API void zhbmv_(const char* uplo, const int* n, const int* k, const b200_c64* alpha, const b200_c64* a, const int* lda, const b200_c64* x, const int* incx, const b200_c64* beta, b200_c64* y, const int* incy);
+B200_API void zhpmv_(const char* uplo, const int* n, const b200_c64* alpha, const b200_c64* ap, const b200_c64* x, const int* incx, const b200_c64* beta, b200_c64* y, const int* incy);
+B200_API void zhemv_(const char* uplo, const int* n, const b200_c64* alpha, const b200_c64* a, const int* lda, const b200_c64* x, const int* incx, const b200_c64* beta, b200_c64* y, const int* incy);
+B200_API void zgeru_(const int* m, const int* n, const b200_c64* alpha, const b200_c64* x, const int* incx, const b200_c64* y, const int* incy, b200_c64* a, const int* lda);
+B200_API void zgerc_(const int* m, const int* n, const b200_c64* alpha, const b200_c64* x, const int* incx, const b200_c64* y, const int* incy, b200_c64* a, const int* lda);
+B200_API void zher_(const char* uplo, const int* n, const double* alpha, const b200_c64* x, const int* incx, b200_c64* a, const int* lda);
+B200_API void zher2_(const char* uplo, const int* n, const b200_c64* alpha, const b200_c64* x, const int* incx, const b200_c64* y, const int* incy, b200_c64* a, const int* lda);
+B200_API void zhpr_(const char* uplo, const int* n, const double* alpha, const b200_c64* x, const int* incx, b200_c64* ap);
+B200_API void zhpr2_(const char* uplo, const int* n, const b200_c64* alpha, const b200_c64* x, const int* incx, const b200_c64* y, const int* incy, b200_c64* ap);
+B200_API void ztrmv_(const char* uplo, const char* trans, const char* diag, const int* n, const b200_c64* a, const int* lda, b200_c64* x, const int* incx);
+
+/* more Level 1 (reference blas_level1/rotm.cc, rotmg.cc, amin.cc; cblas.h dsdot / sdsdot; netlib CSROT / ZDROT).  i?amin_ is not
+ * netlib; the reference's amin.cc names it and the CPU BLAS (OpenBLAS) exports it: 1-based index of the first smallest |x|. */
+B200_API void srotm_(const int* n, float* x, const int* incx, float* y, const int* incy, const float* param);
+B200_API void drotm_(const int* n, double* x, const int* incx, double* y, const int* incy, const double* param);
+B200_API void srotmg_(float* d1, float* d2, float* x1, const float* y1, float* param);
+B200_API void drotmg_(double* d1, double* d2, double* x1, const double* y1, double* param);
+B200_API void csrot_(const int* n, b200_c32* x, const int* incx, b200_c32* y, const int* incy, const float* c, const float* s);
+B200_API void zdrot_(const int* n, b200_c64* x, const int* incx, b200_c64* y, const int* incy, const double* c, const double* s);
+B200_API int isamin_(const int* n, const float* x, const int* incx);
+B200_API int idamin_(const int* n, const double* x, const int* incx);
+B200_API int icamin_(const int* n, const b200_c32* x, const int* incx);
+B200_API int izamin_(const int* n, const b200_c64* x, const int* incx);
+B200_API double dsdot_(const int* n, const float* x, const int* incx, const float* y, const int* incy);
+B200_API float sdsdot_(const int* n, const float* sb, const float* x, const int* incx, const float* y, const int* incy);
+
 /* ------------------------------ 2. CBLAS ABI ------------------------------ */
 /* enums: reference cblas.h:21-25 */
 enum CBLAS_ORDER { CblasRowMajor = 101, CblasColMajor = 102 };
@@ -215,6 +284,86 @@ B200_API void cblas_dsymv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, d
 B200_API void cblas_dtrmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const double* a, int lda, double* x, int incx);
 B200_API void cblas_drot(int n, double* x, int incx, double* y, int incy, double c, double s);
 B200_API void cblas_drotg(double* a, double* b, double* c, double* s);
+
+/* CBLAS forms of the banded / packed / Hermitian / complex Level 2 (row-major handled by the transposed view: uplo flipped, kl/ku swapped,
+ * ConjTrans as conjugate-no-transpose; reference cblas.h DECLARE_CBLAS__GBMV ... __TRMV) */
+B200_API void cblas_sgbmv(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE trans, int m, int n, int kl, int ku, float alpha, const float* a, int lda, const float* x, int incx, float beta, float* y, int incy);
+B200_API void cblas_stbmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, int k, const float* a, int lda, float* x, int incx);
+B200_API void cblas_stbsv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, int k, const float* a, int lda, float* x, int incx);
+B200_API void cblas_stpmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const float* ap, float* x, int incx);
+B200_API void cblas_stpsv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const float* ap, float* x, int incx);
+B200_API void cblas_ssbmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, int k, float alpha, const float* a, int lda, const float* x, int incx, float beta, float* y, int incy);
+B200_API void cblas_sspmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, float alpha, const float* ap, const float* x, int incx, float beta, float* y, int incy);
+B200_API void cblas_ssyr2(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, float alpha, const float* x, int incx, const float* y, int incy, float* a, int lda);
+B200_API void cblas_sspr(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, float alpha, const float* x, int incx, float* ap);
+B200_API void cblas_sspr2(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, float alpha, const float* x, int incx, const float* y, int incy, float* ap);
+B200_API void cblas_dgbmv(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE trans, int m, int n, int kl, int ku, double alpha, const double* a, int lda, const double* x, int incx, double beta, double* y, int incy);
+B200_API void cblas_dtbmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, int k, const double* a, int lda, double* x, int incx);
+B200_API void cblas_dtbsv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, int k, const double* a, int lda, double* x, int incx);
+B200_API void cblas_dtpmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const double* ap, double* x, int incx);
+B200_API void cblas_dtpsv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const double* ap, double* x, int incx);
+B200_API void cblas_dsbmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, int k, double alpha, const double* a, int lda, const double* x, int incx, double beta, double* y, int incy);
+B200_API void cblas_dspmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, double alpha, const double* ap, const double* x, int incx, double beta, double* y, int incy);
+B200_API void cblas_dsyr2(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, double alpha, const double* x, int incx, const double* y, int incy, double* a, int lda);
+B200_API void cblas_dspr(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, double alpha, const double* x, int incx, double* ap);
+B200_API void cblas_dspr2(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, double alpha, const double* x, int incx, const double* y, int incy, double* ap);
+B200_API void cblas_cgbmv(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE trans, int m, int n, int kl, int ku, const void* alpha, const void* a, int lda, const void* x, int incx, const void* beta, void* y, int incy);
+B200_API void cblas_ctbmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, int k, const void* a, int lda, void* x, int incx);
+B200_API void cblas_ctbsv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, int k, const void* a, int lda, void* x, int incx);
+B200_API void cblas_ctpmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const void* ap, void* x, int incx);
+B200_API void cblas_ctpsv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const void* ap, void* x, int incx);
+B200_API void cblas_chbmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, int k, const void* alpha, const void* a, int lda, const void* x, int incx, const void* beta, void* y, int incy);
+B200_API void cblas_chpmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, const void* alpha, const void* ap, const void* x, int incx, const void* beta, void* y, int incy);
+B200_API void cblas_chemv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, const void* alpha, const void* a, int lda, const void* x, int incx, const void* beta, void* y, int incy);
+B200_API void cblas_cgeru(enum CBLAS_ORDER order, int m, int n, const void* alpha, const void* x, int incx, const void* y, int incy, void* a, int lda);
+B200_API void cblas_cgerc(enum CBLAS_ORDER order, int m, int n, const void* alpha, const void* x, int incx, const void* y, int incy, void* a, int lda);
+B200_API void cblas_cher(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, float alpha, const void* x, int incx, void* a, int lda);
+B200_API void cblas_cher2(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, const void* alpha, const void* x, int incx, const void* y, int incy, void* a, int lda);
+B200_API void cblas_chpr(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, float alpha, const void* x, int incx, void* ap);
+B200_API void cblas_chpr2(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, const void* alpha, const void* x, int incx, const void* y, int incy, void* ap);
+B200_API void cblas_ctrmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const void* a, int lda, void* x, int incx);
+B200_API void cblas_cgemv(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE trans, int m, int n, const void* alpha, const void* a, int lda, const void* x, int incx, const void* beta, void* y, int incy);
+B200_API void cblas_zgbmv(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE trans, int m, int n, int kl, int ku, const void* alpha, const void* a, int lda, const void* x, int incx, const void* beta, void* y, int incy);
+B200_API void cblas_ztbmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, int k, const void* a, int lda, void* x, int incx);
+B200_API void cblas_ztbsv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, int k, const void* a, int lda, void* x, int incx);
+B200_API void cblas_ztpmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const void* ap, void* x, int incx);
+B200_API void cblas_ztpsv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const void* ap, void* x, int incx);
+B200_API void cblas_zhbmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, int k, const void* alpha, const void* a, int lda, const void* x, int incx, const void* beta, void* y, int incy);
+B200_API void cblas_zhpmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, const void* alpha, const void* ap, const void* x, int incx, const void* beta, void* y, int incy);
+B200_API void cblas_zhemv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, const void* alpha, const void* a, int lda, const void* x, int incx, const void* beta, void* y, int incy);
+B200_API void cblas_zgeru(enum CBLAS_ORDER order, int m, int n, const void* alpha, const void* x, int incx, const void* y, int incy, void* a, int lda);
+B200_API void cblas_zgerc(enum CBLAS_ORDER order, int m, int n, const void* alpha, const void* x, int incx, const void* y, int incy, void* a, int lda);
+B200_API void cblas_zher(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, double alpha, const void* x, int incx, void* a, int lda);
+B200_API void cblas_zher2(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, const void* alpha, const void* x, int incx, const void* y, int incy, void* a, int lda);
+B200_API void cblas_zhpr(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, double alpha, const void* x, int incx, void* ap);
+B200_API void cblas_zhpr2(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, int n, const void* alpha, const void* x, int incx, const void* y, int incy, void* ap);
+B200_API void cblas_ztrmv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const void* a, int lda, void* x, int incx);
+B200_API void cblas_zgemv(enum CBLAS_ORDER order, enum CBLAS_TRANSPOSE trans, int m, int n, const void* alpha, const void* a, int lda, const void* x, int incx, const void* beta, void* y, int incy);
+
+B200_API void cblas_srotm(int n, float* x, int incx, float* y, int incy, const float* param);
+B200_API void cblas_drotm(int n, double* x, int incx, double* y, int incy, const double* param);
+B200_API void cblas_srotmg(float* d1, float* d2, float* x1, float y1, float* param);
+B200_API void cblas_drotmg(double* d1, double* d2, double* x1, double y1, double* param);
+B200_API void cblas_csrot(int n, void* x, int incx, void* y, int incy, float c, float s);
+B200_API void cblas_zdrot(int n, void* x, int incx, void* y, int incy, double c, double s);
+B200_API CBLAS_INDEX cblas_isamin(int n, const float* x, int incx);
+B200_API CBLAS_INDEX cblas_idamin(int n, const double* x, int incx);
+B200_API CBLAS_INDEX cblas_icamin(int n, const void* x, int incx);
+B200_API CBLAS_INDEX cblas_izamin(int n, const void* x, int incx);
+B200_API double cblas_dsdot(int n, const float* x, int incx, const float* y, int incy);
+B200_API float cblas_sdsdot(int n, float sb, const float* x, int incx, const float* y, int incy);
+B200_API void cblas_ccopy(int n, const void* x, int incx, void* y, int incy);
+B200_API void cblas_zcopy(int n, const void* x, int incx, void* y, int incy);
+B200_API void cblas_cswap(int n, void* x, int incx, void* y, int incy);
+B200_API void cblas_zswap(int n, void* x, int incx, void* y, int incy);
+B200_API void cblas_cscal(int n, const void* alpha, void* x, int incx);
+B200_API void cblas_zscal(int n, const void* alpha, void* x, int incx);
+B200_API void cblas_csscal(int n, float alpha, void* x, int incx);
+B200_API void cblas_zdscal(int n, double alpha, void* x, int incx);
+B200_API float cblas_scasum(int n, const void* x, int incx);
+B200_API double cblas_dzasum(int n, const void* x, int incx);
+B200_API void cblas_ctrsv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const void* a, int lda, void* x, int incx);
+B200_API void cblas_ztrsv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const void* a, int lda, void* x, int incx);
 
 /* ------------------------------ 3. allocator symbols ------------------------------ */
 /* malloc / calloc / realloc / free are exported with their libc prototypes (<stdlib.h>);

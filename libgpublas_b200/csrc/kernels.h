@@ -69,6 +69,8 @@ template <typename T> void dot_dev(cudaStream_t s, int64_t n, const T* x, int64_
 template <typename T, typename R> void nrm2_dev(cudaStream_t s, int64_t n, const T* x, int64_t incx, R* out);
 template <typename T, typename R> void asum_dev(cudaStream_t s, int64_t n, const T* x, int64_t incx, R* out);
 template <typename T> void iamax_dev(cudaStream_t s, int64_t n, const T* x, int64_t incx, long long* out);   // 0-based, -1 if none
+template <typename T> void iamin_dev(cudaStream_t s, int64_t n, const T* x, int64_t incx, long long* out);   // 0-based, -1 if none
+void dsdot_dev(cudaStream_t s, int64_t n, const float* x, int64_t incx, const float* y, int64_t incy, double sb, void* out, bool out_double);
 template <typename T> void axpy_dev(cudaStream_t s, int64_t n, T alpha, const T* x, int64_t incx, T* y, int64_t incy);
 template <typename T, typename S> void scal_dev(cudaStream_t s, int64_t n, S alpha, T* x, int64_t incx);
 template <typename T> void copy_dev(cudaStream_t s, int64_t n, const T* x, int64_t incx, T* y, int64_t incy);

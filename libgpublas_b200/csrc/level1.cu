@@ -154,10 +154,11 @@ __global__ void __launch_bounds__(L1_THREADS) ddot_kernel(int64_t n, const doubl
     grid_finish<double, SumOp<double>>(v, partials, ticket, sm, [=](double r) { *out = r; });
 }
 
+template <typename OutT>
 __global__ void __launch_bounds__(L1_THREADS) sdot_kernel(int64_t n, const float* __restrict__ x, int64_t incx,
                                                          const float* __restrict__ y, int64_t incy, double* partials,
-                                                         unsigned int* ticket, float* out, bool vec) {
-    // float inputs, double accumulation (tighter than the CPU BLAS's float sum)
+                                                         unsigned int* ticket, OutT* out, bool vec, double addend) {
+    // float inputs, double accumulation (tighter than the CPU BLAS's float sum; exactly what netlib DSDOT / SDSDOT specify)
     __shared__ double sm[32];
     double a0 = 0, a1 = 0;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(L1_THREADS) sdot_kernel(int64_t n, const float
         for (int64_t i = tid; i < n; i += nth) a0 += (double)x[vix(i, n, incx)] * y[vix(i, n, incy)];
     }
     double v = block_reduce<double, SumOp<double>>(a0 + a1, sm);
-    grid_finish<double, SumOp<double>>(v, partials, ticket, sm, [=](double r) { *out = (float)r; });
+    grid_finish<double, SumOp<double>>(v, partials, ticket, sm, [=](double r) { *out = (OutT)(r + addend); });
 }
 
 template <typename CT, bool CONJ>
@@ -206,7 +207,13 @@ template <> void dot_dev<double>(cudaStream_t s, int64_t n, const double* x, int
 }
 template <> void dot_dev<float>(cudaStream_t s, int64_t n, const float* x, int64_t incx, const float* y, int64_t incy, float* out, bool) {
     L1Scratch sc = l1_scratch(sizeof(double));
-    sdot_kernel<<<l1_blocks(n, 8), L1_THREADS, 0, s>>>(n, x, incx, y, incy, (double*)sc.partials, sc.ticket, out, vec_ok(x, y, incx, incy));
+    sdot_kernel<float><<<l1_blocks(n, 8), L1_THREADS, 0, s>>>(n, x, incx, y, incy, (double*)sc.partials, sc.ticket, out, vec_ok(x, y, incx, incy), 0.0);
+}
+// netlib DSDOT (double result) / SDSDOT (sb + dot, rounded to float once): float operands, double accumulation
+void dsdot_dev(cudaStream_t s, int64_t n, const float* x, int64_t incx, const float* y, int64_t incy, double sb, void* out, bool out_double) {
+    L1Scratch sc = l1_scratch(sizeof(double));
+    if (out_double) sdot_kernel<double><<<l1_blocks(n, 8), L1_THREADS, 0, s>>>(n, x, incx, y, incy, (double*)sc.partials, sc.ticket, (double*)out, vec_ok(x, y, incx, incy), sb);
+    else sdot_kernel<float><<<l1_blocks(n, 8), L1_THREADS, 0, s>>>(n, x, incx, y, incy, (double*)sc.partials, sc.ticket, (float*)out, vec_ok(x, y, incx, incy), sb);
 }
 template <> void dot_dev<cuDoubleComplex>(cudaStream_t s, int64_t n, const cuDoubleComplex* x, int64_t incx, const cuDoubleComplex* y,
                                           int64_t incy, cuDoubleComplex* out, bool conj_x) {
@@ -370,6 +377,44 @@ B200_IAMAX(float, float, 1)
 B200_IAMAX(cuDoubleComplex, double, 2)
 B200_IAMAX(cuFloatComplex, float, 2)
 #undef B200_IAMAX
+
+// ------------------------------------------ I?AMIN ------------------------------------------
+// reference blas_level1/amin.cc:10-56 (cublasI<t>amin): index of the first element of smallest |x| (|re|+|im| for complex)
+struct ArgMinOp {
+    static __device__ ArgMax identity() { return ArgMax{0.0, -1}; }
+    static __device__ ArgMax combine(ArgMax a, ArgMax b) {
+        if (b.i < 0) return a;
+        if (a.i < 0) return b;
+        if (b.v < a.v || (b.v == a.v && b.i < a.i)) return b;
+        return a;
+    }
+    static __device__ ArgMax shfl_down(ArgMax v, int o) { return ArgMax{__shfl_down_sync(0xffffffffu, v.v, o), __shfl_down_sync(0xffffffffu, v.i, o)}; }
+};
+template <typename T, int NC>
+__global__ void __launch_bounds__(L1_THREADS) iamin_kernel(int64_t n, const T* __restrict__ x, int64_t incx, ArgMax* partials, unsigned int* ticket,
+                                                          long long* out) {
+    __shared__ ArgMax sm[32];
+    ArgMax best = {0.0, -1};
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < n; i += nth) {   // increasing index per thread: strictly smaller values only => first minimum
+        const T* p = x + i * incx * NC;
+        double v = fabs((double)p[0]);
+        if (NC == 2) v += fabs((double)p[NC - 1]);
+        if (best.i < 0 || v < best.v) { best.v = v; best.i = i; }
+    }
+    ArgMax v = block_reduce<ArgMax, ArgMinOp>(best, sm);
+    grid_finish<ArgMax, ArgMinOp>(v, partials, ticket, sm, [=](ArgMax r) { *out = r.i; });
+}
+#define B200_IAMIN(T, CT, NC)                                                                                  \
+    template <> void iamin_dev<T>(cudaStream_t s, int64_t n, const T* x, int64_t incx, long long* out) {       \
+        L1Scratch sc = l1_scratch(sizeof(ArgMax));                                                              \
+        iamin_kernel<CT, NC><<<l1_blocks(n, 8), L1_THREADS, 0, s>>>(n, (const CT*)x, incx, (ArgMax*)sc.partials, sc.ticket, out); \
+    }
+B200_IAMIN(double, double, 1)
+B200_IAMIN(float, float, 1)
+B200_IAMIN(cuDoubleComplex, double, 2)
+B200_IAMIN(cuFloatComplex, float, 2)
+#undef B200_IAMIN
 
 // ------------------------------------------ AXPY / SCAL / COPY / SWAP ------------------------------------------
 __global__ void __launch_bounds__(L1_THREADS) daxpy_vec_kernel(int64_t n, double alpha, const double* __restrict__ x, double* __restrict__ y) {

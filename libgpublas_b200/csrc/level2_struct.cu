@@ -1,0 +1,452 @@
+// level2_struct.cu -- the banded, packed, Hermitian and complex Level-2 routines the reference's dead wrappers name
+// (blas_level2/gbmv.cc, bmv.cc, pmv.cc, hemv.cc, her.cc, her2.cc, hpr.cc, hpr2.cc, spr.cc,
+// spr2.cc, syr2.cc, tbmv.cc, tbsv.cc, tpmv.cc, tpsv.cc, ger.cc (geru/gerc), trmv.cc (c/z) forward to cublas<t>...).
+// Fortran + CBLAS entry points with the netlib argument checks; s/d/c/z as netlib defines them.
+//
+// All are one pass over the stored part of the matrix (HBM-bound).  The index logic of every storage scheme lives in
+// structured.cuh; the kernels here are its three bodies behind a launch shape:
+//   matrix-vector   y = alpha*(N part + T part [+ x]) + beta*y    "N part": thread per row, column chunks, partial rows summed
+//                                                                   in chunk order; "T part": warp per column, butterfly sum
+//       GBMV 'N' = N part, 'T'/'C' = T part; SBMV/HBMV/SPMV/HPMV/HEMV = N part over the stored triangle + T part over
+//       the strict triangle (conjugated for Hermitian); TBMV/TPMV/TRMV pick one part by trans.
+//   rank updates    thread per row over the stored columns (GERU/GERC/HER/HER2/SYR2/SPR/SPR2/HPR/HPR2)
+//   solves          TBSV/TPSV: 32-wide diagonal blocks solved by one warp (coefficients preloaded, x passed by shuffle),
+//                   then the same N/T bodies subtract the block's contribution from the rows it reaches.
+// Row-major CBLAS calls map onto the same kernels: the row-major array is the column-major storage of the transpose with
+// uplo flipped (kl/ku swapped); ConjTrans becomes "conjugate, no transpose" (a flag of the bodies), and Hermitian
+// row-major operands are the conjugate of the column-major view (flags toggled / vectors conjugated while gathered).
+// Deterministic: fixed grids, fixed summation order.
+#include "abi_common.h"
+#include "structured.cuh"
+#include "../../include/b200blas.h"
+#include <cstdlib>
+
+namespace b200 {
+using namespace st;
+
+typedef cuFloatComplex c32;
+typedef cuDoubleComplex c64;
+
+// ------------------------------------------------ kernels ------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ c32 warp_sum(c32 v) { return make_cuFloatComplex(warp_sum(v.x), warp_sum(v.y)); }
+__device__ __forceinline__ c64 warp_sum(c64 v) { return make_cuDoubleComplex(warp_sum(v.x), warp_sum(v.y)); }
+__device__ __forceinline__ float warp_bcast(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double warp_bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ c32 warp_bcast(c32 v, int src) { return make_cuFloatComplex(warp_bcast(v.x, src), warp_bcast(v.y, src)); }
+__device__ __forceinline__ c64 warp_bcast(c64 v, int src) { return make_cuDoubleComplex(warp_bcast(v.x, src), warp_bcast(v.y, src)); }
+
+// dst(i) = [conj] src(element i of the strided BLAS vector)
+template <typename T> __global__ void gather_kernel(int n, const T* __restrict__ src, int64_t inc, T* __restrict__ dst, bool conj) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T v = src[vpos(i, n, inc)];
+    dst[i] = conj ? el<T>::conj(v) : v;
+}
+template <typename T> __global__ void scatter_kernel(int n, const T* __restrict__ src, T* __restrict__ dst, int64_t inc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dst[vpos(i, n, inc)] = src[i];
+}
+// part[chunk][i] = N part of row i over the chunk's columns; rows [row0,row1), columns [c_lo,c_hi) cut into chunks of cpc
+template <typename T>
+__global__ void __launch_bounds__(128) npart_kernel(Desc D, const T* __restrict__ A, const T* __restrict__ v, int row0, int row1, int c_lo, int c_hi, int cpc,
+                                                    int flags, T* __restrict__ part, int64_t npad) {
+    const int i = row0 + blockIdx.x * 128 + threadIdx.x;
+    if (i >= row1) return;
+    const int c0 = c_lo + blockIdx.y * cpc, c1 = st_min(c_hi, c0 + cpc);
+    part[(int64_t)blockIdx.y * npad + i] = npart_row<T>(D, A, v, i, c0, c1, flags);
+}
+// tpart[j] = T part of column j over rows [r0,r1); one warp per column in [col0,col1)
+template <typename T>
+__global__ void __launch_bounds__(128) tpart_kernel(Desc D, const T* __restrict__ A, const T* __restrict__ v, int col0, int col1, int r0, int r1, int flags,
+                                                    T* __restrict__ tpart) {
+    const int j = col0 + blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= col1) return;   // whole warp
+    const T acc = warp_sum(tpart_lane<T>(D, A, v, j, lane, 32, r0, r1, flags));
+    if (lane == 0) tpart[j] = acc;
+}
+template <typename T>
+__global__ void smv_finish_kernel(int n, int nparts, const T* __restrict__ part, int64_t npad, const T* __restrict__ tpart, const T* __restrict__ vunit, T alpha,
+                                  T beta, T* __restrict__ out, int64_t inco) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T* p = out + vpos(i, n, inco);
+    const bool beta0 = el<T>::is_zero(beta);
+    *p = finish_elem<T>(i, nparts, part, npad, tpart, vunit, alpha, beta, beta0, beta0 ? el<T>::zero() : *p);
+}
+template <typename T>
+__global__ void __launch_bounds__(128) rank_kernel(Desc D, T* __restrict__ A, int rows, int ncols, int cpc, T alpha, const T* __restrict__ x, const T* __restrict__ y,
+                                                   int mode) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= rows) return;
+    const int c0 = blockIdx.y * cpc, c1 = st_min(ncols, c0 + cpc);
+    rank_row<T>(D, A, i, c0, c1, alpha, x, y, mode);
+}
+// x(i) -= N part of row i over the solved block's columns [b0,b1)      (rows [row0,row1) lie outside the block)
+template <typename T>
+__global__ void __launch_bounds__(128) solve_nupdate_kernel(Desc D, const T* __restrict__ A, T* x, int row0, int row1, int b0, int b1, int flags) {
+    const int i = row0 + blockIdx.x * 128 + threadIdx.x;
+    if (i >= row1) return;
+    x[i] = el<T>::sub(x[i], npart_row<T>(D, A, x, i, b0, b1, flags));
+}
+// x(j) -= T part of column j over the solved block's rows [b0,b1)      (columns [col0,col1) lie outside the block)
+template <typename T>
+__global__ void __launch_bounds__(128) solve_tupdate_kernel(Desc D, const T* __restrict__ A, T* x, int col0, int col1, int b0, int b1, int flags) {
+    const int j = col0 + blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= col1) return;
+    const T acc = warp_sum(tpart_lane<T>(D, A, x, j, lane, 32, b0, b1, flags));
+    if (lane == 0) x[j] = el<T>::sub(x[j], acc);
+}
+// One warp solves the nb <= 32 unknowns of a diagonal block of op(S): lane l owns x(b0+l).  The lane's row of
+// coefficients is loaded up front (independent loads, one memory latency) in elimination order; each step divides on
+// the pivot lane, broadcasts the solved unknown by shuffle and eliminates it from the lanes still waiting.
+template <typename T>
+__global__ void __launch_bounds__(32) solve_diag_kernel(Desc D, const T* __restrict__ A, T* x, int b0, int nb, bool trans, bool conj, bool unit, bool forward) {
+    const int lane = threadIdx.x, r = b0 + lane;
+    T coef[32];
+#pragma unroll
+    for (int step = 0; step < 32; step++) {
+        const int jj = forward ? step : nb - 1 - step;
+        coef[step] = el<T>::zero();
+        if (step < nb && lane < nb) {
+            const bool waiting = forward ? lane > jj : lane < jj;
+            T a;
+            if ((waiting || (lane == jj && !unit)) && solve_coef<T>(D, A, r, b0 + jj, trans, conj, a)) coef[step] = a;
+        }
+    }
+    T xv = lane < nb ? x[r] : el<T>::zero();
+#pragma unroll
+    for (int step = 0; step < 32; step++) {
+        if (step < nb) {   // uniform across the warp
+            const int jj = forward ? step : nb - 1 - step;
+            if (lane == jj && !unit) xv = el<T>::div(xv, coef[step]);
+            const T xj = warp_bcast(xv, jj);
+            const bool waiting = forward ? (lane > jj && lane < nb) : lane < jj;
+            if (waiting) xv = el<T>::sub(xv, el<T>::mul(coef[step], xj));
+        }
+    }
+    if (lane < nb) x[r] = xv;
+}
+
+// ------------------------------------------------ the device backend of the plans ------------------------------------------------
+struct DeviceBackend {
+    cudaStream_t s;
+    explicit DeviceBackend(cudaStream_t st) : s(st) {}
+    void* alloc(size_t bytes) { return ws_alloc(bytes); }
+    int sm_target() const { return (sm_count() > 0 ? sm_count() : 148) * 8; }
+    template <typename T> void gather(int n, const T* src, int64_t inc, T* dst, bool conj) { gather_kernel<T><<<(n + 255) / 256, 256, 0, s>>>(n, src, inc, dst, conj); }
+    template <typename T> void scatter(int n, const T* src, T* dst, int64_t inc) { scatter_kernel<T><<<(n + 255) / 256, 256, 0, s>>>(n, src, dst, inc); }
+    template <typename T>
+    void npart(const Desc& D, const T* A, const T* v, int row0, int row1, int c_lo, int c_hi, int cpc, int nchunks, int flags, T* part, int64_t npad) {
+        npart_kernel<T><<<dim3((row1 - row0 + 127) / 128, nchunks), 128, 0, s>>>(D, A, v, row0, row1, c_lo, c_hi, cpc, flags, part, npad);
+    }
+    template <typename T> void tpart(const Desc& D, const T* A, const T* v, int col0, int col1, int r0, int r1, int flags, T* tp) {
+        tpart_kernel<T><<<(col1 - col0 + 3) / 4, 128, 0, s>>>(D, A, v, col0, col1, r0, r1, flags, tp);
+    }
+    template <typename T>
+    void finish(int n, int nparts, const T* part, int64_t npad, const T* tp, const T* vunit, T alpha, T beta, T* out, int64_t inco) {
+        smv_finish_kernel<T><<<(n + 255) / 256, 256, 0, s>>>(n, nparts, part, npad, tp, vunit, alpha, beta, out, inco);
+        last_variant = VAR_GENERIC_TILE;
+    }
+    template <typename T> void rank(const Desc& D, T* A, int rows, int ncols, int cpc, int nchunks, T alpha, const T* x, const T* y, int mode) {
+        rank_kernel<T><<<dim3((rows + 127) / 128, nchunks), 128, 0, s>>>(D, A, rows, ncols, cpc, alpha, x, y, mode);
+        last_variant = VAR_GENERIC_TILE;
+    }
+    template <typename T> void solve_diag(const Desc& D, const T* A, T* x, int b0, int nb, bool trans, bool conj, bool unit, bool forward) {
+        solve_diag_kernel<T><<<1, 32, 0, s>>>(D, A, x, b0, nb, trans, conj, unit, forward);
+        last_variant = VAR_GENERIC_TILE;
+    }
+    template <typename T> void solve_nupdate(const Desc& D, const T* A, T* x, int row0, int row1, int b0, int b1, int flags) {
+        solve_nupdate_kernel<T><<<(row1 - row0 + 127) / 128, 128, 0, s>>>(D, A, x, row0, row1, b0, b1, flags);
+    }
+    template <typename T> void solve_tupdate(const Desc& D, const T* A, T* x, int col0, int col1, int b0, int b1, int flags) {
+        solve_tupdate_kernel<T><<<(col1 - col0 + 3) / 4, 128, 0, s>>>(D, A, x, col0, col1, b0, b1, flags);
+    }
+};
+
+}  // namespace b200
+
+using namespace b200;
+
+namespace {
+
+struct Vec : Operand {   // BLAS vector of n elements with increment inc: 1+(n-1)|inc| elements from the pointer
+    Vec(const void* p, int64_t n, int64_t inc, size_t elem, int access)
+        : Operand(p, n > 0 ? 1 + (n - 1) * (inc < 0 ? -inc : inc) : 0, 1, n > 0 ? 1 + (n - 1) * (inc < 0 ? -inc : inc) : 1, elem, access) {}
+};
+inline char trans_code(const char* trans) { return lsame(trans, 'N') ? 'N' : (lsame(trans, 'T') ? 'T' : (lsame(trans, 'C') ? 'C' : '?')); }
+
+// ---- GBMV: netlib info 1,2,3,4,5,8,10,13 ----
+template <typename T>
+void gbmv_entry(const char* name, bool rowmajor, const char* trans, int m, int n, int kl, int ku, const T* alpha, const T* a, int lda, const T* x, int incx,
+                const T* beta, T* y, int incy) {
+    const char op = trans_code(trans);
+    int info = 0;
+    if (op == '?') info = 1; else if (m < 0) info = 2; else if (n < 0) info = 3; else if (kl < 0) info = 4; else if (ku < 0) info = 5;
+    else if (lda < kl + ku + 1) info = 8; else if (incx == 0) info = 10; else if (incy == 0) info = 13;
+    if (info) { call_xerbla(name, info); return; }
+    if (m == 0 || n == 0 || (is0(*alpha) && is1(*beta))) return;
+    const int lenx = op == 'N' ? n : m, leny = op == 'N' ? m : n;
+    CallScope scope(name);
+    const bool a0 = is0(*alpha);   // netlib: A and x are not referenced
+    Operand oa(a0 ? nullptr : a, kl + ku + 1, rowmajor ? m : n, lda, sizeof(T), ACC_IN);
+    Vec ox(a0 ? nullptr : x, lenx, incx, sizeof(T), ACC_IN), oy(y, leny, incy, sizeof(T), ACC_INOUT);
+    DeviceBackend be(current_stream());
+    plan_gbmv<T>(be, rowmajor, op, m, n, kl, ku, *alpha, (const T*)oa.dev(), oa.ld(), (const T*)ox.dev(), incx, *beta, (T*)oy.dev(), incy);
+    oy.release();
+    log_exec(name, "%c%s m=%d n=%d kl=%d ku=%d lda=%d", op, rowmajor ? " row-major" : "", m, n, kl, ku, lda);
+}
+
+// ---- symmetric / Hermitian matrix-vector products: SBMV/HBMV (info 1,2,3,6,8,11), SPMV/HPMV (1,2,6,9), HEMV (1,2,5,7,10) ----
+template <typename T>
+void symv_like_entry(const char* name, int kind, bool herm, bool rowmajor, const char* uplo, int n, int k, const T* alpha, const T* a, int lda, const T* x,
+                     int incx, const T* beta, T* y, int incy) {
+    const bool upper = lsame(uplo, 'U');
+    int info = 0;
+    if (!upper && !lsame(uplo, 'L')) info = 1; else if (n < 0) info = 2;
+    else if (kind == K_BAND_TRI) { if (k < 0) info = 3; else if (lda < k + 1) info = 6; else if (incx == 0) info = 8; else if (incy == 0) info = 11; }
+    else if (kind == K_PACKED) { if (incx == 0) info = 6; else if (incy == 0) info = 9; }
+    else { if (lda < imax(1, n)) info = 5; else if (incx == 0) info = 7; else if (incy == 0) info = 10; }
+    if (info) { call_xerbla(name, info); return; }
+    if (n == 0 || (is0(*alpha) && is1(*beta))) return;
+    CallScope scope(name);
+    const bool a0 = is0(*alpha);
+    const int64_t arows = kind == K_BAND_TRI ? k + 1 : (kind == K_PACKED ? packed_len(n) : n), acols = kind == K_PACKED ? 1 : n;
+    Operand oa(a0 ? nullptr : a, arows, acols, kind == K_PACKED ? packed_len(n) : lda, sizeof(T), ACC_IN);
+    Vec ox(a0 ? nullptr : x, n, incx, sizeof(T), ACC_IN), oy(y, n, incy, sizeof(T), ACC_INOUT);
+    DeviceBackend be(current_stream());
+    plan_symv_like<T>(be, kind, herm, rowmajor, upper, n, k, *alpha, (const T*)oa.dev(), oa.ld(), (const T*)ox.dev(), incx, *beta, (T*)oy.dev(), incy);
+    oy.release();
+    log_exec(name, "%c%s n=%d k=%d", upper ? 'U' : 'L', rowmajor ? " row-major" : "", n, k);
+}
+
+// ---- triangular products and solves: TBMV/TBSV (info 1,2,3,4,5,7,9), TPMV/TPSV (1,2,3,4,7), TRMV (1,2,3,4,6,8) ----
+template <typename T>
+void tri_entry(const char* name, int kind, bool solve, bool rowmajor, const char* uplo, const char* trans, const char* diag, int n, int k, const T* a, int lda,
+               T* x, int incx) {
+    const bool upper = lsame(uplo, 'U'), unit = lsame(diag, 'U');
+    const char op = trans_code(trans);
+    int info = 0;
+    if (!upper && !lsame(uplo, 'L')) info = 1; else if (op == '?') info = 2; else if (!unit && !lsame(diag, 'N')) info = 3;
+    else if (n < 0) info = 4;
+    else if (kind == K_BAND_TRI) { if (k < 0) info = 5; else if (lda < k + 1) info = 7; else if (incx == 0) info = 9; }
+    else if (kind == K_PACKED) { if (incx == 0) info = 7; }
+    else { if (lda < imax(1, n)) info = 6; else if (incx == 0) info = 8; }
+    if (info) { call_xerbla(name, info); return; }
+    if (n == 0) return;
+    CallScope scope(name);
+    const int64_t arows = kind == K_BAND_TRI ? k + 1 : (kind == K_PACKED ? packed_len(n) : n), acols = kind == K_PACKED ? 1 : n;
+    Operand oa(a, arows, acols, kind == K_PACKED ? packed_len(n) : lda, sizeof(T), ACC_IN);
+    Vec ox(x, n, incx, sizeof(T), ACC_INOUT);
+    DeviceBackend be(current_stream());
+    plan_tri<T>(be, kind, solve, rowmajor, upper, op, unit, n, k, (const T*)oa.dev(), oa.ld(), (T*)ox.dev(), incx);
+    ox.release();
+    log_exec(name, "%c%c%c%s n=%d k=%d", upper ? 'U' : 'L', op, unit ? 'U' : 'N', rowmajor ? " row-major" : "", n, k);
+}
+
+// ---- GERU / GERC: netlib info 1,2,5,7,9 ----
+template <typename T>
+void gerx_entry(const char* name, bool conjy, bool rowmajor, int m, int n, const T* alpha, const T* x, int incx, const T* y, int incy, T* a, int lda) {
+    int info = 0;
+    if (m < 0) info = 1; else if (n < 0) info = 2; else if (incx == 0) info = 5; else if (incy == 0) info = 7;
+    else if (lda < imax(1, rowmajor ? n : m)) info = 9;
+    if (info) { call_xerbla(name, info); return; }
+    if (m == 0 || n == 0 || is0(*alpha)) return;
+    CallScope scope(name);
+    Vec ox(x, m, incx, sizeof(T), ACC_IN), oy(y, n, incy, sizeof(T), ACC_IN);
+    Operand oa(a, rowmajor ? n : m, rowmajor ? m : n, lda, sizeof(T), ACC_INOUT);
+    DeviceBackend be(current_stream());
+    plan_ger<T>(be, conjy, rowmajor, m, n, *alpha, (const T*)ox.dev(), incx, (const T*)oy.dev(), incy, (T*)oa.dev(), oa.ld());
+    oa.release();
+    log_exec(name, "m=%d n=%d lda=%d%s", m, n, lda, rowmajor ? " row-major" : "");
+}
+
+// ---- symmetric / Hermitian rank-1 and rank-2 updates ----
+// full storage: HER (info 1,2,5,7), HER2 / SYR2 (1,2,5,7,9); packed: SPR / HPR (1,2,5), SPR2 / HPR2 (1,2,5,7)
+template <typename T>
+void rank_sym_entry(const char* name, int kind, int mode, bool rowmajor, const char* uplo, int n, T alpha, const T* x, int incx, const T* y, int incy, T* a,
+                    int lda) {
+    const bool upper = lsame(uplo, 'U');
+    const bool two = mode == R_SYR2 || mode == R_HER2;
+    int info = 0;
+    if (!upper && !lsame(uplo, 'L')) info = 1; else if (n < 0) info = 2; else if (incx == 0) info = 5;
+    else if (two && incy == 0) info = 7;
+    else if (kind == K_FULL_TRI && lda < imax(1, n)) info = two ? 9 : 7;
+    if (info) { call_xerbla(name, info); return; }
+    if (n == 0 || is0(alpha)) return;
+    CallScope scope(name);
+    Vec ox(x, n, incx, sizeof(T), ACC_IN), oy(two ? y : nullptr, n, incy, sizeof(T), ACC_IN);
+    const int64_t arows = kind == K_PACKED ? packed_len(n) : n, acols = kind == K_PACKED ? 1 : n;
+    Operand oa(a, arows, acols, kind == K_PACKED ? packed_len(n) : lda, sizeof(T), ACC_INOUT);
+    DeviceBackend be(current_stream());
+    plan_rank_sym<T>(be, kind, mode, rowmajor, upper, n, alpha, (const T*)ox.dev(), incx, (const T*)oy.dev(), incy, (T*)oa.dev(), oa.ld());
+    oa.release();
+    log_exec(name, "%c%s n=%d", upper ? 'U' : 'L', rowmajor ? " row-major" : "", n);
+}
+
+// ---- CBLAS row-major complex GEMV with ConjTrans: y = alpha*conj(S)*x + beta*y on the column-major m x n view S = A^T ----
+template <typename T>
+void gemv_conj_notrans(const char* name, int m, int n, const T* alpha, const T* a, int lda, const T* x, int incx, const T* beta, T* y, int incy) {
+    CallScope scope(name);   // the caller has validated the arguments
+    Operand oa(a, m, n, lda, sizeof(T), ACC_IN);
+    Vec ox(x, n, incx, sizeof(T), ACC_IN), oy(y, m, incy, sizeof(T), ACC_INOUT);
+    DeviceBackend be(current_stream());
+    plan_gemv_conj<T>(be, m, n, *alpha, (const T*)oa.dev(), oa.ld(), (const T*)ox.dev(), incx, *beta, (T*)oy.dev(), incy);
+    oy.release();
+    log_exec(name, "R m=%d n=%d lda=%d", m, n, lda);
+}
+
+inline const char* uplo_c(enum CBLAS_UPLO u) { return u == CblasUpper ? "U" : (u == CblasLower ? "L" : "?"); }
+inline const char* trans_c(enum CBLAS_TRANSPOSE t) { return t == CblasNoTrans ? "N" : (t == CblasTrans ? "T" : (t == CblasConjTrans ? "C" : "?")); }
+inline const char* diag_c(enum CBLAS_DIAG d) { return d == CblasUnit ? "U" : (d == CblasNonUnit ? "N" : "?"); }
+inline bool rm(enum CBLAS_ORDER o) { return o == CblasRowMajor; }
+inline c32 mkc(float r) { return make_cuFloatComplex(r, 0.f); }
+inline c64 mkc(double r) { return make_cuDoubleComplex(r, 0.0); }
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------- real + complex families with identical signatures -------------------------------
+#define B200_GBMV(P, T, CT, SC)                                                                                                                        \
+    void P##gbmv_(const char* trans, const int* m, const int* n, const int* kl, const int* ku, const T* alpha, const T* a, const int* lda, const T* x,  \
+                  const int* incx, const T* beta, T* y, const int* incy) {                                                                              \
+        gbmv_entry<CT>(#P "gbmv_", false, trans, *m, *n, *kl, *ku, (const CT*)alpha, (const CT*)a, *lda, (const CT*)x, *incx, (const CT*)beta, (CT*)y, *incy); } \
+    void P##tbmv_(const char* uplo, const char* trans, const char* diag, const int* n, const int* k, const T* a, const int* lda, T* x, const int* incx) { \
+        tri_entry<CT>(#P "tbmv_", K_BAND_TRI, false, false, uplo, trans, diag, *n, *k, (const CT*)a, *lda, (CT*)x, *incx); }                            \
+    void P##tbsv_(const char* uplo, const char* trans, const char* diag, const int* n, const int* k, const T* a, const int* lda, T* x, const int* incx) { \
+        tri_entry<CT>(#P "tbsv_", K_BAND_TRI, true, false, uplo, trans, diag, *n, *k, (const CT*)a, *lda, (CT*)x, *incx); }                             \
+    void P##tpmv_(const char* uplo, const char* trans, const char* diag, const int* n, const T* ap, T* x, const int* incx) {                           \
+        tri_entry<CT>(#P "tpmv_", K_PACKED, false, false, uplo, trans, diag, *n, 0, (const CT*)ap, 1, (CT*)x, *incx); }                                 \
+    void P##tpsv_(const char* uplo, const char* trans, const char* diag, const int* n, const T* ap, T* x, const int* incx) {                           \
+        tri_entry<CT>(#P "tpsv_", K_PACKED, true, false, uplo, trans, diag, *n, 0, (const CT*)ap, 1, (CT*)x, *incx); }                                  \
+    void cblas_##P##tbmv(enum CBLAS_ORDER o, enum CBLAS_UPLO u, enum CBLAS_TRANSPOSE t, enum CBLAS_DIAG d, int n, int k, const SC* a, int lda, SC* x, int incx) { \
+        tri_entry<CT>(#P "tbmv_", K_BAND_TRI, false, rm(o), uplo_c(u), trans_c(t), diag_c(d), n, k, (const CT*)a, lda, (CT*)x, incx); }                 \
+    void cblas_##P##tbsv(enum CBLAS_ORDER o, enum CBLAS_UPLO u, enum CBLAS_TRANSPOSE t, enum CBLAS_DIAG d, int n, int k, const SC* a, int lda, SC* x, int incx) { \
+        tri_entry<CT>(#P "tbsv_", K_BAND_TRI, true, rm(o), uplo_c(u), trans_c(t), diag_c(d), n, k, (const CT*)a, lda, (CT*)x, incx); }                  \
+    void cblas_##P##tpmv(enum CBLAS_ORDER o, enum CBLAS_UPLO u, enum CBLAS_TRANSPOSE t, enum CBLAS_DIAG d, int n, const SC* ap, SC* x, int incx) {      \
+        tri_entry<CT>(#P "tpmv_", K_PACKED, false, rm(o), uplo_c(u), trans_c(t), diag_c(d), n, 0, (const CT*)ap, 1, (CT*)x, incx); }                    \
+    void cblas_##P##tpsv(enum CBLAS_ORDER o, enum CBLAS_UPLO u, enum CBLAS_TRANSPOSE t, enum CBLAS_DIAG d, int n, const SC* ap, SC* x, int incx) {      \
+        tri_entry<CT>(#P "tpsv_", K_PACKED, true, rm(o), uplo_c(u), trans_c(t), diag_c(d), n, 0, (const CT*)ap, 1, (CT*)x, incx); }
+B200_GBMV(s, float, float, float)
+B200_GBMV(d, double, double, double)
+B200_GBMV(c, b200_c32, c32, void)
+B200_GBMV(z, b200_c64, c64, void)
+#undef B200_GBMV
+
+void cblas_sgbmv(enum CBLAS_ORDER o, enum CBLAS_TRANSPOSE t, int m, int n, int kl, int ku, float alpha, const float* a, int lda, const float* x, int incx, float beta,
+                 float* y, int incy) { gbmv_entry<float>("sgbmv_", rm(o), trans_c(t), m, n, kl, ku, &alpha, a, lda, x, incx, &beta, y, incy); }
+void cblas_dgbmv(enum CBLAS_ORDER o, enum CBLAS_TRANSPOSE t, int m, int n, int kl, int ku, double alpha, const double* a, int lda, const double* x, int incx,
+                 double beta, double* y, int incy) { gbmv_entry<double>("dgbmv_", rm(o), trans_c(t), m, n, kl, ku, &alpha, a, lda, x, incx, &beta, y, incy); }
+void cblas_cgbmv(enum CBLAS_ORDER o, enum CBLAS_TRANSPOSE t, int m, int n, int kl, int ku, const void* alpha, const void* a, int lda, const void* x, int incx,
+                 const void* beta, void* y, int incy) {
+    gbmv_entry<c32>("cgbmv_", rm(o), trans_c(t), m, n, kl, ku, (const c32*)alpha, (const c32*)a, lda, (const c32*)x, incx, (const c32*)beta, (c32*)y, incy); }
+void cblas_zgbmv(enum CBLAS_ORDER o, enum CBLAS_TRANSPOSE t, int m, int n, int kl, int ku, const void* alpha, const void* a, int lda, const void* x, int incx,
+                 const void* beta, void* y, int incy) {
+    gbmv_entry<c64>("zgbmv_", rm(o), trans_c(t), m, n, kl, ku, (const c64*)alpha, (const c64*)a, lda, (const c64*)x, incx, (const c64*)beta, (c64*)y, incy); }
+
+// ------------------------------- real symmetric: SBMV, SPMV, SYR2, SPR, SPR2 -------------------------------
+#define B200_REALSYM(P, T)                                                                                                                              \
+    void P##sbmv_(const char* uplo, const int* n, const int* k, const T* alpha, const T* a, const int* lda, const T* x, const int* incx, const T* beta, T* y, \
+                  const int* incy) { symv_like_entry<T>(#P "sbmv_", K_BAND_TRI, false, false, uplo, *n, *k, alpha, a, *lda, x, *incx, beta, y, *incy); } \
+    void P##spmv_(const char* uplo, const int* n, const T* alpha, const T* ap, const T* x, const int* incx, const T* beta, T* y, const int* incy) {      \
+        symv_like_entry<T>(#P "spmv_", K_PACKED, false, false, uplo, *n, 0, alpha, ap, 1, x, *incx, beta, y, *incy); }                                   \
+    void P##syr2_(const char* uplo, const int* n, const T* alpha, const T* x, const int* incx, const T* y, const int* incy, T* a, const int* lda) {      \
+        rank_sym_entry<T>(#P "syr2_", K_FULL_TRI, R_SYR2, false, uplo, *n, *alpha, x, *incx, y, *incy, a, *lda); }                                       \
+    void P##spr_(const char* uplo, const int* n, const T* alpha, const T* x, const int* incx, T* ap) {                                                   \
+        rank_sym_entry<T>(#P "spr_", K_PACKED, R_SYR, false, uplo, *n, *alpha, x, *incx, nullptr, 1, ap, 1); }                                           \
+    void P##spr2_(const char* uplo, const int* n, const T* alpha, const T* x, const int* incx, const T* y, const int* incy, T* ap) {                     \
+        rank_sym_entry<T>(#P "spr2_", K_PACKED, R_SYR2, false, uplo, *n, *alpha, x, *incx, y, *incy, ap, 1); }                                           \
+    void cblas_##P##sbmv(enum CBLAS_ORDER o, enum CBLAS_UPLO u, int n, int k, T alpha, const T* a, int lda, const T* x, int incx, T beta, T* y, int incy) { \
+        symv_like_entry<T>(#P "sbmv_", K_BAND_TRI, false, rm(o), uplo_c(u), n, k, &alpha, a, lda, x, incx, &beta, y, incy); }                            \
+    void cblas_##P##spmv(enum CBLAS_ORDER o, enum CBLAS_UPLO u, int n, T alpha, const T* ap, const T* x, int incx, T beta, T* y, int incy) {             \
+        symv_like_entry<T>(#P "spmv_", K_PACKED, false, rm(o), uplo_c(u), n, 0, &alpha, ap, 1, x, incx, &beta, y, incy); }                               \
+    void cblas_##P##syr2(enum CBLAS_ORDER o, enum CBLAS_UPLO u, int n, T alpha, const T* x, int incx, const T* y, int incy, T* a, int lda) {             \
+        rank_sym_entry<T>(#P "syr2_", K_FULL_TRI, R_SYR2, rm(o), uplo_c(u), n, alpha, x, incx, y, incy, a, lda); }                                       \
+    void cblas_##P##spr(enum CBLAS_ORDER o, enum CBLAS_UPLO u, int n, T alpha, const T* x, int incx, T* ap) {                                            \
+        rank_sym_entry<T>(#P "spr_", K_PACKED, R_SYR, rm(o), uplo_c(u), n, alpha, x, incx, nullptr, 1, ap, 1); }                                         \
+    void cblas_##P##spr2(enum CBLAS_ORDER o, enum CBLAS_UPLO u, int n, T alpha, const T* x, int incx, const T* y, int incy, T* ap) {                     \
+        rank_sym_entry<T>(#P "spr2_", K_PACKED, R_SYR2, rm(o), uplo_c(u), n, alpha, x, incx, y, incy, ap, 1); }
+B200_REALSYM(s, float)
+B200_REALSYM(d, double)
+#undef B200_REALSYM
+
+// ------------------------------- complex: HBMV, HPMV, HEMV, GERU, GERC, HER, HER2, HPR, HPR2, TRMV -------------------------------
+#define B200_CPLX(P, T, CT, RT)                                                                                                                         \
+    void P##hbmv_(const char* uplo, const int* n, const int* k, const T* alpha, const T* a, const int* lda, const T* x, const int* incx, const T* beta, T* y, \
+                  const int* incy) {                                                                                                                     \
+        symv_like_entry<CT>(#P "hbmv_", K_BAND_TRI, true, false, uplo, *n, *k, (const CT*)alpha, (const CT*)a, *lda, (const CT*)x, *incx, (const CT*)beta, (CT*)y, *incy); } \
+    void P##hpmv_(const char* uplo, const int* n, const T* alpha, const T* ap, const T* x, const int* incx, const T* beta, T* y, const int* incy) {      \
+        symv_like_entry<CT>(#P "hpmv_", K_PACKED, true, false, uplo, *n, 0, (const CT*)alpha, (const CT*)ap, 1, (const CT*)x, *incx, (const CT*)beta, (CT*)y, *incy); } \
+    void P##hemv_(const char* uplo, const int* n, const T* alpha, const T* a, const int* lda, const T* x, const int* incx, const T* beta, T* y, const int* incy) { \
+        symv_like_entry<CT>(#P "hemv_", K_FULL_TRI, true, false, uplo, *n, 0, (const CT*)alpha, (const CT*)a, *lda, (const CT*)x, *incx, (const CT*)beta, (CT*)y, *incy); } \
+    void P##geru_(const int* m, const int* n, const T* alpha, const T* x, const int* incx, const T* y, const int* incy, T* a, const int* lda) {          \
+        gerx_entry<CT>(#P "geru_", false, false, *m, *n, (const CT*)alpha, (const CT*)x, *incx, (const CT*)y, *incy, (CT*)a, *lda); }                    \
+    void P##gerc_(const int* m, const int* n, const T* alpha, const T* x, const int* incx, const T* y, const int* incy, T* a, const int* lda) {          \
+        gerx_entry<CT>(#P "gerc_", true, false, *m, *n, (const CT*)alpha, (const CT*)x, *incx, (const CT*)y, *incy, (CT*)a, *lda); }                     \
+    void P##her_(const char* uplo, const int* n, const RT* alpha, const T* x, const int* incx, T* a, const int* lda) {                                   \
+        rank_sym_entry<CT>(#P "her_", K_FULL_TRI, R_HER, false, uplo, *n, mkc(*alpha), (const CT*)x, *incx, nullptr, 1, (CT*)a, *lda); }                 \
+    void P##her2_(const char* uplo, const int* n, const T* alpha, const T* x, const int* incx, const T* y, const int* incy, T* a, const int* lda) {      \
+        rank_sym_entry<CT>(#P "her2_", K_FULL_TRI, R_HER2, false, uplo, *n, *(const CT*)alpha, (const CT*)x, *incx, (const CT*)y, *incy, (CT*)a, *lda); } \
+    void P##hpr_(const char* uplo, const int* n, const RT* alpha, const T* x, const int* incx, T* ap) {                                                  \
+        rank_sym_entry<CT>(#P "hpr_", K_PACKED, R_HER, false, uplo, *n, mkc(*alpha), (const CT*)x, *incx, nullptr, 1, (CT*)ap, 1); }                     \
+    void P##hpr2_(const char* uplo, const int* n, const T* alpha, const T* x, const int* incx, const T* y, const int* incy, T* ap) {                     \
+        rank_sym_entry<CT>(#P "hpr2_", K_PACKED, R_HER2, false, uplo, *n, *(const CT*)alpha, (const CT*)x, *incx, (const CT*)y, *incy, (CT*)ap, 1); }    \
+    void P##trmv_(const char* uplo, const char* trans, const char* diag, const int* n, const T* a, const int* lda, T* x, const int* incx) {              \
+        tri_entry<CT>(#P "trmv_", K_FULL_TRI, false, false, uplo, trans, diag, *n, 0, (const CT*)a, *lda, (CT*)x, *incx); }                              \
+    void cblas_##P##hbmv(enum CBLAS_ORDER o, enum CBLAS_UPLO u, int n, int k, const void* alpha, const void* a, int lda, const void* x, int incx,        \
+                         const void* beta, void* y, int incy) {                                                                                          \
+        symv_like_entry<CT>(#P "hbmv_", K_BAND_TRI, true, rm(o), uplo_c(u), n, k, (const CT*)alpha, (const CT*)a, lda, (const CT*)x, incx, (const CT*)beta, (CT*)y, incy); } \
+    void cblas_##P##hpmv(enum CBLAS_ORDER o, enum CBLAS_UPLO u, int n, const void* alpha, const void* ap, const void* x, int incx, const void* beta,     \
+                         void* y, int incy) {                                                                                                            \
+        symv_like_entry<CT>(#P "hpmv_", K_PACKED, true, rm(o), uplo_c(u), n, 0, (const CT*)alpha, (const CT*)ap, 1, (const CT*)x, incx, (const CT*)beta, (CT*)y, incy); } \
+    void cblas_##P##hemv(enum CBLAS_ORDER o, enum CBLAS_UPLO u, int n, const void* alpha, const void* a, int lda, const void* x, int incx,               \
+                         const void* beta, void* y, int incy) {                                                                                          \
+        symv_like_entry<CT>(#P "hemv_", K_FULL_TRI, true, rm(o), uplo_c(u), n, 0, (const CT*)alpha, (const CT*)a, lda, (const CT*)x, incx, (const CT*)beta, (CT*)y, incy); } \
+    void cblas_##P##geru(enum CBLAS_ORDER o, int m, int n, const void* alpha, const void* x, int incx, const void* y, int incy, void* a, int lda) {      \
+        gerx_entry<CT>(#P "geru_", false, rm(o), m, n, (const CT*)alpha, (const CT*)x, incx, (const CT*)y, incy, (CT*)a, lda); }                         \
+    void cblas_##P##gerc(enum CBLAS_ORDER o, int m, int n, const void* alpha, const void* x, int incx, const void* y, int incy, void* a, int lda) {      \
+        gerx_entry<CT>(#P "gerc_", true, rm(o), m, n, (const CT*)alpha, (const CT*)x, incx, (const CT*)y, incy, (CT*)a, lda); }                          \
+    void cblas_##P##her(enum CBLAS_ORDER o, enum CBLAS_UPLO u, int n, RT alpha, const void* x, int incx, void* a, int lda) {                             \
+        rank_sym_entry<CT>(#P "her_", K_FULL_TRI, R_HER, rm(o), uplo_c(u), n, mkc(alpha), (const CT*)x, incx, nullptr, 1, (CT*)a, lda); }                \
+    void cblas_##P##her2(enum CBLAS_ORDER o, enum CBLAS_UPLO u, int n, const void* alpha, const void* x, int incx, const void* y, int incy, void* a, int lda) { \
+        rank_sym_entry<CT>(#P "her2_", K_FULL_TRI, R_HER2, rm(o), uplo_c(u), n, *(const CT*)alpha, (const CT*)x, incx, (const CT*)y, incy, (CT*)a, lda); } \
+    void cblas_##P##hpr(enum CBLAS_ORDER o, enum CBLAS_UPLO u, int n, RT alpha, const void* x, int incx, void* ap) {                                     \
+        rank_sym_entry<CT>(#P "hpr_", K_PACKED, R_HER, rm(o), uplo_c(u), n, mkc(alpha), (const CT*)x, incx, nullptr, 1, (CT*)ap, 1); }                   \
+    void cblas_##P##hpr2(enum CBLAS_ORDER o, enum CBLAS_UPLO u, int n, const void* alpha, const void* x, int incx, const void* y, int incy, void* ap) {  \
+        rank_sym_entry<CT>(#P "hpr2_", K_PACKED, R_HER2, rm(o), uplo_c(u), n, *(const CT*)alpha, (const CT*)x, incx, (const CT*)y, incy, (CT*)ap, 1); }  \
+    void cblas_##P##trmv(enum CBLAS_ORDER o, enum CBLAS_UPLO u, enum CBLAS_TRANSPOSE t, enum CBLAS_DIAG d, int n, const void* a, int lda, void* x, int incx) { \
+        tri_entry<CT>(#P "trmv_", K_FULL_TRI, false, rm(o), uplo_c(u), trans_c(t), diag_c(d), n, 0, (const CT*)a, lda, (CT*)x, incx); }                  \
+    /* column-major: the blocked TRSV of level2.cu; row-major (uplo flipped, ConjTrans as conjugate-no-transpose): the block solve above */                \
+    void cblas_##P##trsv(enum CBLAS_ORDER o, enum CBLAS_UPLO u, enum CBLAS_TRANSPOSE t, enum CBLAS_DIAG d, int n, const void* a, int lda, void* x, int incx) { \
+        if (!rm(o)) P##trsv_(uplo_c(u), trans_c(t), diag_c(d), &n, (const T*)a, &lda, (T*)x, &incx);                                                     \
+        else tri_entry<CT>(#P "trsv_", K_FULL_TRI, true, true, uplo_c(u), trans_c(t), diag_c(d), n, 0, (const CT*)a, lda, (CT*)x, incx); }               \
+    void cblas_##P##gemv(enum CBLAS_ORDER o, enum CBLAS_TRANSPOSE t, int m, int n, const void* alpha, const void* a, int lda, const void* x, int incx,   \
+                         const void* beta, void* y, int incy) {                                                                                          \
+        const char* tc = trans_c(t);                                                                                                                     \
+        if (!rm(o)) { P##gemv_(tc, &m, &n, (const T*)alpha, (const T*)a, &lda, (const T*)x, &incx, (const T*)beta, (T*)y, &incy); return; }             \
+        if (*tc != 'C') { const char* t2 = *tc == 'N' ? "T" : (*tc == 'T' ? "N" : "?");                                                                  \
+            P##gemv_(t2, &n, &m, (const T*)alpha, (const T*)a, &lda, (const T*)x, &incx, (const T*)beta, (T*)y, &incy); return; }                        \
+        /* row-major A^H x: conj(S) x on the column-major n x m view S; netlib xGEMV checks in the view's terms (info 2,3,6,8,11) */                       \
+        int info = 0;                                                                                                                                    \
+        if (n < 0) info = 2; else if (m < 0) info = 3; else if (lda < imax(1, n)) info = 6; else if (incx == 0) info = 8; else if (incy == 0) info = 11; \
+        if (info) { call_xerbla(#P "gemv_", info); return; }                                                                                             \
+        const CT al = *(const CT*)alpha, be = *(const CT*)beta;                                                                                          \
+        if (m == 0 || n == 0 || (is0(al) && is1(be))) return;                                                                                            \
+        if (is0(al)) { P##gemv_("N", &n, &m, (const T*)alpha, (const T*)a, &lda, (const T*)x, &incx, (const T*)beta, (T*)y, &incy); return; }           \
+        gemv_conj_notrans<CT>(#P "gemv_", n, m, &al, (const CT*)a, lda, (const CT*)x, incx, &be, (CT*)y, incy); }
+B200_CPLX(c, b200_c32, c32, float)
+B200_CPLX(z, b200_c64, c64, double)
+#undef B200_CPLX
+
+}  // extern "C"

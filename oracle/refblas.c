@@ -46,6 +46,7 @@ static int ref_lsame(char a, char b)
 #define R(name) ref_d##name
 #define RI(name) ref_id##name
 #include "refblas_real.inc"
+#include "refblas_l2x.inc"
 #undef T
 #undef R
 #undef RI
@@ -54,6 +55,7 @@ static int ref_lsame(char a, char b)
 #define R(name) ref_s##name
 #define RI(name) ref_is##name
 #include "refblas_real.inc"
+#include "refblas_l2x.inc"
 #undef T
 #undef R
 #undef RI
@@ -63,6 +65,9 @@ static int ref_lsame(char a, char b)
 #define R(name) ref_z##name
 #define RI(name) ref_iz##name
 #include "refblas_cplx.inc"
+#define L2X_COMPLEX 1
+#include "refblas_l2x.inc"
+#undef L2X_COMPLEX
 #undef T
 #undef RT
 #undef R
@@ -73,10 +78,25 @@ static int ref_lsame(char a, char b)
 #define R(name) ref_c##name
 #define RI(name) ref_ic##name
 #include "refblas_cplx.inc"
+#define L2X_COMPLEX 1
+#include "refblas_l2x.inc"
+#undef L2X_COMPLEX
 #undef T
 #undef RT
 #undef R
 #undef RI
+
+/* netlib DSDOT / SDSDOT (reference cblas.h declares cblas_dsdot / cblas_sdsdot): float operands, double accumulation */
+double ref_dsdot(int n, const float *x, int incx, const float *y, int incy)
+{
+    double s = 0;
+    for (int i = 0; i < n; i++) {
+        size_t ix = incx > 0 ? (size_t)i * incx : (size_t)(n - 1 - i) * (-incx), iy = incy > 0 ? (size_t)i * incy : (size_t)(n - 1 - i) * (-incy);
+        s += (double)x[ix] * (double)y[iy];
+    }
+    return s;
+}
+float ref_sdsdot(int n, float sb, const float *x, int incx, const float *y, int incy) { return (float)((double)sb + ref_dsdot(n, x, incx, y, incy)); }
 
 /* reference runtime-blas.c:38-52 func_name_to_f77: "dgemm_" -> "DGEMM " (upper-case,
  * '_' -> ' '); out must hold strlen(name)+1 bytes. */

@@ -1,0 +1,146 @@
+// struct_emul.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Compiles libgpublas_b200/csrc/structured.cuh (the index logic and the plans of the banded / packed / Hermitian Level-2
+// routines) with g++ and supplies a backend that walks the kernels' (block, thread) grids on the CPU, lane by lane, in the
+// launch shapes level2_struct.cu uses.  tests/test_level2_struct_cpu.py checks its results against the oracle, so the
+// storage arithmetic, the flag choices per routine and the row-major mappings are verified where there is no GPU; the CUDA
+// kernels themselves are verified on the GPU by tests/test_zz_level2_struct_gpu.py.  libb200blas.so never loads this file.
+#include "../../libgpublas_b200/csrc/structured.cuh"
+
+#include <cstring>
+#include <memory>
+#include <vector>
+
+using namespace b200::st;
+
+namespace {
+
+template <typename T> T butterfly(T* v) {   // the warp_sum of level2_struct.cu: xor offsets 16, 8, 4, 2, 1; lane 0's value
+    T t[32];
+    for (int o = 16; o > 0; o >>= 1) {
+        for (int l = 0; l < 32; l++) t[l] = el<T>::add(v[l], v[l ^ o]);
+        std::memcpy(v, t, sizeof t);
+    }
+    return v[0];
+}
+
+struct HostBackend {
+    std::vector<std::unique_ptr<char[]>> pool;
+    void* alloc(size_t bytes) { pool.emplace_back(new char[bytes ? bytes : 1]); return pool.back().get(); }
+    int sm_target() const { return 148 * 8; }
+    template <typename T> void gather(int n, const T* src, int64_t inc, T* dst, bool conj) {
+        for (int bx = 0; bx < (n + 255) / 256; bx++)
+            for (int tx = 0; tx < 256; tx++) {
+                const int i = bx * 256 + tx;
+                if (i >= n) continue;
+                T v = src[vpos(i, n, inc)];
+                dst[i] = conj ? el<T>::conj(v) : v;
+            }
+    }
+    template <typename T> void scatter(int n, const T* src, T* dst, int64_t inc) {
+        for (int i = 0; i < n; i++) dst[vpos(i, n, inc)] = src[i];
+    }
+    template <typename T>
+    void npart(const Desc& D, const T* A, const T* v, int row0, int row1, int c_lo, int c_hi, int cpc, int nchunks, int flags, T* part, int64_t npad) {
+        for (int by = 0; by < nchunks; by++)
+            for (int bx = 0; bx < (row1 - row0 + 127) / 128; bx++)
+                for (int tx = 0; tx < 128; tx++) {
+                    const int i = row0 + bx * 128 + tx;
+                    if (i >= row1) continue;
+                    const int c0 = c_lo + by * cpc, c1 = st_min(c_hi, c0 + cpc);
+                    part[(int64_t)by * npad + i] = npart_row<T>(D, A, v, i, c0, c1, flags);
+                }
+    }
+    template <typename T> void tpart(const Desc& D, const T* A, const T* v, int col0, int col1, int r0, int r1, int flags, T* tp) {
+        for (int bx = 0; bx < (col1 - col0 + 3) / 4; bx++)
+            for (int w = 0; w < 4; w++) {
+                const int j = col0 + bx * 4 + w;
+                if (j >= col1) continue;
+                T lanes[32];
+                for (int lane = 0; lane < 32; lane++) lanes[lane] = tpart_lane<T>(D, A, v, j, lane, 32, r0, r1, flags);
+                tp[j] = butterfly(lanes);
+            }
+    }
+    template <typename T>
+    void finish(int n, int nparts, const T* part, int64_t npad, const T* tp, const T* vunit, T alpha, T beta, T* out, int64_t inco) {
+        for (int i = 0; i < n; i++) {
+            T* p = out + vpos(i, n, inco);
+            const bool beta0 = el<T>::is_zero(beta);
+            *p = finish_elem<T>(i, nparts, part, npad, tp, vunit, alpha, beta, beta0, beta0 ? el<T>::zero() : *p);
+        }
+    }
+    template <typename T> void rank(const Desc& D, T* A, int rows, int ncols, int cpc, int nchunks, T alpha, const T* x, const T* y, int mode) {
+        for (int by = 0; by < nchunks; by++)
+            for (int bx = 0; bx < (rows + 127) / 128; bx++)
+                for (int tx = 0; tx < 128; tx++) {
+                    const int i = bx * 128 + tx;
+                    if (i >= rows) continue;
+                    const int c0 = by * cpc, c1 = st_min(ncols, c0 + cpc);
+                    rank_row<T>(D, A, i, c0, c1, alpha, x, y, mode);
+                }
+    }
+    // the warp of solve_diag_kernel, lane by lane in lock step
+    template <typename T> void solve_diag(const Desc& D, const T* A, T* x, int b0, int nb, bool trans, bool conj, bool unit, bool forward) {
+        T coef[32][32], xv[32];
+        for (int lane = 0; lane < 32; lane++) {
+            const int r = b0 + lane;
+            for (int step = 0; step < 32; step++) {
+                const int jj = forward ? step : nb - 1 - step;
+                coef[lane][step] = el<T>::zero();
+                if (step < nb && lane < nb) {
+                    const bool waiting = forward ? lane > jj : lane < jj;
+                    T a;
+                    if ((waiting || (lane == jj && !unit)) && solve_coef<T>(D, A, r, b0 + jj, trans, conj, a)) coef[lane][step] = a;
+                }
+            }
+            xv[lane] = lane < nb ? x[r] : el<T>::zero();
+        }
+        for (int step = 0; step < 32; step++) {
+            if (step >= nb) continue;
+            const int jj = forward ? step : nb - 1 - step;
+            if (!unit) xv[jj] = el<T>::div(xv[jj], coef[jj][step]);
+            const T xj = xv[jj];
+            for (int lane = 0; lane < 32; lane++) {
+                const bool waiting = forward ? (lane > jj && lane < nb) : lane < jj;
+                if (waiting) xv[lane] = el<T>::sub(xv[lane], el<T>::mul(coef[lane][step], xj));
+            }
+        }
+        for (int lane = 0; lane < nb; lane++) x[b0 + lane] = xv[lane];
+    }
+    template <typename T> void solve_nupdate(const Desc& D, const T* A, T* x, int row0, int row1, int b0, int b1, int flags) {
+        for (int i = row0; i < row1; i++) x[i] = el<T>::sub(x[i], npart_row<T>(D, A, x, i, b0, b1, flags));
+    }
+    template <typename T> void solve_tupdate(const Desc& D, const T* A, T* x, int col0, int col1, int b0, int b1, int flags) {
+        for (int j = col0; j < col1; j++) {
+            T lanes[32];
+            for (int lane = 0; lane < 32; lane++) lanes[lane] = tpart_lane<T>(D, A, x, j, lane, 32, b0, b1, flags);
+            x[j] = el<T>::sub(x[j], butterfly(lanes));
+        }
+    }
+};
+
+inline cuFloatComplex mkc(float r) { cuFloatComplex c; c.x = r; c.y = 0; return c; }
+inline cuDoubleComplex mkc(double r) { cuDoubleComplex c; c.x = r; c.y = 0; return c; }
+
+}  // namespace
+
+#define EMU(P, T)                                                                                                                                      \
+    extern "C" void emu_##P##gbmv(int rowmajor, char trans, int m, int n, int kl, int ku, const T* alpha, const T* a, int lda, const T* x, int incx,  \
+                                  const T* beta, T* y, int incy) {                                                                                     \
+        HostBackend be; plan_gbmv<T>(be, rowmajor != 0, trans, m, n, kl, ku, *alpha, a, lda, x, incx, *beta, y, incy); }                               \
+    extern "C" void emu_##P##symv_like(int kind, int herm, int rowmajor, char uplo, int n, int k, const T* alpha, const T* a, int lda, const T* x,     \
+                                       int incx, const T* beta, T* y, int incy) {                                                                      \
+        HostBackend be; plan_symv_like<T>(be, kind, herm != 0, rowmajor != 0, uplo == 'U', n, k, *alpha, a, kind == K_PACKED ? packed_len(n) : lda, x, incx, *beta, y, incy); } \
+    extern "C" void emu_##P##tri(int kind, int solve, int rowmajor, char uplo, char trans, char diag, int n, int k, const T* a, int lda, T* x, int incx) { \
+        HostBackend be; plan_tri<T>(be, kind, solve != 0, rowmajor != 0, uplo == 'U', trans, diag == 'U', n, k, a, kind == K_PACKED ? packed_len(n) : lda, x, incx); } \
+    extern "C" void emu_##P##ger(int conjy, int rowmajor, int m, int n, const T* alpha, const T* x, int incx, const T* y, int incy, T* a, int lda) {   \
+        HostBackend be; plan_ger<T>(be, conjy != 0, rowmajor != 0, m, n, *alpha, x, incx, y, incy, a, lda); }                                          \
+    extern "C" void emu_##P##rank_sym(int kind, int mode, int rowmajor, char uplo, int n, const T* alpha, const T* x, int incx, const T* y, int incy,  \
+                                      T* a, int lda) {                                                                                                 \
+        HostBackend be; plan_rank_sym<T>(be, kind, mode, rowmajor != 0, uplo == 'U', n, *alpha, x, incx, y, incy, a, kind == K_PACKED ? packed_len(n) : lda); } \
+    extern "C" void emu_##P##gemv_conj(int m, int n, const T* alpha, const T* a, int lda, const T* x, int incx, const T* beta, T* y, int incy) {       \
+        HostBackend be; plan_gemv_conj<T>(be, m, n, *alpha, a, lda, x, incx, *beta, y, incy); }
+EMU(s, float)
+EMU(d, double)
+EMU(c, cuFloatComplex)
+EMU(z, cuDoubleComplex)

@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(ROOT, "libgpublas_b200", "libb200blas.so")
 
 def build_oracle():
     so = os.path.join(ORACLE_DIR, "librefblas.so")
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("refblas.c", "refblas_real.inc", "refblas_cplx.inc")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("refblas.c", "refblas_real.inc", "refblas_cplx.inc", "refblas_l2x.inc")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "librefblas.so"], stdout=subprocess.DEVNULL)
     return so

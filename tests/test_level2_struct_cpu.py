@@ -1,0 +1,213 @@
+"""CPU-only legs for the banded / packed / Hermitian / complex Level-2 routines:
+
+  1. the oracle's restatements (oracle/refblas_l2x.inc) pinned against the CPU BLAS of this image (OpenBLAS) and against an
+     independent numpy model on the dense logical matrix, on the shared case list (tests/l2x.py);
+  2. the index logic and per-routine plans the CUDA kernels are built from (libgpublas_b200/csrc/structured.cuh), compiled
+     for the host and walked grid by grid (tests/drivers/struct_emul.cpp), against the same expectations -- column-major
+     (Fortran) and row-major (CBLAS) meanings;
+  3. the product library's argument checks and quick returns for these routines, which run before any CUDA call.
+
+The CUDA kernels themselves are checked on the GPU by tests/test_zz_level2_struct_gpu.py."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import l2x
+from helpers import f77, load_openblas, oracle_call
+
+
+def _worst(cs, runner):
+    worst, tag = 0.0, None
+    for c in cs:
+        args = c.fresh_args()
+        runner(c, args)
+        e = l2x.compare(args[c.out], c)
+        if e > worst:
+            worst, tag = e, c.tag
+    return worst, tag
+
+
+@pytest.mark.parametrize("p", ["s", "d", "c", "z"])
+def test_oracle_l2x_vs_openblas_and_model(p):
+    ob = load_openblas()
+    if ob is None:
+        pytest.skip("no CPU BLAS in this image")
+    cs = l2x.cases(p, sizes=(1, 2, 5, 33))
+
+    def run_oracle(c, args):
+        assert oracle_call(c.name, *args) == 0, c.tag
+
+    def run_openblas(c, args):
+        f77(ob, c.name + "_", *args)
+
+    w, tag = _worst(cs, run_oracle)
+    assert w < 1.0, ("oracle vs model", tag, w)
+    w, tag = _worst(cs, run_openblas)
+    assert w < 1.0, ("OpenBLAS vs model", tag, w)
+    # and directly against each other, on the arrays as a whole (padding included)
+    for c in cs[::3]:
+        a1, a2 = c.fresh_args(), c.fresh_args()
+        run_oracle(c, a1); run_openblas(c, a2)
+        o1, o2 = a1[c.out].astype(np.complex128), a2[c.out].astype(np.complex128)
+        assert np.abs(o1 - o2).max() <= c.tol * max(1.0, np.abs(c.expect[c.expect != c.expect.dtype.type(l2x.ROGUE)]).max()), c.tag
+
+
+@pytest.mark.parametrize("rowmajor", [False, True], ids=["colmajor", "rowmajor"])
+@pytest.mark.parametrize("p", ["s", "d", "c", "z"])
+def test_kernel_index_logic_emulated(p, rowmajor):
+    cs = l2x.cases(p, rowmajor=rowmajor)
+    w, tag = _worst(cs, lambda c, args: l2x.emu_call(c.name, *args, rowmajor=rowmajor))
+    assert w < 1.0, (tag, w)
+
+
+def test_emulated_solves_cross_block_boundaries():
+    """n > 32 with every reach: the diagonal-block solve + update chain of TBSV/TPSV over several blocks, both directions"""
+    for p in "dz":
+        cs = [c for c in l2x.cases(p, sizes=(31, 32, 33, 64, 97)) if c.name[1:] in ("tbsv", "tpsv")]
+        assert len(cs) > 200
+        w, tag = _worst(cs, lambda c, args: l2x.emu_call(c.name, *args))
+        assert w < 1.0, (tag, w)
+
+
+def test_emulated_gemv_conj_notrans():
+    """CBLAS row-major ConjTrans GEMV: y = alpha*A^H*x + beta*y on a row-major m x n A"""
+    lib = l2x.load_emul()
+    for p in "cz":
+        m, n = 37, 21
+        A = l2x.rnd(1, (m, n + 2), p); A = np.ascontiguousarray(A)          # row-major, lda = n+2
+        x = l2x.vec(2, m, 2, p); y = l2x.vec(3, n, -1, p)
+        al, be = l2x.ALPHA[p], l2x.BETA[p]
+        want = al * (A[:, :n].astype(np.complex128).conj().T @ l2x.logical(x, m, 2)) + be * l2x.logical(y, n, -1)
+        # column-major view: n x m with ld = n+2
+        getattr(lib, "emu_" + p + "gemv_conj")(n, m, l2x._sp(p, al), l2x._ptr(A), n + 2, l2x._ptr(x), 2, l2x._sp(p, be), l2x._ptr(y), -1)
+        assert np.allclose(l2x.logical(y, n, -1), want, rtol=64 * l2x.EPS[p] * m, atol=64 * l2x.EPS[p] * m)
+
+
+def test_struct_error_exits_and_quick_returns():
+    """netlib INFO numbering of the new entry points and their quick returns: all decided on the host before the first CUDA
+    call, so this runs without a GPU (reference: the ?BLAT2-style DCHKE tables; gemm.cc:87-127 shows the pattern)."""
+    import libgpublas_b200 as g
+    lib = g.load(); seen = []
+    CB = ctypes.CFUNCTYPE(None, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.c_size_t)
+    cb = CB(lambda name, info, ln: seen.append((name[:6].decode(), info[0])))
+    lib.b200blas_set_xerbla(cb)
+    A = np.zeros((4, 4), order="F"); v = np.ones(8); Z = np.zeros((4, 4), dtype=np.complex128, order="F"); w = np.ones(8, dtype=np.complex128)
+    try:
+        table = [
+            ("dgbmv_", [(("X", 2, 2, 1, 1, 1.0, A, 3, v, 1, 1.0, v, 1), 1), (("N", -1, 2, 1, 1, 1.0, A, 3, v, 1, 1.0, v, 1), 2), (("N", 2, -1, 1, 1, 1.0, A, 3, v, 1, 1.0, v, 1), 3),
+                        (("N", 2, 2, -1, 1, 1.0, A, 3, v, 1, 1.0, v, 1), 4), (("N", 2, 2, 1, -1, 1.0, A, 3, v, 1, 1.0, v, 1), 5), (("N", 2, 2, 1, 1, 1.0, A, 2, v, 1, 1.0, v, 1), 8),
+                        (("N", 2, 2, 1, 1, 1.0, A, 3, v, 0, 1.0, v, 1), 10), (("N", 2, 2, 1, 1, 1.0, A, 3, v, 1, 1.0, v, 0), 13)]),
+            ("dsbmv_", [(("X", 2, 1, 1.0, A, 2, v, 1, 1.0, v, 1), 1), (("U", -1, 1, 1.0, A, 2, v, 1, 1.0, v, 1), 2), (("U", 2, -1, 1.0, A, 2, v, 1, 1.0, v, 1), 3),
+                        (("U", 2, 1, 1.0, A, 1, v, 1, 1.0, v, 1), 6), (("U", 2, 1, 1.0, A, 2, v, 0, 1.0, v, 1), 8), (("U", 2, 1, 1.0, A, 2, v, 1, 1.0, v, 0), 11)]),
+            ("dspmv_", [(("X", 2, 1.0, A, v, 1, 1.0, v, 1), 1), (("U", -1, 1.0, A, v, 1, 1.0, v, 1), 2), (("U", 2, 1.0, A, v, 0, 1.0, v, 1), 6), (("U", 2, 1.0, A, v, 1, 1.0, v, 0), 9)]),
+            ("zhemv_", [(("X", 2, 1j, Z, 2, w, 1, 1j, w, 1), 1), (("U", -1, 1j, Z, 2, w, 1, 1j, w, 1), 2), (("U", 2, 1j, Z, 1, w, 1, 1j, w, 1), 5),
+                        (("U", 2, 1j, Z, 2, w, 0, 1j, w, 1), 7), (("U", 2, 1j, Z, 2, w, 1, 1j, w, 0), 10)]),
+            ("zhbmv_", [(("U", 2, 1, 1j, Z, 1, w, 1, 1j, w, 1), 6), (("U", 2, 1, 1j, Z, 2, w, 1, 1j, w, 0), 11)]),
+            ("zhpmv_", [(("U", 2, 1j, Z, w, 0, 1j, w, 1), 6), (("U", 2, 1j, Z, w, 1, 1j, w, 0), 9)]),
+            ("dtbmv_", [(("X", "N", "N", 2, 1, A, 2, v, 1), 1), (("U", "X", "N", 2, 1, A, 2, v, 1), 2), (("U", "N", "X", 2, 1, A, 2, v, 1), 3), (("U", "N", "N", -1, 1, A, 2, v, 1), 4),
+                        (("U", "N", "N", 2, -1, A, 2, v, 1), 5), (("U", "N", "N", 2, 1, A, 1, v, 1), 7), (("U", "N", "N", 2, 1, A, 2, v, 0), 9)]),
+            ("ztbsv_", [(("U", "N", "N", 2, 1, Z, 1, w, 1), 7), (("U", "N", "N", 2, 1, Z, 2, w, 0), 9)]),
+            ("dtpmv_", [(("X", "N", "N", 2, A, v, 1), 1), (("U", "X", "N", 2, A, v, 1), 2), (("U", "N", "X", 2, A, v, 1), 3), (("U", "N", "N", -1, A, v, 1), 4), (("U", "N", "N", 2, A, v, 0), 7)]),
+            ("ctpsv_", [(("U", "N", "N", 2, Z, w, 0), 7)]),
+            ("ztrmv_", [(("U", "N", "N", 2, Z, 1, w, 1), 6), (("U", "N", "N", 2, Z, 2, w, 0), 8)]),
+            ("zgeru_", [((-1, 2, 1j, w, 1, w, 1, Z, 2), 1), ((2, -1, 1j, w, 1, w, 1, Z, 2), 2), ((2, 2, 1j, w, 0, w, 1, Z, 2), 5), ((2, 2, 1j, w, 1, w, 0, Z, 2), 7), ((2, 2, 1j, w, 1, w, 1, Z, 1), 9)]),
+            ("cgerc_", [((2, 2, 1j, w, 1, w, 1, Z, 1), 9)]),
+            ("zher_", [(("X", 2, 1.0, w, 1, Z, 2), 1), (("U", -1, 1.0, w, 1, Z, 2), 2), (("U", 2, 1.0, w, 0, Z, 2), 5), (("U", 2, 1.0, w, 1, Z, 1), 7)]),
+            ("zher2_", [(("U", 2, 1j, w, 1, w, 0, Z, 2), 7), (("U", 2, 1j, w, 1, w, 1, Z, 1), 9)]),
+            ("dsyr2_", [(("X", 2, 1.0, v, 1, v, 1, A, 2), 1), (("U", 2, 1.0, v, 0, v, 1, A, 2), 5), (("U", 2, 1.0, v, 1, v, 0, A, 2), 7), (("U", 2, 1.0, v, 1, v, 1, A, 1), 9)]),
+            ("dspr_", [(("X", 2, 1.0, v, 1, A), 1), (("U", -1, 1.0, v, 1, A), 2), (("U", 2, 1.0, v, 0, A), 5)]),
+            ("dspr2_", [(("U", 2, 1.0, v, 1, v, 0, A), 7)]),
+            ("zhpr_", [(("U", 2, 1.0, w, 0, Z), 5)]),
+            ("zhpr2_", [(("U", 2, 1j, w, 0, w, 1, Z), 5), (("U", 2, 1j, w, 1, w, 0, Z), 7)]),
+        ]
+        for name, rows in table:
+            for args, want in rows:
+                seen.clear(); f77(lib, name, *args)
+                assert seen == [((name[:-1].upper() + "      ")[:6], want)], (name, args[:3], seen)
+        # quick returns: n == 0, alpha == 0 (& beta == 1): nothing is touched and no device is needed
+        seen.clear()
+        f77(lib, "dgbmv_", "N", 0, 2, 1, 1, 1.0, A, 3, v, 1, 1.0, v, 1); f77(lib, "dgbmv_", "N", 2, 2, 1, 1, 0.0, A, 3, v, 1, 1.0, v, 1)
+        f77(lib, "dsbmv_", "U", 0, 1, 1.0, A, 2, v, 1, 0.0, v, 1); f77(lib, "zhpmv_", "L", 2, 0j, Z, w, 1, 1 + 0j, w, 1)
+        f77(lib, "dtbsv_", "U", "N", "N", 0, 1, A, 2, v, 1); f77(lib, "ztpmv_", "U", "N", "N", 0, Z, w, 1)
+        f77(lib, "zgeru_", 2, 2, 0j, w, 1, w, 1, Z, 2); f77(lib, "zher_", "U", 2, 0.0, w, 1, Z, 2); f77(lib, "dspr2_", "U", 2, 0.0, v, 1, v, 1, A)
+        assert seen == [] and np.all(A == 0) and np.all(Z == 0) and np.all(v == 1) and np.all(w == 1)
+    finally:
+        lib.b200blas_set_xerbla(CB(0))
+
+
+@pytest.mark.parametrize("p", ["d", "z"])
+def test_rowmajor_model_vs_openblas_cblas(p):
+    """The row-major expectations (explicit CBLAS row-major storage builders + numpy model) agree with the CPU BLAS's own
+    cblas_* entry points -- so the GPU test's row-major leg compares against something pinned."""
+    ob = load_openblas()
+    if ob is None:
+        pytest.skip("no CPU BLAS in this image")
+    for order, rowmajor in (("R", True), ("C", False)):
+        cs = l2x.cases(p, rowmajor=rowmajor, sizes=(1, 2, 5, 33))
+        w, tag = _worst(cs, lambda c, args: l2x.cblas_call(ob, c.name, order, *args))
+        assert w < 1.0, (order, tag, w)
+
+
+def _rotmg_inputs():
+    return [(2.0, 3.0, 0.5, 0.7), (3.0, 2.0, 0.7, -0.5), (1.0, 1.0, 1.0, 1.0), (-1.0, 2.0, 1.0, 1.0), (2.0, 0.0, 1.0, 1.0), (2.0, 3.0, 1.0, 0.0),
+            (1e-9, 2.0, 3.0, 1e-3), (2.0, 1e9, 1e-3, 5.0), (4.0e8, 3.0, 2.0, 1e-6), (1.0, -0.5, 1.0, 1.0), (0.5, 0.25, 3.0, -4.0), (1e10, 1e-10, 1e-4, 1e4)]
+
+
+def test_level1_extras_oracle_vs_openblas():
+    """ROTM / ROTMG / I?AMIN / DSDOT / SDSDOT / CSROT / ZDROT restatements against the CPU BLAS; and the product library's
+    ROTMG, which is scalar host work (no device needed)."""
+    import libgpublas_b200 as g
+    ob = load_openblas()
+    if ob is None:
+        pytest.skip("no CPU BLAS in this image")
+    lib = g.load()
+    for p, dt, tol in (("s", np.float32, 1e-6), ("d", np.float64, 1e-14)):
+        for flag in (-2.0, -1.0, 0.0, 1.0):
+            param = np.array([flag, 0.3, -0.4, 0.5, 0.6], dtype=dt)
+            for n, ix, iy in [(1, 1, 1), (33, 2, -3), (100, -1, 1)]:
+                x = l2x.vec(1, n, ix, p); y = l2x.vec(2, n, iy, p)
+                x1, y1, x2, y2 = x.copy(), y.copy(), x.copy(), y.copy()
+                f77(ob, p + "rotm_", n, x1, ix, y1, iy, param); oracle_call(p + "rotm", n, x2, ix, y2, iy, param, restype=None)
+                assert np.allclose(x1, x2, rtol=tol, atol=tol) and np.allclose(y1, y2, rtol=tol, atol=tol), (p, flag, n)
+        for (d1, d2, x1, y1) in _rotmg_inputs():
+            outs = []
+            for who in ("openblas", "oracle", "product"):
+                a = [np.array([v], dtype=dt) for v in (d1, d2, x1)]; prm = np.full(5, 9.0, dtype=dt)
+                if who == "openblas":
+                    f77(ob, p + "rotmg_", a[0], a[1], a[2], np.array([y1], dtype=dt), prm)
+                elif who == "product":
+                    f77(lib, p + "rotmg_", a[0], a[1], a[2], np.array([y1], dtype=dt), prm)
+                else:
+                    oracle_call(p + "rotmg", a[0], a[1], a[2], dt(y1), prm, restype=None)
+                outs.append(np.concatenate([a[0], a[1], a[2], prm]).astype(np.float64))
+            assert np.allclose(outs[0], outs[1], rtol=64 * tol, atol=1e-30), (p, d1, d2, x1, y1, outs[0], outs[1])
+            assert np.array_equal(outs[1], outs[2]), (p, d1, d2, x1, y1, outs[1], outs[2])
+    for p in "sdcz":
+        for n, inc in [(1, 1), (7, 2), (1000, 1), (1000, 3)]:
+            x = l2x.vec(3, n, inc, p)
+            if n > 5:
+                x[0] = x[3 * inc] = x[5 * inc] * 0 + 1e-3      # planted ties for the minimum
+                x[5 * inc] = 1e-3
+            fn = getattr(ob, "i" + p + "amin_"); fn.restype = ctypes.c_int
+            want = f77(ob, "i" + p + "amin_", n, x, inc, restype=ctypes.c_int)
+            assert oracle_call("i" + p + "amin", n, x, inc) == want, (p, n, inc)
+    for n, ix, iy in [(1, 1, 1), (33, 2, -3), (1001, 1, 1)]:
+        x = l2x.vec(4, n, ix, "s"); y = l2x.vec(5, n, iy, "s")
+        want = f77(ob, "dsdot_", n, x, ix, y, iy, restype=ctypes.c_double)
+        got = oracle_call("dsdot", n, x, ix, y, iy, restype=ctypes.c_double)
+        exact = float(np.dot(l2x.logical(x, n, ix).astype(np.float64), l2x.logical(y, n, iy).astype(np.float64)))
+        assert abs(got - exact) <= 1e-13 * n      # netlib DSDOT: every product and the sum in double
+        assert abs(got - want) <= 2e-7 * n        # OpenBLAS 0.3.15 sums blocks of its SDOT kernel in float: float-level agreement only
+        sb = np.float32(0.37)
+        want = f77(ob, "sdsdot_", n, sb, x, ix, y, iy, restype=ctypes.c_float)
+        got = oracle_call("sdsdot", n, sb, x, ix, y, iy, restype=ctypes.c_float)
+        assert abs(got - want) <= 2e-6 * max(1.0, abs(want))
+    for p, rp, tol in (("c", "s", 1e-6), ("z", "d", 1e-14)):
+        nm = "csrot" if p == "c" else "zdrot"
+        for n, ix, iy in [(1, 1, 1), (33, 2, -3)]:
+            x = l2x.vec(6, n, ix, p); y = l2x.vec(7, n, iy, p)
+            x1, y1, x2, y2 = x.copy(), y.copy(), x.copy(), y.copy()
+            c, s_ = l2x.DT[rp](0.6), l2x.DT[rp](0.8)
+            f77(ob, nm + "_", n, x1, ix, y1, iy, c, s_); oracle_call(p + "srot", n, x2, ix, y2, iy, c, s_, restype=None)
+            assert np.allclose(x1, x2, rtol=tol, atol=tol) and np.allclose(y1, y2, rtol=tol, atol=tol)

@@ -1,0 +1,152 @@
+"""GPU parity tests for the banded / packed / Hermitian / complex Level-2 routines (SURVEY.md section 8(f) rank 3;
+libgpublas_b200/csrc/level2_struct.cu) through the C ABI: Fortran symbols and cblas_* in both layouts, on the shared case
+list of tests/l2x.py (netlib ?BLAT2-style: rogue padding that must come back bit-identical, LDA = rows + 1, k / kl / ku from
+0 to n-1, positive and negative increments, alpha = 0 / beta = 0 / beta = 1 corner cases, unit diagonals never read).
+
+Expectations: the numpy model on the dense logical matrix -- which tests/test_level2_struct_cpu.py pins against the oracle
+and against OpenBLAS (Fortran and cblas_*, both layouts) -- plus, for the Fortran form, the oracle directly.
+Tolerance (in the case list): 16 * eps * max(n, 4) * max|expected| for products and updates, 4x that for the solves
+(well-conditioned triangles)."""
+import numpy as np
+import pytest
+
+import l2x
+import libgpublas_b200 as g
+from helpers import f77, oracle_call
+
+pytestmark = pytest.mark.gpu
+
+
+def _worst(cs, runner):
+    worst, tag = 0.0, None
+    for c in cs:
+        args = c.fresh_args()
+        runner(c, args)
+        e = l2x.compare(args[c.out], c)
+        if e > worst:
+            worst, tag = e, c.tag
+    return worst, tag
+
+
+@pytest.mark.parametrize("p", ["s", "d", "c", "z"])
+def test_struct_fortran_symbols_vs_model_and_oracle(p):
+    lib = g.load()
+    cs = l2x.cases(p, big=(257,))
+    w, tag = _worst(cs, lambda c, args: f77(lib, c.name + "_", *args))
+    assert w < 1.0, (tag, w)
+    assert g.last_variant() == "generic_tile"
+    for c in cs[::5]:      # the oracle itself, on the same call
+        a1, a2 = c.fresh_args(), c.fresh_args()
+        f77(lib, c.name + "_", *a1)
+        assert oracle_call(c.name, *a2) == 0
+        o1, o2 = a1[c.out], a2[c.out]
+        rogue = o2 == o2.dtype.type(l2x.ROGUE)
+        assert np.array_equal(o1[rogue], o2[rogue]), c.tag
+        scale = max(1.0, float(np.abs(o2[~rogue]).max()) if (~rogue).any() else 1.0)
+        assert np.abs(o1.astype(np.complex128) - o2.astype(np.complex128)).max() <= c.tol * scale, c.tag
+
+
+@pytest.mark.parametrize("order", ["C", "R"])
+@pytest.mark.parametrize("p", ["s", "d", "c", "z"])
+def test_struct_cblas_both_layouts(p, order):
+    lib = g.load()
+    cs = l2x.cases(p, rowmajor=(order == "R"), sizes=(1, 2, 5, 33, 70))
+    w, tag = _worst(cs, lambda c, args: l2x.cblas_call(lib, c.name, order, *args))
+    assert w < 1.0, (order, tag, w)
+
+
+@pytest.mark.parametrize("p", ["c", "z"])
+def test_cblas_complex_gemv_all_layouts(p):
+    """cblas_{c,z}gemv: column-major and row-major, NoTrans / Trans / ConjTrans (row-major ConjTrans runs as
+    conjugate-no-transpose on the transposed view)"""
+    import ctypes
+    lib = g.load()
+    dt, eps = l2x.DT[p], l2x.EPS[p]
+    al, be = l2x.ALPHA[p], l2x.BETA[p]
+    fn = getattr(lib, "cblas_" + p + "gemv"); fn.restype = None
+    r = l2x.CREAL[p]
+    for (m, n) in [(1, 1), (7, 5), (130, 77), (300, 513)]:
+        M = l2x.rnd(11, (m, n), p)
+        for order in "CR":
+            if order == "C":
+                A = np.full((m + 1, n), l2x.ROGUE, dtype=dt, order="F"); A[:m] = M; lda = m + 1
+            else:
+                A = np.full((m, n + 1), l2x.ROGUE, dtype=dt, order="C"); A[:, :n] = M; lda = n + 1
+            for tr in "NTC":
+                for (ix, iy) in [(1, 1), (2, -3)]:
+                    lx, ly = (n, m) if tr == "N" else (m, n)
+                    x = l2x.vec(12, lx, ix, p); y = l2x.vec(13, ly, iy, p); y0 = y.copy()
+                    want = al * (l2x.opmat(M.astype(np.complex128), tr) @ l2x.logical(x, lx, ix)) + be * l2x.logical(y0, ly, iy)
+                    ca, cb = (r * 2)(al.real, al.imag), (r * 2)(be.real, be.imag)
+                    fn(ctypes.c_int(l2x.CBLAS_ENUM["R" if order == "R" else "Cm"]), ctypes.c_int(l2x.CBLAS_ENUM[tr]), ctypes.c_int(m), ctypes.c_int(n),
+                       ctypes.byref(ca), l2x._ptr(A), ctypes.c_int(lda), l2x._ptr(x), ctypes.c_int(ix), ctypes.byref(cb), l2x._ptr(y), ctypes.c_int(iy))
+                    tol = 32 * eps * max(m, n)
+                    assert np.allclose(l2x.logical(y, ly, iy), want, rtol=tol, atol=tol), (p, m, n, order, tr, ix, iy)
+
+
+def test_struct_solves_many_blocks_device_resident():
+    """TPSV / TBSV over many 32-blocks with the operands already on the device (no staging): n = 3000, reach 5 and full"""
+    import torch
+    lib = g.load()
+    n = 3000
+    for p in "dz":
+        dt = l2x.DT[p]
+        G = l2x.well_conditioned_tri(5, n, p)
+        b = l2x.rnd(6, (n,), p)
+        for ul in "UL":
+            for tr in "NTC":
+                T = np.where(l2x.tri_mask(n, ul), G, 0)
+                want = np.linalg.solve(l2x.opmat(T.astype(l2x.wide(p)), tr), b.astype(l2x.wide(p)))
+                ap = torch.from_numpy(l2x.packed(T.astype(dt), ul)).cuda(); x = torch.from_numpy(b.copy()).cuda()
+                f77(lib, p + "tpsv_", ul, tr, "N", n, ap, x, 1)
+                assert np.allclose(x.cpu().numpy(), want, rtol=1e-9, atol=1e-9), (p, ul, tr, "tpsv")
+                k = 5
+                Tk = np.where(l2x.tri_mask(n, ul, k), G, 0)
+                wantk = np.linalg.solve(l2x.opmat(Tk.astype(l2x.wide(p)), tr), b.astype(l2x.wide(p)))
+                i, j = np.indices((k + 1, n))       # vectorised band storage: AB[k+i-j, j] (upper) / AB[i-j, j] (lower)
+                rows = (j - k + i) if ul == "U" else (j + i)
+                ok = (rows >= 0) & (rows < n)
+                ab = np.zeros((k + 1, n), dtype=dt, order="F"); ab[ok] = Tk[rows[ok], j[ok]]
+                abd = torch.from_numpy(np.ascontiguousarray(ab.T)).cuda()      # (n, k+1) C-order == (k+1, n) F-order in memory
+                xk = torch.from_numpy(b.copy()).cuda()
+                f77(lib, p + "tbsv_", ul, tr, "N", n, k, abd, k + 1, xk, 1)
+                assert np.allclose(xk.cpu().numpy(), wantk, rtol=1e-9, atol=1e-9), (p, ul, tr, "tbsv")
+
+
+def test_level1_extras_gpu():
+    """ROTM / CSROT / ZDROT / I?AMIN / DSDOT / SDSDOT on the GPU against the oracle (pinned against OpenBLAS on the CPU)."""
+    import ctypes
+    lib = g.load()
+    for p, dt, tol in (("s", np.float32, 2e-6), ("d", np.float64, 1e-14)):
+        for flag in (-2.0, -1.0, 0.0, 1.0):
+            param = np.array([flag, 0.3, -0.4, 0.5, 0.6], dtype=dt)
+            for n, ix, iy in [(1, 1, 1), (33, 2, -3), (100003, 1, 1), (5000, -1, 2)]:
+                x = l2x.vec(1, n, ix, p); y = l2x.vec(2, n, iy, p)
+                x1, y1, x2, y2 = x.copy(), y.copy(), x.copy(), y.copy()
+                f77(lib, p + "rotm_", n, x1, ix, y1, iy, param); oracle_call(p + "rotm", n, x2, ix, y2, iy, param, restype=None)
+                assert np.allclose(x1, x2, rtol=tol, atol=tol) and np.allclose(y1, y2, rtol=tol, atol=tol), (p, flag, n)
+    for p, rp, tol in (("c", "s", 2e-6), ("z", "d", 1e-14)):
+        nm = "csrot" if p == "c" else "zdrot"
+        for n, ix, iy in [(1, 1, 1), (33, 2, -3), (70001, 1, 1)]:
+            x = l2x.vec(6, n, ix, p); y = l2x.vec(7, n, iy, p)
+            x1, y1, x2, y2 = x.copy(), y.copy(), x.copy(), y.copy()
+            c, s_ = l2x.DT[rp](0.6), l2x.DT[rp](0.8)
+            f77(lib, nm + "_", n, x1, ix, y1, iy, c, s_); oracle_call(p + "srot", n, x2, ix, y2, iy, c, s_, restype=None)
+            assert np.allclose(x1, x2, rtol=tol, atol=tol) and np.allclose(y1, y2, rtol=tol, atol=tol)
+    for p in "sdcz":
+        for n, inc in [(1, 1), (7, 2), (1000, 1), (100003, 3), (1 << 20, 1)]:
+            x = l2x.vec(3, n, inc, p)
+            if n > 5:
+                x[(n // 2) * inc] = 1e-9; x[(n - 1) * inc] = 1e-9; x[5 * inc] = 1e-9      # ties: the first one wins
+            want = oracle_call("i" + p + "amin", n, x, inc)
+            assert f77(lib, "i" + p + "amin_", n, x, inc, restype=ctypes.c_int) == want, (p, n, inc)
+            fn = getattr(lib, "cblas_i" + p + "amin"); fn.restype = ctypes.c_size_t
+            assert fn(ctypes.c_int(n), l2x._ptr(x), ctypes.c_int(inc)) == want - 1
+    for n, ix, iy in [(1, 1, 1), (33, 2, -3), (1000003, 1, 1)]:
+        x = l2x.vec(4, n, ix, "s"); y = l2x.vec(5, n, iy, "s")
+        exact = float(np.dot(l2x.logical(x, n, ix).astype(np.float64), l2x.logical(y, n, iy).astype(np.float64)))
+        got = f77(lib, "dsdot_", n, x, ix, y, iy, restype=ctypes.c_double)
+        assert abs(got - exact) <= 1e-13 * n, (n, got, exact)
+        sb = np.float32(0.37)
+        got = f77(lib, "sdsdot_", n, sb, x, ix, y, iy, restype=ctypes.c_float)
+        assert abs(got - (exact + float(sb))) <= 2e-7 * max(1.0, abs(exact)), (n, got, exact)
