@@ -6,6 +6,7 @@
 // inherited: axpy dropping y (axpy.cc:28-30), cblas_i?amax returning a 1-based index
 // (amax.cc:25,33-36), nrm2 exported under a misspelt name (nrm2.cc:31-54).
 #include "abi_common.h"
+#include <type_traits>
 #include "../../include/b200blas.h"
 
 using namespace b200;
@@ -21,11 +22,12 @@ struct VecOperand : Operand {
 // Scalar results: the reduction kernel's finishing block stores the value straight into pinned, device-mapped host
 // memory (zero-copy), so returning it costs one stream synchronisation and no separate copy (these routines are
 // synchronous by nature: they return a value).
-template <typename R> R* scalar_slot() { return (R*)pinned_scalar(); }
+template <typename R> R* scalar_slot() { return (R*)armed_scalar(sizeof(R)); }
 template <typename R> R fetch_scalar(const void* slot) {
-    B200_CUDA(cudaStreamSynchronize(current_stream()));
+    // spins on the slot instead of synchronising the stream (runtime.h); float / complex-float results arrive as 4-byte stores
+    wait_scalar(slot, sizeof(R), (sizeof(R) == 4 || std::is_same<R, cuFloatComplex>::value) ? 4 : 8);
     R r;
-    memcpy(&r, slot, sizeof(R));     // pinned host memory, written by the kernel before the synchronise returned
+    memcpy(&r, slot, sizeof(R));     // pinned host memory, written by the kernel's finishing block
     return r;
 }
 

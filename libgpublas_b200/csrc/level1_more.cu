@@ -52,8 +52,8 @@ struct Vec : Operand {
     Vec(const void* p, int64_t n, int64_t inc, size_t elem, int access)
         : Operand(p, n > 0 ? 1 + (n - 1) * (inc < 0 ? -inc : inc) : 0, 1, n > 0 ? 1 + (n - 1) * (inc < 0 ? -inc : inc) : 1, elem, access) {}
 };
-template <typename R> R fetch_scalar(const void* slot) {   // the kernel's finishing block wrote into pinned, device-mapped host memory
-    B200_CUDA(cudaStreamSynchronize(current_stream()));
+template <typename R> R fetch_scalar(const void* slot) {   // the kernel's finishing block writes into pinned, device-mapped host memory
+    wait_scalar(slot, sizeof(R), sizeof(R) == 4 ? 4 : 8);
     R r;
     memcpy(&r, slot, sizeof(R));
     return r;
@@ -129,7 +129,7 @@ template <typename T> int iamin_entry(const char* name, const int* n, const T* x
     if (*n < 1 || *incx <= 0) return 0;
     CallScope scope(name);
     Vec ox(x, *n, *incx, sizeof(T), ACC_IN);
-    long long* out = (long long*)pinned_scalar();
+    long long* out = (long long*)armed_scalar(sizeof(long long));
     iamin_dev<T>(current_stream(), *n, (const T*)ox.dev(), *incx, out);
     const long long r = fetch_scalar<long long>(out);
     log_exec(name, "n=%d incx=%d", *n, *incx);
@@ -140,7 +140,7 @@ double dsdot_entry(const char* name, const int* n, float sb, const float* x, con
     if (*n <= 0) return out_double ? (double)sb : (double)(float)sb;
     CallScope scope(name);
     Vec ox(x, *n, *incx, sizeof(float), ACC_IN), oy(y, *n, *incy, sizeof(float), ACC_IN);
-    void* out = pinned_scalar();
+    void* out = armed_scalar(out_double ? sizeof(double) : sizeof(float));
     dsdot_dev(current_stream(), *n, (const float*)ox.dev(), *incx, (const float*)oy.dev(), *incy, (double)sb, out, out_double);
     const double r = out_double ? fetch_scalar<double>(out) : (double)fetch_scalar<float>(out);
     log_exec(name, "n=%d incx=%d incy=%d", *n, *incx, *incy);

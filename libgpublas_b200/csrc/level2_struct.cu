@@ -10,8 +10,9 @@
 //       GBMV 'N' = N part, 'T'/'C' = T part; SBMV/HBMV/SPMV/HPMV/HEMV = N part over the stored triangle + T part over
 //       the strict triangle (conjugated for Hermitian); TBMV/TPMV/TRMV pick one part by trans.
 //   rank updates    thread per row over the stored columns (GERU/GERC/HER/HER2/SYR2/SPR/SPR2/HPR/HPR2)
-//   solves          TBSV/TPSV: 32-wide diagonal blocks solved by one warp (coefficients preloaded, x passed by shuffle),
-//                   then the same N/T bodies subtract the block's contribution from the rows it reaches.
+//   solves          TBSV/TPSV: a panel of columns per CTA (32-wide diagonal blocks solved by one warp -- coefficients
+//                   preloaded, x passed by shuffle -- the CTA updating the rest of the panel in between), then the same
+//                   N/T bodies subtract the panel's contribution from the rows it reaches outside; a narrow band is one launch.
 // Row-major CBLAS calls map onto the same kernels: the row-major array is the column-major storage of the transpose with
 // uplo flipped (kl/ku swapped); ConjTrans becomes "conjugate, no transpose" (a flag of the bodies), and Hermitian
 // row-major operands are the conjugate of the column-major view (flags toggled / vectors conjugated while gathered).
@@ -108,12 +109,15 @@ __global__ void __launch_bounds__(128) solve_tupdate_kernel(Desc D, const T* __r
     if (lane == 0) x[j] = el<T>::sub(x[j], acc);
 }
 // One warp solves the nb <= 32 unknowns of a diagonal block of op(S): lane l owns x(b0+l).  The lane's row of
-// coefficients is loaded up front (independent loads, one memory latency) in elimination order; each step divides on
-// the pivot lane, broadcasts the solved unknown by shuffle and eliminates it from the lanes still waiting.
+// coefficients is loaded up front (independent loads, one memory latency) in elimination order together with the
+// reciprocal of its pivot; each step scales on the pivot lane, broadcasts the solved unknown by shuffle and eliminates it
+// from the lanes still waiting.  (x * (1/d) instead of x / d: one FP64 division per lane off the critical path instead
+// of 32 in sequence; within the solves' stated tolerance.)
 template <typename T>
-__global__ void __launch_bounds__(32) solve_diag_kernel(Desc D, const T* __restrict__ A, T* x, int b0, int nb, bool trans, bool conj, bool unit, bool forward) {
-    const int lane = threadIdx.x, r = b0 + lane;
+__device__ __forceinline__ void solve_diag_warp(const Desc& D, const T* __restrict__ A, T* x, int b0, int nb, bool trans, bool conj, bool unit, bool forward) {
+    const int lane = threadIdx.x & 31, r = b0 + lane;
     T coef[32];
+    T dinv = el<T>::one();
 #pragma unroll
     for (int step = 0; step < 32; step++) {
         const int jj = forward ? step : nb - 1 - step;
@@ -121,7 +125,9 @@ __global__ void __launch_bounds__(32) solve_diag_kernel(Desc D, const T* __restr
         if (step < nb && lane < nb) {
             const bool waiting = forward ? lane > jj : lane < jj;
             T a;
-            if ((waiting || (lane == jj && !unit)) && solve_coef<T>(D, A, r, b0 + jj, trans, conj, a)) coef[step] = a;
+            if ((waiting || (lane == jj && !unit)) && solve_coef<T>(D, A, r, b0 + jj, trans, conj, a)) {
+                if (lane == jj) dinv = el<T>::div(el<T>::one(), a); else coef[step] = a;
+            }
         }
     }
     T xv = lane < nb ? x[r] : el<T>::zero();
@@ -129,13 +135,29 @@ __global__ void __launch_bounds__(32) solve_diag_kernel(Desc D, const T* __restr
     for (int step = 0; step < 32; step++) {
         if (step < nb) {   // uniform across the warp
             const int jj = forward ? step : nb - 1 - step;
-            if (lane == jj && !unit) xv = el<T>::div(xv, coef[step]);
+            if (lane == jj && !unit) xv = el<T>::mul(xv, dinv);
             const T xj = warp_bcast(xv, jj);
             const bool waiting = forward ? (lane > jj && lane < nb) : lane < jj;
             if (waiting) xv = el<T>::sub(xv, el<T>::mul(coef[step], xj));
         }
     }
     if (lane < nb) x[r] = xv;
+}
+// One CTA solves the panel [p0,p1) of op(S) in place: per 32-block, warp 0 solves the diagonal block, then every thread
+// takes panel rows the block reaches and subtracts its contribution (x lives in global memory; __syncthreads orders the
+// phases).  See structured.cuh: solve().
+template <typename T>
+__global__ void __launch_bounds__(SOLVE_THREADS) solve_panel_kernel(Desc D, const T* __restrict__ A, T* x, int p0, int p1, bool trans, bool conj, bool unit,
+                                                                    bool forward) {
+    const int nblk = (p1 - p0 + SOLVE_NB - 1) / SOLVE_NB, flags = conj ? F_CONJ : 0;
+    for (int bi = 0; bi < nblk; bi++) {
+        int b0, b1, u0, u1;
+        panel_block(D, p0, p1, forward, bi, b0, b1, u0, u1);
+        if (threadIdx.x < 32) solve_diag_warp<T>(D, A, x, b0, b1 - b0, trans, conj, unit, forward);
+        __syncthreads();
+        for (int r = u0 + threadIdx.x; r < u1; r += SOLVE_THREADS) x[r] = el<T>::sub(x[r], panel_update<T>(D, A, x, r, b0, b1, trans, flags));
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------ the device backend of the plans ------------------------------------------------
@@ -162,8 +184,8 @@ struct DeviceBackend {
         rank_kernel<T><<<dim3((rows + 127) / 128, nchunks), 128, 0, s>>>(D, A, rows, ncols, cpc, alpha, x, y, mode);
         last_variant = VAR_GENERIC_TILE;
     }
-    template <typename T> void solve_diag(const Desc& D, const T* A, T* x, int b0, int nb, bool trans, bool conj, bool unit, bool forward) {
-        solve_diag_kernel<T><<<1, 32, 0, s>>>(D, A, x, b0, nb, trans, conj, unit, forward);
+    template <typename T> void solve_panel(const Desc& D, const T* A, T* x, int p0, int p1, bool trans, bool conj, bool unit, bool forward) {
+        solve_panel_kernel<T><<<1, SOLVE_THREADS, 0, s>>>(D, A, x, p0, p1, trans, conj, unit, forward);
         last_variant = VAR_GENERIC_TILE;
     }
     template <typename T> void solve_nupdate(const Desc& D, const T* A, T* x, int row0, int row1, int b0, int b1, int flags) {

@@ -1,4 +1,5 @@
 // runtime.cu -- see runtime.h.
+#include <time.h>
 #include "runtime.h"
 #include "common.cuh"
 #include "kernels.h"
@@ -199,6 +200,33 @@ void* pinned_scalar() {
     if (!t_ctx.pinned) { TrackerGuard guard; B200_CUDA(cudaMallocHost(&t_ctx.pinned, 256)); }
     return t_ctx.pinned;
 }
+static thread_local bool t_result_observed = false;
+void* armed_scalar(size_t bytes) {
+    void* p = pinned_scalar();
+    memset(p, 0xFF, bytes);      // all-ones words: a NaN no arithmetic produces / an index no reduction returns
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    return p;
+}
+void wait_scalar(const void* slot, size_t bytes, size_t word_bytes) {
+    // the kernel stores the result word by word (a complex value is two stores): every word must have changed
+    const int nw = (int)(bytes / word_bytes);
+    struct timespec t0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (unsigned it = 1;; it++) {
+        bool done = true;
+        if (word_bytes == 4) { for (int w = 0; w < nw; w++) done = done && ((const volatile uint32_t*)slot)[w] != 0xFFFFFFFFu; }
+        else { for (int w = 0; w < nw; w++) done = done && ((const volatile uint64_t*)slot)[w] != ~0ull; }
+        if (done) { __atomic_thread_fence(__ATOMIC_ACQUIRE); t_result_observed = true; return; }
+        __builtin_ia32_pause();
+        if ((it & 1023u) == 0) {   // bounded: a result that really is all-ones, or a faulted kernel, ends in the synchronise below
+            struct timespec t1;
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            if ((t1.tv_sec - t0.tv_sec) * 1000000000ll + (t1.tv_nsec - t0.tv_nsec) > 20000000ll) break;
+        }
+    }
+    B200_CUDA(cudaStreamSynchronize(current_stream()));
+    t_result_observed = true;
+}
 void* device_scalar() {
     if (!t_ctx.dscalar) {
         TrackerGuard guard;
@@ -213,7 +241,9 @@ void finish_call() {
     // reference skips this on concurrentManagedAccess devices (runtime.h:33-34) and so races
     // with the caller on every modern GPU; here the per-thread stream is drained unless the
     // caller opted out (device-resident pipelines, b200blas_set_sync(0)).
-    if (g_opts.sync) {
+    const bool observed = t_result_observed;   // a reduction whose value the host has already read (wait_scalar)
+    t_result_observed = false;
+    if (g_opts.sync && !(observed && !g_opts.debug_execfail)) {
         B200_CUDA(cudaStreamSynchronize(current_stream()));
     } else if (g_opts.debug_execfail) {
         B200_CUDA(cudaStreamSynchronize(current_stream()));

@@ -48,6 +48,12 @@ bool encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, void*
 void* ws_alloc(size_t bytes);       // 256-B aligned device memory valid until the call returns
 void ws_reset();
 void* pinned_scalar();              // 64 B of pinned host memory for scalar results (per thread)
+// Scalar results without a stream synchronisation: armed_scalar() hands out the pinned slot pre-filled with an "unwritten"
+// pattern, the reduction's finishing block stores the value straight into it (zero-copy), and wait_scalar() spins on the
+// slot until every word has changed (bounded; falls back to cudaStreamSynchronize, which also surfaces kernel faults).
+// Once the value is seen the call's only kernel has done its work, so finish_call() skips its own synchronisation.
+void* armed_scalar(size_t bytes);
+void wait_scalar(const void* slot, size_t bytes, size_t word_bytes);   // word_bytes: size of the stores the kernel makes (4 or 8)
 void* device_scalar();              // 64 B of device memory for scalar results (per thread)
 
 enum Access { ACC_IN = 1, ACC_OUT = 2, ACC_INOUT = 3 };

@@ -155,29 +155,70 @@ template <typename T> ST_HD T load_elem(const Desc& D, const T* A, int i, int j,
     return a;
 }
 
-// r(i) = sum over the stored columns j of row i inside [c0, c1) of op(S(i,j)) * v(j)
+// offset(i, j+1) - offset(i, j): the walk along a row is a pointer bump (no 64-bit multiply per element)
+ST_HD int64_t col_step(const Desc& D, int j) {
+    switch (D.kind) {
+        case K_BAND_GEN:
+        case K_BAND_TRI: return D.ld - 1;
+        case K_PACKED: return D.upper ? (int64_t)j + 1 : (int64_t)D.n - j - 1;
+        default: return D.ld;
+    }
+}
+// the flags applied to a loaded element; a skipped diagonal becomes an exact zero (its stored value, rogue or NaN, is dropped)
+template <typename T> ST_HD T apply_flags(T a, int i, int j, int flags) {
+    if (i == j) {
+        if (flags & F_NODIAG) return el<T>::zero();
+        if (flags & F_HERM) a = el<T>::realpart(a);
+    }
+    return (flags & F_CONJ) ? el<T>::conj(a) : a;
+}
+// r(i) = sum over the stored columns j of row i inside [c0, c1) of op(S(i,j)) * v(j).
+// Four columns per step, loads issued before the arithmetic: with one thread per row the loads in flight per SM are what
+// sets the bandwidth (first version, one load per step: 24-33 % of the HBM peak; profiles/r01e_level2_struct_perf_v1.txt).
 template <typename T> ST_HD T npart_row(const Desc& D, const T* A, const T* v, int i, int c0, int c1, int flags) {
     int j0, j1;
     row_cols(D, i, j0, j1);
     j0 = st_max(j0, c0); j1 = st_min(j1, c1);
-    T acc = el<T>::zero();
-    for (int j = j0; j < j1; j++) {
-        if ((flags & F_NODIAG) && i == j) continue;
-        acc = el<T>::mad(load_elem<T>(D, A, i, j, flags), v[j], acc);
+    T acc0 = el<T>::zero(), acc1 = el<T>::zero(), acc2 = el<T>::zero(), acc3 = el<T>::zero();
+    if (j0 >= j1) return acc0;
+    const T* p = A + off(D, i, j0);
+    int j = j0;
+    for (; j + 4 <= j1; j += 4) {
+        const int64_t s0 = col_step(D, j), s1 = s0 + col_step(D, j + 1), s2 = s1 + col_step(D, j + 2), s3 = s2 + col_step(D, j + 3);
+        const T a0 = p[0], a1 = p[s0], a2 = p[s1], a3 = p[s2];
+        const T v0 = v[j], v1 = v[j + 1], v2 = v[j + 2], v3 = v[j + 3];
+        p += s3;
+        acc0 = el<T>::mad(apply_flags<T>(a0, i, j, flags), v0, acc0);
+        acc1 = el<T>::mad(apply_flags<T>(a1, i, j + 1, flags), v1, acc1);
+        acc2 = el<T>::mad(apply_flags<T>(a2, i, j + 2, flags), v2, acc2);
+        acc3 = el<T>::mad(apply_flags<T>(a3, i, j + 3, flags), v3, acc3);
     }
-    return acc;
+    for (; j < j1; j++) {
+        acc0 = el<T>::mad(apply_flags<T>(*p, i, j, flags), v[j], acc0);
+        p += col_step(D, j);
+    }
+    return el<T>::add(el<T>::add(acc0, acc1), el<T>::add(acc2, acc3));
 }
-// this lane's share of r(j) = sum over the stored rows i of column j inside [r0, r1) of op(S(i,j)) * v(i)
+// this lane's share of r(j) = sum over the stored rows i of column j inside [r0, r1) of op(S(i,j)) * v(i); the stored rows
+// of a column are contiguous in every scheme, so the lane walks a pointer in steps of nlanes, four loads in flight
 template <typename T> ST_HD T tpart_lane(const Desc& D, const T* A, const T* v, int j, int lane, int nlanes, int r0, int r1, int flags) {
     int i0, i1;
     col_rows(D, j, i0, i1);
     i0 = st_max(i0, r0); i1 = st_min(i1, r1);
-    T acc = el<T>::zero();
-    for (int i = i0 + lane; i < i1; i += nlanes) {
-        if ((flags & F_NODIAG) && i == j) continue;
-        acc = el<T>::mad(load_elem<T>(D, A, i, j, flags), v[i], acc);
+    T acc0 = el<T>::zero(), acc1 = el<T>::zero(), acc2 = el<T>::zero(), acc3 = el<T>::zero();
+    int i = i0 + lane;
+    if (i >= i1) return acc0;
+    const T* p = A + off(D, i, j);
+    for (; (int64_t)i + 3 * (int64_t)nlanes < i1; i += 4 * nlanes, p += 4 * nlanes) {
+        const T a0 = p[0], a1 = p[nlanes], a2 = p[2 * nlanes], a3 = p[3 * nlanes];
+        const T v0 = v[i], v1 = v[i + nlanes], v2 = v[i + 2 * nlanes], v3 = v[i + 3 * nlanes];
+        acc0 = el<T>::mad(apply_flags<T>(a0, i, j, flags), v0, acc0);
+        acc1 = el<T>::mad(apply_flags<T>(a1, i + nlanes, j, flags), v1, acc1);
+        acc2 = el<T>::mad(apply_flags<T>(a2, i + 2 * nlanes, j, flags), v2, acc2);
+        acc3 = el<T>::mad(apply_flags<T>(a3, i + 3 * nlanes, j, flags), v3, acc3);
     }
-    return acc;
+    for (; i < i1; i += nlanes, p += nlanes) acc0 = el<T>::mad(apply_flags<T>(*p, i, j, flags), v[i], acc0);
+    return el<T>::add(el<T>::add(acc0, acc1), el<T>::add(acc2, acc3));
 }
 // out = alpha*(sum of the partial rows + tpart + vunit) + beta*old   (beta == 0: old is never read, like netlib)
 template <typename T>
@@ -199,6 +240,18 @@ enum RankMode {
     R_HER2 = 4,   // S(i,j) += alpha x(i) conj(y(j)) + conj(alpha) y(i) conj(x(j)); diagonal kept real
     R_SYR = 5     // S(i,j) += alpha x(i) x(j)
 };
+template <typename T> ST_HD T rank_elem(T a, int i, int j, T axi, T ayi, const T* x, const T* y, int mode) {
+    switch (mode) {
+        case R_GERU: a = el<T>::mad(axi, y[j], a); break;
+        case R_GERC: a = el<T>::mad(axi, el<T>::conj(y[j]), a); break;
+        case R_SYR: a = el<T>::mad(axi, x[j], a); break;
+        case R_SYR2: a = el<T>::mad(axi, y[j], a); a = el<T>::mad(ayi, x[j], a); break;
+        case R_HER: a = el<T>::mad(axi, el<T>::conj(x[j]), a); break;
+        default: a = el<T>::mad(axi, el<T>::conj(y[j]), a); a = el<T>::mad(ayi, el<T>::conj(x[j]), a); break;
+    }
+    if ((mode == R_HER || mode == R_HER2) && i == j) a = el<T>::realpart(a);
+    return a;
+}
 template <typename T> ST_HD void rank_row(const Desc& D, T* A, int i, int c0, int c1, T alpha, const T* x, const T* y, int mode) {
     int j0, j1;
     row_cols(D, i, j0, j1);
@@ -208,19 +261,20 @@ template <typename T> ST_HD void rank_row(const Desc& D, T* A, int i, int c0, in
     const T yi = (mode == R_SYR2 || mode == R_HER2) ? y[i] : el<T>::zero();
     const T axi = el<T>::mul(alpha, xi);                                          // alpha x(i)
     const T ayi = el<T>::mul(mode == R_HER2 ? el<T>::conj(alpha) : alpha, yi);     // alpha y(i)  /  conj(alpha) y(i)
-    for (int j = j0; j < j1; j++) {
-        T* p = A + off(D, i, j);
-        T a = *p;
-        switch (mode) {
-            case R_GERU: a = el<T>::mad(axi, y[j], a); break;
-            case R_GERC: a = el<T>::mad(axi, el<T>::conj(y[j]), a); break;
-            case R_SYR: a = el<T>::mad(axi, x[j], a); break;
-            case R_SYR2: a = el<T>::mad(axi, y[j], a); a = el<T>::mad(ayi, x[j], a); break;
-            case R_HER: a = el<T>::mad(axi, el<T>::conj(x[j]), a); break;
-            default: a = el<T>::mad(axi, el<T>::conj(y[j]), a); a = el<T>::mad(ayi, el<T>::conj(x[j]), a); break;
-        }
-        if ((mode == R_HER || mode == R_HER2) && i == j) a = el<T>::realpart(a);
-        *p = a;
+    T* p = A + off(D, i, j0);
+    int j = j0;
+    for (; j + 4 <= j1; j += 4) {   // four read-modify-writes per step, loads first (memory-level parallelism, as in npart_row)
+        const int64_t s0 = col_step(D, j), s1 = s0 + col_step(D, j + 1), s2 = s1 + col_step(D, j + 2), s3 = s2 + col_step(D, j + 3);
+        const T a0 = p[0], a1 = p[s0], a2 = p[s1], a3 = p[s2];
+        p[0] = rank_elem<T>(a0, i, j, axi, ayi, x, y, mode);
+        p[s0] = rank_elem<T>(a1, i, j + 1, axi, ayi, x, y, mode);
+        p[s1] = rank_elem<T>(a2, i, j + 2, axi, ayi, x, y, mode);
+        p[s2] = rank_elem<T>(a3, i, j + 3, axi, ayi, x, y, mode);
+        p += s3;
+    }
+    for (; j < j1; j++) {
+        *p = rank_elem<T>(*p, i, j, axi, ayi, x, y, mode);
+        p += col_step(D, j);
     }
 }
 
@@ -247,7 +301,7 @@ ST_HD int64_t vpos(int64_t i, int64_t n, int64_t inc) { return inc >= 0 ? i * in
 //   BE::tpart(D, A, v, col0, col1, r0, r1, flags, tpart)
 //   BE::finish(n, nparts, part, npad, tpart, vunit, alpha, beta, out, inco)
 //   BE::rank(D, A, rows, ncols, cpc, nchunks, alpha, x, y, mode)
-//   BE::solve_diag(D, A, x, b0, nb, trans, conj, unit, forward)
+//   BE::solve_panel(D, A, x, p0, p1, trans, conj, unit, forward)     one CTA: the whole panel [p0,p1) in place
 //   BE::solve_nupdate(D, A, x, row0, row1, b0, b1, flags) / solve_tupdate(D, A, x, col0, col1, b0, b1, flags)
 // =====================================================================================================================
 
@@ -296,22 +350,40 @@ inline void smv(BE& be, const Desc& D, const T* A, const T* v, int nflags, int t
     }
     be.finish(nout, nch, part, npad, tpart, vunit, alpha, beta, out, inco);
 }
-// solve op(S) x = b in place on a contiguous x: 32-wide diagonal blocks in dependency order, each followed by the update
-// of the rows it reaches (right-looking)
+// solve op(S) x = b in place on a contiguous x.  A panel of columns is solved by ONE CTA (32-wide diagonal blocks by a warp,
+// the rest of the panel updated by the CTA between them, see panel_block); the rows the panel reaches outside itself are
+// then updated by a grid-wide pass.  A narrow band never reaches outside a panel as wide as the matrix, so TBSV with a
+// small k is a single launch; packed / full triangles take n/256 panel launches + updates.
+// (first version: one launch per 32-block + one per update -- 31 ms for DTPSV n=32768, 286 ms for DTBSV n=2^18 k=127,
+//  all launch latency; profiles/r01e_level2_struct_perf_v1.txt)
+enum { SOLVE_NB = 32, SOLVE_PANEL = 256, SOLVE_BAND_REACH = 1024, SOLVE_THREADS = 256 };
+// block bi (in dependency order) of panel [p0,p1): its columns [b0,b1) and the panel rows [u0,u1) it must update
+ST_HD void panel_block(const Desc& D, int p0, int p1, bool forward, int bi, int& b0, int& b1, int& u0, int& u1) {
+    const int nblk = (p1 - p0 + SOLVE_NB - 1) / SOLVE_NB, b = forward ? bi : nblk - 1 - bi, rch = reach(D);
+    b0 = p0 + b * SOLVE_NB; b1 = st_min(p1, b0 + SOLVE_NB);
+    const int64_t reach_end = (int64_t)b1 + rch;   // op(S)(r,c) != 0 needs |r-c| <= reach
+    u0 = forward ? b1 : st_max(p0, b0 - rch);
+    u1 = forward ? (int)(reach_end < p1 ? reach_end : p1) : b0;
+}
+// the in-panel update of one unknown r by the solved block [b0,b1)
+template <typename T> ST_HD T panel_update(const Desc& D, const T* A, const T* x, int r, int b0, int b1, bool trans, int flags) {
+    return trans ? tpart_lane<T>(D, A, x, r, 0, 1, b0, b1, flags) : npart_row<T>(D, A, x, r, b0, b1, flags);
+}
 template <typename T, typename BE> inline void solve(BE& be, const Desc& D, const T* A, T* x, bool trans, bool conj, bool unit) {
-    const int n = D.n, NB = 32, rch = reach(D);
+    const int n = D.n, rch = reach(D);
     const bool forward = (D.upper != 0) == trans;   // op(S) is lower triangular
     const int flags = conj ? F_CONJ : 0;
-    const int nblk = (n + NB - 1) / NB;
-    for (int bi = 0; bi < nblk; bi++) {
-        const int b = forward ? bi : nblk - 1 - bi;
-        const int b0 = b * NB, b1 = st_min(n, b0 + NB);
-        be.solve_diag(D, A, x, b0, b1 - b0, trans, conj, unit, forward);
-        const int64_t reach_end = (int64_t)b1 + rch;   // op(S)(r,c) != 0 needs |r-c| <= reach
-        const int u0 = forward ? b1 : st_max(0, b0 - rch), u1 = forward ? (int)(reach_end < n ? reach_end : n) : b0;
+    const int pw = rch <= SOLVE_BAND_REACH ? n : SOLVE_PANEL;
+    const int npan = (n + pw - 1) / pw;
+    for (int pi = 0; pi < npan; pi++) {
+        const int pb = forward ? pi : npan - 1 - pi;
+        const int p0 = pb * pw, p1 = (int64_t)p0 + pw < n ? p0 + pw : n;
+        be.solve_panel(D, A, x, p0, p1, trans, conj, unit, forward);
+        const int64_t reach_end = (int64_t)p1 + rch;
+        const int u0 = forward ? p1 : st_max(0, p0 - rch), u1 = forward ? (int)(reach_end < n ? reach_end : n) : p0;
         if (u1 <= u0) continue;
-        if (!trans) be.solve_nupdate(D, A, x, u0, u1, b0, b1, flags);
-        else be.solve_tupdate(D, A, x, u0, u1, b0, b1, flags);
+        if (!trans) be.solve_nupdate(D, A, x, u0, u1, p0, p1, flags);
+        else be.solve_tupdate(D, A, x, u0, u1, p0, p1, flags);
     }
 }
 

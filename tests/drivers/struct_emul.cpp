@@ -79,18 +79,21 @@ struct HostBackend {
                     rank_row<T>(D, A, i, c0, c1, alpha, x, y, mode);
                 }
     }
-    // the warp of solve_diag_kernel, lane by lane in lock step
+    // the warp of solve_diag_warp, lane by lane in lock step
     template <typename T> void solve_diag(const Desc& D, const T* A, T* x, int b0, int nb, bool trans, bool conj, bool unit, bool forward) {
-        T coef[32][32], xv[32];
+        T coef[32][32], dinv[32], xv[32];
         for (int lane = 0; lane < 32; lane++) {
             const int r = b0 + lane;
+            dinv[lane] = el<T>::one();
             for (int step = 0; step < 32; step++) {
                 const int jj = forward ? step : nb - 1 - step;
                 coef[lane][step] = el<T>::zero();
                 if (step < nb && lane < nb) {
                     const bool waiting = forward ? lane > jj : lane < jj;
                     T a;
-                    if ((waiting || (lane == jj && !unit)) && solve_coef<T>(D, A, r, b0 + jj, trans, conj, a)) coef[lane][step] = a;
+                    if ((waiting || (lane == jj && !unit)) && solve_coef<T>(D, A, r, b0 + jj, trans, conj, a)) {
+                        if (lane == jj) dinv[lane] = el<T>::div(el<T>::one(), a); else coef[lane][step] = a;
+                    }
                 }
             }
             xv[lane] = lane < nb ? x[r] : el<T>::zero();
@@ -98,7 +101,7 @@ struct HostBackend {
         for (int step = 0; step < 32; step++) {
             if (step >= nb) continue;
             const int jj = forward ? step : nb - 1 - step;
-            if (!unit) xv[jj] = el<T>::div(xv[jj], coef[jj][step]);
+            if (!unit) xv[jj] = el<T>::mul(xv[jj], dinv[jj]);
             const T xj = xv[jj];
             for (int lane = 0; lane < 32; lane++) {
                 const bool waiting = forward ? (lane > jj && lane < nb) : lane < jj;
@@ -106,6 +109,18 @@ struct HostBackend {
             }
         }
         for (int lane = 0; lane < nb; lane++) x[b0 + lane] = xv[lane];
+    }
+    // solve_panel_kernel: the CTA's phases in order; within the update phase every thread reads only solved unknowns of the
+    // block and writes only its own rows, so the thread order does not matter
+    template <typename T> void solve_panel(const Desc& D, const T* A, T* x, int p0, int p1, bool trans, bool conj, bool unit, bool forward) {
+        const int nblk = (p1 - p0 + SOLVE_NB - 1) / SOLVE_NB, flags = conj ? F_CONJ : 0;
+        for (int bi = 0; bi < nblk; bi++) {
+            int b0, b1, u0, u1;
+            panel_block(D, p0, p1, forward, bi, b0, b1, u0, u1);
+            solve_diag<T>(D, A, x, b0, b1 - b0, trans, conj, unit, forward);
+            for (int tx = 0; tx < SOLVE_THREADS; tx++)
+                for (int r = u0 + tx; r < u1; r += SOLVE_THREADS) x[r] = el<T>::sub(x[r], panel_update<T>(D, A, x, r, b0, b1, trans, flags));
+        }
     }
     template <typename T> void solve_nupdate(const Desc& D, const T* A, T* x, int row0, int row1, int b0, int b1, int flags) {
         for (int i = row0; i < row1; i++) x[i] = el<T>::sub(x[i], npart_row<T>(D, A, x, i, b0, b1, flags));

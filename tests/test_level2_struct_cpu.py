@@ -62,12 +62,28 @@ def test_kernel_index_logic_emulated(p, rowmajor):
 
 
 def test_emulated_solves_cross_block_boundaries():
-    """n > 32 with every reach: the diagonal-block solve + update chain of TBSV/TPSV over several blocks, both directions"""
+    """n > 32 with every reach: the diagonal-block solve + update chain of TBSV/TPSV over several blocks, both directions;
+    n > 256: several panels with the grid-wide update between them (packed / wide band), and a band wider than the
+    single-launch limit (reach > 1024)"""
     for p in "dz":
         cs = [c for c in l2x.cases(p, sizes=(31, 32, 33, 64, 97)) if c.name[1:] in ("tbsv", "tpsv")]
         assert len(cs) > 200
         w, tag = _worst(cs, lambda c, args: l2x.emu_call(c.name, *args))
         assert w < 1.0, (tag, w)
+    cs = [c for c in l2x.cases("d", sizes=(255, 256, 257, 600)) if c.name[1:] in ("tbsv", "tpsv")]
+    w, tag = _worst(cs, lambda c, args: l2x.emu_call(c.name, *args))
+    assert w < 1.0, (tag, w)
+    n, k = 1300, 1100
+    G = l2x.well_conditioned_tri(3, n, "d")
+    b = l2x.rnd(4, (n,), "d")
+    for ul in "UL":
+        Tk = np.where(l2x.tri_mask(n, ul, k), G, 0)
+        i, j = np.indices((k + 1, n)); rows = (j - k + i) if ul == "U" else (j + i); ok = (rows >= 0) & (rows < n)
+        ab = np.zeros((k + 1, n), order="F"); ab[ok] = Tk[rows[ok], j[ok]]
+        for tr in "NT":
+            x = b.copy()
+            l2x.emu_call("dtbsv", ul, tr, "N", n, k, ab, k + 1, x, 1)
+            assert np.allclose(x, np.linalg.solve(l2x.opmat(Tk, tr), b), rtol=1e-10, atol=1e-10), (ul, tr)
 
 
 def test_emulated_gemv_conj_notrans():
