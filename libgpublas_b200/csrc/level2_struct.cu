@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(128) npart_kernel(Desc D, const T* __restrict_
     const int i = row0 + blockIdx.x * 128 + threadIdx.x;
     if (i >= row1) return;
     const int c0 = c_lo + blockIdx.y * cpc, c1 = st_min(c_hi, c0 + cpc);
-    part[(int64_t)blockIdx.y * npad + i] = npart_row<T>(D, A, v, i, c0, c1, flags);
+    part[(int64_t)blockIdx.y * npad + i] = npart_row<T>(D, A, v, i, c0, c1, flags, i - (threadIdx.x & 31));
 }
 // tpart[j] = T part of column j over rows [r0,r1); one warp per column in [col0,col1)
 template <typename T>
@@ -91,14 +91,14 @@ __global__ void __launch_bounds__(128) rank_kernel(Desc D, T* __restrict__ A, in
     const int i = blockIdx.x * 128 + threadIdx.x;
     if (i >= rows) return;
     const int c0 = blockIdx.y * cpc, c1 = st_min(ncols, c0 + cpc);
-    rank_row<T>(D, A, i, c0, c1, alpha, x, y, mode);
+    rank_row<T>(D, A, i, c0, c1, alpha, x, y, mode, i - (threadIdx.x & 31));
 }
 // x(i) -= N part of row i over the solved block's columns [b0,b1)      (rows [row0,row1) lie outside the block)
 template <typename T>
 __global__ void __launch_bounds__(128) solve_nupdate_kernel(Desc D, const T* __restrict__ A, T* x, int row0, int row1, int b0, int b1, int flags) {
     const int i = row0 + blockIdx.x * 128 + threadIdx.x;
     if (i >= row1) return;
-    x[i] = el<T>::sub(x[i], npart_row<T>(D, A, x, i, b0, b1, flags));
+    x[i] = el<T>::sub(x[i], npart_row<T>(D, A, x, i, b0, b1, flags, i - (threadIdx.x & 31)));
 }
 // x(j) -= T part of column j over the solved block's rows [b0,b1)      (columns [col0,col1) lie outside the block)
 template <typename T>
@@ -118,17 +118,30 @@ __device__ __forceinline__ void solve_diag_warp(const Desc& D, const T* __restri
     const int lane = threadIdx.x & 31, r = b0 + lane;
     T coef[32];
     T dinv = el<T>::one();
+    // Every load is unconditional (a lane with nothing to fetch re-reads its own diagonal element, which always exists), so
+    // the 32 loads issue back to back; behind a branch each one waited for the previous (32 memory latencies per block:
+    // 30 us, the whole cost of the first version -- profiles/r01f_level2_struct_perf_v2.txt).
+    const int rs = r < D.n ? r : D.n - 1;
+    const int64_t safe = off(D, rs, rs);
+    unsigned okmask = 0;
 #pragma unroll
-    for (int step = 0; step < 32; step++) {
+    for (int step = 0; step < 32; step++) {   // pass 1: addresses and loads only -- nothing here consumes a loaded value
         const int jj = forward ? step : nb - 1 - step;
-        coef[step] = el<T>::zero();
-        if (step < nb && lane < nb) {
-            const bool waiting = forward ? lane > jj : lane < jj;
-            T a;
-            if ((waiting || (lane == jj && !unit)) && solve_coef<T>(D, A, r, b0 + jj, trans, conj, a)) {
-                if (lane == jj) dinv = el<T>::div(el<T>::one(), a); else coef[step] = a;
-            }
-        }
+        const int c = b0 + jj, ci = trans ? c : r, cj = trans ? r : c;
+        const bool waiting = forward ? lane > jj : lane < jj;
+        const bool want = step < nb && lane < nb && (waiting || (lane == jj && !unit));
+        const bool ok = want && stored(D, ci, cj);
+        coef[step] = A[ok ? off(D, ci, cj) : safe];
+        okmask |= (ok ? 1u : 0u) << step;
+    }
+#pragma unroll
+    for (int step = 0; step < 32; step++) {   // pass 2: conjugate, mask, pivot reciprocal
+        const int jj = forward ? step : nb - 1 - step;
+        const bool ok = (okmask >> step) & 1u;
+        T a = coef[step];
+        if (conj) a = el<T>::conj(a);
+        coef[step] = (ok && lane != jj) ? a : el<T>::zero();
+        if (ok && lane == jj) dinv = el<T>::div(el<T>::one(), a);
     }
     T xv = lane < nb ? x[r] : el<T>::zero();
 #pragma unroll

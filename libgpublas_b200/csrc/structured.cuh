@@ -173,31 +173,43 @@ template <typename T> ST_HD T apply_flags(T a, int i, int j, int flags) {
     return (flags & F_CONJ) ? el<T>::conj(a) : a;
 }
 // r(i) = sum over the stored columns j of row i inside [c0, c1) of op(S(i,j)) * v(j).
-// Four columns per step, loads issued before the arithmetic: with one thread per row the loads in flight per SM are what
-// sets the bandwidth (first version, one load per step: 24-33 % of the HBM peak; profiles/r01e_level2_struct_perf_v1.txt).
-template <typename T> ST_HD T npart_row(const Desc& D, const T* A, const T* v, int i, int c0, int c1, int flags) {
-    int j0, j1;
+// Memory behaviour is the point of this body (one thread per row):
+//  * the threads of a warp must read the SAME column in the same step, or their addresses are a leading dimension apart:
+//    the walk starts at the first stored column of the warp's first row (i_first; the start column never decreases with
+//    the row) and a thread simply masks the columns left of its own range (upper triangles, bands);
+//  * NU columns per step, all loads issued before the arithmetic: with one thread per row the bytes in flight per SM set
+//    the bandwidth (one load per step: 24-33 % of the HBM peak, profiles/r01e_level2_struct_perf_v1.txt).
+template <typename T> struct unroll_of { enum { N = sizeof(T) >= 16 ? 4 : 8 }; };
+template <typename T> ST_HD T npart_row(const Desc& D, const T* A, const T* v, int i, int c0, int c1, int flags, int i_first) {
+    enum { NU = unroll_of<T>::N };
+    int j0, j1, jf0, jf1;
     row_cols(D, i, j0, j1);
     j0 = st_max(j0, c0); j1 = st_min(j1, c1);
-    T acc0 = el<T>::zero(), acc1 = el<T>::zero(), acc2 = el<T>::zero(), acc3 = el<T>::zero();
-    if (j0 >= j1) return acc0;
-    const T* p = A + off(D, i, j0);
-    int j = j0;
-    for (; j + 4 <= j1; j += 4) {
-        const int64_t s0 = col_step(D, j), s1 = s0 + col_step(D, j + 1), s2 = s1 + col_step(D, j + 2), s3 = s2 + col_step(D, j + 3);
-        const T a0 = p[0], a1 = p[s0], a2 = p[s1], a3 = p[s2];
-        const T v0 = v[j], v1 = v[j + 1], v2 = v[j + 2], v3 = v[j + 3];
-        p += s3;
-        acc0 = el<T>::mad(apply_flags<T>(a0, i, j, flags), v0, acc0);
-        acc1 = el<T>::mad(apply_flags<T>(a1, i, j + 1, flags), v1, acc1);
-        acc2 = el<T>::mad(apply_flags<T>(a2, i, j + 2, flags), v2, acc2);
-        acc3 = el<T>::mad(apply_flags<T>(a3, i, j + 3, flags), v3, acc3);
+    row_cols(D, i_first, jf0, jf1);
+    const int jstart = st_min(j0, st_max(jf0, c0));
+    T acc[NU];
+#pragma unroll
+    for (int u = 0; u < NU; u++) acc[u] = el<T>::zero();
+    if (j0 >= j1) return acc[0];
+    const T* p = A + off(D, i, jstart);   // may point outside the stored part for columns left of j0: never dereferenced there
+    for (int j = jstart; j < j1; j += NU) {
+        T a[NU], w[NU];
+        int64_t s = 0;
+#pragma unroll
+        for (int u = 0; u < NU; u++) {
+            const bool in = j + u >= j0 && j + u < j1;
+            a[u] = in ? p[s] : el<T>::zero();
+            w[u] = in ? v[j + u] : el<T>::zero();
+            s += col_step(D, j + u);
+        }
+        p += s;
+#pragma unroll
+        for (int u = 0; u < NU; u++) acc[u] = el<T>::mad(apply_flags<T>(a[u], i, j + u, flags), w[u], acc[u]);
     }
-    for (; j < j1; j++) {
-        acc0 = el<T>::mad(apply_flags<T>(*p, i, j, flags), v[j], acc0);
-        p += col_step(D, j);
-    }
-    return el<T>::add(el<T>::add(acc0, acc1), el<T>::add(acc2, acc3));
+    T r = acc[0];
+#pragma unroll
+    for (int u = 1; u < NU; u++) r = el<T>::add(r, acc[u]);
+    return r;
 }
 // this lane's share of r(j) = sum over the stored rows i of column j inside [r0, r1) of op(S(i,j)) * v(i); the stored rows
 // of a column are contiguous in every scheme, so the lane walks a pointer in steps of nlanes, four loads in flight
@@ -252,29 +264,33 @@ template <typename T> ST_HD T rank_elem(T a, int i, int j, T axi, T ayi, const T
     if ((mode == R_HER || mode == R_HER2) && i == j) a = el<T>::realpart(a);
     return a;
 }
-template <typename T> ST_HD void rank_row(const Desc& D, T* A, int i, int c0, int c1, T alpha, const T* x, const T* y, int mode) {
-    int j0, j1;
+template <typename T> ST_HD void rank_row(const Desc& D, T* A, int i, int c0, int c1, T alpha, const T* x, const T* y, int mode, int i_first) {
+    enum { NU = unroll_of<T>::N };
+    int j0, j1, jf0, jf1;
     row_cols(D, i, j0, j1);
     j0 = st_max(j0, c0); j1 = st_min(j1, c1);
     if (j0 >= j1) return;
+    row_cols(D, i_first, jf0, jf1);
+    const int jstart = st_min(j0, st_max(jf0, c0));   // the warp walks the same columns in the same steps (see npart_row)
     const T xi = x[i];
     const T yi = (mode == R_SYR2 || mode == R_HER2) ? y[i] : el<T>::zero();
     const T axi = el<T>::mul(alpha, xi);                                          // alpha x(i)
     const T ayi = el<T>::mul(mode == R_HER2 ? el<T>::conj(alpha) : alpha, yi);     // alpha y(i)  /  conj(alpha) y(i)
-    T* p = A + off(D, i, j0);
-    int j = j0;
-    for (; j + 4 <= j1; j += 4) {   // four read-modify-writes per step, loads first (memory-level parallelism, as in npart_row)
-        const int64_t s0 = col_step(D, j), s1 = s0 + col_step(D, j + 1), s2 = s1 + col_step(D, j + 2), s3 = s2 + col_step(D, j + 3);
-        const T a0 = p[0], a1 = p[s0], a2 = p[s1], a3 = p[s2];
-        p[0] = rank_elem<T>(a0, i, j, axi, ayi, x, y, mode);
-        p[s0] = rank_elem<T>(a1, i, j + 1, axi, ayi, x, y, mode);
-        p[s1] = rank_elem<T>(a2, i, j + 2, axi, ayi, x, y, mode);
-        p[s2] = rank_elem<T>(a3, i, j + 3, axi, ayi, x, y, mode);
-        p += s3;
-    }
-    for (; j < j1; j++) {
-        *p = rank_elem<T>(*p, i, j, axi, ayi, x, y, mode);
-        p += col_step(D, j);
+    T* p = A + off(D, i, jstart);
+    for (int j = jstart; j < j1; j += NU) {   // NU read-modify-writes per step, loads first
+        T a[NU];
+        int64_t st[NU], s = 0;
+#pragma unroll
+        for (int u = 0; u < NU; u++) {
+            const bool in = j + u >= j0 && j + u < j1;
+            st[u] = s;
+            if (in) a[u] = p[s];
+            s += col_step(D, j + u);
+        }
+#pragma unroll
+        for (int u = 0; u < NU; u++)
+            if (j + u >= j0 && j + u < j1) p[st[u]] = rank_elem<T>(a[u], i, j + u, axi, ayi, x, y, mode);
+        p += s;
     }
 }
 
@@ -367,7 +383,7 @@ ST_HD void panel_block(const Desc& D, int p0, int p1, bool forward, int bi, int&
 }
 // the in-panel update of one unknown r by the solved block [b0,b1)
 template <typename T> ST_HD T panel_update(const Desc& D, const T* A, const T* x, int r, int b0, int b1, bool trans, int flags) {
-    return trans ? tpart_lane<T>(D, A, x, r, 0, 1, b0, b1, flags) : npart_row<T>(D, A, x, r, b0, b1, flags);
+    return trans ? tpart_lane<T>(D, A, x, r, 0, 1, b0, b1, flags) : npart_row<T>(D, A, x, r, b0, b1, flags, r);
 }
 template <typename T, typename BE> inline void solve(BE& be, const Desc& D, const T* A, T* x, bool trans, bool conj, bool unit) {
     const int n = D.n, rch = reach(D);

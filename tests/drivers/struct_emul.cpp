@@ -48,7 +48,7 @@ struct HostBackend {
                     const int i = row0 + bx * 128 + tx;
                     if (i >= row1) continue;
                     const int c0 = c_lo + by * cpc, c1 = st_min(c_hi, c0 + cpc);
-                    part[(int64_t)by * npad + i] = npart_row<T>(D, A, v, i, c0, c1, flags);
+                    part[(int64_t)by * npad + i] = npart_row<T>(D, A, v, i, c0, c1, flags, i - (tx & 31));
                 }
     }
     template <typename T> void tpart(const Desc& D, const T* A, const T* v, int col0, int col1, int r0, int r1, int flags, T* tp) {
@@ -76,7 +76,7 @@ struct HostBackend {
                     const int i = bx * 128 + tx;
                     if (i >= rows) continue;
                     const int c0 = by * cpc, c1 = st_min(ncols, c0 + cpc);
-                    rank_row<T>(D, A, i, c0, c1, alpha, x, y, mode);
+                    rank_row<T>(D, A, i, c0, c1, alpha, x, y, mode, i - (tx & 31));
                 }
     }
     // the warp of solve_diag_warp, lane by lane in lock step
@@ -123,7 +123,11 @@ struct HostBackend {
         }
     }
     template <typename T> void solve_nupdate(const Desc& D, const T* A, T* x, int row0, int row1, int b0, int b1, int flags) {
-        for (int i = row0; i < row1; i++) x[i] = el<T>::sub(x[i], npart_row<T>(D, A, x, i, b0, b1, flags));
+        for (int bx = 0; bx < (row1 - row0 + 127) / 128; bx++)
+            for (int tx = 0; tx < 128; tx++) {
+                const int i = row0 + bx * 128 + tx;
+                if (i < row1) x[i] = el<T>::sub(x[i], npart_row<T>(D, A, x, i, b0, b1, flags, i - (tx & 31)));
+            }
     }
     template <typename T> void solve_tupdate(const Desc& D, const T* A, T* x, int col0, int col1, int b0, int b1, int flags) {
         for (int j = col0; j < col1; j++) {
