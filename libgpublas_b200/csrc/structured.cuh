@@ -195,12 +195,17 @@ template <typename T> ST_HD T npart_row(const Desc& D, const T* A, const T* v, i
     for (int j = jstart; j < j1; j += NU) {
         T a[NU], w[NU];
         int64_t s = 0;
+        if (j >= j0 && j + NU <= j1) {   // interior step: no masks
 #pragma unroll
-        for (int u = 0; u < NU; u++) {
-            const bool in = j + u >= j0 && j + u < j1;
-            a[u] = in ? p[s] : el<T>::zero();
-            w[u] = in ? v[j + u] : el<T>::zero();
-            s += col_step(D, j + u);
+            for (int u = 0; u < NU; u++) { a[u] = p[s]; w[u] = v[j + u]; s += col_step(D, j + u); }
+        } else {                         // head (columns left of this row's range) or tail
+#pragma unroll
+            for (int u = 0; u < NU; u++) {
+                const bool in = j + u >= j0 && j + u < j1;
+                a[u] = in ? p[s] : el<T>::zero();
+                w[u] = in ? v[j + u] : el<T>::zero();
+                s += col_step(D, j + u);
+            }
         }
         p += s;
 #pragma unroll
@@ -280,16 +285,22 @@ template <typename T> ST_HD void rank_row(const Desc& D, T* A, int i, int c0, in
     for (int j = jstart; j < j1; j += NU) {   // NU read-modify-writes per step, loads first
         T a[NU];
         int64_t st[NU], s = 0;
+        if (j >= j0 && j + NU <= j1) {        // interior step: no masks
 #pragma unroll
-        for (int u = 0; u < NU; u++) {
-            const bool in = j + u >= j0 && j + u < j1;
-            st[u] = s;
-            if (in) a[u] = p[s];
-            s += col_step(D, j + u);
+            for (int u = 0; u < NU; u++) { st[u] = s; a[u] = p[s]; s += col_step(D, j + u); }
+#pragma unroll
+            for (int u = 0; u < NU; u++) p[st[u]] = rank_elem<T>(a[u], i, j + u, axi, ayi, x, y, mode);
+        } else {                              // head (columns left of this row's range) or tail
+#pragma unroll
+            for (int u = 0; u < NU; u++) {
+                st[u] = s;
+                a[u] = (j + u >= j0 && j + u < j1) ? p[s] : el<T>::zero();
+                s += col_step(D, j + u);
+            }
+#pragma unroll
+            for (int u = 0; u < NU; u++)
+                if (j + u >= j0 && j + u < j1) p[st[u]] = rank_elem<T>(a[u], i, j + u, axi, ayi, x, y, mode);
         }
-#pragma unroll
-        for (int u = 0; u < NU; u++)
-            if (j + u >= j0 && j + u < j1) p[st[u]] = rank_elem<T>(a[u], i, j + u, axi, ayi, x, y, mode);
         p += s;
     }
 }
