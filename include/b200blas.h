@@ -200,6 +200,8 @@ B200_API void srotmg_(float* d1, float* d2, float* x1, const float* y1, float* p
 B200_API void drotmg_(double* d1, double* d2, double* x1, const double* y1, double* param);
 B200_API void csrot_(const int* n, b200_c32* x, const int* incx, b200_c32* y, const int* incy, const float* c, const float* s);
 B200_API void zdrot_(const int* n, b200_c64* x, const int* incx, b200_c64* y, const int* incy, const double* c, const double* s);
+B200_API void crotg_(b200_c32* ca, const b200_c32* cb, float* c, b200_c32* s);
+B200_API void zrotg_(b200_c64* ca, const b200_c64* cb, double* c, b200_c64* s);
 B200_API int isamin_(const int* n, const float* x, const int* incx);
 B200_API int idamin_(const int* n, const double* x, const int* incx);
 B200_API int icamin_(const int* n, const b200_c32* x, const int* incx);
@@ -346,6 +348,8 @@ B200_API void cblas_srotmg(float* d1, float* d2, float* x1, float y1, float* par
 B200_API void cblas_drotmg(double* d1, double* d2, double* x1, double y1, double* param);
 B200_API void cblas_csrot(int n, void* x, int incx, void* y, int incy, float c, float s);
 B200_API void cblas_zdrot(int n, void* x, int incx, void* y, int incy, double c, double s);
+B200_API void cblas_crotg(void* a, void* b, float* c, void* s);
+B200_API void cblas_zrotg(void* a, void* b, double* c, void* s);
 B200_API CBLAS_INDEX cblas_isamin(int n, const float* x, int incx);
 B200_API CBLAS_INDEX cblas_idamin(int n, const double* x, int incx);
 B200_API CBLAS_INDEX cblas_icamin(int n, const void* x, int incx);
@@ -364,6 +368,18 @@ B200_API float cblas_scasum(int n, const void* x, int incx);
 B200_API double cblas_dzasum(int n, const void* x, int incx);
 B200_API void cblas_ctrsv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const void* a, int lda, void* x, int incx);
 B200_API void cblas_ztrsv(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, enum CBLAS_DIAG diag, int n, const void* a, int lda, void* x, int incx);
+
+/* complex SYMM / HEMM / SYR2K / HERK / HER2K (reference cblas.h DECLARE_CBLAS__SYMM, __HEMM, __SYR2K, __HERK, __HER2K; complex scalars by pointer) */
+B200_API void cblas_csymm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, int m, int n, const void* alpha, const void* a, int lda, const void* b, int ldb, const void* beta, void* c, int ldc);
+B200_API void cblas_chemm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, int m, int n, const void* alpha, const void* a, int lda, const void* b, int ldb, const void* beta, void* c, int ldc);
+B200_API void cblas_csyr2k(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, const void* alpha, const void* a, int lda, const void* b, int ldb, const void* beta, void* c, int ldc);
+B200_API void cblas_cherk(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, float alpha, const void* a, int lda, float beta, void* c, int ldc);
+B200_API void cblas_cher2k(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, const void* alpha, const void* a, int lda, const void* b, int ldb, float beta, void* c, int ldc);
+B200_API void cblas_zsymm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, int m, int n, const void* alpha, const void* a, int lda, const void* b, int ldb, const void* beta, void* c, int ldc);
+B200_API void cblas_zhemm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, int m, int n, const void* alpha, const void* a, int lda, const void* b, int ldb, const void* beta, void* c, int ldc);
+B200_API void cblas_zsyr2k(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, const void* alpha, const void* a, int lda, const void* b, int ldb, const void* beta, void* c, int ldc);
+B200_API void cblas_zherk(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, double alpha, const void* a, int lda, double beta, void* c, int ldc);
+B200_API void cblas_zher2k(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, const void* alpha, const void* a, int lda, const void* b, int ldb, double beta, void* c, int ldc);
 
 /* ------------------------------ 3. allocator symbols ------------------------------ */
 /* malloc / calloc / realloc / free are exported with their libc prototypes (<stdlib.h>);

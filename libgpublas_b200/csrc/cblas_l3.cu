@@ -103,4 +103,44 @@ B200_CBLAS_REAL(d, double)
     }
 B200_CBLAS_CPLX(c, b200_c32)
 B200_CBLAS_CPLX(z, b200_c64)
+
+// complex SYMM / HEMM / SYR2K / HERK / HER2K (reference cblas.h DECLARE_CBLAS__SYMM, __HEMM, __SYR2K, __HERK, __HER2K).
+// Row-major: C^T is the column-major matrix.  symm/hemm: other side and triangle, m <-> n (the row-major array of a Hermitian
+// A is the column-major conj(A) = A^T, which is what the transposed product needs).  syr2k: other triangle, N <-> T.
+// herk / her2k: conj(C) = C^T, so NoTrans <-> ConjTrans on the other triangle, and her2k's alpha is conjugated.
+static inline char flip_herm_tr(char t) { return t == 'N' ? 'C' : (t == 'C' ? 'N' : '?'); }
+#define B200_CBLAS_CPLX_MORE(P, CT, RT)                                                                                           \
+    void cblas_##P##symm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, int m, int n, const void* alpha,     \
+                         const void* a, int lda, const void* b, int ldb, const void* beta, void* c, int ldc) {                    \
+        char s = sd(side), u = up(uplo);                                                                                          \
+        if (order == CblasRowMajor) { s = flip_sd(s); u = flip_up(u); P##symm_(&s, &u, &n, &m, (const CT*)alpha, (const CT*)a, &lda, (const CT*)b, &ldb, (const CT*)beta, (CT*)c, &ldc); } \
+        else P##symm_(&s, &u, &m, &n, (const CT*)alpha, (const CT*)a, &lda, (const CT*)b, &ldb, (const CT*)beta, (CT*)c, &ldc);   \
+    }                                                                                                                             \
+    void cblas_##P##hemm(enum CBLAS_ORDER order, enum CBLAS_SIDE side, enum CBLAS_UPLO uplo, int m, int n, const void* alpha,     \
+                         const void* a, int lda, const void* b, int ldb, const void* beta, void* c, int ldc) {                    \
+        char s = sd(side), u = up(uplo);                                                                                          \
+        if (order == CblasRowMajor) { s = flip_sd(s); u = flip_up(u); P##hemm_(&s, &u, &n, &m, (const CT*)alpha, (const CT*)a, &lda, (const CT*)b, &ldb, (const CT*)beta, (CT*)c, &ldc); } \
+        else P##hemm_(&s, &u, &m, &n, (const CT*)alpha, (const CT*)a, &lda, (const CT*)b, &ldb, (const CT*)beta, (CT*)c, &ldc);   \
+    }                                                                                                                             \
+    void cblas_##P##syr2k(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, const void* alpha, \
+                          const void* a, int lda, const void* b, int ldb, const void* beta, void* c, int ldc) {                   \
+        char u = up(uplo), t = tr(trans);                                                                                         \
+        if (order == CblasRowMajor) { u = flip_up(u); t = t == 'N' ? 'T' : (t == 'T' ? 'N' : '?'); }                              \
+        P##syr2k_(&u, &t, &n, &k, (const CT*)alpha, (const CT*)a, &lda, (const CT*)b, &ldb, (const CT*)beta, (CT*)c, &ldc);       \
+    }                                                                                                                             \
+    void cblas_##P##herk(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, RT alpha,        \
+                         const void* a, int lda, RT beta, void* c, int ldc) {                                                     \
+        char u = up(uplo), t = tr(trans);                                                                                         \
+        if (order == CblasRowMajor) { u = flip_up(u); t = flip_herm_tr(t); }                                                      \
+        P##herk_(&u, &t, &n, &k, &alpha, (const CT*)a, &lda, &beta, (CT*)c, &ldc);                                                \
+    }                                                                                                                             \
+    void cblas_##P##her2k(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CBLAS_TRANSPOSE trans, int n, int k, const void* alpha, \
+                          const void* a, int lda, const void* b, int ldb, RT beta, void* c, int ldc) {                            \
+        char u = up(uplo), t = tr(trans);                                                                                         \
+        CT al = *(const CT*)alpha;                                                                                                \
+        if (order == CblasRowMajor) { u = flip_up(u); t = flip_herm_tr(t); al.im = -al.im; }                                      \
+        P##her2k_(&u, &t, &n, &k, &al, (const CT*)a, &lda, (const CT*)b, &ldb, &beta, (CT*)c, &ldc);                              \
+    }
+B200_CBLAS_CPLX_MORE(c, b200_c32, float)
+B200_CBLAS_CPLX_MORE(z, b200_c64, double)
 }

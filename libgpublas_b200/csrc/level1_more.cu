@@ -115,6 +115,20 @@ template <typename T> void rotmg_host(T* d1, T* d2, T* x1, const T* y1, T* param
     param[0] = flag;
 }
 
+// netlib CROTG / ZROTG (reference BLAS 3.8 formulation): complex Givens rotation, scalar host work
+template <typename CT, typename R> void crotg_host(CT* ca, const CT* cb, R* c, CT* s) {
+    const R aa = std::hypot(ca->re, ca->im), ab = std::hypot(cb->re, cb->im);
+    if (aa == R(0)) { *c = 0; s->re = 1; s->im = 0; *ca = *cb; return; }
+    const R scale = aa + ab;
+    const R norm = scale * std::sqrt((aa / scale) * (aa / scale) + (ab / scale) * (ab / scale));
+    const R alr = ca->re / aa, ali = ca->im / aa;                 // alpha = ca / |ca|
+    *c = aa / norm;
+    // s = alpha * conj(cb) / norm
+    s->re = (alr * cb->re + ali * cb->im) / norm;
+    s->im = (ali * cb->re - alr * cb->im) / norm;
+    ca->re = alr * norm; ca->im = ali * norm;
+}
+
 template <typename CT, typename R> void crot_entry(const char* name, const int* n, CT* x, const int* incx, CT* y, const int* incy, const R* c, const R* s) {
     if (*n <= 0) return;
     CallScope scope(name);
@@ -159,6 +173,10 @@ void srotmg_(float* d1, float* d2, float* x1, const float* y1, float* param) { r
 void drotmg_(double* d1, double* d2, double* x1, const double* y1, double* param) { rotmg_host<double>(d1, d2, x1, y1, param); }
 void csrot_(const int* n, b200_c32* x, const int* incx, b200_c32* y, const int* incy, const float* c, const float* s) { crot_entry<c32, float>("csrot_", n, (c32*)x, incx, (c32*)y, incy, c, s); }
 void zdrot_(const int* n, b200_c64* x, const int* incx, b200_c64* y, const int* incy, const double* c, const double* s) { crot_entry<c64, double>("zdrot_", n, (c64*)x, incx, (c64*)y, incy, c, s); }
+void crotg_(b200_c32* ca, const b200_c32* cb, float* c, b200_c32* s) { crotg_host<b200_c32, float>(ca, cb, c, s); }
+void zrotg_(b200_c64* ca, const b200_c64* cb, double* c, b200_c64* s) { crotg_host<b200_c64, double>(ca, cb, c, s); }
+void cblas_crotg(void* a, void* b, float* c, void* s) { crotg_host<b200_c32, float>((b200_c32*)a, (const b200_c32*)b, c, (b200_c32*)s); }
+void cblas_zrotg(void* a, void* b, double* c, void* s) { crotg_host<b200_c64, double>((b200_c64*)a, (const b200_c64*)b, c, (b200_c64*)s); }
 // I?AMIN (1-based; 0 if n < 1 or incx <= 0) -- not in netlib; the reference's amin.cc and the CPU BLAS (OpenBLAS) export it
 int isamin_(const int* n, const float* x, const int* incx) { return iamin_entry<float>("isamin_", n, x, incx); }
 int idamin_(const int* n, const double* x, const int* incx) { return iamin_entry<double>("idamin_", n, x, incx); }

@@ -227,3 +227,40 @@ def test_level1_extras_oracle_vs_openblas():
             c, s_ = l2x.DT[rp](0.6), l2x.DT[rp](0.8)
             f77(ob, nm + "_", n, x1, ix, y1, iy, c, s_); oracle_call(p + "srot", n, x2, ix, y2, iy, c, s_, restype=None)
             assert np.allclose(x1, x2, rtol=tol, atol=tol) and np.allclose(y1, y2, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("p", ["c", "z"])
+def test_cblas_complex_level3_case_list_on_openblas(p):
+    """The numpy expectations of the GPU test for cblas_{c,z}symm / hemm / syr2k / herk / her2k (both layouts) hold for the CPU
+    BLAS's own cblas_* entry points, so that GPU leg compares against something pinned."""
+    import importlib
+    ob = load_openblas()
+    if ob is None:
+        pytest.skip("no CPU BLAS in this image")
+    zz = importlib.import_module("test_zz_level2_struct_gpu")
+
+    def call(name, *cargs):
+        fn = getattr(ob, "cblas_" + name); fn.restype = None
+        fn(*cargs)
+    assert zz._cblas_l3_cases(call, p) < 1.0
+
+
+def test_complex_rotg_host_path_vs_openblas():
+    """CROTG / ZROTG are scalar host work in the product (no device): against the CPU BLAS, and the rotation must zero b."""
+    import libgpublas_b200 as g
+    ob = load_openblas()
+    if ob is None:
+        pytest.skip("no CPU BLAS in this image")
+    lib = g.load()
+    for p, dt, rt, tol in (("c", np.complex64, np.float32, 2e-6), ("z", np.complex128, np.float64, 1e-14)):
+        for (a, b) in [(3 + 4j, 1 - 2j), (-1 + 0.5j, 2 + 2j), (0j, 1 + 1j), (2 - 1j, 0j), (1e-3 + 0j, 5j)]:
+            outs = []
+            for L in (ob, lib):
+                ca, cb = np.array([a], dtype=dt), np.array([b], dtype=dt); c = np.zeros(1, dtype=rt); s = np.zeros(1, dtype=dt)
+                f77(L, p + "rotg_", ca, cb, c, s)
+                outs.append((ca[0], c[0], s[0]))
+            (r1, c1, s1), (r2, c2, s2) = outs
+            assert abs(r1 - r2) <= tol * max(1, abs(r1)) and abs(c1 - c2) <= tol and abs(s1 - s2) <= tol, (p, a, b, outs)
+            # [c s; -conj(s) c] (a, b)^T = (r, 0)
+            assert abs(-np.conj(s2) * a + c2 * b) <= 8 * tol * max(1.0, abs(a) + abs(b))
+            assert abs(c2 * a + s2 * b - r2) <= 8 * tol * max(1.0, abs(a) + abs(b))

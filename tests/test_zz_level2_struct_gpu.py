@@ -150,3 +150,80 @@ def test_level1_extras_gpu():
         sb = np.float32(0.37)
         got = f77(lib, "sdsdot_", n, sb, x, ix, y, iy, restype=ctypes.c_float)
         assert abs(got - (exact + float(sb))) <= 2e-7 * max(1.0, abs(exact)), (n, got, exact)
+
+
+def _cblas_l3_cases(lib_call, p):
+    """cblas_{c,z}symm / hemm / syr2k / herk / her2k in both layouts against numpy; lib_call(name, *cargs) issues the call."""
+    import ctypes
+    dt, eps, r = l2x.DT[p], l2x.EPS[p], l2x.CREAL[p]
+    al, be = l2x.ALPHA[p], l2x.BETA[p]
+    E = l2x.CBLAS_ENUM
+    I = ctypes.c_int
+    cs = lambda v: (r * 2)(v.real, v.imag)
+    worst = 0.0
+    for order in "CR":
+        def store(M, ld_extra=1):
+            rows, cols = M.shape
+            if order == "C":
+                A = np.full((rows + ld_extra, cols), l2x.ROGUE, dtype=dt, order="F"); A[:rows] = M; return A, rows + ld_extra
+            A = np.full((rows, cols + ld_extra), l2x.ROGUE, dtype=dt, order="C"); A[:, :cols] = M; return A, cols + ld_extra
+        def logical(A, rows, cols):
+            return A[:rows, :cols]
+        o = I(E["R" if order == "R" else "Cm"])
+        for (m, n) in [(5, 7), (70, 33)]:
+            for side in "LR":
+                ka = m if side == "L" else n
+                for ul in "UL":
+                    T = l2x.rnd(21, (ka, ka), p).astype(np.complex128)
+                    keep = l2x.tri_mask(ka, ul)
+                    B = l2x.rnd(22, (m, n), p); C0 = l2x.rnd(23, (m, n), p)
+                    for herm in (False, True):
+                        S = l2x.sym_from_tri(np.where(keep, T, 0), ul, herm)
+                        Astore, lda = store(np.where(keep, T, l2x.ROGUE).astype(dt))
+                        Bs, ldb = store(B); Cs, ldc = store(C0)
+                        want = al * (S @ B.astype(np.complex128) if side == "L" else B.astype(np.complex128) @ S) + be * C0
+                        ca, cb = cs(al), cs(be)
+                        lib_call(p + ("hemm" if herm else "symm"), o, I(141 if side == "L" else 142), I(E[ul]), I(m), I(n), ctypes.byref(ca), l2x._ptr(Astore), I(lda),
+                                 l2x._ptr(Bs), I(ldb), ctypes.byref(cb), l2x._ptr(Cs), I(ldc))
+                        worst = max(worst, float(np.abs(logical(Cs, m, n) - want).max()) / (64 * eps * ka))
+                        assert np.array_equal(Cs == dt(l2x.ROGUE), store(C0)[0] == dt(l2x.ROGUE))
+        for (n, k) in [(6, 4), (65, 37)]:
+            for ul in "UL":
+                keep = l2x.tri_mask(n, ul)
+                for tr in "NC":      # herk / her2k: N or C;  syr2k: N or T
+                    shp = (n, k) if tr == "N" else (k, n)
+                    A = l2x.rnd(24, shp, p); B = l2x.rnd(25, shp, p); C0 = l2x.rnd(26, (n, n), p)
+                    Aw, Bw = A.astype(np.complex128), B.astype(np.complex128)
+                    Cw = C0.astype(np.complex128)
+                    As, lda = store(A); Bs, ldb = store(B)
+                    # HERK (real alpha, beta): the imaginary part of the diagonal of C is taken as zero on input and output
+                    ra, rb = 0.7, 1.3
+                    Ch = Cw.copy(); Ch[np.arange(n), np.arange(n)] = Ch.diagonal().real
+                    want = ra * (Aw @ Aw.conj().T if tr == "N" else Aw.conj().T @ Aw) + rb * Ch
+                    Cs, ldc = store(C0)
+                    lib_call(p + "herk", o, I(E[ul]), I(E[tr]), I(n), I(k), r(ra), l2x._ptr(As), I(lda), r(rb), l2x._ptr(Cs), I(ldc))
+                    got = logical(Cs, n, n)
+                    worst = max(worst, float(np.abs(np.where(keep, got - want, 0)).max()) / (64 * eps * k))
+                    assert np.array_equal(np.where(keep, 0, got), np.where(keep, 0, C0)), "herk wrote outside the triangle"
+                    want = al * (Aw @ Bw.conj().T if tr == "N" else Aw.conj().T @ Bw); want = want + want.conj().T + rb * Ch
+                    Cs, ldc = store(C0); ca = cs(al)
+                    lib_call(p + "her2k", o, I(E[ul]), I(E[tr]), I(n), I(k), ctypes.byref(ca), l2x._ptr(As), I(lda), l2x._ptr(Bs), I(ldb), r(rb), l2x._ptr(Cs), I(ldc))
+                    got = logical(Cs, n, n)
+                    worst = max(worst, float(np.abs(np.where(keep, got - want, 0)).max()) / (64 * eps * k))
+                    trs = "N" if tr == "N" else "T"
+                    want = al * (Aw @ Bw.T + Bw @ Aw.T if tr == "N" else Aw.T @ Bw + Bw.T @ Aw) + be * Cw
+                    Cs, ldc = store(C0); ca, cb = cs(al), cs(be)
+                    lib_call(p + "syr2k", o, I(E[ul]), I(E[trs]), I(n), I(k), ctypes.byref(ca), l2x._ptr(As), I(lda), l2x._ptr(Bs), I(ldb), ctypes.byref(cb), l2x._ptr(Cs), I(ldc))
+                    got = logical(Cs, n, n)
+                    worst = max(worst, float(np.abs(np.where(keep, got - want, 0)).max()) / (64 * eps * k))
+    return worst
+
+
+@pytest.mark.parametrize("p", ["c", "z"])
+def test_cblas_complex_level3_both_layouts(p):
+    lib = g.load()
+
+    def call(name, *cargs):
+        fn = getattr(lib, "cblas_" + name); fn.restype = None
+        fn(*cargs)
+    assert _cblas_l3_cases(call, p) < 1.0
