@@ -47,7 +47,7 @@ volatile uintptr_t g_lo = UINTPTR_MAX, g_hi = 0;   // address envelope of all bl
 struct ThreadSlot { volatile uintptr_t tp; int inside; };
 constexpr size_t kSlots = 4096;                 // live threads beyond this are simply never tracked
 ThreadSlot g_slots[kSlots];
-int g_overflow_inside = 1;
+int g_overflow_inside = 1 << 30;   // shared by every thread beyond the table: large, so racing ++/-- never reach zero (such threads are never tracked)
 
 inline int& inside_ref() {
     const uintptr_t tp = (uintptr_t)__builtin_thread_pointer();

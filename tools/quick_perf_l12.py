@@ -5,7 +5,11 @@ import torch
 import libgpublas_b200 as g
 
 lib = g.load(); g.use_torch_stream(); g.set_sync(False)
-PEAK = 6553.9
+import json
+try:
+    PEAK = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    PEAK = 6553.9     # the round's first measurement, used when the driver's file is absent
 
 
 def time_call(fn, reps=10, warm=3):
