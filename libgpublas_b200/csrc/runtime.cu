@@ -330,8 +330,10 @@ Operand::Operand(const void* host, int64_t rows, int64_t cols, int64_t ld, size_
     dev_ = ws_alloc((size_t)dld_ * cols * elem);
     if (access & ACC_IN) {
         TrackerGuard guard;
-        B200_CUDA(cudaMemcpy2DAsync(dev_, (size_t)dld_ * elem, host, (size_t)ld * elem, (size_t)rows * elem, (size_t)cols,
-                                    cudaMemcpyHostToDevice, s));
+        // one column (every vector, packed matrices): a flat copy -- a 2-D copy's pitch is capped at cudaDeviceProp::memPitch (2 GiB)
+        if (cols == 1) B200_CUDA(cudaMemcpyAsync(dev_, host, (size_t)rows * elem, cudaMemcpyHostToDevice, s));
+        else B200_CUDA(cudaMemcpy2DAsync(dev_, (size_t)dld_ * elem, host, (size_t)ld * elem, (size_t)rows * elem, (size_t)cols,
+                                         cudaMemcpyHostToDevice, s));
         __atomic_fetch_add(&g_stats.h2d_bytes, (unsigned long long)(rows * cols * elem), __ATOMIC_RELAXED);
         if (g_opts.trace_copy)
             b200_writef(STDOUT_FILENO, "b200blas: copy %zu B from %p (CPU) ---> %p (GPU)\n", (size_t)(rows * cols * elem), host, dev_);
@@ -343,8 +345,9 @@ void Operand::release() {
     done_ = true;
     if (staged_ && (access_ & ACC_OUT)) {
         TrackerGuard guard;
-        B200_CUDA(cudaMemcpy2DAsync((void*)host_, (size_t)ld_ * elem_, dev_, (size_t)dld_ * elem_, (size_t)rows_ * elem_,
-                                    (size_t)cols_, cudaMemcpyDeviceToHost, current_stream()));
+        if (cols_ == 1) B200_CUDA(cudaMemcpyAsync((void*)host_, dev_, (size_t)rows_ * elem_, cudaMemcpyDeviceToHost, current_stream()));
+        else B200_CUDA(cudaMemcpy2DAsync((void*)host_, (size_t)ld_ * elem_, dev_, (size_t)dld_ * elem_, (size_t)rows_ * elem_,
+                                         (size_t)cols_, cudaMemcpyDeviceToHost, current_stream()));
         __atomic_fetch_add(&g_stats.d2h_bytes, (unsigned long long)(rows_ * cols_ * elem_), __ATOMIC_RELAXED);
         if (g_opts.trace_copy)
             b200_writef(STDOUT_FILENO, "b200blas: copy %zu B from %p (GPU) ---> %p (CPU)\n", (size_t)(rows_ * cols_ * elem_), dev_, host_);
