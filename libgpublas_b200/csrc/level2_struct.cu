@@ -1,5 +1,5 @@
 // level2_struct.cu -- the banded, packed, Hermitian and complex Level-2 routines the reference's dead wrappers name
-// (blas_level2/gbmv.cc, bmv.cc, pmv.cc, hemv.cc, her.cc, her2.cc, hpr.cc, hpr2.cc, spr.cc,
+// (blas_level2/ger.cc, syr.cc, symv.cc, trmv.cc (real) and blas_level2/gbmv.cc, bmv.cc, pmv.cc, hemv.cc, her.cc, her2.cc, hpr.cc, hpr2.cc, spr.cc,
 // spr2.cc, syr2.cc, tbmv.cc, tbsv.cc, tpmv.cc, tpsv.cc, ger.cc (geru/gerc), trmv.cc (c/z) forward to cublas<t>...).
 // Fortran + CBLAS entry points with the netlib argument checks; s/d/c/z as netlib defines them.
 //
@@ -415,6 +415,28 @@ void cblas_zgbmv(enum CBLAS_ORDER o, enum CBLAS_TRANSPOSE t, int m, int n, int k
 B200_REALSYM(s, float)
 B200_REALSYM(d, double)
 #undef B200_REALSYM
+
+// ------------------------------- real, full storage: GER, SYR, SYMV, TRMV (reference blas_level2/ger.cc, syr.cc, symv.cc, trmv.cc) -------------------------------
+#define B200_REALFULL(P, T)                                                                                                                             \
+    void P##ger_(const int* m, const int* n, const T* alpha, const T* x, const int* incx, const T* y, const int* incy, T* a, const int* lda) {           \
+        gerx_entry<T>(#P "ger_", false, false, *m, *n, alpha, x, *incx, y, *incy, a, *lda); }                                                            \
+    void P##syr_(const char* uplo, const int* n, const T* alpha, const T* x, const int* incx, T* a, const int* lda) {                                    \
+        rank_sym_entry<T>(#P "syr_", K_FULL_TRI, R_SYR, false, uplo, *n, *alpha, x, *incx, nullptr, 1, a, *lda); }                                       \
+    void P##symv_(const char* uplo, const int* n, const T* alpha, const T* a, const int* lda, const T* x, const int* incx, const T* beta, T* y,          \
+                  const int* incy) { symv_like_entry<T>(#P "symv_", K_FULL_TRI, false, false, uplo, *n, 0, alpha, a, *lda, x, *incx, beta, y, *incy); }  \
+    void P##trmv_(const char* uplo, const char* trans, const char* diag, const int* n, const T* a, const int* lda, T* x, const int* incx) {              \
+        tri_entry<T>(#P "trmv_", K_FULL_TRI, false, false, uplo, trans, diag, *n, 0, a, *lda, x, *incx); }                                               \
+    void cblas_##P##ger(enum CBLAS_ORDER o, int m, int n, T alpha, const T* x, int incx, const T* y, int incy, T* a, int lda) {                          \
+        gerx_entry<T>(#P "ger_", false, rm(o), m, n, &alpha, x, incx, y, incy, a, lda); }                                                                \
+    void cblas_##P##syr(enum CBLAS_ORDER o, enum CBLAS_UPLO u, int n, T alpha, const T* x, int incx, T* a, int lda) {                                    \
+        rank_sym_entry<T>(#P "syr_", K_FULL_TRI, R_SYR, rm(o), uplo_c(u), n, alpha, x, incx, nullptr, 1, a, lda); }                                      \
+    void cblas_##P##symv(enum CBLAS_ORDER o, enum CBLAS_UPLO u, int n, T alpha, const T* a, int lda, const T* x, int incx, T beta, T* y, int incy) {     \
+        symv_like_entry<T>(#P "symv_", K_FULL_TRI, false, rm(o), uplo_c(u), n, 0, &alpha, a, lda, x, incx, &beta, y, incy); }                            \
+    void cblas_##P##trmv(enum CBLAS_ORDER o, enum CBLAS_UPLO u, enum CBLAS_TRANSPOSE t, enum CBLAS_DIAG d, int n, const T* a, int lda, T* x, int incx) { \
+        tri_entry<T>(#P "trmv_", K_FULL_TRI, false, rm(o), uplo_c(u), trans_c(t), diag_c(d), n, 0, a, lda, x, incx); }
+B200_REALFULL(s, float)
+B200_REALFULL(d, double)
+#undef B200_REALFULL
 
 // ------------------------------- complex: HBMV, HPMV, HEMV, GERU, GERC, HER, HER2, HPR, HPR2, TRMV -------------------------------
 #define B200_CPLX(P, T, CT, RT)                                                                                                                         \

@@ -192,9 +192,9 @@ def emu_call(name, *args, rowmajor=False):
     elif r in ("spmv", "hpmv"):
         ul, n, al, a, x, ix, be, y, iy = args
         fn("symv_like")(K_PACKED, int(r[0] == "h"), rmj, _ch(ul), n, 0, _sp(p, al), _ptr(a), 1, _ptr(x), ix, _sp(p, be), _ptr(y), iy)
-    elif r == "hemv":
+    elif r in ("hemv", "symv"):
         ul, n, al, a, lda, x, ix, be, y, iy = args
-        fn("symv_like")(K_FULL_TRI, 1, rmj, _ch(ul), n, 0, _sp(p, al), _ptr(a), lda, _ptr(x), ix, _sp(p, be), _ptr(y), iy)
+        fn("symv_like")(K_FULL_TRI, int(r == "hemv"), rmj, _ch(ul), n, 0, _sp(p, al), _ptr(a), lda, _ptr(x), ix, _sp(p, be), _ptr(y), iy)
     elif r in ("tbmv", "tbsv"):
         ul, tr, dg, n, k, a, lda, x, ix = args
         fn("tri")(K_BAND_TRI, int(r == "tbsv"), rmj, _ch(ul), _ch(tr), _ch(dg), n, k, _ptr(a), lda, _ptr(x), ix)
@@ -204,15 +204,15 @@ def emu_call(name, *args, rowmajor=False):
     elif r in ("trmv", "trsv"):
         ul, tr, dg, n, a, lda, x, ix = args
         fn("tri")(K_FULL_TRI, int(r == "trsv"), rmj, _ch(ul), _ch(tr), _ch(dg), n, 0, _ptr(a), lda, _ptr(x), ix)
-    elif r in ("geru", "gerc"):
+    elif r in ("geru", "gerc", "ger"):
         m, n, al, x, ix, y, iy, a, lda = args
         fn("ger")(int(r == "gerc"), rmj, m, n, _sp(p, al), _ptr(x), ix, _ptr(y), iy, _ptr(a), lda)
     elif r in ("syr2", "her2"):
         ul, n, al, x, ix, y, iy, a, lda = args
         fn("rank_sym")(K_FULL_TRI, R_SYR2 if r == "syr2" else R_HER2, rmj, _ch(ul), n, _sp(p, al), _ptr(x), ix, _ptr(y), iy, _ptr(a), lda)
-    elif r == "her":
+    elif r in ("her", "syr"):
         ul, n, al, x, ix, a, lda = args
-        fn("rank_sym")(K_FULL_TRI, R_HER, rmj, _ch(ul), n, _sp(p, al), _ptr(x), ix, _ptr(None), 1, _ptr(a), lda)
+        fn("rank_sym")(K_FULL_TRI, R_HER if r == "her" else R_SYR, rmj, _ch(ul), n, _sp(p, al), _ptr(x), ix, _ptr(None), 1, _ptr(a), lda)
     elif r in ("spr", "hpr"):
         ul, n, al, x, ix, a = args
         fn("rank_sym")(K_PACKED, R_SYR if r == "spr" else R_HER, rmj, _ch(ul), n, _sp(p, al), _ptr(x), ix, _ptr(None), 1, _ptr(a), 1)
@@ -241,7 +241,7 @@ def cblas_call(lib, name, order, *args):
         roles = ["trans"]
     elif r in ("tbmv", "tbsv", "tpmv", "tpsv", "trmv", "trsv"):
         roles = ["uplo", "trans", "diag"]
-    elif r in ("geru", "gerc"):
+    elif r in ("geru", "gerc", "ger"):
         roles = []
     else:
         roles = ["uplo"]
@@ -359,8 +359,7 @@ def cases(p, rowmajor=False, sizes=(1, 2, 5, 33, 70), big=()):
                 x = x0[ix]; y = vec(nxt(), n, iy, p)
                 r = scal(p, al) * (S @ logical(x, n, ix).astype(W)) + scal(p, be) * logical(y, n, iy).astype(W)
                 add("hpmv" if is_c else "spmv", [ul, n, scal(p, al), AP, x, ix, scal(p, be), y, iy], 7, _put(y, n, iy, r), n, "%s n=%d inc=%d,%d" % (ul, n, ix, iy))
-                if is_c:
-                    add("hemv", [ul, n, scal(p, al), AF, n + 1, x, ix, scal(p, be), y, iy], 8, _put(y, n, iy, r), n, "%s n=%d inc=%d,%d" % (ul, n, ix, iy))
+                add("hemv" if is_c else "symv", [ul, n, scal(p, al), AF, n + 1, x, ix, scal(p, be), y, iy], 8, _put(y, n, iy, r), n, "%s n=%d inc=%d,%d" % (ul, n, ix, iy))
             # ---- rank updates on the stored triangle
             for (ix, iy) in incs[: (3 if n < 40 else 1)]:
                 x = x0[ix]; y = vec(nxt(), n, iy, p)
@@ -380,6 +379,7 @@ def cases(p, rowmajor=False, sizes=(1, 2, 5, 33, 70), big=()):
                     U1 = np.where(keep, Tt + al * np.outer(xl, xl), 0)
                     U2 = np.where(keep, Tt + al * np.outer(xl, yl) + al * np.outer(yl, xl), 0)
                     add("syr2", [ul, n, al, x, ix, y, iy, AF, n + 1], 7, full_tri(U2.astype(dt), ul, n + 1, rowmajor), n, "%s n=%d inc=%d,%d" % (ul, n, ix, iy))
+                    add("syr", [ul, n, al, x, ix, AF, n + 1], 5, full_tri(U1.astype(dt), ul, n + 1, rowmajor), n, "%s n=%d inc=%d" % (ul, n, ix))
                     add("spr", [ul, n, al, x, ix, AP], 5, packed(U1.astype(dt), ul, rowmajor), n, "%s n=%d inc=%d" % (ul, n, ix))
                     add("spr2", [ul, n, al, x, ix, y, iy, AP], 7, packed(U2.astype(dt), ul, rowmajor), n, "%s n=%d inc=%d,%d" % (ul, n, ix, iy))
             # ---- triangular products and solves
@@ -407,18 +407,18 @@ def cases(p, rowmajor=False, sizes=(1, 2, 5, 33, 70), big=()):
                                 AP2 = packed(stored, ul, rowmajor)
                                 add("tpmv", [ul, tr, dg, n, AP2, x, ix], 5, _put(x, n, ix, prod), n, tag)
                                 add("tpsv", [ul, tr, dg, n, AP2, x, ix], 5, _put(x, n, ix, sol), 4 * n, tag)
-                                if is_c:
-                                    AF2 = full_tri(stored, ul, n + 1, rowmajor)
-                                    add("trmv", [ul, tr, dg, n, AF2, n + 1, x, ix], 6, _put(x, n, ix, prod), n, tag)
+                                AF2 = full_tri(stored, ul, n + 1, rowmajor)
+                                add("trmv", [ul, tr, dg, n, AF2, n + 1, x, ix], 6, _put(x, n, ix, prod), n, tag)
+                                if is_c:   # (real TRSV is level2.cu's blocked solve, tested in test_level12_gpu.py)
                                     add("trsv", [ul, tr, dg, n, AF2, n + 1, x, ix], 6, _put(x, n, ix, sol), 4 * n, tag)
-    # ---- GERU / GERC
-    if is_c:
+    # ---- GER / GERU / GERC
+    if True:
         for (m, n) in [(1, 1), (7, 5), (33, 70)] + [(b, b + 5) for b in big]:
             for (ix, iy) in incs[: (3 if m < 40 else 1)]:
                 x = vec(nxt(), m, ix, p); y = vec(nxt(), n, iy, p)
                 M = rnd(nxt(), (m, n), p).astype(W)
                 xl, yl = logical(x, m, ix).astype(W), logical(y, n, iy).astype(W)
-                for nm, U in (("geru", M + al * np.outer(xl, yl)), ("gerc", M + al * np.outer(xl, yl.conj()))):
+                for nm, U in ((("geru", M + al * np.outer(xl, yl)), ("gerc", M + al * np.outer(xl, yl.conj()))) if is_c else (("ger", M + al * np.outer(xl, yl)),)):
                     if not rowmajor:
                         A = np.full((m + 1, n), ROGUE, dtype=dt, order="F"); A[:m] = M; E = A.copy(order="F"); E[:m] = U; lda = m + 1
                     else:
