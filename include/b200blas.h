@@ -383,7 +383,10 @@ B200_API void cblas_zher2k(enum CBLAS_ORDER order, enum CBLAS_UPLO uplo, enum CB
 
 /* ------------------------------ 3. allocator symbols ------------------------------ */
 /* malloc / calloc / realloc / free are exported with their libc prototypes (<stdlib.h>);
- * reference lib/obj_tracker.c:789 (malloc), :842 (calloc), :902 (realloc), :948 (free). */
+ * reference lib/obj_tracker.c:789 (malloc), :842 (calloc), :902 (realloc), :948 (free).
+ * Also exported, which the reference leaves to glibc (so aligned operands are never tracked there): posix_memalign,
+ * aligned_alloc, memalign, valloc -- a managed block is handed out when the placement heuristic says so and its base
+ * satisfies the alignment -- and malloc_usable_size (answers for managed blocks from the registry). */
 
 /* ------------------------------ 4. control API ------------------------------ */
 struct b200blas_stats {

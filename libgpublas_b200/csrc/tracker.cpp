@@ -8,7 +8,9 @@
 //  * the registry is a sorted array under a rwlock with an address-range pre-filter, so free() of
 //    ordinary heap pointers never takes the lock (the reference does a tsearch under a rwlock for
 //    every free, obj_tracker.c:948-982);
-//  * the default heuristic is size-based, not random (obj_tracker.c:52).
+//  * the default heuristic is size-based, not random (obj_tracker.c:52);
+//  * posix_memalign / aligned_alloc / memalign / valloc / malloc_usable_size are interposed too (the reference leaves them to
+//    glibc, so aligned operands are never tracked).
 #include "tracker.h"
 #include "runtime.h"
 #include <cuda_runtime_api.h>
@@ -27,6 +29,7 @@ void* __libc_malloc(size_t);
 void* __libc_calloc(size_t, size_t);
 void* __libc_realloc(void*, size_t);
 void __libc_free(void*);
+void* __libc_memalign(size_t, size_t);
 }
 
 namespace {
@@ -350,6 +353,54 @@ void free(void* ptr) noexcept {
     uintptr_t p = (uintptr_t)ptr;
     if (p >= g_lo && p < g_hi && tracker_free_managed(ptr)) return;
     __libc_free(ptr);
+}
+
+// ---- the aligned allocators (not interposed by the reference, SURVEY.md section 8b: "real programs use them") ----
+// Eigen, FFTW-style codes and C++17 aligned new allocate BLAS operands with posix_memalign / aligned_alloc; left to glibc
+// they would be untracked and staged on every call.  A managed block is handed out when the placement heuristic says so
+// AND its base happens to satisfy the alignment (cudaMallocManaged bases are at least 256-byte aligned, far more for
+// large blocks); otherwise the request goes to glibc.  free() / realloc() already route by registry lookup.
+static void* aligned_common(size_t alignment, size_t request, const char* fun) {
+    if (bypass()) return __libc_memalign(alignment, request);
+    uint64_t nth = __sync_fetch_and_add(&g_nth, 1);
+    if (request && should_manage(request, nth)) {
+        void* p = managed_new(request, nth, fun);
+        if (p && ((uintptr_t)p & (alignment - 1)) == 0) return p;
+        if (p) tracker_free_managed(p);
+    }
+    return __libc_memalign(alignment, request);
+}
+static inline bool pow2(size_t a) { return a && (a & (a - 1)) == 0; }
+__attribute__((visibility("default"))) int posix_memalign(void** out, size_t alignment, size_t request) noexcept {
+    if (!pow2(alignment) || alignment % sizeof(void*) != 0) return EINVAL;
+    void* p = aligned_common(alignment, request, "posix_memalign");
+    if (!p) return ENOMEM;      // posix_memalign reports through its return value and leaves errno alone
+    *out = p;
+    return 0;
+}
+__attribute__((visibility("default"))) void* aligned_alloc(size_t alignment, size_t request) noexcept {
+    if (!pow2(alignment)) { errno = EINVAL; return nullptr; }
+    return aligned_common(alignment, request, "aligned_alloc");
+}
+__attribute__((visibility("default"))) void* memalign(size_t alignment, size_t request) noexcept {
+    if (!pow2(alignment)) { errno = EINVAL; return nullptr; }
+    return aligned_common(alignment, request, "memalign");
+}
+__attribute__((visibility("default"))) void* valloc(size_t request) noexcept { return aligned_common((size_t)sysconf(_SC_PAGESIZE), request, "valloc"); }
+// glibc would read its chunk header in front of the pointer: answer for managed blocks from the registry
+__attribute__((visibility("default"))) size_t malloc_usable_size(void* ptr) noexcept {
+    typedef size_t (*usable_t)(void*);
+    static usable_t real = nullptr;
+    if (!ptr) return 0;
+    void* base; size_t size;
+    if (tracker_lookup(ptr, &base, &size) && base == ptr) return size;
+    if (!real) {
+        t_inside++;
+        real = (usable_t)dlsym(RTLD_NEXT, "malloc_usable_size");
+        t_inside--;
+        if (!real) return 0;
+    }
+    return real(ptr);
 }
 
 }  // extern "C"

@@ -89,6 +89,17 @@ def test_allocs_on_glibc():
     assert "RESULT ok=1 tracked=0" in out
 
 
+def test_aligned_allocators_fall_through_without_a_device(tmp_path):
+    """posix_memalign / aligned_alloc / memalign / valloc / malloc_usable_size are interposed (the reference leaves them to
+    glibc).  With heuristic=false nothing is ever placed in managed memory, so the interposers' pass-through path
+    runs under LD_PRELOAD on a machine without a GPU; the managed path is tests/test_zz_level2_struct_gpu.py's."""
+    exe = build_driver("aligned_allocs")
+    out, _ = run(exe)
+    assert "RESULT ok=1 tracked=0" in out
+    out, _ = run(exe, preload=True, env_extra={"BLAS2CUDA_OPTIONS": "heuristic=false"}, cwd=str(tmp_path), timeout=90)
+    assert "RESULT ok=1 tracked=0" in out
+
+
 # ------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 def test_gemm_fixture_under_preload(tmp_path):

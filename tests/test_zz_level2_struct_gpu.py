@@ -227,3 +227,16 @@ def test_cblas_complex_level3_both_layouts(p):
         fn = getattr(lib, "cblas_" + name); fn.restype = None
         fn(*cargs)
     assert _cblas_l3_cases(call, p) < 1.0
+
+
+def test_aligned_allocators_under_preload(tmp_path):
+    """posix_memalign / aligned_alloc / memalign / valloc under LD_PRELOAD: blocks >= the threshold whose managed base
+    satisfies the alignment are tracked (in place for BLAS), contents survive realloc, malloc_usable_size answers from the
+    registry, everything frees cleanly.  (Sorted here, after the established preload tests.)"""
+    from test_preload import build_driver, fields, run
+    exe = build_driver("aligned_allocs")
+    out, _ = run(exe, preload=True, cwd=str(tmp_path), timeout=120)
+    r = fields([l for l in out.splitlines() if l.startswith("RESULT")][0])
+    assert r["ok"] == "1" and int(r["tracked"]) >= 20, out       # 70000 B / 1 MiB / 4 MiB requests at alignments <= 256 at the very least
+    out, _ = run(exe, preload=True, env_extra={"BLAS2CUDA_OPTIONS": "heuristic=false"}, cwd=str(tmp_path), timeout=120)
+    assert "RESULT ok=1 tracked=0" in out
