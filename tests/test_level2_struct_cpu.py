@@ -264,3 +264,61 @@ def test_complex_rotg_host_path_vs_openblas():
             # [c s; -conj(s) c] (a, b)^T = (r, 0)
             assert abs(-np.conj(s2) * a + c2 * b) <= 8 * tol * max(1.0, abs(a) + abs(b))
             assert abs(c2 * a + s2 * b - r2) <= 8 * tol * max(1.0, abs(a) + abs(b))
+
+
+def test_kernel_index_logic_fuzzed():
+    """Random shapes, bandwidths, increments, triangles and operations through the emulated kernels against the oracle:
+    the fixed case list walks a grid of corner cases, this walks the space between them (seeded: reproducible)."""
+    rng = np.random.default_rng(20261017)
+    worst = 0.0
+    for it in range(300):
+        p = "sdcz"[it % 4]
+        dt, W = l2x.DT[p], l2x.wide(p)
+        n = int(rng.integers(1, 140)); m = int(rng.integers(1, 140))
+        ul = "UL"[int(rng.integers(2))]; tr = "NTC"[int(rng.integers(3))]; dg = "NU"[int(rng.integers(2))]
+        ix = int(rng.choice([1, 2, -1, -3])); iy = int(rng.choice([1, 3, -2]))
+        al, be = l2x.scal(p, l2x.ALPHA[p]), l2x.scal(p, l2x.BETA[p])
+        kind = it % 5
+        if kind == 0:
+            kl = int(rng.integers(0, m)); ku = int(rng.integers(0, n)); lda = kl + ku + 1 + int(rng.integers(0, 3))
+            A = l2x.rnd(it, (lda, n), p); lx, ly = (n, m) if tr == "N" else (m, n)
+            x = l2x.vec(it + 1, lx, ix, p); y = l2x.vec(it + 2, ly, iy, p); y2 = y.copy()
+            l2x.emu_call(p + "gbmv", tr, m, n, kl, ku, al, A, lda, x, ix, be, y, iy)
+            assert oracle_call(p + "gbmv", tr, m, n, kl, ku, al, A, lda, x, ix, be, y2, iy) == 0
+            got, want, scale = y, y2, max(m, n)
+        elif kind == 1:
+            k = int(rng.integers(0, n)); lda = k + 1 + int(rng.integers(0, 3))
+            A = l2x.rnd(it, (lda, n), p); x = l2x.vec(it + 1, n, ix, p); y = l2x.vec(it + 2, n, iy, p); y2 = y.copy()
+            nm = p + ("hbmv" if l2x.cplx(p) else "sbmv")
+            l2x.emu_call(nm, ul, n, k, al, A, lda, x, ix, be, y, iy)
+            assert oracle_call(nm, ul, n, k, al, A, lda, x, ix, be, y2, iy) == 0
+            got, want, scale = y, y2, n
+        elif kind == 2:
+            k = int(rng.integers(0, n)); lda = k + 1 + int(rng.integers(0, 3))
+            G = l2x.well_conditioned_tri(it, n, p)
+            A = l2x.band_tri(np.where(l2x.tri_mask(n, ul, k), G, 0).astype(dt), ul, k, lda)
+            x = l2x.vec(it + 1, n, ix, p); x2 = x.copy()
+            nm = p + ("tbsv" if it % 2 else "tbmv")
+            l2x.emu_call(nm, ul, tr, dg, n, k, A, lda, x, ix)
+            assert oracle_call(nm, ul, tr, dg, n, k, A, lda, x2, ix) == 0
+            got, want, scale = x, x2, 4 * n
+        elif kind == 3:
+            G = l2x.well_conditioned_tri(it, n, p)
+            AP = l2x.packed(np.where(l2x.tri_mask(n, ul), G, 0).astype(dt), ul)
+            x = l2x.vec(it + 1, n, ix, p); x2 = x.copy()
+            nm = p + ("tpsv" if it % 2 else "tpmv")
+            l2x.emu_call(nm, ul, tr, dg, n, AP, x, ix)
+            assert oracle_call(nm, ul, tr, dg, n, AP, x2, ix) == 0
+            got, want, scale = x, x2, 4 * n
+        else:
+            AP = l2x.rnd(it, (n * (n + 1) // 2,), p); AP2 = AP.copy()
+            x = l2x.vec(it + 1, n, ix, p); y = l2x.vec(it + 2, n, iy, p)
+            nm = p + ("hpr2" if l2x.cplx(p) else "spr2")
+            l2x.emu_call(nm, ul, n, al, x, ix, y, iy, AP)
+            assert oracle_call(nm, ul, n, al, x, ix, y, iy, AP2) == 0
+            got, want, scale = AP, AP2, 4
+        err = float(np.abs(got.astype(np.complex128) - want.astype(np.complex128)).max()) if got.size else 0.0
+        tol = 16 * l2x.EPS[p] * max(scale, 4) * max(1.0, float(np.abs(want).max()) if want.size else 1.0)
+        worst = max(worst, err / tol)
+        assert err <= tol, (it, p, kind, n, m, ul, tr, dg, ix, iy, err, tol)
+    assert worst < 1.0
