@@ -1,6 +1,6 @@
 // gemm_generic.cuh -- type-generic register-tiled GEMM for every (type, transpose, alignment)
 // combination: the small-problem / odd-type variant of the selector and the kernel the
-// complex-float and (for now) float paths run on.  64x64 CTA tile, 16x16 threads, 4x4 per
+// complex-float path and small float problems run on (large SGEMM: gemm_f32.cu).  64x64 CTA tile, 16x16 threads, 4x4 per
 // thread, BK=16, operands staged through shared memory with the transpose/conjugate applied
 // while staging so the inner loop is layout-free.  HBM-coalesced along whichever dimension is
 // contiguous in memory.
