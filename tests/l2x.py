@@ -14,7 +14,7 @@ import subprocess
 
 import numpy as np
 
-from helpers import ROOT, f77, oracle_call, splitmix_uniform
+from helpers import ROOT, splitmix_uniform
 
 DT = {"s": np.float32, "d": np.float64, "c": np.complex64, "z": np.complex128}
 EPS = {"s": 2.0 ** -24, "d": 2.0 ** -53, "c": 2.0 ** -24, "z": 2.0 ** -53}
@@ -83,24 +83,6 @@ def packed(M, uplo, rowmajor=False):
     else:
         cols = [M[i, i:] if uplo == "U" else M[i, : i + 1] for i in range(n)]
     return np.ascontiguousarray(np.concatenate(cols)) if n else np.zeros(0, M.dtype)
-
-
-def unpack(ap, n, uplo, rowmajor=False, dtype=None):
-    """packed triangle -> dense n x n with zeros in the other triangle"""
-    M = np.zeros((n, n), dtype or ap.dtype)
-    pos = 0
-    for t in range(n):
-        if not rowmajor:
-            if uplo == "U":
-                M[: t + 1, t] = ap[pos: pos + t + 1]; pos += t + 1
-            else:
-                M[t:, t] = ap[pos: pos + n - t]; pos += n - t
-        else:
-            if uplo == "U":
-                M[t, t:] = ap[pos: pos + n - t]; pos += n - t
-            else:
-                M[t, : t + 1] = ap[pos: pos + t + 1]; pos += t + 1
-    return M
 
 
 def full_tri(M, uplo, lda, rowmajor=False):
