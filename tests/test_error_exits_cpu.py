@@ -111,3 +111,67 @@ def test_level2_info_numbering_product_and_oracle(p):
             # an illegal call touches nothing (netlib: return right after XERBLA)
             assert all(np.array_equal(a, b) for a, b in zip(arrays, before)), name
     assert checks >= 80
+
+
+QUICK_RETURN_SCRIPT = r'''
+import sys
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import libgpublas_b200 as g
+from helpers import f77
+from test_error_exits_cpu import SIG, DT, _valid, _routines
+lib = g.load()
+n_calls = 0
+for p in "sdcz":
+    cplx = p in "cz"
+    one, zero = ((1 + 0j), 0j) if cplx else (1.0, 0.0)
+    A = np.full((3, 3), 5.0, dtype=DT[p], order="F"); B = A.copy(order="F"); C = A.copy(order="F")
+    x = np.full(4, 7.0, dtype=DT[p]); y = np.full(4, 9.0, dtype=DT[p])
+    # Level 2: a zero dimension; alpha == 0 with beta == 1 (matrix-vector) or alpha == 0 (rank updates)
+    for r in _routines(p):
+        valid = [_valid(k, p, [A, x, y]) for k in SIG[r]]
+        for dim in ("m", "n"):
+            if dim in SIG[r]:
+                args = list(valid); args[SIG[r].index(dim)] = 0
+                f77(lib, p + r + "_", *args); n_calls += 1
+        for ak in ("alpha", "ralpha"):
+            if ak in SIG[r] and (("beta" in SIG[r]) or r in ("ger", "geru", "gerc", "syr", "her", "spr", "hpr", "syr2", "her2", "spr2", "hpr2")):
+                args = list(valid); args[SIG[r].index(ak)] = zero if ak == "alpha" else 0.0
+                f77(lib, p + r + "_", *args); n_calls += 1
+    # Level 3 (netlib quick returns: a zero dimension; (alpha == 0 or k == 0) with beta == 1)
+    f77(lib, p + "gemm_", "N", "N", 0, 2, 2, one, A, 3, B, 3, one, C, 3); f77(lib, p + "gemm_", "N", "N", 2, 0, 2, one, A, 3, B, 3, one, C, 3)
+    f77(lib, p + "gemm_", "N", "N", 2, 2, 0, one, A, 3, B, 3, one, C, 3); f77(lib, p + "gemm_", "N", "T", 2, 2, 2, zero, A, 3, B, 3, one, C, 3)
+    f77(lib, p + "syrk_", "U", "N", 0, 2, one, A, 3, one, C, 3); f77(lib, p + "syrk_", "L", "T", 2, 0, one, A, 3, one, C, 3)
+    f77(lib, p + "syr2k_", "U", "N", 0, 2, one, A, 3, B, 3, one, C, 3); f77(lib, p + "symm_", "L", "U", 0, 2, one, A, 3, B, 3, one, C, 3)
+    f77(lib, p + "symm_", "R", "L", 2, 2, zero, A, 3, B, 3, one, C, 3)
+    f77(lib, p + "trsm_", "L", "U", "N", "N", 0, 2, one, A, 3, B, 3); f77(lib, p + "trmm_", "R", "L", "T", "U", 2, 0, one, A, 3, B, 3)
+    n_calls += 11
+    if cplx:
+        rone = 1.0
+        f77(lib, p + "hemm_", "L", "U", 2, 0, one, A, 3, B, 3, one, C, 3); f77(lib, p + "herk_", "U", "N", 0, 2, rone, A, 3, rone, C, 3)
+        f77(lib, p + "herk_", "U", "N", 2, 0, rone, A, 3, rone, C, 3); f77(lib, p + "her2k_", "L", "C", 0, 2, one, A, 3, B, 3, rone, C, 3)
+        n_calls += 4
+    # Level 1 with n <= 0
+    import ctypes
+    f77(lib, p + "axpy_", 0, one, x, 1, y, 1); f77(lib, p + "scal_", 0, one, x, 1); f77(lib, p + "copy_", 0, x, 1, y, 1); f77(lib, p + "swap_", -1, x, 1, y, 1)
+    assert f77(lib, "i" + p + "amax_", 0, x, 1, restype=ctypes.c_int) == 0 and f77(lib, "i" + p + "amin_", 3, x, 0, restype=ctypes.c_int) == 0
+    n_calls += 6
+    assert np.all(A == 5) and np.all(B == 5) and np.all(C == 5) and np.all(x == 7) and np.all(y == 9), p
+assert f77(lib, "ddot_", 0, np.ones(1), 1, np.ones(1), 1, restype=ctypes.c_double) == 0.0
+assert f77(lib, "dnrm2_", 0, np.ones(1), 1, restype=ctypes.c_double) == 0.0 and f77(lib, "dasum_", 3, np.ones(3), 0, restype=ctypes.c_double) == 0.0
+st = g.stats()
+print("QUICK_RETURNS_OK", n_calls, st["calls"] if isinstance(st, dict) else st)
+'''
+
+
+def test_quick_returns_need_no_device():
+    """netlib quick returns (a zero dimension, alpha == 0 with beta == 1, n <= 0 in Level 1) are decided on the host: the call
+    returns without touching its operands and without bringing a device up.  Run in a child process: a quick return that did
+    reach the device would abort there ("no CUDA device: libb200blas has no CPU fallback")."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", QUICK_RETURN_SCRIPT, root], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert out.returncode == 0 and "QUICK_RETURNS_OK" in out.stdout, (out.stdout[-2000:], out.stderr[-2000:])
