@@ -7,6 +7,7 @@ import re
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 
 from helpers import LIB_PATH, ROOT, find_openblas
@@ -98,6 +99,58 @@ def test_aligned_allocators_fall_through_without_a_device(tmp_path):
     assert "RESULT ok=1 tracked=0" in out
     out, _ = run(exe, preload=True, env_extra={"BLAS2CUDA_OPTIONS": "heuristic=false"}, cwd=str(tmp_path), timeout=90)
     assert "RESULT ok=1 tracked=0" in out
+
+
+REF_MICRO = [("copy", 20000, np.float32), ("dsdot", 3000, np.float64), ("rot", 20000, np.complex64), ("gbmv", 400, np.float32),
+             ("trmv", 400, np.float32), ("trsm", 300, np.float64), ("hemm", 200, np.complex64)]
+
+
+def run_ref_micro(tmp_path, preload):
+    """the reference's tests/c micro-tests (restated in tests/drivers/ref_micro.c): result arrays and RESULT fields per test"""
+    exe = build_driver("ref_micro")
+    res = {}
+    for name, n, dt in REF_MICRO:
+        outp = os.path.join(str(tmp_path), "%s_%d.bin" % (name, int(preload)))
+        out, _ = run(exe, [name, n, outp], preload=preload, cwd=str(tmp_path), timeout=120)
+        res[name] = (np.fromfile(outp, dtype=dt), fields([l for l in out.splitlines() if l.startswith("RESULT")][0]))
+    return res
+
+
+def test_ref_micro_tests_on_cpu_blas(tmp_path):
+    """The reference's own micro-tests (tests/c/copy.c, dsdot.c, rot.c, gbmv.c, trmv.c, trsm.c, hemm.c) against the CPU BLAS:
+    closed forms where the fill has one, and a numpy evaluation of the same fills for the matrix routines."""
+    res = run_ref_micro(tmp_path, preload=False)
+    assert float(res["copy"][1]["closed_form_err"]) == 0.0 and float(res["rot"][1]["closed_form_err"]) == 0.0
+    assert float(res["dsdot"][1]["closed_form_err"]) <= 1e-7 * 9.0e9     # OpenBLAS sums blocks of its float kernel in float (5e-9 relative here);
+    #                                                                    # netlib DSDOT -- and the GPU kernel -- are exact on this input
+    n = 400      # gbmv: A read as column-major band storage AB[ku+i-j, j] with lda = n, as cblas_sgbmv(ColMajor) reads the reference's array
+    raw = np.zeros((n, n), np.float32)
+    for row in range(n):
+        for col in range(max(0, row - 2), min(n, row + 3)):
+            raw.ravel()[(2 - row + col) + row * n] = 1
+    AB = raw.reshape((n, n)).T                      # AB[r, j] = raw[r + j*n]
+    x = np.arange(n, dtype=np.float64)
+    y = x.copy()
+    for j in range(n):
+        for i in range(max(0, j - 2), min(n, j + 3)):
+            y[i] += AB[2 + i - j, j] * x[j]
+    assert np.allclose(res["gbmv"][0], y, rtol=1e-5, atol=1e-3)
+    A = np.zeros((n, n)); mod = (n * n) // 10
+    for r in range(n):
+        A[r, r:] = (r * n + np.arange(r, n)) % mod
+    assert np.allclose(res["trmv"][0], A @ np.arange(n, dtype=np.float64), rtol=2e-5)
+    m, nrhs = 300, 150
+    A = np.zeros((m, m))
+    for r in range(m):
+        A[r, r:] = (r * m + np.arange(r, m)) % 10
+    A += 10 * np.eye(m)
+    B = ((np.arange(m)[:, None] * nrhs + np.arange(nrhs)[None, :]) % 10).astype(np.float64)
+    assert np.allclose(res["trsm"][0].reshape((nrhs, m)).T, np.linalg.solve(A, B), rtol=1e-9, atol=1e-9)
+    m = 200
+    r, c = np.indices((m, m))
+    H = np.where(c > r, c + 1j * r, np.where(c < r, r - 1j * c, c)).astype(np.complex128)
+    Bm = ((r * m + c) % m + 1j * (r % 10)).astype(np.complex128)
+    assert np.allclose(res["hemm"][0].reshape((m, m)).T, H @ Bm, rtol=1e-4, atol=1e-2)
 
 
 # ------------------------------------------------------------------------------------------ GPU
