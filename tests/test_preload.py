@@ -101,6 +101,36 @@ def test_aligned_allocators_fall_through_without_a_device(tmp_path):
     assert "RESULT ok=1 tracked=0" in out
 
 
+# one trace line of the reference's TRACE_OUTPUT format (lib/obj_tracker.c:426-483)
+TRACE_LINE = re.compile(r"^([TUC]) #(\d+) \[(0x[0-9a-f]+)\] fun=\[(\w+)\] reqsize=\[(\d+)\] tid=\[\d+\] time=\[\d+s\+\d+ns\] uid=\[(\d+)\]$")
+
+
+def test_trace_line_format_matches_the_real_reference_tracer(tmp_path):
+    """oracle/_ref/libobjtracker.so is the reference's own stand-alone tracer compiled from its sources where they lie
+    (oracle/build_ref.sh).  Preloaded into the allocator-churn driver it prints real T/U lines: every one of them must parse
+    with the pattern the GPU test applies to the lines libb200blas.so prints under BLAS2CUDA_OPTIONS=trace, and obey the same
+    invariants (T/U pair up by uid, U repeats the T's address and size)."""
+    tracer = os.path.join(ROOT, "oracle", "_ref", "libobjtracker.so")
+    if not os.path.exists(tracer):
+        pytest.skip("oracle/_ref/libobjtracker.so not built (needs /root/reference)")
+    exe = build_driver("allocs")
+    env = dict(os.environ, LD_PRELOAD=tracer, OBJTRACKER_OPTIONS="")
+    out = subprocess.run([exe], env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=120)
+    assert "RESULT ok=1" in out.stdout
+    lines = [l for l in out.stdout.splitlines() if l[:2] in ("T ", "U ", "C ")]
+    assert len(lines) > 1000
+    ev = [TRACE_LINE.match(l) for l in lines]
+    assert all(ev), [l for l, m in zip(lines, ev) if not m][:3]
+    live = {}
+    for m in ev:
+        kind, nth, addr, fun, size, uid = m.groups()
+        if kind == "T":
+            assert fun in ("malloc", "calloc", "realloc")
+            live[uid] = (addr, size)
+        elif kind == "U":
+            assert live.pop(uid) == (addr, size)
+
+
 REF_MICRO = [("copy", 20000, np.float32), ("dsdot", 3000, np.float64), ("rot", 20000, np.complex64), ("gbmv", 400, np.float32),
              ("trmv", 400, np.float32), ("trsm", 300, np.float64), ("hemm", 200, np.complex64)]
 
@@ -265,7 +295,7 @@ def test_object_trace_feeds_the_oracle_heuristic(tmp_path):
     exe = build_driver("cg_chain")
     # 1024 doubles = 8 KiB per vector: above stdio's own 4 KiB buffer malloc, which must stay on the heap
     out, _ = run(exe, [1024, 3], preload=True, env_extra={"BLAS2CUDA_OPTIONS": "trace;threshold=8192"}, cwd=str(tmp_path))
-    pat = re.compile(r"^([TUC]) #(\d+) \[(0x[0-9a-f]+)\] fun=\[(\w+)\] reqsize=\[(\d+)\] tid=\[\d+\] time=\[\d+s\+\d+ns\] uid=\[(\d+)\]$")
+    pat = TRACE_LINE
     ev = [pat.match(l).groups() for l in out.splitlines() if l[:2] in ("T ", "U ", "C ")]
     tracked = [e for e in ev if e[0] == "T"]
     assert len(tracked) == 5 and {e[3] for e in tracked} == {"calloc"}            # A, x, r, p, q
