@@ -322,3 +322,21 @@ def test_kernel_index_logic_fuzzed():
         worst = max(worst, err / tol)
         assert err <= tol, (it, p, kind, n, m, ul, tr, dg, ix, iy, err, tol)
     assert worst < 1.0
+
+
+@pytest.mark.parametrize("p", ["d", "z"])
+def test_oracle_reproduces_the_committed_openblas_vectors(p):
+    """tests/golden/level2_struct_openblas.npz (generator: tests/golden/make_golden_level2.py) holds what the CPU BLAS computed for a
+    slice of the case list; the oracle must reproduce it -- no CPU BLAS needed at test time."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "level2_struct_openblas.npz"))
+    cs = l2x.cases(p, sizes=(5, 33))[::7]
+    assert [c.tag for c in cs] == list(gold[p + "/tags"])
+    for i, c in enumerate(cs):
+        args = c.fresh_args()
+        assert oracle_call(c.name, *args) == 0
+        want = gold["%s/%d" % (p, i)]
+        rogue = want == want.dtype.type(l2x.ROGUE)
+        assert np.array_equal(args[c.out][rogue], want[rogue])
+        scale = max(1.0, float(np.abs(want[~rogue]).max()) if (~rogue).any() else 1.0)
+        assert float(np.abs(args[c.out].astype(np.complex128) - want.astype(np.complex128)).max()) <= c.tol * scale, c.tag

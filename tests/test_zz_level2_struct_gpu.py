@@ -229,6 +229,25 @@ def test_cblas_complex_level3_both_layouts(p):
     assert _cblas_l3_cases(call, p) < 1.0
 
 
+@pytest.mark.parametrize("p", ["d", "z"])
+def test_struct_against_committed_openblas_vectors(p):
+    """The GPU results against tests/golden/level2_struct_openblas.npz -- what the CPU BLAS behind the reference's interposer
+    computed for a slice of the case list (generator: tests/golden/make_golden_level2.py)."""
+    import os
+    lib = g.load()
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "level2_struct_openblas.npz"))
+    cs = l2x.cases(p, sizes=(5, 33))[::7]
+    assert [c.tag for c in cs] == list(gold[p + "/tags"])
+    for i, c in enumerate(cs):
+        args = c.fresh_args()
+        f77(lib, c.name + "_", *args)
+        want = gold["%s/%d" % (p, i)]
+        rogue = want == want.dtype.type(l2x.ROGUE)
+        assert np.array_equal(args[c.out][rogue], want[rogue]), c.tag
+        scale = max(1.0, float(np.abs(want[~rogue]).max()) if (~rogue).any() else 1.0)
+        assert float(np.abs(args[c.out].astype(np.complex128) - want.astype(np.complex128)).max()) <= c.tol * scale, c.tag
+
+
 def test_aligned_allocators_under_preload(tmp_path):
     """posix_memalign / aligned_alloc / memalign / valloc under LD_PRELOAD: blocks >= the threshold whose managed base
     satisfies the alignment are tracked (in place for BLAS), contents survive realloc, malloc_usable_size answers from the
