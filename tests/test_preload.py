@@ -101,6 +101,21 @@ def test_aligned_allocators_fall_through_without_a_device(tmp_path):
     assert "RESULT ok=1 tracked=0" in out
 
 
+def test_options_grammar_without_a_device(tmp_path):
+    """BLAS2CUDA_OPTIONS keeps the reference's grammar (blas2cuda.c:59-124): ';'-separated keys, `help` prints the option list,
+    an unknown key is reported and ignored, an unknown heuristic is fatal.  heuristic=false keeps every allocation on the heap,
+    so the preloaded program runs to completion on a machine without a GPU."""
+    exe = build_driver("allocs")
+    env = dict(os.environ, LD_PRELOAD=LIB_PATH, BLAS2CUDA_OPTIONS="help;heuristic=false;no_such_option;threshold=4096")
+    out = subprocess.run([exe], env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "RESULT ok=1 tracked=0" in out.stdout
+    assert "heuristic=<val>" in out.stderr and "unknown option 'no_such_option'" in out.stderr and "selecting heuristic false" in out.stderr
+    env["BLAS2CUDA_OPTIONS"] = "heuristic=sometimes"
+    out = subprocess.run([exe], env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=120)
+    assert out.returncode != 0 and "unsupported heuristic 'sometimes'" in out.stderr
+    assert not os.path.exists(os.path.join(str(tmp_path), "statistics.csv"))      # written only when a BLAS call was served
+
+
 # one trace line of the reference's TRACE_OUTPUT format (lib/obj_tracker.c:426-483)
 TRACE_LINE = re.compile(r"^([TUC]) #(\d+) \[(0x[0-9a-f]+)\] fun=\[(\w+)\] reqsize=\[(\d+)\] tid=\[\d+\] time=\[\d+s\+\d+ns\] uid=\[(\d+)\]$")
 
