@@ -191,9 +191,20 @@ def cpu_reference_run(n, ksample, steps, warmup):
     for _ in range(steps):
         f77(ob, "dgemm_", "N", "N", n, n, ksample, 1.0, A, n, B, ksample, 0.0, C, n)
     dt = (time.perf_counter() - t0) / steps
+    host = {"nproc": cores}      # report the host the CPU number comes from
+    try:
+        host["cpu_model"] = next(l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name"))
+    except Exception:
+        pass
+    try:
+        ob.openblas_get_config.restype = ctypes.c_char_p
+        host["openblas_config"] = ob.openblas_get_config().decode()
+        host["openblas_coretype"] = os.environ.get("OPENBLAS_CORETYPE")
+    except Exception:
+        pass
     return {"value": 2.0 * n * n * ksample / dt / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "reference",
             "sample": "OpenBLAS 0.3.15 dgemm_ NN m=n=%d, k=%d slice of the k=%d workload, %d threads, %.2f s/step" % (n, ksample, n, cores, dt),
-            "_seconds": dt}
+            "host": host, "_seconds": dt}
 
 
 def main():
