@@ -26,3 +26,12 @@ if "l12" in which:
     g.call("ddot_", n, x, 1, y, 1, restype=ctypes.c_double); g.call("daxpy_", n, 1e-9, x, 1, y, 1); g.call("dnrm2_", n, x, 1, restype=ctypes.c_double)
     z = torch.rand(1 << 28, dtype=torch.float64, device="cuda")
     g.call("idamax_", 1 << 28, z, 1, restype=ctypes.c_int); torch.cuda.synchronize()
+if "l2x" in which:      # banded / packed Level-2 (csrc/level2_struct.cu): N part, T part, rank row, panel solve
+    nb, kl, ku = 1 << 22, 63, 64
+    ab = torch.rand((nb, kl + ku + 1), dtype=torch.float64, device="cuda"); xb = torch.rand(nb, dtype=torch.float64, device="cuda"); yb = torch.zeros(nb, dtype=torch.float64, device="cuda")
+    g.call("dgbmv_", "N", nb, nb, kl, ku, 1.0, ab, kl + ku + 1, xb, 1, 0.0, yb, 1); g.call("dgbmv_", "T", nb, nb, kl, ku, 1.0, ab, kl + ku + 1, xb, 1, 0.0, yb, 1)
+    torch.cuda.synchronize(); del ab, xb, yb
+    n = 32768
+    ap = torch.rand(n * (n + 1) // 2, dtype=torch.float64, device="cuda") * 1e-5; x = torch.rand(n, dtype=torch.float64, device="cuda"); y = torch.rand(n, dtype=torch.float64, device="cuda")
+    g.call("dtpmv_", "U", "N", "N", n, ap, x, 1); g.call("dtpmv_", "U", "T", "N", n, ap, x, 1); g.call("dspmv_", "U", n, 1.0, ap, x, 1, 0.0, y, 1)
+    g.call("dspr2_", "L", n, 1e-9, y, 1, x, 1, ap); torch.cuda.synchronize()
