@@ -25,7 +25,7 @@ def build_driver(name):
     src = os.path.join(DRV, name + ".c")
     if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
         d = os.path.dirname(ob)
-        subprocess.check_call(["gcc", "-O2", "-o", exe, src, "-L" + d, "-l:" + os.path.basename(ob), "-Wl,-rpath," + d, "-Wl,--disable-new-dtags",
+        subprocess.check_call(["gcc", "-O2", "-pthread", "-o", exe, src, "-L" + d, "-l:" + os.path.basename(ob), "-Wl,-rpath," + d, "-Wl,--disable-new-dtags",
                                "-Wl,--allow-shlib-undefined", "-ldl", "-lm"])
     return exe
 
@@ -99,6 +99,17 @@ def test_aligned_allocators_fall_through_without_a_device(tmp_path):
     assert "RESULT ok=1 tracked=0" in out
     out, _ = run(exe, preload=True, env_extra={"BLAS2CUDA_OPTIONS": "heuristic=false"}, cwd=str(tmp_path), timeout=90)
     assert "RESULT ok=1 tracked=0" in out
+
+
+def test_threaded_allocator_churn_passes_through_without_a_device(tmp_path):
+    """16 threads x 20000 malloc / calloc / realloc / posix_memalign / free with blocks freed on other threads, under LD_PRELOAD
+    with heuristic=false: the interposers' bookkeeping (re-entrancy slots, range pre-filter, pass-through) under contention.
+    The managed path of the same driver runs in the GPU suite."""
+    exe = build_driver("allocs_mt")
+    out, _ = run(exe, [16, 20000, 50])
+    assert "RESULT ok=1" in out
+    out, _ = run(exe, [16, 20000, 50], preload=True, env_extra={"BLAS2CUDA_OPTIONS": "heuristic=false"}, cwd=str(tmp_path), timeout=300)
+    assert "RESULT ok=1 threads=16 iters=20000 tracked_seen=0" in out
 
 
 def test_options_grammar_without_a_device(tmp_path):

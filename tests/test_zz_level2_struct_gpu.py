@@ -278,3 +278,16 @@ def test_ref_micro_tests_under_preload(tmp_path):
         # float sums of n terms in different orders: n * eps(float) = 400 * 6e-8 = 2.4e-5 of the largest result; f64 solve: 1e-12
         tol = {"copy": 0.0, "rot": 0.0, "dsdot": 1e-7, "gbmv": 1e-6, "trmv": 3e-5, "trsm": 1e-12, "hemm": 3e-5}[name]
         assert float(np.abs(arr.astype(np.complex128) - ref.astype(np.complex128)).max()) <= tol * scale, name
+
+
+def test_threaded_allocator_churn_under_preload(tmp_path):
+    """tests/drivers/allocs_mt.c with the default size heuristic: 8 threads, every 10th block >= 64 KiB comes from the managed
+    allocator (registry insert / lookup / remove and cudaMallocManaged / cudaFree from several threads at once, blocks freed on
+    a thread other than the allocating one)."""
+    from test_preload import build_driver, fields, run
+    exe = build_driver("allocs_mt")
+    out, _ = run(exe, [8, 600, 10], preload=True, cwd=str(tmp_path), timeout=300)
+    r = fields([l for l in out.splitlines() if l.startswith("RESULT")][0])
+    # 8 x 60 big blocks; the malloc / calloc / posix_memalign ones (3 of the 4 random kinds) are managed, a realloc that grows a small
+    # heap block stays on the heap: expect ~360, require half of the big blocks
+    assert r["ok"] == "1" and int(r["tracked_seen"]) >= 8 * 60 // 2, out
