@@ -164,13 +164,15 @@ ST_HD int64_t col_step(const Desc& D, int j) {
         default: return D.ld;
     }
 }
-// the flags applied to a loaded element; a skipped diagonal becomes an exact zero (its stored value, rogue or NaN, is dropped)
-template <typename T> ST_HD T apply_flags(T a, int i, int j, int flags) {
+// acc + op(a) * w with the flags applied to the loaded element a = S(i,j).  A skipped diagonal takes no part at all: its stored
+// value (rogue, NaN) is dropped and no 0 * w product is formed, so an Inf in the vector cannot turn into a NaN (netlib never
+// multiplies a unit diagonal either).
+template <typename T> ST_HD T mad_elem(T a, T w, int i, int j, int flags, T acc) {
     if (i == j) {
-        if (flags & F_NODIAG) return el<T>::zero();
+        if (flags & F_NODIAG) return acc;
         if (flags & F_HERM) a = el<T>::realpart(a);
     }
-    return (flags & F_CONJ) ? el<T>::conj(a) : a;
+    return el<T>::mad((flags & F_CONJ) ? el<T>::conj(a) : a, w, acc);
 }
 // r(i) = sum over the stored columns j of row i inside [c0, c1) of op(S(i,j)) * v(j).
 // Memory behaviour is the point of this body (one thread per row):
@@ -209,7 +211,7 @@ template <typename T> ST_HD T npart_row(const Desc& D, const T* A, const T* v, i
         }
         p += s;
 #pragma unroll
-        for (int u = 0; u < NU; u++) acc[u] = el<T>::mad(apply_flags<T>(a[u], i, j + u, flags), w[u], acc[u]);
+        for (int u = 0; u < NU; u++) acc[u] = mad_elem<T>(a[u], w[u], i, j + u, flags, acc[u]);
     }
     T r = acc[0];
 #pragma unroll
@@ -229,12 +231,12 @@ template <typename T> ST_HD T tpart_lane(const Desc& D, const T* A, const T* v, 
     for (; (int64_t)i + 3 * (int64_t)nlanes < i1; i += 4 * nlanes, p += 4 * nlanes) {
         const T a0 = p[0], a1 = p[nlanes], a2 = p[2 * nlanes], a3 = p[3 * nlanes];
         const T v0 = v[i], v1 = v[i + nlanes], v2 = v[i + 2 * nlanes], v3 = v[i + 3 * nlanes];
-        acc0 = el<T>::mad(apply_flags<T>(a0, i, j, flags), v0, acc0);
-        acc1 = el<T>::mad(apply_flags<T>(a1, i + nlanes, j, flags), v1, acc1);
-        acc2 = el<T>::mad(apply_flags<T>(a2, i + 2 * nlanes, j, flags), v2, acc2);
-        acc3 = el<T>::mad(apply_flags<T>(a3, i + 3 * nlanes, j, flags), v3, acc3);
+        acc0 = mad_elem<T>(a0, v0, i, j, flags, acc0);
+        acc1 = mad_elem<T>(a1, v1, i + nlanes, j, flags, acc1);
+        acc2 = mad_elem<T>(a2, v2, i + 2 * nlanes, j, flags, acc2);
+        acc3 = mad_elem<T>(a3, v3, i + 3 * nlanes, j, flags, acc3);
     }
-    for (; i < i1; i += nlanes, p += nlanes) acc0 = el<T>::mad(apply_flags<T>(*p, i, j, flags), v[i], acc0);
+    for (; i < i1; i += nlanes, p += nlanes) acc0 = mad_elem<T>(*p, v[i], i, j, flags, acc0);
     return el<T>::add(el<T>::add(acc0, acc1), el<T>::add(acc2, acc3));
 }
 // out = alpha*(sum of the partial rows + tpart + vunit) + beta*old   (beta == 0: old is never read, like netlib)

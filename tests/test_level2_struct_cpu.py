@@ -340,3 +340,23 @@ def test_oracle_reproduces_the_committed_openblas_vectors(p):
         assert np.array_equal(args[c.out][rogue], want[rogue])
         scale = max(1.0, float(np.abs(want[~rogue]).max()) if (~rogue).any() else 1.0)
         assert float(np.abs(args[c.out].astype(np.complex128) - want.astype(np.complex128)).max()) <= c.tol * scale, c.tag
+
+
+def test_emulated_unit_diagonal_never_multiplies_the_diagonal():
+    """A unit diagonal takes no part in the product: with Inf in x, x(j) is added as is (netlib adds it; a 0 * Inf term would be NaN),
+    and whatever is stored on the diagonal -- NaN here -- is never used."""
+    for p in "dz":
+        n = 70
+        G = l2x.well_conditioned_tri(9, n, p)
+        for ul in "UL":
+            T = np.where(l2x.tri_mask(n, ul), G, 0).astype(l2x.DT[p])
+            T[np.arange(n), np.arange(n)] = np.nan
+            AP = l2x.packed(T, ul)
+            for tr in "NT":
+                x = l2x.rnd(10, (n,), p); x[17] = np.inf
+                x2 = x.copy()
+                l2x.emu_call(p + "tpmv", ul, tr, "U", n, AP, x, 1)
+                assert oracle_call(p + "tpmv", ul, tr, "U", n, AP, x2, 1) == 0
+                assert np.isinf(x[17].real) and not np.isnan(x[17].real), (p, ul, tr, x[17])
+                fin = np.isfinite(x2)
+                assert np.array_equal(np.isfinite(x), fin) and np.allclose(x[fin], x2[fin], rtol=1e-12, atol=1e-12)
