@@ -23,6 +23,11 @@
 #else
 #define ST_HD inline
 #endif
+#if defined(__CUDA_ARCH__)
+#define ST_UNROLL _Pragma("unroll")     // device pass only: the host pass of these __host__ __device__ bodies does not know the pragma
+#else
+#define ST_UNROLL
+#endif
 
 namespace b200 {
 namespace st {
@@ -190,7 +195,7 @@ template <typename T> ST_HD T npart_row(const Desc& D, const T* A, const T* v, i
     row_cols(D, i_first, jf0, jf1);
     const int jstart = st_min(j0, st_max(jf0, c0));
     T acc[NU];
-#pragma unroll
+ST_UNROLL
     for (int u = 0; u < NU; u++) acc[u] = el<T>::zero();
     if (j0 >= j1) return acc[0];
     const T* p = A + off(D, i, jstart);   // may point outside the stored part for columns left of j0: never dereferenced there
@@ -198,10 +203,10 @@ template <typename T> ST_HD T npart_row(const Desc& D, const T* A, const T* v, i
         T a[NU], w[NU];
         int64_t s = 0;
         if (j >= j0 && j + NU <= j1) {   // interior step: no masks
-#pragma unroll
+ST_UNROLL
             for (int u = 0; u < NU; u++) { a[u] = p[s]; w[u] = v[j + u]; s += col_step(D, j + u); }
         } else {                         // head (columns left of this row's range) or tail
-#pragma unroll
+ST_UNROLL
             for (int u = 0; u < NU; u++) {
                 const bool in = j + u >= j0 && j + u < j1;
                 a[u] = in ? p[s] : el<T>::zero();
@@ -210,11 +215,11 @@ template <typename T> ST_HD T npart_row(const Desc& D, const T* A, const T* v, i
             }
         }
         p += s;
-#pragma unroll
+ST_UNROLL
         for (int u = 0; u < NU; u++) acc[u] = mad_elem<T>(a[u], w[u], i, j + u, flags, acc[u]);
     }
     T r = acc[0];
-#pragma unroll
+ST_UNROLL
     for (int u = 1; u < NU; u++) r = el<T>::add(r, acc[u]);
     return r;
 }
@@ -288,18 +293,18 @@ template <typename T> ST_HD void rank_row(const Desc& D, T* A, int i, int c0, in
         T a[NU];
         int64_t st[NU], s = 0;
         if (j >= j0 && j + NU <= j1) {        // interior step: no masks
-#pragma unroll
+ST_UNROLL
             for (int u = 0; u < NU; u++) { st[u] = s; a[u] = p[s]; s += col_step(D, j + u); }
-#pragma unroll
+ST_UNROLL
             for (int u = 0; u < NU; u++) p[st[u]] = rank_elem<T>(a[u], i, j + u, axi, ayi, x, y, mode);
         } else {                              // head (columns left of this row's range) or tail
-#pragma unroll
+ST_UNROLL
             for (int u = 0; u < NU; u++) {
                 st[u] = s;
                 a[u] = (j + u >= j0 && j + u < j1) ? p[s] : el<T>::zero();
                 s += col_step(D, j + u);
             }
-#pragma unroll
+ST_UNROLL
             for (int u = 0; u < NU; u++)
                 if (j + u >= j0 && j + u < j1) p[st[u]] = rank_elem<T>(a[u], i, j + u, axi, ayi, x, y, mode);
         }
