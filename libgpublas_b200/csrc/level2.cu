@@ -8,11 +8,20 @@
 //        by a finishing kernel that also applies alpha/beta.
 //   'T': CTA = 4 columns x all rows; x is read once per 4 columns (L2-resident), block tree reduce.
 #include "common.cuh"
+#include <cstring>
 #include "kernels.h"
 #include "gemm_generic.cuh"
 #include "runtime.h"
 
 namespace b200 {
+
+// the fast DGEMV path is taken only when T is double; this keeps the other instantiations free of type punning
+template <typename T> static inline double scalar_as_f64(const T& v) {
+    double d = 0;
+    if (sizeof(T) == sizeof(double)) memcpy(&d, &v, sizeof d);
+    return d;
+}
+
 
 __device__ __forceinline__ double2 ldg_stream2(const double2* p) {
     double2 v;
@@ -212,8 +221,8 @@ void gemv_dev(cudaStream_t s, char trans, int m, int n, T alpha, const T* A, int
         gemv_finish_kernel<T><<<(m + 255) / 256, 256, 0, s>>>(m, nchunks, part, mpad, alpha, beta, y, incy);
     } else {
         const bool vecx = vec && incx == 1 && ((uintptr_t)x % 16 == 0) && (op == 1 || std::is_same<T, double>::value);
-        if (vecx) dgemv_t_vec_kernel<<<(n + GT_COLS - 1) / GT_COLS, GT_THREADS, 0, s>>>(m, n, *(double*)&alpha, (const double*)A, lda,
-                                                                                       (const double*)x, *(double*)&beta, (double*)y, incy);
+        if (vecx) dgemv_t_vec_kernel<<<(n + GT_COLS - 1) / GT_COLS, GT_THREADS, 0, s>>>(m, n, scalar_as_f64(alpha), (const double*)A, lda,
+                                                                                       (const double*)x, scalar_as_f64(beta), (double*)y, incy);
         else if (op == 2) gemv_t_generic_kernel<T, true><<<n, 128, 0, s>>>(m, n, alpha, A, lda, x, incx, beta, y, incy);
         else gemv_t_generic_kernel<T, false><<<n, 128, 0, s>>>(m, n, alpha, A, lda, x, incx, beta, y, incy);
     }

@@ -409,7 +409,7 @@ __attribute__((visibility("default"))) size_t malloc_usable_size(void* ptr) noex
 // b200blas_entry, lifecycle.cu): the kernel needs a program interpreter to relocate it
 // (reference entry.c:4, same mechanism).
 extern "C" {
-__attribute__((used, visibility("default"), section(".interp"))) const char b200blas_interp[] = "/lib64/ld-linux-x86-64.so.2";
+__attribute__((used, section(".interp"))) const char b200blas_interp[] = "/lib64/ld-linux-x86-64.so.2";
 void b200blas_print_help(void);
 // ELF entry point (-e b200blas_entry): entered without a return address on the stack, so the stack
 // must be re-aligned before calling into libc.
