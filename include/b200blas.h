@@ -6,11 +6,13 @@
  * interposer exports for this path, with the CPU BLAS's own (gfortran) calling convention:
  *
  *   1. Fortran BLAS symbols  (reference blas.h:202-314, blas_level3/[star].cc F77_xxx wrappers;
- *      Level 1/2 follow the CPU BLAS ABI because blas.h:11-198 is unreliable)
- *   2. CBLAS symbols         (reference cblas.h:46-824; complex scalars by pointer as in
+ *      Level 1/2 -- every routine blas_level1/[star].cc and blas_level2/[star].cc name -- follow the CPU BLAS
+ *      ABI because blas.h:11-198 is unreliable)
+ *   2. CBLAS symbols         (reference cblas.h:46-824, both layouts; complex scalars by pointer as in
  *      standard CBLAS, not by value as cblas.h:662-677 mis-declares)
- *   3. allocator symbols     (reference lib/obj_tracker.c:789,842,902,948)
+ *   3. allocator symbols     (reference lib/obj_tracker.c:789,842,902,948, plus the aligned allocators)
  *   4. a small control API   (b200blas_[star]) for embedding, tests and benchmarks.
+ * COVERAGE.md lists the 300 BLAS entry points by level, precision and symbol family.
  *
  * Operands may live in: tracked managed memory (from the interposed malloc/calloc), any other
  * CUDA managed or device memory (used in place), or ordinary host memory (staged).  Every entry
