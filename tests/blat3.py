@@ -374,9 +374,10 @@ def chk_r2k(p, call, which="syr2k"):
 
 
 def chke(p, call_capture):
-    """DCHKE restated for the routines built: every illegal argument must report its INFO through
-    XERBLA under the routine's SRNAME and touch nothing.  `call_capture(name, *args)` performs the call
-    and returns the list of (srname, info) pairs XERBLA saw."""
+    """DCHKE / ZCHKE restated: every illegal argument must report its INFO through XERBLA under the routine's SRNAME and
+    touch nothing.  `call_capture(name, *args)` performs the call and returns the list of (srname, info) pairs XERBLA saw.
+    Returns the number of checks: 162 for s/d (netlib DCHKE: 162), 291 for c/z (netlib ZCHKE's 288 + '/' as the illegal TRANS of
+    ?SYRK, ?SYR2K, ?HER2K, where netlib only tries the letter that is legal for the sister routine)."""
     dt = DT[p]
     one = 1.0 if p in "sd" else 1.0 + 0j
     A = np.zeros((2, 2), dtype=dt, order="F"); B = np.zeros((2, 2), dtype=dt, order="F"); C = np.zeros((2, 2), dtype=dt, order="F")
@@ -388,28 +389,30 @@ def chke(p, call_capture):
         assert seen == [((name[:-1]).upper().ljust(6), info)], (name, info, seen)
         n_checked += 1
 
+    # netlib ?CHKE walks every legal transpose letter: N, T for the real programs (dblat3.f DCHKE), N, C, T for the complex
+    # ones (zblat3.f ZCHKE) -- 162 checks in s/d, 288 in c/z
+    ops = "NT" if p in "sd" else "NCT"
     g = p + "gemm_"
-    for tb in "NT":
+    for tb in ops:
         expect(g, 1, "/", tb, 0, 0, 0, one, A, 1, B, 1, one, C, 1)
-    for ta in "NT":
+    for ta in ops:
         expect(g, 2, ta, "/", 0, 0, 0, one, A, 1, B, 1, one, C, 1)
-    for ta in "NT":
-        for tb in "NT":
+    for ta in ops:
+        for tb in ops:
             expect(g, 3, ta, tb, -1, 0, 0, one, A, 1, B, 1, one, C, 1)
             expect(g, 4, ta, tb, 0, -1, 0, one, A, 1, B, 1, one, C, 1)
             expect(g, 5, ta, tb, 0, 0, -1, one, A, 1, B, 1, one, C, 1)
-    expect(g, 8, "N", "N", 2, 0, 0, one, A, 1, B, 1, one, C, 2)
-    expect(g, 8, "N", "T", 2, 0, 0, one, A, 1, B, 1, one, C, 2)
-    expect(g, 8, "T", "N", 0, 0, 2, one, A, 1, B, 2, one, C, 1)
-    expect(g, 8, "T", "T", 0, 0, 2, one, A, 1, B, 1, one, C, 1)
-    expect(g, 10, "N", "N", 0, 0, 2, one, A, 1, B, 1, one, C, 1)
-    expect(g, 10, "T", "N", 0, 0, 2, one, A, 2, B, 1, one, C, 1)
-    expect(g, 10, "N", "T", 0, 2, 0, one, A, 1, B, 1, one, C, 1)
-    expect(g, 10, "T", "T", 0, 2, 0, one, A, 1, B, 1, one, C, 1)
-    expect(g, 13, "N", "N", 2, 0, 0, one, A, 2, B, 1, one, C, 1)
-    expect(g, 13, "N", "T", 2, 0, 0, one, A, 2, B, 1, one, C, 1)
-    expect(g, 13, "T", "N", 2, 0, 0, one, A, 1, B, 1, one, C, 1)
-    expect(g, 13, "T", "T", 2, 0, 0, one, A, 1, B, 1, one, C, 1)
+            # LDA: op(A) is m x k -- 'N' stores m rows, otherwise k rows
+            if ta == "N":
+                expect(g, 8, ta, tb, 2, 0, 0, one, A, 1, B, 1, one, C, 2)
+            else:
+                expect(g, 8, ta, tb, 0, 0, 2, one, A, 1, B, 2 if tb == "N" else 1, one, C, 1)
+            # LDB: op(B) is k x n -- 'N' stores k rows, otherwise n rows
+            if tb == "N":
+                expect(g, 10, ta, tb, 0, 0, 2, one, A, 1 if ta == "N" else 2, B, 1, one, C, 1)
+            else:
+                expect(g, 10, ta, tb, 0, 2, 0, one, A, 1, B, 1, one, C, 1)
+            expect(g, 13, ta, tb, 2, 0, 0, one, A, 2 if ta == "N" else 1, B, 1, one, C, 1)
     for r in ("trmm_", "trsm_"):
         t = p + r
         expect(t, 1, "/", "U", "N", "N", 0, 0, one, A, 1, B, 1)
@@ -418,11 +421,11 @@ def chke(p, call_capture):
         expect(t, 4, "L", "U", "N", "/", 0, 0, one, A, 1, B, 1)
         for side in "LR":
             for uplo in "UL":
-                for ta in "NT":
+                for ta in ops:
                     expect(t, 5, side, uplo, ta, "N", -1, 0, one, A, 1, B, 1)
                     expect(t, 6, side, uplo, ta, "N", 0, -1, one, A, 1, B, 1)
         for uplo in "UL":
-            for ta in "NT":
+            for ta in ops:
                 expect(t, 9, "L", uplo, ta, "N", 2, 0, one, A, 1, B, 2)
                 expect(t, 9, "R", uplo, ta, "N", 0, 2, one, A, 1, B, 1)
                 expect(t, 11, "L", uplo, ta, "N", 2, 0, one, A, 2, B, 1)
