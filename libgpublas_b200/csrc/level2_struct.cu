@@ -60,18 +60,18 @@ template <typename T> __global__ void scatter_kernel(int n, const T* __restrict_
 }
 // part[chunk][i] = N part of row i over the chunk's columns; rows [row0,row1), columns [c_lo,c_hi) cut into chunks of cpc
 template <typename T>
-__global__ void __launch_bounds__(128) npart_kernel(Desc D, const T* __restrict__ A, const T* __restrict__ v, int row0, int row1, int c_lo, int c_hi, int cpc,
+__global__ void __launch_bounds__(ROW_THREADS) npart_kernel(Desc D, const T* __restrict__ A, const T* __restrict__ v, int row0, int row1, int c_lo, int c_hi, int cpc,
                                                     int flags, T* __restrict__ part, int64_t npad) {
-    const int i = row0 + blockIdx.x * 128 + threadIdx.x;
+    const int i = row0 + blockIdx.x * ROW_THREADS + threadIdx.x;
     if (i >= row1) return;
     const int c0 = c_lo + blockIdx.y * cpc, c1 = st_min(c_hi, c0 + cpc);
     part[(int64_t)blockIdx.y * npad + i] = npart_row<T>(D, A, v, i, c0, c1, flags, i - (threadIdx.x & 31));
 }
 // tpart[j] = T part of column j over rows [r0,r1); one warp per column in [col0,col1)
 template <typename T>
-__global__ void __launch_bounds__(128) tpart_kernel(Desc D, const T* __restrict__ A, const T* __restrict__ v, int col0, int col1, int r0, int r1, int flags,
+__global__ void __launch_bounds__(COL_WARPS * 32) tpart_kernel(Desc D, const T* __restrict__ A, const T* __restrict__ v, int col0, int col1, int r0, int r1, int flags,
                                                     T* __restrict__ tpart) {
-    const int j = col0 + blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int j = col0 + blockIdx.x * COL_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (j >= col1) return;   // whole warp
     const T acc = warp_sum(tpart_lane<T>(D, A, v, j, lane, 32, r0, r1, flags));
     if (lane == 0) tpart[j] = acc;
@@ -86,24 +86,24 @@ __global__ void smv_finish_kernel(int n, int nparts, const T* __restrict__ part,
     *p = finish_elem<T>(i, nparts, part, npad, tpart, vunit, alpha, beta, beta0, beta0 ? el<T>::zero() : *p);
 }
 template <typename T>
-__global__ void __launch_bounds__(128) rank_kernel(Desc D, T* __restrict__ A, int rows, int ncols, int cpc, T alpha, const T* __restrict__ x, const T* __restrict__ y,
+__global__ void __launch_bounds__(ROW_THREADS) rank_kernel(Desc D, T* __restrict__ A, int rows, int ncols, int cpc, T alpha, const T* __restrict__ x, const T* __restrict__ y,
                                                    int mode) {
-    const int i = blockIdx.x * 128 + threadIdx.x;
+    const int i = blockIdx.x * ROW_THREADS + threadIdx.x;
     if (i >= rows) return;
     const int c0 = blockIdx.y * cpc, c1 = st_min(ncols, c0 + cpc);
     rank_row<T>(D, A, i, c0, c1, alpha, x, y, mode, i - (threadIdx.x & 31));
 }
 // x(i) -= N part of row i over the solved block's columns [b0,b1)      (rows [row0,row1) lie outside the block)
 template <typename T>
-__global__ void __launch_bounds__(128) solve_nupdate_kernel(Desc D, const T* __restrict__ A, T* x, int row0, int row1, int b0, int b1, int flags) {
-    const int i = row0 + blockIdx.x * 128 + threadIdx.x;
+__global__ void __launch_bounds__(ROW_THREADS) solve_nupdate_kernel(Desc D, const T* __restrict__ A, T* x, int row0, int row1, int b0, int b1, int flags) {
+    const int i = row0 + blockIdx.x * ROW_THREADS + threadIdx.x;
     if (i >= row1) return;
     x[i] = el<T>::sub(x[i], npart_row<T>(D, A, x, i, b0, b1, flags, i - (threadIdx.x & 31)));
 }
 // x(j) -= T part of column j over the solved block's rows [b0,b1)      (columns [col0,col1) lie outside the block)
 template <typename T>
-__global__ void __launch_bounds__(128) solve_tupdate_kernel(Desc D, const T* __restrict__ A, T* x, int col0, int col1, int b0, int b1, int flags) {
-    const int j = col0 + blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(COL_WARPS * 32) solve_tupdate_kernel(Desc D, const T* __restrict__ A, T* x, int col0, int col1, int b0, int b1, int flags) {
+    const int j = col0 + blockIdx.x * COL_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (j >= col1) return;
     const T acc = warp_sum(tpart_lane<T>(D, A, x, j, lane, 32, b0, b1, flags));
     if (lane == 0) x[j] = el<T>::sub(x[j], acc);
@@ -183,10 +183,10 @@ struct DeviceBackend {
     template <typename T> void scatter(int n, const T* src, T* dst, int64_t inc) { scatter_kernel<T><<<(n + 255) / 256, 256, 0, s>>>(n, src, dst, inc); }
     template <typename T>
     void npart(const Desc& D, const T* A, const T* v, int row0, int row1, int c_lo, int c_hi, int cpc, int nchunks, int flags, T* part, int64_t npad) {
-        npart_kernel<T><<<dim3((row1 - row0 + 127) / 128, nchunks), 128, 0, s>>>(D, A, v, row0, row1, c_lo, c_hi, cpc, flags, part, npad);
+        npart_kernel<T><<<dim3((row1 - row0 + ROW_THREADS - 1) / ROW_THREADS, nchunks), ROW_THREADS, 0, s>>>(D, A, v, row0, row1, c_lo, c_hi, cpc, flags, part, npad);
     }
     template <typename T> void tpart(const Desc& D, const T* A, const T* v, int col0, int col1, int r0, int r1, int flags, T* tp) {
-        tpart_kernel<T><<<(col1 - col0 + 3) / 4, 128, 0, s>>>(D, A, v, col0, col1, r0, r1, flags, tp);
+        tpart_kernel<T><<<(col1 - col0 + COL_WARPS - 1) / COL_WARPS, COL_WARPS * 32, 0, s>>>(D, A, v, col0, col1, r0, r1, flags, tp);
     }
     template <typename T>
     void finish(int n, int nparts, const T* part, int64_t npad, const T* tp, const T* vunit, T alpha, T beta, T* out, int64_t inco) {
@@ -194,7 +194,7 @@ struct DeviceBackend {
         last_variant = VAR_GENERIC_TILE;
     }
     template <typename T> void rank(const Desc& D, T* A, int rows, int ncols, int cpc, int nchunks, T alpha, const T* x, const T* y, int mode) {
-        rank_kernel<T><<<dim3((rows + 127) / 128, nchunks), 128, 0, s>>>(D, A, rows, ncols, cpc, alpha, x, y, mode);
+        rank_kernel<T><<<dim3((rows + ROW_THREADS - 1) / ROW_THREADS, nchunks), ROW_THREADS, 0, s>>>(D, A, rows, ncols, cpc, alpha, x, y, mode);
         last_variant = VAR_GENERIC_TILE;
     }
     template <typename T> void solve_panel(const Desc& D, const T* A, T* x, int p0, int p1, bool trans, bool conj, bool unit, bool forward) {
@@ -202,10 +202,10 @@ struct DeviceBackend {
         last_variant = VAR_GENERIC_TILE;
     }
     template <typename T> void solve_nupdate(const Desc& D, const T* A, T* x, int row0, int row1, int b0, int b1, int flags) {
-        solve_nupdate_kernel<T><<<(row1 - row0 + 127) / 128, 128, 0, s>>>(D, A, x, row0, row1, b0, b1, flags);
+        solve_nupdate_kernel<T><<<(row1 - row0 + ROW_THREADS - 1) / ROW_THREADS, ROW_THREADS, 0, s>>>(D, A, x, row0, row1, b0, b1, flags);
     }
     template <typename T> void solve_tupdate(const Desc& D, const T* A, T* x, int col0, int col1, int b0, int b1, int flags) {
-        solve_tupdate_kernel<T><<<(col1 - col0 + 3) / 4, 128, 0, s>>>(D, A, x, col0, col1, b0, b1, flags);
+        solve_tupdate_kernel<T><<<(col1 - col0 + COL_WARPS - 1) / COL_WARPS, COL_WARPS * 32, 0, s>>>(D, A, x, col0, col1, b0, b1, flags);
     }
 };
 

@@ -40,6 +40,12 @@ enum Kind {
     K_PACKED = 4      // n x n triangle packed by columns: upper AP[i + j(j+1)/2], lower AP[i + j(2n-j-1)/2]  (SPMV, HPMV, SPR*, HPR*, TPMV, TPSV)
 };
 
+// launch shapes shared by the kernels (level2_struct.cu) and their CPU emulation (tests/drivers/struct_emul.cpp)
+enum {
+    ROW_THREADS = 128,   // N part / rank row / solve update: one thread per row, this many rows per CTA
+    COL_WARPS = 4        // T part / transposed solve update: one warp per column, this many columns per CTA
+};
+
 struct Desc {
     int kind, m, n, kl, ku, upper;   // K_BAND_TRI keeps its k in both kl and ku
     int64_t ld;
@@ -351,7 +357,7 @@ inline int64_t packed_len(int n) { return (int64_t)n * ((int64_t)n + 1) / 2; }
 
 template <typename BE> inline int col_chunks(BE& be, const Desc& D, int rows, int ncols) {
     if (D.kind == K_BAND_GEN || D.kind == K_BAND_TRI) return 1;   // a row holds at most kl+ku+1 stored columns
-    const int rb = (rows + 127) / 128;
+    const int rb = (rows + ROW_THREADS - 1) / ROW_THREADS;
     int c = (be.sm_target() + rb - 1) / rb;
     const int maxc = (ncols + 63) / 64;
     if (c > maxc) c = maxc;

@@ -43,18 +43,18 @@ struct HostBackend {
     template <typename T>
     void npart(const Desc& D, const T* A, const T* v, int row0, int row1, int c_lo, int c_hi, int cpc, int nchunks, int flags, T* part, int64_t npad) {
         for (int by = 0; by < nchunks; by++)
-            for (int bx = 0; bx < (row1 - row0 + 127) / 128; bx++)
-                for (int tx = 0; tx < 128; tx++) {
-                    const int i = row0 + bx * 128 + tx;
+            for (int bx = 0; bx < (row1 - row0 + ROW_THREADS - 1) / ROW_THREADS; bx++)
+                for (int tx = 0; tx < ROW_THREADS; tx++) {
+                    const int i = row0 + bx * ROW_THREADS + tx;
                     if (i >= row1) continue;
                     const int c0 = c_lo + by * cpc, c1 = st_min(c_hi, c0 + cpc);
                     part[(int64_t)by * npad + i] = npart_row<T>(D, A, v, i, c0, c1, flags, i - (tx & 31));
                 }
     }
     template <typename T> void tpart(const Desc& D, const T* A, const T* v, int col0, int col1, int r0, int r1, int flags, T* tp) {
-        for (int bx = 0; bx < (col1 - col0 + 3) / 4; bx++)
-            for (int w = 0; w < 4; w++) {
-                const int j = col0 + bx * 4 + w;
+        for (int bx = 0; bx < (col1 - col0 + COL_WARPS - 1) / COL_WARPS; bx++)
+            for (int w = 0; w < COL_WARPS; w++) {
+                const int j = col0 + bx * COL_WARPS + w;
                 if (j >= col1) continue;
                 T lanes[32];
                 for (int lane = 0; lane < 32; lane++) lanes[lane] = tpart_lane<T>(D, A, v, j, lane, 32, r0, r1, flags);
@@ -71,9 +71,9 @@ struct HostBackend {
     }
     template <typename T> void rank(const Desc& D, T* A, int rows, int ncols, int cpc, int nchunks, T alpha, const T* x, const T* y, int mode) {
         for (int by = 0; by < nchunks; by++)
-            for (int bx = 0; bx < (rows + 127) / 128; bx++)
-                for (int tx = 0; tx < 128; tx++) {
-                    const int i = bx * 128 + tx;
+            for (int bx = 0; bx < (rows + ROW_THREADS - 1) / ROW_THREADS; bx++)
+                for (int tx = 0; tx < ROW_THREADS; tx++) {
+                    const int i = bx * ROW_THREADS + tx;
                     if (i >= rows) continue;
                     const int c0 = by * cpc, c1 = st_min(ncols, c0 + cpc);
                     rank_row<T>(D, A, i, c0, c1, alpha, x, y, mode, i - (tx & 31));
@@ -123,9 +123,9 @@ struct HostBackend {
         }
     }
     template <typename T> void solve_nupdate(const Desc& D, const T* A, T* x, int row0, int row1, int b0, int b1, int flags) {
-        for (int bx = 0; bx < (row1 - row0 + 127) / 128; bx++)
-            for (int tx = 0; tx < 128; tx++) {
-                const int i = row0 + bx * 128 + tx;
+        for (int bx = 0; bx < (row1 - row0 + ROW_THREADS - 1) / ROW_THREADS; bx++)
+            for (int tx = 0; tx < ROW_THREADS; tx++) {
+                const int i = row0 + bx * ROW_THREADS + tx;
                 if (i < row1) x[i] = el<T>::sub(x[i], npart_row<T>(D, A, x, i, b0, b1, flags, i - (tx & 31)));
             }
     }
