@@ -75,8 +75,12 @@ __device__ __forceinline__ void grid_finish(V block_val, V* partials, unsigned i
     __syncthreads();
     v = block_reduce<V, Op>(v, smem);
     if (threadIdx.x == 0) {
+        // Ticket first, result second: the host acts on the result the moment it sees it (wait_scalar spins on the zero-copy
+        // slot), possibly launching the next reduction on another stream; by then the ticket must already read zero.  Every
+        // other block has taken its ticket (this block drew the last one), so nobody else still needs the old value.
+        *ticket = 0;
+        __threadfence_system();
         fin(v);
-        *ticket = 0;   // ready for the next launch on this stream
     }
 }
 
