@@ -112,6 +112,45 @@ def test_threaded_allocator_churn_passes_through_without_a_device(tmp_path):
     assert "RESULT ok=1 threads=16 iters=20000 tracked_seen=0" in out
 
 
+def build_tracker_mock():
+    """tracker.cpp + tests/drivers/tracker_mock.cpp (a stand-in for cudaMallocManaged / cudaFree) -> _build/libtracker_mock.so"""
+    os.makedirs(BUILD, exist_ok=True)
+    out = os.path.join(BUILD, "libtracker_mock.so")
+    srcs = [os.path.join(ROOT, "libgpublas_b200", "csrc", "tracker.cpp"), os.path.join(DRV, "tracker_mock.cpp")]
+    deps = srcs + [os.path.join(ROOT, "libgpublas_b200", "csrc", "tracker.h")]
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-I/usr/local/cuda/include", "-o", out] + srcs
+                              + ["-ldl", "-lpthread"])
+    return out
+
+
+def test_managed_path_bookkeeping_with_mocked_cuda(tmp_path):
+    """The tracker's MANAGED path without a GPU: tracker.cpp linked against a mock of the CUDA calls it makes (mmap for
+    cudaMallocManaged), preloaded into the allocator drivers.  Same expectations as the GPU tests of the real library:
+    blocks >= 64 KiB are tracked, interior pointers resolve, realloc keeps contents, aligned allocators hand out tracked blocks
+    whose base satisfies the alignment, and 16 threads x 20000 allocations with cross-thread frees keep the registry consistent
+    (heuristic=true: every one of the 320000 blocks goes through registry insert / remove)."""
+    mock = build_tracker_mock()
+
+    def run_mock(name, args=(), heuristic=None):
+        env = dict(os.environ, LD_PRELOAD=mock)
+        if heuristic:
+            env["TRACKER_MOCK_HEURISTIC"] = heuristic
+        out = subprocess.run([build_driver(name)] + [str(a) for a in args], env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, (name, out.stdout[-1000:], out.stderr[-1000:])
+        return fields([l for l in out.stdout.splitlines() if l.startswith("RESULT")][0])
+
+    r = run_mock("allocs")
+    assert r["ok"] == "1" and int(r["tracked"]) > 300
+    assert run_mock("allocs", heuristic="true")["tracked"] == "512" and run_mock("allocs", heuristic="false")["tracked"] == "0"
+    r = run_mock("aligned_allocs")
+    assert r["ok"] == "1" and int(r["tracked"]) >= 20
+    r = run_mock("allocs_mt", [8, 600, 10])
+    assert r["ok"] == "1" and int(r["tracked_seen"]) >= 8 * 60 // 2
+    r = run_mock("allocs_mt", [16, 20000, 50], heuristic="true")
+    assert r["ok"] == "1" and r["tracked_seen"] == "320000"
+
+
 def test_options_grammar_without_a_device(tmp_path):
     """BLAS2CUDA_OPTIONS keeps the reference's grammar (blas2cuda.c:59-124): ';'-separated keys, `help` prints the option list,
     an unknown key is reported and ignored, an unknown heuristic is fatal.  heuristic=false keeps every allocation on the heap,
