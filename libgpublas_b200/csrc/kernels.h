@@ -1,6 +1,6 @@
 // kernels.h -- device-level routines (operands are device-accessible pointers; all work is
 // enqueued on `s`, nothing synchronises).  The ABI layers (fortran_l3.cu, fortran_l12.cu, cblas_l3.cu, and the
-// entry points at the bottom of level2_struct.cu / level2_more.cu / level1_more.cu) sit above this and own argument
+// entry points at the bottom of level2_struct.cu / level1_more.cu) sit above this and own argument
 // checking, residency and the synchronous return.
 #pragma once
 #include <cuda_runtime.h>

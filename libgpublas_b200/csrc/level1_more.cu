@@ -1,11 +1,12 @@
 // level1_more.cu -- the rest of the Level-1 surface the reference's dead wrappers name:
-// blas_level1/rotm.cc:10-57 (cublas<t>rotm), rotmg.cc:11-28 (cublas<t>rotmg), amin.cc:10-56 (cublasI<t>amin), the
+// blas_level1/rot.cc, rotg.cc (cublas<t>rot / rotg), rotm.cc:10-57 (cublas<t>rotm), rotmg.cc:11-28 (cublas<t>rotmg), amin.cc:10-56 (cublasI<t>amin), the
 // DSDOT / SDSDOT prototypes of cblas.h, CSROT / ZDROT, and the cblas_ forms of the complex copy / swap / scal / asum that
 // fortran_l12.cu exports as Fortran symbols only.  Element-wise kernels are one coalesced pass; ROTMG is scalar work and
-// stays on the host (like ROTG in level2_more.cu).
+// stays on the host, like ROTG.
 #include "abi_common.h"
 #include "../../include/b200blas.h"
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace b200 {
@@ -36,6 +37,22 @@ __global__ void crot_kernel(int64_t n, CT* x, int64_t incx, CT* y, int64_t incy,
         *px = nx; *py = ny;
     }
 }
+// netlib xROT (reference blas_level1/rot.cc): real plane rotation
+template <typename T> __global__ void rot_kernel(int64_t n, T* x, int64_t incx, T* y, int64_t incy, T c, T s) {
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth) {
+        T* px = x + l1m_pos(i, n, incx); T* py = y + l1m_pos(i, n, incy);
+        const T xv = *px, yv = *py;
+        *px = c * xv + s * yv;
+        *py = c * yv - s * xv;
+    }
+}
+template <typename T> void rot_dev(cudaStream_t s, int64_t n, T* x, int64_t incx, T* y, int64_t incy, T c, T sn) {
+    int64_t b = (n + 255) / 256; if (b > 148 * 16) b = 148 * 16;
+    rot_kernel<T><<<(int)b, 256, 0, s>>>(n, x, incx, y, incy, c, sn);
+    last_variant = VAR_GENERIC_TILE;
+}
+
 static int l1m_blocks(int64_t n) {
     int64_t b = (n + 255) / 256;
     const int cap = (sm_count() > 0 ? sm_count() : 148) * 16;
@@ -161,12 +178,46 @@ double dsdot_entry(const char* name, const int* n, float sb, const float* x, con
     return r;
 }
 
+template <typename T>
+void rot_entry(const char* name, const int* n, T* x, const int* incx, T* y, const int* incy, const T* c, const T* s) {
+    if (*n <= 0) return;
+    CallScope scope(name);
+    Operand ox(x, 1 + (int64_t)(*n - 1) * abs(*incx), 1, 1 + (int64_t)(*n - 1) * abs(*incx), sizeof(T), ACC_INOUT);
+    Operand oy(y, 1 + (int64_t)(*n - 1) * abs(*incy), 1, 1 + (int64_t)(*n - 1) * abs(*incy), sizeof(T), ACC_INOUT);
+    rot_dev<T>(current_stream(), *n, (T*)ox.dev(), *incx, (T*)oy.dev(), *incy, *c, *s);
+    ox.release(); oy.release();
+    log_exec(name, "n=%d", *n);
+}
+// netlib xROTG (reference BLAS 3.8 formulation): scalar work, host only
+template <typename T> void rotg_host(T* a, T* b, T* c, T* s) {
+    const T aa = std::fabs(*a), ab = std::fabs(*b);
+    const T roe = aa > ab ? *a : *b, scale = aa + ab;
+    T r, z;
+    if (scale == T(0)) { *c = 1; *s = 0; r = 0; z = 0; }
+    else {
+        r = scale * std::sqrt((*a / scale) * (*a / scale) + (*b / scale) * (*b / scale));
+        r = std::copysign(T(1), roe) * r;
+        *c = *a / r; *s = *b / r; z = 1;
+        if (aa > ab) z = *s;
+        if (ab >= aa && *c != T(0)) z = T(1) / *c;
+    }
+    *a = r; *b = z;
+}
+
 typedef cuFloatComplex c32;
 typedef cuDoubleComplex c64;
 
 }  // namespace
 
 extern "C" {
+#define B200_ROT(P, T)                                                                                                                        \
+    void P##rot_(const int* n, T* x, const int* incx, T* y, const int* incy, const T* c, const T* s) { rot_entry<T>(#P "rot_", n, x, incx, y, incy, c, s); } \
+    void P##rotg_(T* a, T* b, T* c, T* s) { rotg_host<T>(a, b, c, s); }                                                                          \
+    void cblas_##P##rot(int n, T* x, int incx, T* y, int incy, T c, T s) { P##rot_(&n, x, &incx, y, &incy, &c, &s); }                             \
+    void cblas_##P##rotg(T* a, T* b, T* c, T* s) { rotg_host<T>(a, b, c, s); }
+B200_ROT(s, float)
+B200_ROT(d, double)
+#undef B200_ROT
 void srotm_(const int* n, float* x, const int* incx, float* y, const int* incy, const float* param) { rotm_entry<float>("srotm_", n, x, incx, y, incy, param); }
 void drotm_(const int* n, double* x, const int* incx, double* y, const int* incy, const double* param) { rotm_entry<double>("drotm_", n, x, incx, y, incy, param); }
 void srotmg_(float* d1, float* d2, float* x1, const float* y1, float* param) { rotmg_host<float>(d1, d2, x1, y1, param); }
