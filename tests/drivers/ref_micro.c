@@ -12,6 +12,8 @@
  *     trsm  (trsm.c:21-31)   upper A(r,c) = (r m + c) mod 10, B(r,c) = (r n + c) mod 10;    cblas_dtrsm (Left, Upper, NoTrans, NonUnit)
  *                            -- the reference's fill puts zeros on A's diagonal (its own FIXME: "segfault when m > 100");
  *                               here the diagonal gets +10 so the system is solvable and the two runs can be compared
+ *     gemm  (gemm.c:29-43)   the ORIGINAL single-precision form of BASELINE config 1: A(r,c) = r, B(r,c) = c, alpha = 1, beta = 0;
+ *                            cblas_sgemm (ColMajor, NoTrans, NoTrans) => C(r,c) = k r c, exact in f32 while n^3 < 2^24 (n <= 256)
  *     hemm  (hemm.c:27-41)   Hermitian A(r,c) = c + rI (c > r), A(r,r) = r, B(r,c) = c + (r mod 10)I; cblas_chemm (Left, Upper)
  * Usage: ref_micro <test> <n> <outfile>      prints: RESULT test=<..> n=<..> ns=<..> closed_form_err=<..|nan> tracked=<0|1>
  */
@@ -31,6 +33,7 @@ extern void csrot_(const int*, void*, const int*, void*, const int*, const float
 extern void cblas_sgbmv(int, int, int, int, int, int, float, const float*, int, const float*, int, float, float*, int);
 extern void cblas_strmv(int, int, int, int, int, const float*, int, float*, int);
 extern void cblas_dtrsm(int, int, int, int, int, int, int, double, const double*, int, double*, int);
+extern void cblas_sgemm(int, int, int, int, int, int, float, const float*, int, const float*, int, float, float*, int);
 extern void cblas_chemm(int, int, int, int, int, const void*, const void*, int, const void*, int, const void*, void*, int);
 
 static double now_ns(void) {
@@ -42,7 +45,7 @@ static int imin(int a, int b) { return a < b ? a : b; }
 static int imax(int a, int b) { return a > b ? a : b; }
 
 int main(int argc, char** argv) {
-    if (argc < 4) { fprintf(stderr, "usage: %s <copy|dsdot|rot|gbmv|trmv|trsm|hemm> <n> <outfile>\n", argv[0]); return 2; }
+    if (argc < 4) { fprintf(stderr, "usage: %s <copy|dsdot|rot|gbmv|trmv|trsm|gemm|hemm> <n> <outfile>\n", argv[0]); return 2; }
     const char* test = argv[1];
     const int n = atoi(argv[2]);
     int (*is_tracked)(const void*) = (int (*)(const void*))dlsym(RTLD_DEFAULT, "b200blas_is_tracked");
@@ -98,6 +101,18 @@ int main(int argc, char** argv) {
             for (int col = 0; col < nrhs; ++col) B[(size_t)col * m + row] = ((long)row * nrhs + col) % 10;
         t0 = now_ns(); cblas_dtrsm(ColMajor, Left, Upper, NoTrans, NonUnit, m, nrhs, 1.0, A, m, B, m); t1 = now_ns();
         res = B; res_bytes = (size_t)m * nrhs * sizeof *B; biggest = A;
+    } else if (!strcmp(test, "gemm")) {
+        const int m = n, k = n;
+        float* A = calloc(m, k * sizeof *A); float* B = calloc(k, n * sizeof *B); float* C = calloc(m, n * sizeof *C);
+        for (int row = 0; row < m; ++row)
+            for (int col = 0; col < k; ++col) A[(size_t)col * m + row] = (row * k + col) / k;
+        for (int row = 0; row < k; ++row)
+            for (int col = 0; col < n; ++col) B[(size_t)col * k + row] = (row * n + col) % n;
+        t0 = now_ns(); cblas_sgemm(ColMajor, NoTrans, NoTrans, m, n, k, 1.f, A, m, B, k, 0.f, C, m); t1 = now_ns();
+        err = 0;
+        for (int col = 0; col < n; ++col)
+            for (int row = 0; row < m; ++row) err = fmax(err, fabs((double)C[(size_t)col * m + row] - (double)k * row * col));
+        res = C; res_bytes = (size_t)m * n * sizeof *C; biggest = A;
     } else if (!strcmp(test, "hemm")) {
         const int m = n;
         float complex* A = calloc(m, m * sizeof *A); float complex* B = calloc(m, n * sizeof *B); float complex* C = calloc(m, n * sizeof *C);

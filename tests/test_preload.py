@@ -197,7 +197,7 @@ def test_trace_line_format_matches_the_real_reference_tracer(tmp_path):
 
 
 REF_MICRO = [("copy", 20000, np.float32), ("dsdot", 3000, np.float64), ("rot", 20000, np.complex64), ("gbmv", 400, np.float32),
-             ("trmv", 400, np.float32), ("trsm", 300, np.float64), ("hemm", 200, np.complex64)]
+             ("trmv", 400, np.float32), ("trsm", 300, np.float64), ("gemm", 256, np.float32), ("hemm", 200, np.complex64)]
 
 
 def run_ref_micro(tmp_path, preload):
@@ -216,6 +216,7 @@ def test_ref_micro_tests_on_cpu_blas(tmp_path):
     closed forms where the fill has one, and a numpy evaluation of the same fills for the matrix routines."""
     res = run_ref_micro(tmp_path, preload=False)
     assert float(res["copy"][1]["closed_form_err"]) == 0.0 and float(res["rot"][1]["closed_form_err"]) == 0.0
+    assert float(res["gemm"][1]["closed_form_err"]) == 0.0      # the reference's own gemm.c in f32: k*r*c is exact below 2^24 (n = 256)
     assert float(res["dsdot"][1]["closed_form_err"]) <= 1e-7 * 9.0e9     # OpenBLAS sums blocks of its float kernel in float (5e-9 relative here);
     #                                                                    # netlib DSDOT -- and the GPU kernel -- are exact on this input
     n = 400      # gbmv: A read as column-major band storage AB[ku+i-j, j] with lda = n, as cblas_sgbmv(ColMajor) reads the reference's array

@@ -262,13 +262,13 @@ def test_aligned_allocators_under_preload(tmp_path):
 
 
 def test_ref_micro_tests_under_preload(tmp_path):
-    """The reference's tests/c micro-tests (copy, dsdot, csrot, sgbmv, strmv, dtrsm, chemm; restated in tests/drivers/ref_micro.c)
+    """The reference's tests/c micro-tests (copy, dsdot, csrot, sgbmv, strmv, dtrsm, sgemm, chemm; restated in tests/drivers/ref_micro.c)
     under LD_PRELOAD=libb200blas.so against the same binary on the CPU BLAS: every call is intercepted (its calloc'd matrix is a
     tracked managed block), results agree, and the closed forms hold exactly where the fill has one."""
     from test_preload import run_ref_micro
     cpu = run_ref_micro(tmp_path, preload=False)
     gpu = run_ref_micro(tmp_path, preload=True)
-    for name in ("copy", "rot", "dsdot"):
+    for name in ("copy", "rot", "dsdot", "gemm"):
         assert float(gpu[name][1]["closed_form_err"]) == 0.0, (name, gpu[name][1])      # exact on these inputs (DSDOT: all in double)
     for name, (arr, f) in gpu.items():
         assert f["tracked"] == "1" or name == "dsdot", (name, f)        # dsdot's 12 KB vectors stay on the heap (below the threshold)
@@ -276,7 +276,7 @@ def test_ref_micro_tests_under_preload(tmp_path):
         assert arr.shape == ref.shape
         scale = max(1.0, float(np.abs(ref).max()))
         # float sums of n terms in different orders: n * eps(float) = 400 * 6e-8 = 2.4e-5 of the largest result; f64 solve: 1e-12
-        tol = {"copy": 0.0, "rot": 0.0, "dsdot": 1e-7, "gbmv": 1e-6, "trmv": 3e-5, "trsm": 1e-12, "hemm": 3e-5}[name]
+        tol = {"copy": 0.0, "rot": 0.0, "dsdot": 1e-7, "gbmv": 1e-6, "trmv": 3e-5, "trsm": 1e-12, "gemm": 0.0, "hemm": 3e-5}[name]
         assert float(np.abs(arr.astype(np.complex128) - ref.astype(np.complex128)).max()) <= tol * scale, name
 
 
