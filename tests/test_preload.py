@@ -63,6 +63,17 @@ def test_library_exports_every_declared_symbol():
     assert g.load().b200blas_version() >= 100
 
 
+def test_public_header_is_plain_c(tmp_path):
+    """include/b200blas.h is the C-ABI contract: it must compile on its own as C99 (pedantic) and as C++11."""
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "b200blas.h"\nint main(void) { return (int)sizeof(struct b200blas_stats) == 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I" + inc, str(src)])
+    cpp = tmp_path / "hdr.cpp"
+    cpp.write_text(src.read_text())
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I" + inc, str(cpp)])
+
+
 def test_so_is_executable_and_prints_help():
     """reference entry.c:4-11 / meson.build:25: running the .so prints the option help."""
     out = subprocess.run([LIB_PATH], capture_output=True, text=True, timeout=60)
