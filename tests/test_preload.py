@@ -63,6 +63,16 @@ def test_library_exports_every_declared_symbol():
     assert g.load().b200blas_version() >= 100
 
 
+def test_coverage_document_matches_the_built_library(tmp_path):
+    """COVERAGE.md is generated from the library's exports (tools/gen_coverage.py): regenerating it must reproduce the committed file."""
+    committed = open(os.path.join(ROOT, "COVERAGE.md")).read()
+    try:
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_coverage.py")], stdout=subprocess.DEVNULL)
+        assert open(os.path.join(ROOT, "COVERAGE.md")).read() == committed
+    finally:
+        open(os.path.join(ROOT, "COVERAGE.md"), "w").write(committed)
+
+
 def test_public_header_is_plain_c(tmp_path):
     """include/b200blas.h is the C-ABI contract: it must compile on its own as C99 (pedantic) and as C++11."""
     src = tmp_path / "hdr.c"
