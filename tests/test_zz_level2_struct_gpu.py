@@ -248,6 +248,59 @@ def test_struct_against_committed_openblas_vectors(p):
         assert float(np.abs(args[c.out].astype(np.complex128) - want.astype(np.complex128)).max()) <= c.tol * scale, c.tag
 
 
+def test_cblas_level1_wrappers_vs_cpu_blas():
+    """cblas_ forms of the complex copy / swap / scal / asum, cblas_?rotm, cblas_csrot / zdrot, cblas_dsdot / sdsdot, cblas_i?amin
+    (thin wrappers over the Fortran entry points tested above) against the same calls on the CPU BLAS's cblas."""
+    import ctypes
+    from helpers import load_openblas
+    ob = load_openblas()
+    if ob is None:
+        pytest.skip("no CPU BLAS in this image")
+    lib = g.load()
+    I, F, D = ctypes.c_int, ctypes.c_float, ctypes.c_double
+    n, ix, iy = 1000, 2, -3
+
+    def both(name, build_args, outs, restype=None, tol=0.0):
+        """run cblas_<name> on fresh copies through OpenBLAS and through the library; compare the arrays in `outs` and the return value"""
+        res = []
+        for L in (ob, lib):
+            arrs, cargs = build_args()
+            fn = getattr(L, "cblas_" + name); fn.restype = restype
+            r = fn(*cargs)
+            res.append((r, [arrs[k].copy() for k in outs]))
+        (r0, a0), (r1, a1) = res
+        if restype is not None:
+            assert abs(r0 - r1) <= tol * max(1.0, abs(r0)), (name, r0, r1)
+        for u, v in zip(a0, a1):
+            assert np.abs(u.astype(np.complex128) - v.astype(np.complex128)).max() <= tol * max(1.0, float(np.abs(u).max())), name
+
+    for p, rt, R in (("c", F, "s"), ("z", D, "d")):
+        eps = l2x.EPS[p]
+
+        def xy():
+            return {"x": l2x.vec(1, n, ix, p), "y": l2x.vec(2, n, iy, p)}
+        both(p + "copy", lambda: (lambda a: (a, [I(n), l2x._ptr(a["x"]), I(ix), l2x._ptr(a["y"]), I(iy)]))(xy()), ["y"])
+        both(p + "swap", lambda: (lambda a: (a, [I(n), l2x._ptr(a["x"]), I(ix), l2x._ptr(a["y"]), I(iy)]))(xy()), ["x", "y"])
+        al = (l2x.CREAL[p] * 2)(0.7, -0.9)
+        both(p + "scal", lambda: (lambda a: (a, [I(n), ctypes.byref(al), l2x._ptr(a["x"]), I(ix)]))(xy()), ["x"], tol=4 * eps)
+        both(p + ("sscal" if p == "c" else "dscal"), lambda: (lambda a: (a, [I(n), rt(1.7), l2x._ptr(a["x"]), I(ix)]))(xy()), ["x"], tol=4 * eps)
+        both(("scasum" if p == "c" else "dzasum"), lambda: (lambda a: (a, [I(n), l2x._ptr(a["x"]), I(ix)]))(xy()), [], restype=rt, tol=n * eps)
+        both("i" + p + "amin", lambda: (lambda a: (a, [I(n), l2x._ptr(a["x"]), I(ix)]))(xy()), [], restype=ctypes.c_size_t)
+    for p, rt in (("s", F), ("d", D)):
+        eps = l2x.EPS[p]
+        prm = np.array([-1.0, 0.3, -0.4, 0.5, 0.6], dtype=l2x.DT[p])
+
+        def xy():
+            return {"x": l2x.vec(3, n, ix, p), "y": l2x.vec(4, n, iy, p)}
+        both(p + "rotm", lambda: (lambda a: (a, [I(n), l2x._ptr(a["x"]), I(ix), l2x._ptr(a["y"]), I(iy), l2x._ptr(prm)]))(xy()), ["x", "y"], tol=8 * eps)
+        both("i" + p + "amin", lambda: (lambda a: (a, [I(n), l2x._ptr(a["x"]), I(ix)]))(xy()), [], restype=ctypes.c_size_t)
+
+    def sxy():
+        return {"x": l2x.vec(5, n, ix, "s"), "y": l2x.vec(6, n, iy, "s")}
+    both("dsdot", lambda: (lambda a: (a, [I(n), l2x._ptr(a["x"]), I(ix), l2x._ptr(a["y"]), I(iy)]))(sxy()), [], restype=D, tol=1e-6)
+    both("sdsdot", lambda: (lambda a: (a, [I(n), F(0.37), l2x._ptr(a["x"]), I(ix), l2x._ptr(a["y"]), I(iy)]))(sxy()), [], restype=F, tol=1e-5)
+
+
 def test_aligned_allocators_under_preload(tmp_path):
     """posix_memalign / aligned_alloc / memalign / valloc under LD_PRELOAD: blocks >= the threshold whose managed base
     satisfies the alignment are tracked (in place for BLAS), contents survive realloc, malloc_usable_size answers from the
