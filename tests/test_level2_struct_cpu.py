@@ -360,3 +360,42 @@ def test_emulated_unit_diagonal_never_multiplies_the_diagonal():
                 assert np.isinf(x[17].real) and not np.isnan(x[17].real), (p, ul, tr, x[17])
                 fin = np.isfinite(x2)
                 assert np.array_equal(np.isfinite(x), fin) and np.allclose(x[fin], x2[fin], rtol=1e-12, atol=1e-12)
+
+
+def test_cblas_rotmg_rotg_host_paths_vs_openblas():
+    """cblas_?rotmg / cblas_?rotg (all four precisions of ROTG) are scalar host work in the product: compared with the CPU BLAS's
+    cblas on the CPU."""
+    import libgpublas_b200 as g
+    ob = load_openblas()
+    if ob is None:
+        pytest.skip("no CPU BLAS in this image")
+    lib = g.load()
+    for p, dt, ct, tol in (("s", np.float32, ctypes.c_float, 2e-6), ("d", np.float64, ctypes.c_double, 1e-14)):
+        for (d1, d2, x1, y1) in _rotmg_inputs():
+            outs = []
+            for L in (ob, lib):
+                a = [np.array([v], dtype=dt) for v in (d1, d2, x1)]; prm = np.full(5, 9.0, dtype=dt)
+                fn = getattr(L, "cblas_" + p + "rotmg"); fn.restype = None
+                fn(l2x._ptr(a[0]), l2x._ptr(a[1]), l2x._ptr(a[2]), ct(y1), l2x._ptr(prm))
+                outs.append(np.concatenate(a + [prm]).astype(np.float64))
+            assert np.allclose(outs[0], outs[1], rtol=64 * tol, atol=1e-30), (p, d1, d2, x1, y1, outs)
+        for (a_, b_) in [(3.0, 4.0), (-3.0, 4.0), (4.0, -3.0), (0.0, 2.0), (2.0, 0.0)]:
+            outs = []
+            for L in (ob, lib):
+                v = [np.array([x], dtype=dt) for x in (a_, b_, 0.0, 0.0)]
+                fn = getattr(L, "cblas_" + p + "rotg"); fn.restype = None
+                fn(*[l2x._ptr(x) for x in v])
+                outs.append(np.array([x[0] for x in v], dtype=np.float64))
+            assert np.allclose(outs[0], outs[1], rtol=8 * tol, atol=1e-30), (p, a_, b_, outs)
+    for p, dt, rt, tol in (("c", np.complex64, np.float32, 2e-6), ("z", np.complex128, np.float64, 1e-14)):
+        for (a_, b_) in [(3 + 4j, 1 - 2j), (-1 + 0.5j, 2 + 2j), (2 - 1j, 0j)]:
+            outs = []
+            for L in (ob, lib):     # OpenBLAS 0.3.15 exports no cblas_crotg / cblas_zrotg: its Fortran symbol is the expectation
+                ca, cb = np.array([a_], dtype=dt), np.array([b_], dtype=dt); c = np.zeros(1, dtype=rt); s = np.zeros(1, dtype=dt)
+                if L is ob:
+                    f77(ob, p + "rotg_", ca, cb, c, s)
+                else:
+                    fn = getattr(L, "cblas_" + p + "rotg"); fn.restype = None
+                    fn(l2x._ptr(ca), l2x._ptr(cb), l2x._ptr(c), l2x._ptr(s))
+                outs.append(np.array([ca[0], c[0], s[0]], dtype=np.complex128))
+            assert np.allclose(outs[0], outs[1], rtol=16 * tol, atol=16 * tol), (p, a_, b_, outs)
