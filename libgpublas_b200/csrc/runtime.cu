@@ -50,6 +50,7 @@ void fatal(const char* what, const char* file, int line, const char* detail) {
 // ---------------------------------------------------------------------------------------------
 static std::once_flag g_init_once;
 static bool g_ready = false;
+static const char* g_init_error = nullptr;   // set when the device could not come up: fatal for a BLAS call, not for malloc
 static int g_sms = 0;
 static int g_device = 0;
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -61,9 +62,11 @@ static void do_init() {
     TrackerGuard guard;   // CUDA's own allocations must not be routed to managed memory
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0)
-        fatal("cudaGetDeviceCount", __FILE__, __LINE__,
-              "no CUDA device: libb200blas has no CPU fallback (by design); unset LD_PRELOAD to run on the CPU BLAS");
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        g_init_error = "no CUDA device: libb200blas has no CPU fallback (by design); unset LD_PRELOAD to run on the CPU BLAS";
+        return;
+    }
     const char* dev_env = getenv("B200BLAS_DEVICE");
     g_device = dev_env ? atoi(dev_env) : -1;
     if (g_device < 0) {
@@ -97,7 +100,18 @@ static void do_init() {
     });
 }
 
-void ensure_init() { std::call_once(g_init_once, do_init); }
+// A BLAS entry point needs the device: no device is fatal (there is no CPU path).  The allocator only *prefers* managed
+// memory: try_init() reports failure and the interposed malloc keeps serving from the heap, so preloading the library into
+// a process on a box without a GPU (or with CUDA_VISIBLE_DEVICES empty) never kills it unless it actually calls BLAS.
+// Both block in call_once while another thread is bringing the device up.
+void ensure_init() {
+    std::call_once(g_init_once, do_init);
+    if (!g_ready) fatal("cudaGetDeviceCount", __FILE__, __LINE__, g_init_error ? g_init_error : "device initialisation failed");
+}
+bool try_init() {
+    std::call_once(g_init_once, do_init);
+    return g_ready;
+}
 bool device_ready() { return g_ready; }
 int sm_count() { return g_sms; }
 bool tma_available() { return g_encode != nullptr; }

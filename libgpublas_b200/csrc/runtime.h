@@ -29,6 +29,7 @@ struct Stats {
 extern Stats g_stats;
 
 void ensure_init();                 // idempotent, thread-safe; aborts if no CUDA device
+bool try_init();                    // same, but returns false instead of aborting when there is no device (allocator path)
 bool device_ready();                // true once ensure_init() has succeeded
 int sm_count();
 cudaStream_t current_stream();      // per-thread stream (or the one set by b200blas_set_stream)

@@ -69,7 +69,6 @@ inline int& inside_ref() {
 volatile int g_tracking = 0;
 volatile int g_heuristic = B200_H_SIZE;
 volatile size_t g_threshold = 64 * 1024;
-volatile int g_initialising = 0;
 volatile int g_shutdown = 0;      // set at exit, before the CUDA runtime tears itself down
 uint64_t g_nth = 0;
 b200_tracker_stats g_tstats = {0, 0, 0, 0, 0};
@@ -152,14 +151,18 @@ bool should_manage(size_t request, uint64_t nth) {
 }
 
 void* managed_new(size_t request, uint64_t nth = 0, const char* fun = "malloc") {
-    // first qualifying allocation brings the device up; allocations made meanwhile (by CUDA itself,
-    // on this or on helper threads) see t_inside / g_initialising and go to glibc
+    // The first qualifying allocation brings the device up.  Allocations CUDA itself makes meanwhile -- on this thread
+    // (t_inside) or on the helper threads it creates (marked inside for life by the pthread_create hook below) -- go to
+    // glibc.  Every OTHER application thread that asks for a qualifying block during the bring-up blocks here until the
+    // device is ready and is then served from managed memory like any later request: once tracking is on, every
+    // qualifying allocation is tracked (reference obj_tracker.c:789-840; the reference gets there by initialising in
+    // its constructor before tracking is enabled, blas2cuda.c:178-242).  If the device cannot come up at all, tracking
+    // is switched off and the heap serves the process -- only a BLAS call is fatal without a device.
     if (!b200::device_ready()) {
-        if (__sync_lock_test_and_set(&g_initialising, 1)) return nullptr;
         t_inside++;
-        b200::ensure_init();
+        const bool ok = b200::try_init();
         t_inside--;
-        __sync_lock_release(&g_initialising);
+        if (!ok) { g_tracking = 0; return nullptr; }
     }
     void* p = nullptr;
     t_inside++;
@@ -178,7 +181,7 @@ void* managed_new(size_t request, uint64_t nth = 0, const char* fun = "malloc") 
     return p;
 }
 
-bool bypass() { return t_inside || !g_tracking || g_initialising; }
+bool bypass() { return t_inside || !g_tracking; }
 
 }  // namespace
 
@@ -282,8 +285,8 @@ void tracker_set_shutdown(void) { g_shutdown = 1; g_tracking = 0; }
 // ---- threads created by CUDA itself never get managed memory ----
 // The reference keeps CUDA's own allocations out of the managed allocator by return address ("excluded
 // regions" scanned from /proc/self/maps, obj_tracker.c:352-424), which misses allocations CUDA makes through
-// libc helpers.  Here every thread that is created while a thread is inside the library (i.e. by the CUDA
-// runtime / driver during one of our calls) is marked "inside" for its whole life, so a driver worker
+// libc helpers.  Here every thread that is created BY a thread that is inside the library (i.e. by the CUDA
+// runtime / driver during one of our calls, or by one of its own helper threads) is marked "inside" for its whole life, so a driver worker
 // thread can never re-enter cudaMallocManaged from malloc and deadlock on the driver's own locks.
 // (A TCB address is reused once its thread has exited, so every new thread re-initialises its slot.)
 struct ThreadStart { void* (*fn)(void*); void* arg; int depth; };
@@ -305,7 +308,7 @@ __attribute__((visibility("default"))) int pthread_create(pthread_t* thread, con
     ThreadStart* ts = (ThreadStart*)__libc_malloc(sizeof(ThreadStart));
     if (!ts) return real(thread, attr, fn, arg);
     ts->fn = fn; ts->arg = arg;
-    ts->depth = (t_inside > 0 || g_initialising) ? (1 << 20) : 0;
+    ts->depth = t_inside > 0 ? (1 << 20) : 0;   // the CREATOR is inside the library: a CUDA helper thread.  Application threads start at 0.
     int rc = real(thread, attr, thread_trampoline, ts);
     if (rc != 0) __libc_free(ts);
     return rc;
