@@ -75,6 +75,78 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+def verify_rows(torch, A, B, C, n, nrows=128):
+    """Parity of the TIMED result at the benchmarked size (outside the timed region): 128 random rows of C x all columns against a
+    float64 numpy product of the same operands on the host; bound ||C_R - A_R B||_F <= 2 k eps ||A_R||_F ||B||_F (c = 2).
+    torch tensors are row-major, i.e. the column-major operands are their transposes: C_cm[r, :] = A_cm[r, :] B_cm."""
+    import numpy as np
+    rows = torch.from_numpy(np.random.default_rng(11).choice(n, size=min(nrows, n), replace=False)).to(A.device)
+    A_rows = A[:, rows].T.contiguous().cpu().numpy()
+    B_cm = B.cpu().numpy().T
+    C_rows = C[:, rows].T.contiguous().cpu().numpy()
+    ref = A_rows @ B_cm
+    err = float(np.linalg.norm(C_rows - ref)); bound = 2.0 * n * 2.0 ** -53 * float(np.linalg.norm(A_rows)) * float(np.linalg.norm(B_cm))
+    return {"rows_checked": int(rows.numel()), "against": "float64 numpy panel product on the host", "fro_err": err, "fro_bound_c2": bound,
+            "ok": bool(err <= bound), "max_abs_err": float(np.abs(C_rows - ref).max())}
+
+
+def e2e_pageable(g, n, nA, nB, C_dev, flops, reps=2):
+    """dgemm_ on ordinary (pageable) numpy buffers -- what an unmodified program's malloc'd operands are when the tracker did not
+    place them (the reference's miss path, runtime-mem.hpp:84-112)."""
+    import numpy as np
+    pA = np.empty((n, n)); pB = np.empty((n, n)); pC = np.empty((n, n))
+    np.copyto(pA, nA); np.copyto(pB, nB)
+    g.call("dgemm_", "N", "N", n, n, n, 1.0, pA, n, pB, n, 0.0, pC, n)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        g.call("dgemm_", "N", "N", n, n, n, 1.0, pA, n, pB, n, 0.0, pC, n)
+    dt = (time.perf_counter() - t0) / reps
+    d = float(np.abs(pC[:256, :256] - C_dev[:256, :256].cpu().numpy()).max())
+    return {"value": flops / dt / 1e12, "unit": "TFLOP/s", "ms_per_step": dt * 1e3, "host_memory": "pageable (numpy.empty)", "steps": reps,
+            "max_abs_diff_vs_resident": d}
+
+
+def e2e_managed_first_touch(g, lib, n, nA, nB, C_dev, flops, reps=2):
+    """dgemm_ on tracked managed blocks (what the interposed calloc hands out) that the CPU has just filled: the timed call
+    includes the bulk migration to the device (make_resident) and ends with a host read of C."""
+    import numpy as np
+    nbytes = n * n * 8
+    best = None
+    d = None
+    for _ in range(reps):
+        ptrs = [lib.b200blas_malloc_managed(nbytes) for _ in range(3)]
+        assert all(ptrs)
+        mA, mB, mC = (np.frombuffer((ctypes.c_char * nbytes).from_address(p), dtype=np.float64).reshape(n, n) for p in ptrs)
+        np.copyto(mA, nA); np.copyto(mB, nB); mC[:] = 0.0          # first touch on the CPU
+        t0 = time.perf_counter()
+        g.call("dgemm_", "N", "N", n, n, n, 1.0, g.DevPtr(ptrs[0]), n, g.DevPtr(ptrs[1]), n, 0.0, g.DevPtr(ptrs[2]), n)
+        probe = float(mC[0, 0]) + float(mC[n - 1, n - 1])            # the host reads the result (faults two pages back)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        d = float(np.abs(mC[:64, :64] - C_dev[:64, :64].cpu().numpy()).max())
+        del mA, mB, mC
+        for p_ in ptrs:
+            lib.b200blas_free_managed(p_)
+    return {"value": flops / best / 1e12, "unit": "TFLOP/s", "ms_per_step": best * 1e3, "host_memory": "tracked managed (b200blas_malloc_managed), CPU-filled",
+            "steps": reps, "max_abs_diff_vs_resident": d, "_probe": probe}
+
+
+def l1_c_driver(peaks):
+    """Level-1 at the symbol boundary from C, not ctypes: tests/drivers/l1_chain.c under LD_PRELOAD=libb200blas.so on calloc'd
+    (tracked -> managed) vectors of 2^26 doubles -- BASELINE.json configs[2] as an unmodified program runs it; wall clock per call
+    including launch, completion and the scalar's way back."""
+    from test_preload import build_driver, fields, run
+    hbm = peaks.get("hbm_gbs", 6553.9)
+    exe = build_driver("l1_chain")
+    out, _ = run(exe, [1 << 26, 40], preload=True, timeout=600)
+    r = fields([l for l in out.splitlines() if l.startswith("GBS")][0])
+    res = {}
+    for k in ("ddot", "daxpy", "dnrm2", "idamax"):
+        res[k + "_2^26"] = {"gbs": float(r[k]), "frac_of_measured_hbm": float(r[k]) / hbm}
+    res["how"] = "C driver (tests/drivers/l1_chain.c) under LD_PRELOAD, calloc'd managed vectors, clock_gettime per call, mean of 39 steady calls"
+    return res
+
+
 def traffic_from_profile():
     """dram__bytes_read.sum + dram__bytes_write.sum of the DGEMM kernel from the committed ncu --set full capture."""
     try:
@@ -136,6 +208,33 @@ def other_routines(g, torch, dev, peaks, out):
     ms = timed(lambda: g.call("idamax_", n, z, 1, restype=ctypes.c_int), reps=9)
     out["idamax_2^28"] = {"gbs": 8.0 * n / ms / 1e6, "ms": ms, "frac_of_measured_hbm": 8.0 * n / ms / 1e6 / hbm}
     del z
+    # stand-alone DSYRK / DTRSM / DTRMM (north_star (1)); flops: SYRK k*n*(n+1), TRSM/TRMM left m^2*n, right m*n^2
+    fp64 = peaks.get("fp64_tflops_probe") or FP64_PEAK_NOMINAL
+    n = 16384
+    A = torch.rand((n, n), dtype=torch.float64, device=dev) * 2 - 1
+    C = torch.zeros((n, n), dtype=torch.float64, device=dev)
+    ms = timed(lambda: g.call("dsyrk_", "L", "N", n, n, 1.0, A, n, 0.0, C, n), reps=3, warm=1)
+    tf = float(n) * n * (n + 1) / ms / 1e9
+    out["dsyrk_LN_16384"] = {"tflops": tf, "ms": ms, "frac_of_fp64_peak": tf / FP64_PEAK_NOMINAL, "frac_of_fp64_probe": tf / fp64}
+    del C
+    T = torch.triu(A[:8192, :8192]).contiguous()      # row-major upper == column-major LOWER triangle, 8192 x 8192
+    T.mul_(1.0 / 8192); T.diagonal().fill_(1.0)      # small off-diagonals: the solution stays O(1)
+    Bm = torch.rand((8192, 8192), dtype=torch.float64, device=dev)
+    m = 8192
+    for name, fn, fl in (("dtrsm_LLNN_8192", lambda: g.call("dtrsm_", "L", "L", "N", "N", m, m, 1.0, T, m, Bm, m), float(m) ** 3),
+                         ("dtrmm_LLNN_8192", lambda: g.call("dtrmm_", "L", "L", "N", "N", m, m, 1.0, T, m, Bm, m), float(m) ** 3)):
+        Bm.uniform_(-1, 1)
+        ms = timed(fn, reps=3, warm=1)
+        tf = fl / ms / 1e9
+        out[name] = {"tflops": tf, "ms": ms, "frac_of_fp64_peak": tf / FP64_PEAK_NOMINAL, "frac_of_fp64_probe": tf / fp64}
+    # the Cholesky panel solve: X * L^T = B with L 2048 x 2048, B 30720 x 2048 (flops m*n^2)
+    mm, nn = 30720, 2048
+    Lp = torch.triu(A[:nn, :nn]).contiguous(); Lp.mul_(1.0 / nn); Lp.diagonal().fill_(1.0)
+    Bp = torch.rand((nn, mm), dtype=torch.float64, device=dev)          # column-major 30720 x 2048
+    ms = timed(lambda: g.call("dtrsm_", "R", "L", "T", "N", mm, nn, 1.0, Lp, nn, Bp, mm), reps=3, warm=1)
+    tf = float(mm) * nn * nn / ms / 1e9
+    out["dtrsm_RLTN_30720x2048"] = {"tflops": tf, "ms": ms, "frac_of_fp64_peak": tf / FP64_PEAK_NOMINAL, "frac_of_fp64_probe": tf / fp64}
+    del A, T, Bm, Lp, Bp
     # blocked Cholesky workload (BASELINE.json configs[3]) on one GPU: wall clock, the driver synchronises per panel
     from libgpublas_b200.cholesky import blocked_cholesky
     n = 32768
@@ -169,6 +268,16 @@ def other_routines(g, torch, dev, peaks, out):
         out["dtpmv_U%s_32768" % tr] = {"gbs": gbs, "ms": ms, "frac_of_measured_hbm": gbs / hbm}
     del ap, xp
     return out
+
+
+def cpu_ksample_for_budget(n, calls, budget_s):
+    """Largest k (multiple of 1024, <= n) such that `calls` OpenBLAS dgemm_ calls of m=n=`n` fit in budget_s, from a k=256 probe."""
+    r = cpu_reference_run(n, 256, 1, 1)
+    if r is None:
+        return min(n, 1024)
+    rate = r["value"] * 1e12                      # flop/s on this host (a k=256 slice runs a little below the large-k rate)
+    kmax = budget_s * rate / (2.0 * n * n * max(1, calls))
+    return int(max(1024, min(n, int(kmax) // 1024 * 1024))) if n >= 1024 else n
 
 
 def cpu_reference_run(n, ksample, steps, warmup):
@@ -214,11 +323,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--n", "--size", dest="n", type=int, default=16384)   # --size: torchrun's own parser finds a bare --n ambiguous
-    ap.add_argument("--ksample", type=int, default=1024)
+    ap.add_argument("--ksample", type=int, default=0, help="reference arm / cpu_baseline: k of the CPU DGEMM sample (0: the largest "
+                                                             "multiple of 1024 <= n that keeps the run within --cpu-budget seconds)")
+    ap.add_argument("--cpu-budget", type=float, default=240.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the SGEMM/ZGEMM/Level-1/2 lines of BASELINE.json's metric")
-    ap.add_argument("--verify", action="store_true", help="N>1: check the partitioned result against the 1-GPU kernel on rank 0")
+    ap.add_argument("--no-verify", action="store_true", help="skip the parity check of the timed result (outside the timed region): "
+                                                             "N=1 128 rows of C against a float64 numpy product, N>1 the whole C against the 1-GPU kernel")
     ap.add_argument("--kchunk", type=int, default=1024)
     ap.add_argument("--distribute", default=None, help="N>1: p2p_push (default on CUDA) | bcast")
     args = ap.parse_args()
@@ -231,14 +343,18 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        r = cpu_reference_run(n, args.ksample, max(1, args.steps), max(1, min(args.warmup, 1)))
+        # the full k = n call when the host finishes (steps + warmup) of them within the budget (16 cores: ~8 s each), otherwise
+        # the largest k-slice that does; `same_config` says which, and steps / warmup printed are the ones actually run
+        ks = args.ksample or cpu_ksample_for_budget(n, args.steps + args.warmup, args.cpu_budget)
+        r = cpu_reference_run(n, ks, max(1, args.steps), max(0, args.warmup))
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "no CPU BLAS (OpenBLAS) found in this image"}))
             return 0
         sec = r.pop("_seconds")
         line = {"impl": "reference", "metric": "dgemm_tflops", "value": r["value"], "unit": "TFLOP/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload, "sample": r["sample"]},
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload, "sample": r["sample"], "same_config": ks == n},
                 "cpu_baseline": r, "e2e": {"value": r["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -289,8 +405,7 @@ def main():
         value = flops / (ms_per_step * 1e-3) / 1e12
         kernel_ms = sum(per_launch_ms) / len(per_launch_ms)
         launches = args.steps
-        # spot parity inside the bench: a 64x64 corner against an independent fp64 product
-        ref = (A.T[:, :64].T @ B.T[:64, :].T) if False else None
+        verified = verify_rows(torch, A, B, C, n) if not args.no_verify else None
         scaling, parallelism = "strong", "single"
     else:
         tg = TiledGemm(n, n, n, dev, rank, world, kchunk=args.kchunk, distribute=args.distribute)
@@ -325,7 +440,7 @@ def main():
         launches = args.steps * tg.kernels_per_step
         scaling, parallelism = "strong", tg.describe()
         verified = None
-        if args.verify and rank == 0:
+        if not args.no_verify and rank == 0:
             ref = torch.empty(n * n, dtype=torch.float64, device=dev)
             g.call("dgemm_", "N", "N", n, n, n, 1.0, tg.A, n, tg.B, n, 0.0, ref, n)
             torch.cuda.synchronize()
@@ -364,8 +479,25 @@ def main():
                "d2h_bytes_per_step": (s2["d2h_bytes"] - s1["d2h_bytes"]) // args.steps,
                "host_memory": "pinned", "matches_device_result": same, "max_abs_diff_vs_resident": max(d0, d1),
                "path": "dgemm_ on host pointers: chunked H2D of A/B and D2H of C panels overlapped with the DMMA kernel (csrc/staged_gemm.cuh)"}
+        # the reference's real miss path is plain malloc'd memory (runtime-mem.hpp:84-112), and its hit path a calloc'd block
+        # the CPU has just filled: the same call on PAGEABLE host buffers, and on tracked managed buffers at first touch
+        try:
+            e2e["pageable"] = e2e_pageable(g, n, nA, nB, C, flops)
+            e2e["managed_first_touch"] = e2e_managed_first_touch(g, lib, n, nA, nB, C, flops)
+        except Exception as exc:  # noqa: BLE001
+            e2e["pageable_error"] = repr(exc)
         g.set_sync(False)
 
+    probe = None
+    if rank == 0:
+        try:
+            lib.b200blas_probe_fp64_tflops.restype = ctypes.c_double
+            lib.b200blas_probe_fp64_tflops.argtypes = [ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
+            burst = ctypes.c_double(0.0)
+            probe = {"sustained": lib.b200blas_probe_fp64_tflops(1.5, ctypes.byref(burst)), "burst": burst.value,
+                     "how": "register-resident mma.sync m16n8k16 f64 (DMMA) loop, 8 warps/SM, 1.5 s, in this process (csrc/probe.cu)"}
+        except Exception as exc:  # noqa: BLE001
+            probe = {"error": repr(exc)}
     others = None
     if world == 1 and not args.no_others:
         del A, B, C
@@ -374,13 +506,20 @@ def main():
         torch.cuda.empty_cache()
         others = {}
         try:      # the headline line must print whatever happens to a secondary measurement
-            other_routines(g, torch, dev, measured_peaks(), others)
+            pk = measured_peaks()
+            if probe and probe.get("sustained"):
+                pk["fp64_tflops_probe"] = probe["sustained"]
+            other_routines(g, torch, dev, pk, others)
         except Exception as exc:  # noqa: BLE001
             others["error"] = repr(exc)
+        try:
+            others["level1_from_c"] = l1_c_driver(measured_peaks())
+        except BaseException as exc:  # noqa: BLE001  (pytest.skip raises outside Exception)
+            others["level1_from_c"] = {"error": repr(exc)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_reference_run(n, args.ksample, 2, 1)
+        cpu = cpu_reference_run(n, args.ksample or cpu_ksample_for_budget(n, 3, 20.0), 2, 1)
         if cpu:
             cpu.pop("_seconds", None)
 
@@ -397,13 +536,16 @@ def main():
                              "peak_source": "FP64 tensor (DMMA) pipe: nominal 148 SM x 128 flop/clk x 1.965 GHz = 37.2; measured DMMA-only loop %.2f "
                                             "(profiles/r01_probe_peaks_b200.txt); MEASURED_PEAKS.json has no FP64 entry (bf16 %.0f, HBM %.0f GB/s)"
                                             % (FP64_PEAK_MEASURED, peaks.get("bf16_tflops", 0), peaks.get("hbm_gbs", 0)),
-                             "kernel_ms": kernel_ms},
+                             "kernel_ms": kernel_ms,
+                             "peak_measured_in_process": probe,
+                             "frac_of_measured": ((flops / (kernel_ms * 1e-3) / 1e12 if world == 1 else value / world) / probe["sustained"])
+                             if probe and probe.get("sustained") else None},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "others": others}
         tr = traffic_from_profile()
         if tr and world == 1:
             line["roofline"]["traffic"] = tr["dram_bytes_per_launch"]
             line["roofline"]["traffic_source"] = tr["source"]
-        if world > 1 and verified is not None:
+        if verified is not None:
             line["verified"] = verified
         print(json.dumps(line))
     if world > 1:

@@ -413,6 +413,9 @@ B200_API void b200blas_free_managed(void* p);
 B200_API int b200blas_is_tracked(const void* p);
 B200_API int b200blas_tracker_decision(unsigned long long nth, size_t request);   /* would the nth allocation of `request` bytes be managed (current heuristic)? */
 B200_API int b200blas_device_count(void);
+/* FP64 tensor-pipe (DMMA) ceiling measured in this process: sustained TFLOP/s over ~`seconds` of register-resident mma.sync f64
+ * loops (no memory traffic); *burst (may be NULL) = best single launch.  The denominator of bench.py's tensor rooflines. */
+B200_API double b200blas_probe_fp64_tflops(double seconds, double* burst);
 B200_API int b200blas_residency(const void* p, size_t bytes);     /* device ordinal a managed range was last prefetched to; -1 host; -2 unknown */
 /* D := alpha*op(A)*op(B) + beta*C on device pointers with a separate output (may be peer-mapped) */
 B200_API void b200blas_dgemm_out(char transa, char transb, int m, int n, int k, double alpha, const double* a, long long lda, const double* b, long long ldb, double beta, const double* c, long long ldc, double* d, long long ldd);

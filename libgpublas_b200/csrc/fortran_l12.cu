@@ -13,12 +13,6 @@ using namespace b200;
 
 namespace {
 
-struct VecOperand : Operand {
-    // BLAS vector of n elements with increment inc occupies 1+(n-1)|inc| elements from the pointer
-    VecOperand(const void* p, int64_t n, int64_t inc, size_t elem, int access)
-        : Operand(p, n > 0 ? 1 + (n - 1) * (inc < 0 ? -inc : inc) : 0, 1, n > 0 ? 1 + (n - 1) * (inc < 0 ? -inc : inc) : 1, elem, access) {}
-};
-
 // Scalar results: the reduction kernel's finishing block stores the value straight into pinned, device-mapped host
 // memory (zero-copy), so returning it costs one stream synchronisation and no separate copy (these routines are
 // synchronous by nature: they return a value).

@@ -40,31 +40,40 @@ struct SgemmParams {
     float* C; int64_t ldc;
     int mask;
     int tiles_m, tiles_n;
+    const int* nonfinite;     // set by the split pass when an operand holds Inf/NaN: this kernel stands down, the FFMA tile kernel runs
 };
 
 // ------------------------------------------------------------------ split pass
 __device__ __forceinline__ float tf32_rn(float a) {
-    // round-to-nearest (ties away) onto the 10-bit tf32 mantissa; inf/nan pass through
+    // round-to-nearest (ties away) onto the 10-bit tf32 mantissa; inf/nan pass through; a finite value whose rounding
+    // would carry into the exponent 0xFF (|a| >= 0x7F7FF000, e.g. FLT_MAX) is truncated instead, so hi stays finite
     uint32_t b = __float_as_uint(a);
-    if ((b & 0x7f800000u) != 0x7f800000u) b += 0x1000u;
+    if ((b & 0x7f800000u) != 0x7f800000u) {
+        const uint32_t r = b + 0x1000u;
+        if ((r & 0x7f800000u) != 0x7f800000u) b = r;
+    }
     return __uint_as_float(b & 0xffffe000u);
 }
-__device__ __forceinline__ void split_store(float a, float* hi, float* lo) {
+// Inf/NaN operands cannot go through the split: hi = Inf meets the other operand's lo = 0 in the hi*lo term and Inf*0 = NaN
+// where sgemm returns Inf.  The split pass raises a flag instead; the tensor-core kernel then returns at once and the FFMA
+// tile kernel queued behind it (which otherwise returns at once) computes the product with IEEE semantics.
+__device__ __forceinline__ void split_store(float a, float* hi, float* lo, int* nonfinite) {
+    if ((__float_as_uint(a) & 0x7f800000u) == 0x7f800000u) *nonfinite = 1;
     const float h = tf32_rn(a);
     *hi = h;
     *lo = tf32_rn(a - h);
 }
 // source already k-contiguous: element (kk, r) at src[kk + r*ld]
 __global__ void __launch_bounds__(256) split_kmajor_kernel(int rows, int k, const float* __restrict__ src, int64_t ld,
-                                                           float* __restrict__ hi, float* __restrict__ lo, int64_t kpad) {
+                                                           float* __restrict__ hi, float* __restrict__ lo, int64_t kpad, int* nonfinite) {
     const int kk = blockIdx.x * 256 + threadIdx.x;
     if (kk >= k) return;
     for (int r = blockIdx.y; r < rows; r += gridDim.y)
-        split_store(__ldg(src + kk + (int64_t)r * ld), hi + (int64_t)r * kpad + kk, lo + (int64_t)r * kpad + kk);
+        split_store(__ldg(src + kk + (int64_t)r * ld), hi + (int64_t)r * kpad + kk, lo + (int64_t)r * kpad + kk, nonfinite);
 }
 // source row-contiguous: element (r, kk) at src[r + kk*ld]  ->  dst[r*kpad + kk]   (32x32 smem transpose)
 __global__ void __launch_bounds__(256) split_transpose_kernel(int rows, int k, const float* __restrict__ src, int64_t ld,
-                                                              float* __restrict__ hi, float* __restrict__ lo, int64_t kpad) {
+                                                              float* __restrict__ hi, float* __restrict__ lo, int64_t kpad, int* nonfinite) {
     __shared__ float t[32][33];
     const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -77,7 +86,7 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(int rows, int k, c
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const int r = r0 + ty + 8 * j, kk = k0 + tx;
-        if (r < rows && kk < k) split_store(t[tx][ty + 8 * j], hi + (int64_t)r * kpad + kk, lo + (int64_t)r * kpad + kk);
+        if (r < rows && kk < k) split_store(t[tx][ty + 8 * j], hi + (int64_t)r * kpad + kk, lo + (int64_t)r * kpad + kk, nonfinite);
     }
 }
 
@@ -160,6 +169,7 @@ sgemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         tile_n = band * BAND + (r - tile_m * bw);
     }
     const int m0 = tile_m * SG_BM, n0 = tile_n * BN;
+    if (*p.nonfinite) return;                      // Inf/NaN in an operand: the FFMA tile kernel behind this launch does the work
     if (p.mask == MASK_LOWER && m0 + SG_BM - 1 < n0) return;
     if (p.mask == MASK_UPPER && n0 + BN - 1 < m0) return;
 
@@ -311,11 +321,7 @@ static bool launch_sg(cudaStream_t s, const float* as, const float* bs, int64_t 
     CUtensorMap ma, mb;
     memset(&ma, 0, sizeof ma); memset(&mb, 0, sizeof mb);
     if (!make_map_split(&ma, as, p.m, p.k, kpad, SG_BM, BK) || !make_map_split(&mb, bs, p.n, p.k, kpad, BN, BK)) return false;
-    static bool attr_set = false;
-    if (!attr_set) {
-        B200_CUDA(cudaFuncSetAttribute(sgemm_tf32x3_kernel<BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr_set = true;
-    }
+    set_max_dynamic_smem((const void*)sgemm_tf32x3_kernel<BN, BK, STAGES>, SMEM);
     p.tiles_m = (p.m + SG_BM - 1) / SG_BM;
     p.tiles_n = (p.n + BN - 1) / BN;
     sgemm_tf32x3_kernel<BN, BK, STAGES><<<p.tiles_m * p.tiles_n, SG_THREADS, SMEM, s>>>(ma, mb, p);
@@ -328,24 +334,27 @@ static bool sgemm_tf32x3(cudaStream_t s, int oa, int ob, int m, int n, int k, fl
     const int64_t kpad = ((int64_t)k + 3) / 4 * 4;          // 16-byte row pitch for TMA
     float* as = (float*)ws_alloc((size_t)2 * m * kpad * 4);
     float* bs = (float*)ws_alloc((size_t)2 * n * kpad * 4);
+    int* nonfinite = (int*)ws_alloc(256);
+    B200_CUDA(cudaMemsetAsync(nonfinite, 0, 4, s));
     // op(A) is m x k: 'N' stores it m-contiguous (transpose needed), 'T'/'C' store it k-contiguous
-    if (oa == 0) split_transpose_kernel<<<dim3((m + 31) / 32, (k + 31) / 32), 256, 0, s>>>(m, k, A, lda, as, as + (int64_t)m * kpad, kpad);
-    else split_kmajor_kernel<<<dim3((k + 255) / 256, m < 65535 ? m : 65535), 256, 0, s>>>(m, k, A, lda, as, as + (int64_t)m * kpad, kpad);
+    if (oa == 0) split_transpose_kernel<<<dim3((m + 31) / 32, (k + 31) / 32), 256, 0, s>>>(m, k, A, lda, as, as + (int64_t)m * kpad, kpad, nonfinite);
+    else split_kmajor_kernel<<<dim3((k + 255) / 256, m < 65535 ? m : 65535), 256, 0, s>>>(m, k, A, lda, as, as + (int64_t)m * kpad, kpad, nonfinite);
     // op(B) is k x n: 'N' stores it k-contiguous per column, 'T'/'C' n-contiguous
-    if (ob == 0) split_kmajor_kernel<<<dim3((k + 255) / 256, n < 65535 ? n : 65535), 256, 0, s>>>(n, k, B, ldb, bs, bs + (int64_t)n * kpad, kpad);
-    else split_transpose_kernel<<<dim3((n + 31) / 32, (k + 31) / 32), 256, 0, s>>>(n, k, B, ldb, bs, bs + (int64_t)n * kpad, kpad);
+    if (ob == 0) split_kmajor_kernel<<<dim3((k + 255) / 256, n < 65535 ? n : 65535), 256, 0, s>>>(n, k, B, ldb, bs, bs + (int64_t)n * kpad, kpad, nonfinite);
+    else split_transpose_kernel<<<dim3((n + 31) / 32, (k + 31) / 32), 256, 0, s>>>(n, k, B, ldb, bs, bs + (int64_t)n * kpad, kpad, nonfinite);
     SgemmParams p;
-    p.m = m; p.n = n; p.k = k; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.mask = mask; p.tiles_m = p.tiles_n = 0;
-    // tile configuration: B200BLAS_SGEMM_CFG overrides (0: 128x128 BK32 x3, 1: 128x256 BK32 x2, 2: 128x256 BK16 x4)
+    p.m = m; p.n = n; p.k = k; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.mask = mask; p.tiles_m = p.tiles_n = 0; p.nonfinite = nonfinite;
+    // tile configuration: option sgemm_cfg=<n> / B200BLAS_SGEMM_CFG override (0: 128x128 BK32 x3, 1: 128x256 BK32 x2, 2: 128x256 BK16 x4)
     static const int cfg_env = getenv("B200BLAS_SGEMM_CFG") ? atoi(getenv("B200BLAS_SGEMM_CFG")) : -1;
     const int64_t sms = sm_count() > 0 ? sm_count() : 148;
-    int cfg = cfg_env;
+    int cfg = g_opts.sgemm_cfg >= 0 ? g_opts.sgemm_cfg : cfg_env;
     if (cfg < 0) cfg = ((int64_t)((m + 127) / 128) * ((n + 255) / 256) >= sms) ? SG_DEFAULT_WIDE_CFG : 0;
     bool ok;
     if (cfg == 1) ok = launch_sg<256, 32, 2>(s, as, bs, kpad, p);
     else if (cfg == 2) ok = launch_sg<256, 16, 4>(s, as, bs, kpad, p);
     else ok = launch_sg<128, 32, 3>(s, as, bs, kpad, p);
     if (!ok) return false;
+    gemm_generic_launch<float>(s, "NTC"[oa], "NTC"[ob], m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mask, nonfinite);   // runs only if the flag is set
     last_variant = VAR_TF32X3_TCGEN05;
     return true;
 }

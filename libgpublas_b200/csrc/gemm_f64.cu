@@ -300,11 +300,7 @@ static void launch_dmma(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap
     auto kern = dgemm_dmma_kernel<MB, NB, LAYA, LAYB, USE_TMA>;
     static const int extra = getenv("B200BLAS_DBG_EXTRA_SMEM") ? atoi(getenv("B200BLAS_DBG_EXTRA_SMEM")) : 0;   // experiment: force 1 CTA/SM
     const int SMEM = SMEM0 + (MB * NB < 32 ? extra : 0);
-    static bool attr_set = false;
-    if (!attr_set) {
-        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr_set = true;
-    }
+    set_max_dynamic_smem((const void*)kern, SMEM);
     kern<<<p.tiles_m * p.tiles_n, 384, SMEM, s>>>(ma, mb, p);
 }
 

@@ -101,7 +101,8 @@ constexpr int GT_BM = 64, GT_BN = 64, GT_BK = 16;
 template <typename T, int OPA, int OPB>
 __global__ void __launch_bounds__(256) gemm_generic_kernel(int m, int n, int k, T alpha, const T* __restrict__ A,
                                                            int64_t lda, const T* __restrict__ B, int64_t ldb, T beta,
-                                                           T* __restrict__ C, int64_t ldc, int mask) {
+                                                           T* __restrict__ C, int64_t ldc, int mask, const int* __restrict__ gate) {
+    if (gate && *gate == 0) return;                              // conditional launch (SGEMM's Inf/NaN stand-in, gemm_f32.cu)
     const int tm0 = blockIdx.x * GT_BM, tn0 = blockIdx.y * GT_BN;
     if (mask == MASK_LOWER && tm0 + GT_BM - 1 < tn0) return;   // tile entirely above the diagonal
     if (mask == MASK_UPPER && tn0 + GT_BN - 1 < tm0) return;
@@ -177,11 +178,11 @@ static inline int op_code(char t) { return (t == 'N' || t == 'n') ? 0 : ((t == '
 
 template <typename T>
 void gemm_generic_launch(cudaStream_t s, char ta, char tb, int m, int n, int k, T alpha, const T* A, int64_t lda,
-                         const T* B, int64_t ldb, T beta, T* C, int64_t ldc, int mask) {
+                         const T* B, int64_t ldb, T beta, T* C, int64_t ldc, int mask, const int* gate = nullptr) {
     dim3 grd((m + GT_BM - 1) / GT_BM, (n + GT_BN - 1) / GT_BN), blk(256);
     int oa = op_code(ta), ob = op_code(tb);
 #define B200_GG(OA, OB) \
-    gemm_generic_kernel<T, OA, OB><<<grd, blk, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mask)
+    gemm_generic_kernel<T, OA, OB><<<grd, blk, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mask, gate)
     switch (oa * 3 + ob) {
         case 0: B200_GG(0, 0); break;
         case 1: B200_GG(0, 1); break;

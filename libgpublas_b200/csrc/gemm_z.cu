@@ -224,11 +224,7 @@ static void launch_z(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& m
     constexpr int BM = 16 * MB, BN = 32 * NB;
     constexpr int SMEM = ZG_STAGES * (BM + BN) * ZG_BK * 16 + 2 * ZG_STAGES * 8 + 1024;
     auto kern = zgemm_dmma_kernel<MB, NB, LAYA, LAYB, CA, CB>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr_set = true;
-    }
+    set_max_dynamic_smem((const void*)kern, SMEM);
     kern<<<p.tiles_m * p.tiles_n, 384, SMEM, s>>>(ma, mb, p);
 }
 

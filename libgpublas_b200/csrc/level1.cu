@@ -23,6 +23,26 @@ static inline int l1_blocks(int64_t n, int per_thread) {
     if (b < 1) b = 1;
     return (int)(b > cap ? cap : b);
 }
+// Grid of a grid-stride REDUCTION kernel: exactly one resident wave (SMs x CTAs that fit per SM, from the occupancy
+// calculator, cached per kernel).  With 8 CTAs per SM requested and 2-5 resident, the old grid ran in 2-4 waves whose
+// ramps and tails cost ~5 us of a 165 us DDOT, and the finishing block folded 1184 partials instead of ~300-700.
+static int l1_reduce_grid(const void* kernel, int64_t n, int per_thread) {
+    struct Entry { const void* k; int per_sm; };
+    static Entry cache[64];
+    static int ncache = 0;
+    static const int waves = getenv("B200BLAS_L1_WAVES") ? atoi(getenv("B200BLAS_L1_WAVES")) : 1;
+    int per_sm = 0;
+    for (int i = 0; i < ncache; i++) if (cache[i].k == kernel) per_sm = cache[i].per_sm;
+    if (!per_sm) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, L1_THREADS, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 2; }
+        if (ncache < 64) { cache[ncache].k = kernel; cache[ncache].per_sm = per_sm; __atomic_fetch_add(&ncache, 1, __ATOMIC_RELEASE); }
+    }
+    int64_t b = (n + (int64_t)L1_THREADS * per_thread - 1) / ((int64_t)L1_THREADS * per_thread);
+    int64_t cap = (int64_t)(sm_count() > 0 ? sm_count() : 148) * per_sm * (waves > 0 ? waves : 1);
+    if (cap > L1_MAX_BLOCKS) cap = L1_MAX_BLOCKS;
+    if (b < 1) b = 1;
+    return (int)(b > cap ? cap : b);
+}
 
 // BLAS element i of a strided vector (negative increments walk backwards from the end)
 __device__ __forceinline__ int64_t vix(int64_t i, int64_t n, int64_t inc) { return inc >= 0 ? i * inc : (n - 1 - i) * (-inc); }
@@ -131,7 +151,7 @@ template <bool CONJ> __device__ __forceinline__ void cfma(Sum2& acc, double ar, 
     else      { acc.x = fma(ar, br, acc.x); acc.x = fma(-ai, bi, acc.x); acc.y = fma(ar, bi, acc.y); acc.y = fma(ai, br, acc.y); }
 }
 
-__global__ void __launch_bounds__(L1_THREADS) ddot_kernel(int64_t n, const double* __restrict__ x, int64_t incx,
+__global__ void __launch_bounds__(L1_THREADS, 4) ddot_kernel(int64_t n, const double* __restrict__ x, int64_t incx,
                                                          const double* __restrict__ y, int64_t incy, double* partials,
                                                          unsigned int* ticket, double* out, bool vec) {
     __shared__ double sm[32];
@@ -141,6 +161,7 @@ __global__ void __launch_bounds__(L1_THREADS) ddot_kernel(int64_t n, const doubl
         const double2* x2 = (const double2*)x; const double2* y2 = (const double2*)y;
         const int64_t n2 = n >> 1;
         int64_t i = tid;
+#pragma unroll 1
         for (; i + 3 * nth < n2; i += 4 * nth) {
             double2 xa = ldg_stream(x2 + i), xb = ldg_stream(x2 + i + nth), xc = ldg_stream(x2 + i + 2 * nth), xd = ldg_stream(x2 + i + 3 * nth);
             double2 ya = ldg_stream(y2 + i), yb = ldg_stream(y2 + i + nth), yc = ldg_stream(y2 + i + 2 * nth), yd = ldg_stream(y2 + i + 3 * nth);
@@ -207,7 +228,7 @@ static inline bool vec_ok(const void* a, const void* b, int64_t inca, int64_t in
 
 template <> void dot_dev<double>(cudaStream_t s, int64_t n, const double* x, int64_t incx, const double* y, int64_t incy, double* out, bool) {
     L1Scratch sc = l1_scratch(sizeof(double));
-    ddot_kernel<<<l1_blocks(n, 8), L1_THREADS, 0, s>>>(n, x, incx, y, incy, (double*)sc.partials, sc.ticket, out, vec_ok(x, y, incx, incy));
+    ddot_kernel<<<l1_reduce_grid((const void*)ddot_kernel, n, 8), L1_THREADS, 0, s>>>(n, x, incx, y, incy, (double*)sc.partials, sc.ticket, out, vec_ok(x, y, incx, incy));
 }
 template <> void dot_dev<float>(cudaStream_t s, int64_t n, const float* x, int64_t incx, const float* y, int64_t incy, float* out, bool) {
     L1Scratch sc = l1_scratch(sizeof(double));
@@ -273,6 +294,14 @@ __global__ void __launch_bounds__(L1_THREADS) nrm2_kernel(int64_t n, const T* __
         const double2* x2 = (const double2*)x;
         const int64_t tot = n * NC, n2 = tot >> 1;
         int64_t i = tid;
+#pragma unroll 1
+        for (; i + 7 * nth < n2; i += 8 * nth) {       // 8 independent 16-byte loads in flight per thread
+            double2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = ldg_stream(x2 + i + u * nth);
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) { blue_add(a, v[u].x); blue_add(a, v[u].y); blue_add(b, v[u + 1].x); blue_add(b, v[u + 1].y); }
+        }
         for (; i + 3 * nth < n2; i += 4 * nth) {
             double2 p = ldg_stream(x2 + i), q = ldg_stream(x2 + i + nth), r = ldg_stream(x2 + i + 2 * nth), t = ldg_stream(x2 + i + 3 * nth);
             blue_add(a, p.x); blue_add(a, p.y); blue_add(b, q.x); blue_add(b, q.y);
@@ -315,7 +344,7 @@ __global__ void __launch_bounds__(L1_THREADS) asum_kernel(int64_t n, const T* __
 #define B200_NRM2(T, CT, NC, R)                                                                                          \
     template <> void nrm2_dev<T, R>(cudaStream_t s, int64_t n, const T* x, int64_t incx, R* out) {                      \
         L1Scratch sc = l1_scratch(sizeof(Sum3));                                                                         \
-        nrm2_kernel<CT, NC, R><<<l1_blocks(n* NC, 8), L1_THREADS, 0, s>>>(n, (const CT*)x, incx, (Sum3*)sc.partials, sc.ticket, out, \
+        nrm2_kernel<CT, NC, R><<<l1_reduce_grid((const void*)nrm2_kernel<CT, NC, R>, n* NC, 8), L1_THREADS, 0, s>>>(n, (const CT*)x, incx, (Sum3*)sc.partials, sc.ticket, out, \
                                                                           incx == 1 && (uintptr_t)x % 16 == 0);          \
     }                                                                                                                    \
     template <> void asum_dev<T, R>(cudaStream_t s, int64_t n, const T* x, int64_t incx, R* out) {                      \
@@ -330,7 +359,7 @@ B200_NRM2(cuFloatComplex, float, 2, float)
 
 // ------------------------------------------ I?AMAX ------------------------------------------
 template <typename T, int NC>
-__global__ void __launch_bounds__(L1_THREADS) iamax_kernel(int64_t n, const T* __restrict__ x, int64_t incx, ArgMax* partials,
+__global__ void __launch_bounds__(L1_THREADS, 4) iamax_kernel(int64_t n, const T* __restrict__ x, int64_t incx, ArgMax* partials,
                                                           unsigned int* ticket, long long* out, bool vec) {
     __shared__ ArgMax sm[32];
     ArgMax best = {-1.0, -1};
@@ -341,6 +370,7 @@ __global__ void __launch_bounds__(L1_THREADS) iamax_kernel(int64_t n, const T* _
         const double2* x2 = (const double2*)x;
         const int64_t n2 = n >> 1;
         int64_t i = tid;
+#pragma unroll 1
         for (; i + 3 * nth < n2; i += 4 * nth) {
             double2 p = ldg_stream(x2 + i), q = ldg_stream(x2 + i + nth), r = ldg_stream(x2 + i + 2 * nth), t = ldg_stream(x2 + i + 3 * nth);
             double v;
@@ -373,7 +403,7 @@ __global__ void __launch_bounds__(L1_THREADS) iamax_kernel(int64_t n, const T* _
 #define B200_IAMAX(T, CT, NC)                                                                                  \
     template <> void iamax_dev<T>(cudaStream_t s, int64_t n, const T* x, int64_t incx, long long* out) {       \
         L1Scratch sc = l1_scratch(sizeof(ArgMax));                                                              \
-        iamax_kernel<CT, NC><<<l1_blocks(n, 8), L1_THREADS, 0, s>>>(n, (const CT*)x, incx, (ArgMax*)sc.partials, sc.ticket, out, \
+        iamax_kernel<CT, NC><<<l1_reduce_grid((const void*)iamax_kernel<CT, NC>, n, 8), L1_THREADS, 0, s>>>(n, (const CT*)x, incx, (ArgMax*)sc.partials, sc.ticket, out, \
                                                                     incx == 1 && (uintptr_t)x % 16 == 0);       \
     }
 B200_IAMAX(double, double, 1)

@@ -65,10 +65,7 @@ using namespace b200;
 
 namespace {
 
-struct Vec : Operand {
-    Vec(const void* p, int64_t n, int64_t inc, size_t elem, int access)
-        : Operand(p, n > 0 ? 1 + (n - 1) * (inc < 0 ? -inc : inc) : 0, 1, n > 0 ? 1 + (n - 1) * (inc < 0 ? -inc : inc) : 1, elem, access) {}
-};
+typedef VecOperand Vec;   // runtime.h: strided vectors are written back element by element
 template <typename R> R fetch_scalar(const void* slot) {   // the kernel's finishing block writes into pinned, device-mapped host memory
     wait_scalar(slot, sizeof(R), sizeof(R) == 4 ? 4 : 8);
     R r;
@@ -182,8 +179,7 @@ template <typename T>
 void rot_entry(const char* name, const int* n, T* x, const int* incx, T* y, const int* incy, const T* c, const T* s) {
     if (*n <= 0) return;
     CallScope scope(name);
-    Operand ox(x, 1 + (int64_t)(*n - 1) * abs(*incx), 1, 1 + (int64_t)(*n - 1) * abs(*incx), sizeof(T), ACC_INOUT);
-    Operand oy(y, 1 + (int64_t)(*n - 1) * abs(*incy), 1, 1 + (int64_t)(*n - 1) * abs(*incy), sizeof(T), ACC_INOUT);
+    Vec ox(x, *n, *incx, sizeof(T), ACC_INOUT), oy(y, *n, *incy, sizeof(T), ACC_INOUT);
     rot_dev<T>(current_stream(), *n, (T*)ox.dev(), *incx, (T*)oy.dev(), *incy, *c, *s);
     ox.release(); oy.release();
     log_exec(name, "n=%d", *n);

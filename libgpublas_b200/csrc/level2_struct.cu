@@ -215,10 +215,7 @@ using namespace b200;
 
 namespace {
 
-struct Vec : Operand {   // BLAS vector of n elements with increment inc: 1+(n-1)|inc| elements from the pointer
-    Vec(const void* p, int64_t n, int64_t inc, size_t elem, int access)
-        : Operand(p, n > 0 ? 1 + (n - 1) * (inc < 0 ? -inc : inc) : 0, 1, n > 0 ? 1 + (n - 1) * (inc < 0 ? -inc : inc) : 1, elem, access) {}
-};
+typedef VecOperand Vec;   // runtime.h: strided vectors are written back element by element
 inline char trans_code(const char* trans) { return lsame(trans, 'N') ? 'N' : (lsame(trans, 'T') ? 'T' : (lsame(trans, 'C') ? 'C' : '?')); }
 
 // ---- GBMV: netlib info 1,2,3,4,5,8,10,13 ----

@@ -8,9 +8,8 @@
 //  TRMM  recursive 2x2 splitting in place; off-diagonal blocks are GEMMs; a diagonal block of
 //        <= 256 is copied to scratch with the unreferenced triangle zeroed (and the unit diagonal
 //        made explicit), multiplied out of place by the GEMM kernel and copied back.
-//  TRSM  same recursion; the 64x64 diagonal blocks are inverted once up front by a small kernel
-//        (one CTA per block, exact substitution on the identity), so every leaf solve is a GEMM
-//        with the inverted block, and every update is a GEMM.
+//  TRSM  same recursion; diagonal blocks of <= 64 (32 complex) are solved in place by substitution, one
+//        right-hand side per thread in registers (trsm_leaf_kernel); every update is a GEMM.
 #include "common.cuh"
 #include "kernels.h"
 #include "gemm_generic.cuh"
@@ -150,7 +149,21 @@ template void trmm_dev<cuFloatComplex>(cudaStream_t, char, char, char, char, int
 template void trmm_dev<cuDoubleComplex>(cudaStream_t, char, char, char, char, int, int, cuDoubleComplex, const cuDoubleComplex*, int64_t, cuDoubleComplex*, int64_t);
 
 // ------------------------------------------------------------------ TRSM
-constexpr int TRSM_NB = 64;
+// Leaf of the recursion: a diagonal block of at most NBL (64 real / 32 complex) is solved by SUBSTITUTION, in place, like
+// netlib's xTRSM and the cublas<t>trsm the reference forwards to (trsm.cc:54-61) -- backward stable for any diagonal block.
+// (Round 1 inverted the 64x64 diagonal blocks explicitly and applied the inverses by GEMM, which loses accuracy with
+// cond(T_ii) and needed an out-of-place product plus a copy back per leaf.)
+//   left : op(T) X = alpha B_blk, every column of B_blk an independent right-hand side
+//   right: X op(T) = alpha B_blk  <=>  op(T)^T x^T = alpha b^T, every row of B_blk an independent right-hand side
+// so both are "Meff y = alpha b" with Meff = op(T) or op(T)^T, lower (forward) or upper (backward).  One thread owns one
+// right-hand side in registers (fully unrolled, compile-time indices); Meff sits in shared memory column by column with
+// its diagonal already inverted, and is read by warp-wide broadcast loads; the update after each pivot is right-looking
+// (b[i] -= Meff[i][l] * y[l] for all remaining i: independent FMAs).  The 128 right-hand sides of a CTA go through a
+// shared-memory tile so that global loads and stores are coalesced for both sides.
+template <typename T> struct leaf_width { static constexpr int value = 64; };
+template <> struct leaf_width<cuFloatComplex> { static constexpr int value = 32; };
+template <> struct leaf_width<cuDoubleComplex> { static constexpr int value = 32; };
+constexpr int LEAF_RHS = 128;
 
 template <typename T> __device__ __forceinline__ T tdiv(T a, T b);
 template <> __device__ __forceinline__ float tdiv(float a, float b) { return a / b; }
@@ -158,69 +171,99 @@ template <> __device__ __forceinline__ double tdiv(double a, double b) { return 
 template <> __device__ __forceinline__ cuFloatComplex tdiv(cuFloatComplex a, cuFloatComplex b) { return cuCdivf(a, b); }
 template <> __device__ __forceinline__ cuDoubleComplex tdiv(cuDoubleComplex a, cuDoubleComplex b) { return cuCdiv(a, b); }
 
-// One CTA per 64x64 diagonal block: inv := T^{-1} by substitution on the identity.  Thread j owns column j
-// of the inverse (columns are independent); T sits in shared memory.  Output is a full nb x nb block with
-// exact zeros in the unreferenced triangle, so it can be fed to the GEMM kernel.
-template <typename T>
-__global__ void __launch_bounds__(TRSM_NB) tri_inverse_kernel(int n, const T* __restrict__ A, int64_t lda, bool upper, bool unit,
-                                                             T* __restrict__ inv /* [nblk][NB*NB] */) {
-    extern __shared__ __align__(16) unsigned char smem_inv[];
-    T* sT = (T*)smem_inv;                       // sT[i + l*NB]
-    T* sX = sT + TRSM_NB * TRSM_NB;             // sX[i + j*(NB+1)]: column j of the inverse (padded: bank-conflict-free)
-    const int b0 = blockIdx.x * TRSM_NB, nb = min(TRSM_NB, n - b0), j = threadIdx.x;
-    const T* Ab = A + b0 + (int64_t)b0 * lda;
-    for (int l = 0; l < nb; l++)
-        if (j < nb) sT[j + l * TRSM_NB] = Ab[j + (int64_t)l * lda];
-    __syncthreads();
-    // one division per row instead of one per (row, column): thread j replaces T(j,j) by its reciprocal
-    if (j < nb && !unit) sT[j + j * TRSM_NB] = tdiv<T>(num<T>::real(1.0), sT[j + j * TRSM_NB]);
-    __syncthreads();
-    if (j < nb) {
-        T* x = sX + j * (TRSM_NB + 1);
-        for (int i = 0; i < nb; i++) x[i] = num<T>::zero();
-        if (!upper) {   // forward substitution, rows j..nb-1 (rows < j of column j are zero)
-            for (int i = j; i < nb; i++) {
-                T sacc = (i == j) ? num<T>::real(1.0) : num<T>::zero();
-                for (int l = j; l < i; l++) sacc = num<T>::sub(sacc, num<T>::mul(sT[i + l * TRSM_NB], x[l]));
-                x[i] = unit ? sacc : num<T>::mul(sacc, sT[i + i * TRSM_NB]);
-            }
-        } else {        // back substitution, rows j..0
-            for (int i = j; i >= 0; i--) {
-                T sacc = (i == j) ? num<T>::real(1.0) : num<T>::zero();
-                for (int l = i + 1; l <= j; l++) sacc = num<T>::sub(sacc, num<T>::mul(sT[i + l * TRSM_NB], x[l]));
-                x[i] = unit ? sacc : num<T>::mul(sacc, sT[i + i * TRSM_NB]);
-            }
-        }
+template <typename T, bool FWD>
+__global__ void __launch_bounds__(LEAF_RHS) trsm_leaf_kernel(int nd, int64_t nrhs, T alpha, const T* __restrict__ S, int64_t lda, bool stored_upper,
+                                                            int op /*0 N, 1 T, 2 C*/, bool unit, bool left, T* __restrict__ B, int64_t ldb) {
+    constexpr int NBL = leaf_width<T>::value;
+    extern __shared__ __align__(16) unsigned char smem_leaf[];
+    T* sM = (T*)smem_leaf;                   // sM[l * NBL + i] = Meff[i][l]; diagonal holds 1 / Meff[l][l]
+    T* sB = sM + NBL * NBL;                  // sB[c * (NBL + 1) + i]: element i of right-hand side c
+    const int tid = threadIdx.x;
+    const int64_t c0 = (int64_t)blockIdx.x * LEAF_RHS;
+    const T zero = num<T>::zero(), one = num<T>::real(1.0);
+    // ---- Meff from the referenced triangle of the stored block (the other triangle is never read) ----
+    for (int idx = tid; idx < NBL * NBL; idx += LEAF_RHS) {
+        const int i = idx % NBL, l = idx / NBL;                  // Meff[i][l]
+        int a = left ? i : l, b = left ? l : i;                  // = op(S)[a][b]
+        if (op != 0) { const int t = a; a = b; b = t; }          // = S[a][b] (conjugated if op == 2)
+        T v = zero;
+        if (i < nd && l < nd) {
+            if (a == b) v = unit ? one : S[a + (int64_t)b * lda];
+            else if (stored_upper ? a < b : a > b) v = S[a + (int64_t)b * lda];
+            if (op == 2) v = num<T>::conj(v);
+            if (i == l && !unit) v = tdiv<T>(one, v);
+        } else if (i == l) v = one;                              // identity padding
+        sM[l * NBL + i] = v;
+    }
+    // ---- right-hand sides: coalesced along whichever index is contiguous in memory ----
+    for (int idx = tid; idx < NBL * LEAF_RHS; idx += LEAF_RHS) {
+        int i, c;
+        if (left) { i = idx % NBL; c = idx / NBL; } else { c = idx % LEAF_RHS; i = idx / LEAF_RHS; }
+        T v = zero;
+        if (i < nd && c0 + c < nrhs) v = num<T>::mul(alpha, left ? B[i + (c0 + c) * ldb] : B[(c0 + c) + (int64_t)i * ldb]);
+        sB[c * (NBL + 1) + i] = v;
     }
     __syncthreads();
-    T* out = inv + (int64_t)blockIdx.x * TRSM_NB * TRSM_NB;
-    for (int l = 0; l < TRSM_NB; l++)
-        out[j + l * TRSM_NB] = (j < nb && l < nb) ? sX[j + l * (TRSM_NB + 1)] : num<T>::zero();
+    T y[NBL];
+#pragma unroll
+    for (int i = 0; i < NBL; i++) y[i] = sB[tid * (NBL + 1) + i];
+    if (FWD) {
+#pragma unroll
+        for (int l = 0; l < NBL; l++) {
+            y[l] = num<T>::mul(y[l], sM[l * NBL + l]);
+#pragma unroll
+            for (int i = l + 1; i < NBL; i++) y[i] = num<T>::sub(y[i], num<T>::mul(sM[l * NBL + i], y[l]));
+        }
+    } else {
+#pragma unroll
+        for (int l = NBL - 1; l >= 0; l--) {
+            y[l] = num<T>::mul(y[l], sM[l * NBL + l]);
+#pragma unroll
+            for (int i = 0; i < l; i++) y[i] = num<T>::sub(y[i], num<T>::mul(sM[l * NBL + i], y[l]));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NBL; i++) sB[tid * (NBL + 1) + i] = y[i];
+    __syncthreads();
+    for (int idx = tid; idx < NBL * LEAF_RHS; idx += LEAF_RHS) {
+        int i, c;
+        if (left) { i = idx % NBL; c = idx / NBL; } else { c = idx % LEAF_RHS; i = idx / LEAF_RHS; }
+        if (i < nd && c0 + c < nrhs) {
+            const T v = sB[c * (NBL + 1) + i];
+            if (left) B[i + (c0 + c) * ldb] = v; else B[(c0 + c) + (int64_t)i * ldb] = v;
+        }
+    }
 }
 
 template <typename T> struct TsCtx {
     cudaStream_t s; bool left, upper, unit; char trans; const T* A; int64_t lda; T* B; int64_t ldb;
-    const T* inv; T* outw; int64_t ldo;
 };
 
 template <typename T>
+static void trsm_leaf(const TsCtx<T>& c, T alpha, int d0, int nd, int other) {
+    constexpr int NBL = leaf_width<T>::value;
+    const int op = op_code(c.trans);
+    const bool eff_lower = (!c.upper) ^ (op != 0) ^ (!c.left);
+    const int smem = (NBL * NBL + LEAF_RHS * (NBL + 1)) * (int)sizeof(T);
+    const T* S = c.A + d0 + (int64_t)d0 * c.lda;
+    T* Bb = c.left ? c.B + d0 : c.B + (int64_t)d0 * c.ldb;
+    const unsigned grid = (unsigned)((other + LEAF_RHS - 1) / LEAF_RHS);
+    if (eff_lower) {
+        set_max_dynamic_smem((const void*)trsm_leaf_kernel<T, true>, smem);
+        trsm_leaf_kernel<T, true><<<grid, LEAF_RHS, smem, c.s>>>(nd, other, alpha, S, c.lda, c.upper, op, c.unit, c.left, Bb, c.ldb);
+    } else {
+        set_max_dynamic_smem((const void*)trsm_leaf_kernel<T, false>, smem);
+        trsm_leaf_kernel<T, false><<<grid, LEAF_RHS, smem, c.s>>>(nd, other, alpha, S, c.lda, c.upper, op, c.unit, c.left, Bb, c.ldb);
+    }
+}
+
+template <typename T>
 static void trsm_rec(const TsCtx<T>& c, T alpha, int d0, int nd, int other) {
+    constexpr int NBL = leaf_width<T>::value;
     const bool notr = op_code(c.trans) == 0;
     const bool opupper = notr ? c.upper : !c.upper;
-    if (nd <= TRSM_NB) {
-        const T* invb = c.inv + (int64_t)(d0 / TRSM_NB) * TRSM_NB * TRSM_NB;
-        if (c.left) {   // X = alpha * op(T)^{-1} B_blk = alpha * op(T^{-1}) B_blk
-            T* Bb = c.B + d0;
-            gemm_dev<T>(c.s, c.trans, 'N', nd, other, nd, alpha, invb, TRSM_NB, Bb, c.ldb, num<T>::zero(), c.outw, c.ldo);
-            copy_matrix<T>(c.s, nd, other, c.outw, c.ldo, Bb, c.ldb);
-        } else {        // X = alpha * B_blk * op(T^{-1})
-            T* Bb = c.B + (int64_t)d0 * c.ldb;
-            gemm_dev<T>(c.s, 'N', c.trans, other, nd, nd, alpha, Bb, c.ldb, invb, TRSM_NB, num<T>::zero(), c.outw, c.ldo);
-            copy_matrix<T>(c.s, other, nd, c.outw, c.ldo, Bb, c.ldb);
-        }
-        return;
-    }
-    const int n1 = split_point(nd, TRSM_NB), n2 = nd - n1;
+    if (nd <= NBL) { trsm_leaf<T>(c, alpha, d0, nd, other); return; }
+    const int n1 = split_point(nd, NBL), n2 = nd - n1;
     const int a = d0, b = d0 + n1;
     const T one = num<T>::real(1.0), mone = num<T>::real(-1.0);
     const T* Aoff = c.upper ? (c.A + a + (int64_t)b * c.lda) : (c.A + b + (int64_t)a * c.lda);
@@ -260,18 +303,6 @@ void trsm_dev(cudaStream_t s, char side, char uplo, char trans, char diag, int m
     c.trans = op_code(trans) == 0 ? 'N' : (op_code(trans) == 1 ? 'T' : 'C');
     c.A = A; c.lda = lda; c.B = B; c.ldb = ldb;
     const int nd = c.left ? m : n, other = c.left ? n : m;
-    const int nblk = (nd + TRSM_NB - 1) / TRSM_NB;
-    T* inv = (T*)ws_alloc((size_t)nblk * TRSM_NB * TRSM_NB * sizeof(T));
-    c.inv = inv;
-    const int smem = (2 * TRSM_NB + 1) * TRSM_NB * sizeof(T);
-    static bool attr_done = false;
-    if (!attr_done) {
-        B200_CUDA(cudaFuncSetAttribute(tri_inverse_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
-    }
-    tri_inverse_kernel<T><<<nblk, TRSM_NB, smem, s>>>(nd, A, lda, c.upper, c.unit, inv);
-    c.ldo = even_ld(c.left ? TRSM_NB : other, sizeof(T));
-    c.outw = (T*)ws_alloc((size_t)c.ldo * (c.left ? other : TRSM_NB) * sizeof(T));
     trsm_rec(c, alpha, 0, nd, other);
 }
 template void trsm_dev<float>(cudaStream_t, char, char, char, char, int, int, float, const float*, int64_t, float*, int64_t);

@@ -27,6 +27,7 @@ static void print_help() {
         "                      'oracle:<filename>', where <filename> is the name of an object trace\n"
         "   threshold=<n>   -- heuristic=size: allocations of >= n bytes become managed (default 65536)\n"
         "   variant=<name>  -- force a kernel variant: generic_tile | dmma_tma | dmma_ldg | auto\n"
+        "   sgemm_cfg=<n>   -- SGEMM tensor-core tile: -1 size-based (default), 0 128x128, 1 128x256 BK32, 2 128x256 BK16\n"
         "   devices=<n>     -- GPUs used for partitioned Level-3 calls (default 1)\n"
         "   sync=<0|1>      -- block until results are visible before returning (default 1)\n"
         "   prefetch=<0|1|2> -- managed operands: 0 never prefetch, 1 bulk-migrate a tracked block to the device on its\n"
@@ -73,6 +74,7 @@ static void set_options(const char* env) {
         }
         else if (!strncmp(opt, "threshold=", 10)) { g_opts.managed_threshold = strtoull(opt + 10, nullptr, 0); tracker_set_threshold(g_opts.managed_threshold); }
         else if (!strncmp(opt, "variant=", 8)) force_variant = variant_from_name(opt + 8);
+        else if (!strncmp(opt, "sgemm_cfg=", 10)) g_opts.sgemm_cfg = atoi(opt + 10);
         else if (!strncmp(opt, "devices=", 8)) g_opts.devices = atoi(opt + 8);
         else if (!strncmp(opt, "sync=", 5)) g_opts.sync = atoi(opt + 5) != 0;
         else if (!strncmp(opt, "prefetch=", 9)) g_opts.prefetch = atoi(opt + 9);

@@ -116,6 +116,25 @@ bool device_ready() { return g_ready; }
 int sm_count() { return g_sms; }
 bool tma_available() { return g_encode != nullptr; }
 
+void set_max_dynamic_smem(const void* kernel, int bytes) {
+    struct Entry { const void* k; int dev; int bytes; };
+    static Entry table[512];
+    static int count = 0;
+    static std::mutex mu;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < count; i++)
+        if (table[i].k == kernel && table[i].dev == dev) {
+            if (table[i].bytes >= bytes) return;
+            table[i].bytes = bytes;
+            B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            return;
+        }
+    B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (count < 512) table[count++] = Entry{kernel, dev, bytes};
+}
+
 bool encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, void* base, const cuuint64_t* gdim,
                        const cuuint64_t* gstride_bytes, const cuuint32_t* box, const cuuint32_t* estride,
                        CUtensorMapSwizzle swz) {
@@ -359,7 +378,10 @@ void Operand::release() {
     done_ = true;
     if (staged_ && (access_ & ACC_OUT)) {
         TrackerGuard guard;
-        if (cols_ == 1) B200_CUDA(cudaMemcpyAsync((void*)host_, dev_, (size_t)rows_ * elem_, cudaMemcpyDeviceToHost, current_stream()));
+        if (cols_ == 1 && vec_inc_ > 1 && vec_n_ > 0)   // strided vector: only its own elements go back (see runtime.h)
+            B200_CUDA(cudaMemcpy2DAsync((void*)host_, (size_t)vec_inc_ * elem_, dev_, (size_t)vec_inc_ * elem_, elem_, (size_t)vec_n_,
+                                        cudaMemcpyDeviceToHost, current_stream()));
+        else if (cols_ == 1) B200_CUDA(cudaMemcpyAsync((void*)host_, dev_, (size_t)rows_ * elem_, cudaMemcpyDeviceToHost, current_stream()));
         else B200_CUDA(cudaMemcpy2DAsync((void*)host_, (size_t)ld_ * elem_, dev_, (size_t)dld_ * elem_, (size_t)rows_ * elem_,
                                          (size_t)cols_, cudaMemcpyDeviceToHost, current_stream()));
         __atomic_fetch_add(&g_stats.d2h_bytes, (unsigned long long)(rows_ * cols_ * elem_), __ATOMIC_RELAXED);

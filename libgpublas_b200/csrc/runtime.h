@@ -16,6 +16,7 @@ struct Options {
     bool sync = true;              // block until results are visible before returning (BLAS semantics)
     int prefetch = 1;              // managed operands: 0 never prefetch, 1 bulk-migrate a tracked block on first use, 2 prefetch on every call
     size_t managed_threshold = 64 * 1024;   // tracker: allocations >= this go to managed memory
+    int sgemm_cfg = -1;            // SGEMM tcgen05 tile configuration: -1 size-based, 0 128x128 BK32 x3, 1 128x256 BK32 x2, 2 128x256 BK16 x4
     int devices = 1;               // GPUs used by partitioned Level-3 calls
     size_t multi_gpu_min_dim = 8192;
     size_t pipeline_min_bytes = (size_t)64 << 20;   // host-resident GEMM operands above this are staged in overlapped chunks
@@ -39,6 +40,10 @@ void finish_call();                 // the synchronous-return step (replaces cal
 // events, for calls that overlap staging with compute (staged_gemm.cu).  Created lazily, never destroyed.
 cudaStream_t aux_stream(int which);
 cudaEvent_t pooled_event(int idx);
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize, applied once per (kernel, device): thread-safe, and correct when a process
+// drives several devices (the attribute belongs to the function's per-device instance).
+void set_max_dynamic_smem(const void* kernel, int bytes);
 
 bool tma_available();
 bool encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, void* base, const cuuint64_t* gdim,
@@ -66,15 +71,28 @@ void make_resident(const void* p, size_t bytes, cudaStream_t s);   // managed op
 // Tracked-managed / device pointers are used in place (hit); host pointers are staged into the
 // workspace with a 2-D copy that also re-packs them to a TMA-friendly leading dimension (miss),
 // and written back on release if the access mode says so.
+struct VecTag {};
 class Operand {
 public:
     Operand(const void* host, int64_t rows, int64_t cols, int64_t ld, size_t elem, int access);
+    // BLAS vector of n elements with increment inc: occupies 1+(n-1)|inc| elements from the pointer.  A staged strided
+    // vector is read as its whole extent but written back ELEMENT BY ELEMENT (a 2-D copy of n rows of one element, pitch
+    // |inc| elements): the gaps between its elements are not this operand's to write -- in dswap_(n,&A[i],lda,&A[j],lda)
+    // they hold the other operand (LAPACK row swaps, drot in dbdsqr), and other threads may own them.
+    Operand(VecTag, const void* host, int64_t n, int64_t inc, size_t elem, int access)
+        : Operand(host, n > 0 ? 1 + (n - 1) * (inc < 0 ? -inc : inc) : 0, 1, n > 0 ? 1 + (n - 1) * (inc < 0 ? -inc : inc) : 1, elem, access) {
+        vec_n_ = n; vec_inc_ = inc < 0 ? -inc : inc;
+    }
     void* dev() const { return dev_; }
     int64_t ld() const { return dld_; }
     void release();                 // enqueue write-back (if any); idempotent
     bool staged() const { return staged_; }
 private:
     const void* host_; void* dev_; int64_t rows_, cols_, ld_, dld_; size_t elem_; int access_; bool staged_, done_;
+    int64_t vec_n_ = 0, vec_inc_ = 1;
+};
+struct VecOperand : Operand {
+    VecOperand(const void* p, int64_t n, int64_t inc, size_t elem, int access) : Operand(VecTag{}, p, n, inc, elem, access) {}
 };
 
 void log_exec(const char* routine, const char* fmt, ...);

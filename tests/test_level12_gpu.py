@@ -107,6 +107,47 @@ def test_nrm2_asum_scal_copy_swap():
     f77(lib, "dswap_", 1000, a, 1, b, 1); assert np.array_equal(a, b0) and np.array_equal(b, a0)
 
 
+@pytest.mark.parametrize("p", ["s", "d", "c", "z"])
+def test_row_operations_inside_one_host_matrix(p):
+    """LAPACK-style row operations on ONE untracked host matrix: dswap_(n, &A[i], lda, &A[j], lda) (dgetf2 / dlaswp row swaps),
+    drot_ on two rows (dbdsqr), dscal_/daxpy_ on a row.  x and y interleave in the same host array, so a staged copy of the whole
+    extent of one operand contains the other's elements: each operand must write back ONLY its own elements (ADVICE r1, high:
+    the second whole-extent write-back used to overwrite the first with stale data, leaving row i unswapped except column 0),
+    and every other element of A must be bit-unchanged."""
+    lib = g.load(); dt = DT[p]
+    for (m, n, i, j) in [(7, 5, 1, 4), (40, 33, 0, 39), (64, 64, 17, 3), (5, 300, 4, 0)]:
+        A0 = splitmix_uniform(21, (m, n), dt); lda = m
+        # swap
+        A = A0.copy(order="F")
+        f77(lib, p + "swap_", n, A[i:, 0], lda, A[j:, 0], lda)
+        want = A0.copy(order="F"); want[[i, j], :] = want[[j, i], :]
+        assert np.array_equal(A, want), (p, "swap", m, n, i, j)
+        # scal on a row: the other rows stay bit-identical
+        A = A0.copy(order="F"); alpha = 0.7 if p in "sd" else 0.7 - 0.9j
+        f77(lib, p + "scal_", n, alpha, A[i:, 0], lda)
+        want = A0.copy(order="F"); want[i, :] = (dt(alpha) * want[i, :].astype(dt)).astype(dt)
+        rest = np.ones(m, bool); rest[i] = False
+        assert np.array_equal(A[rest], A0[rest]) and np.allclose(A[i], want[i], rtol=4 * EPS[p], atol=0), (p, "scal", m, n)
+        # axpy: row j += alpha * row i
+        A = A0.copy(order="F")
+        f77(lib, p + "axpy_", n, alpha, A[i:, 0], lda, A[j:, 0], lda)
+        rest = np.ones(m, bool); rest[j] = False
+        assert np.array_equal(A[rest], A0[rest]), (p, "axpy rest", m, n)
+        assert np.allclose(A[j], A0[j] + dt(alpha) * A0[i], rtol=8 * EPS[p], atol=8 * EPS[p]), (p, "axpy", m, n)
+        if p in "sd":
+            A = A0.copy(order="F"); c, sn = 0.6, 0.8
+            f77(lib, p + "rot_", n, A[i:, 0], lda, A[j:, 0], lda, c, sn)
+            rest = np.ones(m, bool); rest[[i, j]] = False
+            assert np.array_equal(A[rest], A0[rest]), (p, "rot rest", m, n)
+            assert np.allclose(A[i], dt(c) * A0[i] + dt(sn) * A0[j], rtol=8 * EPS[p], atol=8 * EPS[p])
+            assert np.allclose(A[j], dt(c) * A0[j] - dt(sn) * A0[i], rtol=8 * EPS[p], atol=8 * EPS[p])
+            # columns of the same matrix (contiguous, disjoint): dswap of two columns
+            A = A0.copy(order="F")
+            f77(lib, p + "swap_", m, A[:, 0], 1, A[:, n - 1], 1)
+            want = A0.copy(order="F"); want[:, [0, n - 1]] = want[:, [n - 1, 0]]
+            assert np.array_equal(A, want)
+
+
 def test_iamax_exact_and_tiebreak():
     """I?AMAX must be bit-exact: the FIRST index of maximum |x| (1-based), like the CPU BLAS."""
     lib = g.load(); ob = load_openblas()

@@ -71,6 +71,59 @@ def test_trxm_vs_oracle(p, which):
                             assert np.allclose(B[:m], R[:m], rtol=1e4 * EPS[p], atol=1e4 * EPS[p])
 
 
+def graded_triangle(na, cond, dt, seed):
+    """Lower-triangular L (leading dimension na+1, rogue last row) with cond_2(L) = cond and O(1) entries: the Cholesky factor of
+    Q diag(lambda) Q^H with the spectrum graded geometrically from 1 down to cond^-2.  Unlike a random triangle with a graded
+    diagonal (whose inverse grows like 2^n) the solution stays within cond * |B|, and the diagonal BLOCKS of L are ill-conditioned
+    to varying degrees -- the case explicit block inverses degrade on."""
+    cplx = np.issubdtype(dt, np.complexfloating)
+    G = splitmix_uniform(seed, (na, na), np.complex128 if cplx else np.float64)
+    Q, _ = np.linalg.qr(G)
+    lam = np.power(cond, -2.0 * np.arange(na) / max(na - 1, 1))
+    A = (Q * lam) @ Q.conj().T
+    A = (A + A.conj().T) / 2
+    L = np.linalg.cholesky(A)
+    out = np.full((na + 1, na), -77.0, dtype=dt, order="F")
+    out[:na] = L.astype(dt)
+    return out
+
+
+@pytest.mark.parametrize("p", ["d", "s", "z"])
+def test_trsm_graded_condition(p):
+    """TRSM on ILL-CONDITIONED triangles (ADVICE r1 / VERDICT r1 2d): cond_2(T) = 1e2 ... 1e6 in double precision (Cholesky factors of
+    SPD matrices with graded spectra, `graded_triangle`), 1e1 ... 1e3 in single -- nothing like the diagonally dominant blocks of
+    the other tests.  The leaves solve by substitution (netlib's algorithm), so the result must satisfy the BACKWARD bound of SURVEY 8c
+    with the same constant as the well-conditioned case,
+        ||op(A) X - alpha B||_F <= c * na * eps * ||A||_F * ||X||_F,   c = 4,
+    and the forward error against the float64 solution must stay within c * na * eps * cond.  Sizes cross several leaves and
+    recursion levels (na = 200, 520) on both sides, all transposes, both triangles (the upper one is the transposed factor)."""
+    lib = g.load(); dt = DT[p]
+    hi = np.complex128 if p in "cz" else np.float64
+    al = (0.7 - 0.9j) if p in "cz" else 0.7
+    conds = [1e1, 1e3] if p == "s" else [1e2, 1e4, 1e6]
+    for cond in conds:
+        for (m, n) in [(200, 70), (70, 200), (520, 40)]:
+            for side in "LR":
+                na = m if side == "L" else n
+                Llow = graded_triangle(na, cond, dt, 7)
+                for uplo in "UL":
+                    T = Llow if uplo == "L" else F(np.vstack([Llow[:na].conj().T, Llow[na:]]))
+                    Tm = (np.triu(T[:na]) if uplo == "U" else np.tril(T[:na])).astype(hi)
+                    for ta in ("NTC" if p == "z" else "NT"):
+                        B0 = splitmix_uniform(8, (m + 2, n), dt); B = F(B0)
+                        f77(lib, p + "trsm_", side, uplo, ta, "N", m, n, al, T, na + 1, B, m + 2)
+                        assert np.array_equal(B[m:], B0[m:])
+                        opT = Tm if ta == "N" else (Tm.T if ta == "T" else Tm.conj().T)
+                        X = B[:m].astype(hi)
+                        assert np.all(np.isfinite(X)), (p, cond, side, uplo, ta)
+                        rhs = hi(dt(al)) * B0[:m].astype(hi)
+                        resid = (opT @ X if side == "L" else X @ opT) - rhs
+                        bound = 4 * na * EPS[p] * fro(Tm) * fro(X)
+                        assert fro(resid) <= bound, (p, cond, side, uplo, ta, m, n, fro(resid), bound)
+                        Xref = np.linalg.solve(opT, rhs) if side == "L" else np.linalg.solve(opT.T, rhs.T).T
+                        assert fro(X - Xref) <= 4 * na * EPS[p] * cond * fro(Xref), (p, cond, side, uplo, ta, fro(X - Xref) / fro(Xref))
+
+
 def test_dsyrk_dtrsm_large_device_property():
     """Config-4-shaped panels on the device: SYRK equals the masked GEMM; TRSM round trip X*L^T -> B."""
     import torch
