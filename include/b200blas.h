@@ -413,6 +413,13 @@ B200_API void b200blas_free_managed(void* p);
 B200_API int b200blas_is_tracked(const void* p);
 B200_API int b200blas_tracker_decision(unsigned long long nth, size_t request);   /* would the nth allocation of `request` bytes be managed (current heuristic)? */
 B200_API int b200blas_device_count(void);
+/* Partitioned Level-3 calls (option devices=<n>, csrc/multi_gemm.cu): the hop list a call of this shape issues -- 7 ints per hop
+ * (kind 0 A row-group / 1 B column band, grid row or column, piece, offset, length, forwarding slot or -1 = origin, receiving
+ * slot); returns the hop count.  Pure host logic.  b200blas_mg_geometry: [r0, r1, c0, c1) of a slot's C tile.
+ * b200blas_mg_stats: calls, devices, bytes read from the origin, bytes forwarded between devices, hops -- since load. */
+B200_API int b200blas_mg_plan(int ndev, long long m, long long n, int host_source, int* out, int cap);
+B200_API void b200blas_mg_geometry(int ndev, long long m, long long n, int slot, long long* out4);
+B200_API void b200blas_mg_stats(unsigned long long* out5);
 /* FP64 tensor-pipe (DMMA) ceiling measured in this process: sustained TFLOP/s over ~`seconds` of register-resident mma.sync f64
  * loops (no memory traffic); *burst (may be NULL) = best single launch.  The denominator of bench.py's tensor rooflines. */
 B200_API double b200blas_probe_fp64_tflops(double seconds, double* burst);

@@ -4,6 +4,7 @@
 // problems pick a small-tile GPU variant instead.
 #include "abi_common.h"
 #include "staged_gemm.cuh"
+#include "multi_gemm.h"
 #include <type_traits>
 #include "../../include/b200blas.h"
 
@@ -40,6 +41,11 @@ void gemm_entry(const char* name, const char* transa, const char* transb, const 
     const bool scale_only = is0(*alpha) || *k == 0;
     const char ta = nota ? 'N' : (lsame(transa, 'T') ? 'T' : 'C');
     const char tb = notb ? 'N' : (lsame(transb, 'T') ? 'T' : 'C');
+    // devices=<n>: large products are 2-D tile-partitioned over the GPUs of the box right here, behind the symbol (multi_gemm.cu)
+    if (!scale_only && g_opts.devices > 1 && multi_gemm<T>(ta, tb, *m, *n, *k, *alpha, a, (int64_t)*lda, b, (int64_t)*ldb, *beta, c, (int64_t)*ldc)) {
+        log_exec(name, "%c%c m=%d n=%d k=%d lda=%d ldb=%d ldc=%d (partitioned over %d devices)", ta, tb, *m, *n, *k, *lda, *ldb, *ldc, g_opts.devices);
+        return;
+    }
     // large host-resident operands: chunked staging overlapped with the multiply (staged_gemm.cuh)
     if (!scale_only && gemm_pipelined<T>(GemmDev<T>::fn, ta, tb, *m, *n, *k, *alpha, a, (int64_t)*lda, b, (int64_t)*ldb, *beta, c, (int64_t)*ldc)) {
         log_exec(name, "%c%c m=%d n=%d k=%d lda=%d ldb=%d ldc=%d (pipelined staging)", ta, tb, *m, *n, *k, *lda, *ldb, *ldc);
@@ -216,6 +222,31 @@ void b200blas_dgemm_out_flagged(char transa, char transb, int m, int n, int k, d
         fatal("b200blas_dgemm_out_flagged", __FILE__, __LINE__, "flag group sizes must be positive multiples of 128");
     dgemm_set_panel_flags(aflags, a_group, bflags, b_group, epoch);
     dgemm_out_dev(current_stream(), transa, transb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, d, ldd, MASK_FULL);
+}
+
+// ---- partitioned-call introspection (tests, bench) ----
+// The hop list a partitioned call of this shape would issue, 7 ints per hop: kind, grid index, piece, offset, length, src, dst.
+// Returns the number of hops (may exceed cap: only cap hops are written).  Pure host logic, touches no device.
+int b200blas_mg_plan(int ndev, long long m, long long n, int host_source, int* out, int cap) {
+    const std::vector<MgHop> plan = mg_plan(ndev, m, n, host_source != 0);
+    int w = 0;
+    for (const MgHop& h : plan) {
+        if (w < cap) {
+            int* o = out + 7 * w;
+            o[0] = h.kind; o[1] = h.gidx; o[2] = h.piece; o[3] = (int)h.off; o[4] = (int)h.len; o[5] = h.src; o[6] = h.dst;
+        }
+        w++;
+    }
+    return w;
+}
+void b200blas_mg_geometry(int ndev, long long m, long long n, int slot, long long* out4) {
+    int P, Q; mg_grid(ndev, &P, &Q);
+    int64_t r0, r1, c0, c1;
+    mg_block_range(m, P, slot / Q, &r0, &r1); mg_block_range(n, Q, slot % Q, &c0, &c1);
+    out4[0] = r0; out4[1] = r1; out4[2] = c0; out4[3] = c1;
+}
+void b200blas_mg_stats(unsigned long long* out5) {
+    out5[0] = g_mg_stats.calls; out5[1] = g_mg_stats.devices; out5[2] = g_mg_stats.origin_bytes; out5[3] = g_mg_stats.forward_bytes; out5[4] = g_mg_stats.hops;
 }
 
 void sgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k, const float* alpha,

@@ -28,7 +28,9 @@ static void print_help() {
         "   threshold=<n>   -- heuristic=size: allocations of >= n bytes become managed (default 65536)\n"
         "   variant=<name>  -- force a kernel variant: generic_tile | dmma_tma | dmma_ldg | auto\n"
         "   sgemm_cfg=<n>   -- SGEMM tensor-core tile: -1 size-based (default), 0 128x128, 1 128x256 BK32, 2 128x256 BK16\n"
-        "   devices=<n>     -- GPUs used for partitioned Level-3 calls (default 1)\n"
+        "   devices=<n>     -- GPUs used for partitioned Level-3 calls (default 1): ?gemm_ calls of at least multi_min^3 work are\n"
+        "                      2-D tile-partitioned over n devices of this box from inside the symbol (peer access required)\n"
+        "   multi_min=<n>   -- partition only products with m*n*k >= n^3 (default 8192)\n"
         "   sync=<0|1>      -- block until results are visible before returning (default 1)\n"
         "   prefetch=<0|1|2> -- managed operands: 0 never prefetch, 1 bulk-migrate a tracked block to the device on its\n"
         "                      first use (default), 2 prefetch on every call\n"
@@ -76,6 +78,7 @@ static void set_options(const char* env) {
         else if (!strncmp(opt, "variant=", 8)) force_variant = variant_from_name(opt + 8);
         else if (!strncmp(opt, "sgemm_cfg=", 10)) g_opts.sgemm_cfg = atoi(opt + 10);
         else if (!strncmp(opt, "devices=", 8)) g_opts.devices = atoi(opt + 8);
+        else if (!strncmp(opt, "multi_min=", 10)) g_opts.multi_gpu_min_dim = strtoull(opt + 10, nullptr, 0);
         else if (!strncmp(opt, "sync=", 5)) g_opts.sync = atoi(opt + 5) != 0;
         else if (!strncmp(opt, "prefetch=", 9)) g_opts.prefetch = atoi(opt + 9);
         else if (!strncmp(opt, "pipeline_min=", 13)) g_opts.pipeline_min_bytes = strtoull(opt + 13, nullptr, 0);

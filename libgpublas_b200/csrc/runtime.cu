@@ -156,14 +156,31 @@ struct ThreadCtx {
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t events[64]; int nevents = 0;
 };
-static thread_local ThreadCtx t_ctx;
+// One context per (thread, device): the home device's is what every single-GPU call uses; partitioned Level-3 calls
+// (multi_gemm.cu) switch the calling thread to a peer device with DeviceScope and find that device's own stream, workspace,
+// scalar slots and events here, so every *_dev launcher works unchanged on any device.
+static thread_local ThreadCtx t_ctxs[kMaxDevices];
+static thread_local int t_dev = -1;          // -1: the home device
+#define t_ctx (t_ctxs[t_dev < 0 ? g_device : t_dev])
+
+int home_device() { ensure_init(); return g_device; }
+int current_device() { return t_dev < 0 ? g_device : t_dev; }
+DeviceScope::DeviceScope(int dev) : prev_(t_dev) {
+    ensure_init();
+    t_dev = dev;
+    B200_CUDA(cudaSetDevice(dev));
+}
+DeviceScope::~DeviceScope() {
+    t_dev = prev_;
+    cudaSetDevice(prev_ < 0 ? g_device : prev_);
+}
 
 cudaStream_t current_stream() {
     ensure_init();
     if (t_ctx.external_stream) return t_ctx.ext;
     if (!t_ctx.stream) {
         TrackerGuard guard;
-        B200_CUDA(cudaSetDevice(g_device));
+        B200_CUDA(cudaSetDevice(current_device()));
         B200_CUDA(cudaStreamCreateWithFlags(&t_ctx.stream, cudaStreamNonBlocking));
     }
     return t_ctx.stream;
@@ -179,7 +196,7 @@ cudaStream_t aux_stream(int which) {
     ThreadCtx& c = t_ctx;
     if (!c.aux[which]) {
         TrackerGuard guard;
-        B200_CUDA(cudaSetDevice(g_device));
+        B200_CUDA(cudaSetDevice(current_device()));
         B200_CUDA(cudaStreamCreateWithFlags(&c.aux[which], cudaStreamNonBlocking));
     }
     return c.aux[which];
@@ -328,7 +345,7 @@ void make_resident(const void* p, size_t bytes, cudaStream_t s) {
         if (prev != 0) return;          // already migrated once, or not one of our blocks (the application manages those)
     }
     TrackerGuard guard;
-    int dev; cudaGetDevice(&dev);
+    int dev = current_device();
     void* base = nullptr; size_t bsize = 0;
     if (g_opts.prefetch == 1 && tracker_lookup(p, &base, &bsize)) {    // whole block: later calls may use other parts of it
         cudaMemAdvise(base, bsize, cudaMemAdviseSetPreferredLocation, dev);

@@ -29,7 +29,20 @@ struct Stats {
 };
 extern Stats g_stats;
 
+constexpr int kMaxDevices = 16;
 void ensure_init();                 // idempotent, thread-safe; aborts if no CUDA device
+int home_device();                  // the device single-GPU calls run on (B200BLAS_DEVICE, else the process's current device at first use)
+int current_device();               // the device this thread's library state is bound to right now (home unless inside a DeviceScope)
+// Switches the calling thread (CUDA current device + the library's per-thread stream / workspace / scalar slots) to `dev`
+// for the scope's lifetime: how partitioned calls drive the peer GPUs from the caller's thread.
+struct DeviceScope {
+    explicit DeviceScope(int dev);
+    ~DeviceScope();
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
+private:
+    int prev_;
+};
 bool try_init();                    // same, but returns false instead of aborting when there is no device (allocator path)
 bool device_ready();                // true once ensure_init() has succeeded
 int sm_count();

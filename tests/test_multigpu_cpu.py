@@ -159,3 +159,93 @@ def test_syrk_strip_bounds_equal_area():
         if n >= 128 * parts * 4:
             areas = [(n - b[i]) ** 2 - (n - b[i + 1]) ** 2 for i in range(parts)]
             assert max(areas) <= 1.25 * (n * n / parts), (n, parts, b, areas)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Single-process partitioned GEMM behind the symbol (csrc/multi_gemm.cu, option devices=<n>): the hop list is pure host
+# logic exported by the library (b200blas_mg_plan), so its routing is checked here without a GPU -- by EXECUTING the hops
+# as numpy copies between per-device panel arrays and multiplying the panels (a CPU model of what the copy engines and
+# the per-device kernels do; test infrastructure only).
+def _plan(lib, ndev, m, n, host):
+    cap = 4096
+    buf = (ctypes.c_int * (7 * cap))()
+    cnt = lib.b200blas_mg_plan(ndev, ctypes.c_longlong(m), ctypes.c_longlong(n), int(host), buf, cap)
+    assert 0 <= cnt <= cap
+    return [tuple(buf[7 * i + j] for j in range(7)) for i in range(cnt)]
+
+
+def _geometry(lib, ndev, m, n, slot):
+    out = (ctypes.c_longlong * 4)()
+    lib.b200blas_mg_geometry(ndev, ctypes.c_longlong(m), ctypes.c_longlong(n), slot, out)
+    return tuple(out)
+
+
+@pytest.mark.parametrize("ndev", [2, 3, 4, 6, 8])
+@pytest.mark.parametrize("host", [False, True])
+def test_partitioned_gemm_hop_list_delivers_every_panel_once(ndev, host):
+    import libgpublas_b200 as g
+    lib = g.load()
+    P, Q = grid_for(ndev)
+    for (m, n, k) in [(16384, 16384, 64), (9000, 20000, 32), (2048 * P + 77, 2048 * Q + 130, 16)]:
+        plan = _plan(lib, ndev, m, n, host)
+        geo = [_geometry(lib, ndev, m, n, s) for s in range(ndev)]
+        # tiles partition C
+        cover = np.zeros((m, n), dtype=np.int8) if m * n <= 4e8 else None
+        assert sorted({(r0, r1) for (r0, r1, _, _) in geo})[0][0] == 0 and max(r1 for (_, r1, _, _) in geo) == m
+        assert max(c1 for (_, _, _, c1) in geo) == n
+        assert sum((r1 - r0) * (c1 - c0) for (r0, r1, c0, c1) in geo) == m * n
+        rng = np.random.default_rng(ndev * 2 + host)
+        A = rng.standard_normal((m, k)); B = rng.standard_normal((k, n))
+        panelA = [np.full((geo[s][1] - geo[s][0], k), np.nan) for s in range(ndev)]
+        panelB = [np.full((k, geo[s][3] - geo[s][2]), np.nan) for s in range(ndev)]
+        if not host:          # the home GPU uses its operands in place
+            panelA[0][:] = A[geo[0][0]:geo[0][1]]; panelB[0][:] = B[:, geo[0][2]:geo[0][3]]
+        have = set()          # (slot, kind, piece) delivered so far
+        origin_elems, fwd_elems = 0, 0
+        per_dev_origin = [0] * ndev
+        first_kinds = []
+        for (kind, gidx, piece, off, ln, src, dst) in plan:
+            r0, r1, c0, c1 = geo[dst]
+            assert (dst // Q if kind == 0 else dst % Q) == gidx, "the receiver must be a consumer of the piece"
+            assert (dst, kind, piece) not in have, "delivered twice"
+            assert not (dst == 0 and not host), "the home GPU never receives its own operands"
+            if src >= 0:
+                assert (src, kind, piece) in have, "forwarded before it arrived"
+                blk = panelA[src][off:off + ln] if kind == 0 else panelB[src][:, off:off + ln]
+                fwd_elems += blk.size
+            else:
+                blk = A[r0 + off:r0 + off + ln] if kind == 0 else B[:, c0 + off:c0 + off + ln]
+                origin_elems += blk.size
+                per_dev_origin[dst] += blk.size
+            assert not np.isnan(blk).any()
+            if kind == 0:
+                panelA[dst][off:off + ln] = blk
+            else:
+                panelB[dst][:, off:off + ln] = blk
+            have.add((dst, kind, piece))
+            first_kinds.append(kind)
+        assert first_kinds[0] == 1, "the first pieces are B band 0 (the kernel's tile schedule starts there)"
+        for s in range(ndev):
+            r0, r1, c0, c1 = geo[s]
+            assert np.array_equal(panelA[s], A[r0:r1]) and np.array_equal(panelB[s], B[:, c0:c1]), (ndev, host, s)
+        # every operand element leaves the origin at most once (exactly once, except the part only the home tile uses)
+        if host:
+            assert origin_elems == A.size + B.size
+            shares = [x for x in per_dev_origin]
+            if m == n:         # (ragged shapes with one or two bands per panel cannot split evenly)
+                assert max(shares) <= 1.6 * (sum(shares) / ndev), ("every GPU pulls an equal share over its own PCIe link", shares)
+        else:
+            only_home_a = 0 if Q > 1 else (geo[0][1] - geo[0][0]) * k
+            only_home_b = 0 if P > 1 else k * (geo[0][3] - geo[0][2])
+            assert origin_elems == A.size + B.size - only_home_a - only_home_b
+        naive = sum((geo[s][1] - geo[s][0]) * k + k * (geo[s][3] - geo[s][2]) for s in range(0 if host else 1, ndev))
+        assert origin_elems + fwd_elems == naive, "total inbound bytes are what the tiles need -- only their route changed"
+        if ndev == 8 and not host and m == n:
+            assert origin_elems * 2.5 < naive, "home egress 4.3 GB instead of 11.3 GB at N = 8"
+        # and the product assembled from the per-device tiles is the product
+        if k <= 32:
+            C = np.empty((m, n))
+            for s in range(ndev):
+                r0, r1, c0, c1 = geo[s]
+                C[r0:r1, c0:c1] = panelA[s] @ panelB[s]
+            assert np.allclose(C, A @ B, rtol=1e-12, atol=1e-12)
