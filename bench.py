@@ -131,6 +131,42 @@ def e2e_managed_first_touch(g, lib, n, nA, nB, C_dev, flops, reps=2):
             "steps": reps, "max_abs_diff_vs_resident": d, "_probe": probe}
 
 
+def mg_stats(lib):
+    buf = (ctypes.c_ulonglong * 5)()
+    lib.b200blas_mg_stats(buf)
+    return list(buf)
+
+
+def other_routines_partitioned(g, lib, torch, dev, peaks, out, world):
+    """SGEMM 16384^3 and ZGEMM 8192^3 through sgemm_/zgemm_ with devices=N (bulk mode: panels land, then the ordinary kernel)."""
+    def timed(fn, reps=3, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2]
+    n = 16384
+    A = torch.rand((n, n), dtype=torch.float32, device=dev) * 2 - 1; B = torch.rand((n, n), dtype=torch.float32, device=dev) * 2 - 1
+    C = torch.zeros((n, n), dtype=torch.float32, device=dev)
+    c0 = mg_stats(lib)[0]
+    ms = timed(lambda: g.call("sgemm_", "N", "N", n, n, n, 1.0, A, n, B, n, 0.0, C, n))
+    out["sgemm_16384"] = {"tflops": 2.0 * n ** 3 / ms / 1e9, "ms": ms, "devices": world, "partitioned_calls": mg_stats(lib)[0] - c0}
+    del A, B, C
+    n = 8192
+    A = torch.rand((n, n), dtype=torch.complex128, device=dev); B = torch.rand((n, n), dtype=torch.complex128, device=dev)
+    C = torch.zeros((n, n), dtype=torch.complex128, device=dev)
+    c0 = mg_stats(lib)[0]
+    ms = timed(lambda: g.call("zgemm_", "N", "N", n, n, n, 0.7 - 0.9j, A, n, B, n, 1.3 - 1.1j, C, n))
+    out["zgemm_8192"] = {"tflops": 8.0 * n ** 3 / ms / 1e9, "ms": ms, "devices": world, "partitioned_calls": mg_stats(lib)[0] - c0,
+                         "frac_of_fp64_peak_per_gpu": 8.0 * n ** 3 / ms / 1e9 / world / FP64_PEAK_NOMINAL}
+    del A, B, C
+
+
 def l1_c_driver(peaks):
     """Level-1 at the symbol boundary from C, not ctypes: tests/drivers/l1_chain.c under LD_PRELOAD=libb200blas.so on calloc'd
     (tracked -> managed) vectors of 2^26 doubles -- BASELINE.json configs[2] as an unmodified program runs it; wall clock per call
@@ -139,7 +175,7 @@ def l1_c_driver(peaks):
     hbm = peaks.get("hbm_gbs", 6553.9)
     exe = build_driver("l1_chain")
     out, _ = run(exe, [1 << 26, 40], preload=True, timeout=600)
-    r = fields([l for l in out.splitlines() if l.startswith("GBS")][0])
+    r = dict(kv.split("=", 1) for kv in [l for l in out.splitlines() if l.startswith("GBS")][0].split() if "=" in kv)
     res = {}
     for k in ("ddot", "daxpy", "dnrm2", "idamax"):
         res[k + "_2^26"] = {"gbs": float(r[k]), "frac_of_measured_hbm": float(r[k]) / hbm}
@@ -331,6 +367,8 @@ def main():
     ap.add_argument("--no-others", action="store_true", help="skip the SGEMM/ZGEMM/Level-1/2 lines of BASELINE.json's metric")
     ap.add_argument("--no-verify", action="store_true", help="skip the parity check of the timed result (outside the timed region): "
                                                              "N=1 128 rows of C against a float64 numpy product, N>1 the whole C against the 1-GPU kernel")
+    ap.add_argument("--mode", default="symbol", help="N>1: symbol = one process drives all N GPUs from inside dgemm_ (devices=N); "
+                                                     "ipc = the round-1 one-process-per-GPU CUDA-IPC push (comparison)")
     ap.add_argument("--kchunk", type=int, default=1024)
     ap.add_argument("--distribute", default=None, help="N>1: p2p_push (default on CUDA) | bcast")
     args = ap.parse_args()
@@ -362,12 +400,12 @@ def main():
 
     import torch
     import libgpublas_b200 as g
+    legacy = world > 1 and args.mode == "ipc"
     if world > 1:
         import torch.distributed as dist
         local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        from libgpublas_b200.multigpu import TiledGemm
     else:
         torch.cuda.set_device(0)
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -376,43 +414,25 @@ def main():
     g.set_sync(False)
     sampler = ClockSampler(torch.cuda.current_device())
 
-    if world == 1:
-        gen = torch.Generator(device=dev).manual_seed(2)
-        A = torch.rand((n, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
-        B = torch.rand((n, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
-        C = torch.zeros((n, n), dtype=torch.float64, device=dev)
-
-        def step():
-            g.call("dgemm_", "N", "N", n, n, n, 1.0, A, n, B, n, 0.0, C, n)
-
-        for _ in range(args.warmup):
-            step()
+    def sync_all():
         torch.cuda.synchronize()
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-        if rank == 0:
-            sampler.start()
-            time.sleep(0.3)
-        evs[0].record()
-        for i in range(args.steps):
-            step()
-            evs[i + 1].record()
-        torch.cuda.synchronize()
-        clocks = sampler.stop() if rank == 0 else {}
-        total_ms = evs[0].elapsed_time(evs[-1])
-        per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
-        variant = g.last_variant()
-        ms_per_step = total_ms / args.steps
-        value = flops / (ms_per_step * 1e-3) / 1e12
-        kernel_ms = sum(per_launch_ms) / len(per_launch_ms)
-        launches = args.steps
-        verified = verify_rows(torch, A, B, C, n) if not args.no_verify else None
-        scaling, parallelism = "strong", "single"
-    else:
+        if world > 1:
+            dist.barrier()
+
+    verified = None
+    e2e = None
+    others = None
+    probe = None
+    cpu = None
+    mg = None
+    if legacy:
+        # round-1 path kept for comparison (--mode ipc): one process per GPU, CUDA-IPC panel push by the home GPU
+        from libgpublas_b200.multigpu import TiledGemm
         tg = TiledGemm(n, n, n, dev, rank, world, kchunk=args.kchunk, distribute=args.distribute)
         tg.make_inputs(seed=2)
         for _ in range(args.warmup):
             tg.run()
-        torch.cuda.synchronize(); dist.barrier()
+        sync_all()
         if rank == 0:
             sampler.start()
             time.sleep(0.3)
@@ -422,124 +442,181 @@ def main():
         for _ in range(args.steps):
             tg.run()
         e1.record()
-        torch.cuda.synchronize(); dist.barrier()
+        sync_all()
         clocks = sampler.stop() if rank == 0 else {}
-        if os.environ.get("B200_MG_TRACE"):
-            tg.run(trace=True)
-            for r in range(world):
-                if r == rank:
-                    sys.stderr.write("rank %d trace: %s\n" % (rank, tg.trace))
-                dist.barrier()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = t.item()
-        ms_per_step = total_ms / args.steps
+        ms_per_step = t.item() / args.steps
         value = flops / (ms_per_step * 1e-3) / 1e12
-        kernel_ms = tg.last_kernel_ms()
+        kernel_ms = ms_per_step
         variant = g.last_variant()
         launches = args.steps * tg.kernels_per_step
         scaling, parallelism = "strong", tg.describe()
-        verified = None
         if not args.no_verify and rank == 0:
             ref = torch.empty(n * n, dtype=torch.float64, device=dev)
             g.call("dgemm_", "N", "N", n, n, n, 1.0, tg.A, n, tg.B, n, 0.0, ref, n)
             torch.cuda.synchronize()
             got = tg.home_c()
-            verified = {"max_abs_diff_vs_1gpu": float((got - ref).abs().max().item()),
-                        "bound": 2 * n * 2.0 ** -53 * float(torch.linalg.norm(tg.A[: n * 64]).item()) ** 2 / 64}
+            verified = {"max_abs_diff_vs_1gpu": float((got - ref).abs().max().item())}
             del ref, got
+    else:
+        # N = 1, and N > 1 "behind the symbol": rank 0 calls dgemm_ exactly as on one GPU; with devices=N the library
+        # partitions the product over the N GPUs of the box itself (csrc/multi_gemm.cu).  The other ranks torchrun started
+        # only take part in the barriers: the contract's launch, barrier and max-over-ranks clock stay, the data path has
+        # no process boundary in it -- which is what an unmodified program under LD_PRELOAD gets.
+        if world > 1:
+            lib.b200blas_set_options(("devices=%d" % world).encode())
+        launches = 0
+        clocks = {}
+        ms_local = 0.0
+        if rank == 0:
+            gen = torch.Generator(device=dev).manual_seed(2)
+            A = torch.rand((n, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+            B = torch.rand((n, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+            C = torch.zeros((n, n), dtype=torch.float64, device=dev)
 
-    # ---- end-to-end through the C ABI with pinned host buffers (N = 1) ----
-    e2e = None
-    if world == 1 and not args.no_e2e:
-        g.set_sync(True)
-        hA = torch.empty((n, n), dtype=torch.float64).pin_memory(); hA.copy_(A.cpu())
-        hB = torch.empty((n, n), dtype=torch.float64).pin_memory(); hB.copy_(B.cpu())
-        hC = torch.empty((n, n), dtype=torch.float64).pin_memory()
-        nA, nB, nC = hA.numpy(), hB.numpy(), hC.numpy()
-        s0 = g.stats()
-        for _ in range(min(args.warmup, 2)):
-            g.call("dgemm_", "N", "N", n, n, n, 1.0, nA, n, nB, n, 0.0, nC, n)
-        torch.cuda.synchronize()
-        s1 = g.stats()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            g.call("dgemm_", "N", "N", n, n, n, 1.0, nA, n, nB, n, 0.0, nC, n)
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / args.steps
-        s2 = g.stats()
-        # the result read back must agree with the device-resident one.  The staging pipeline accumulates C over k-chunks
-        # (a different summation order than the single k loop of the resident path): equal to rounding,
-        # |diff| <= 16*eps*k for U(-1,1) data; checked on two corners (first and last column panel).
-        d0 = float((hC[:256, :256].double() - C[:256, :256].cpu().double()).abs().max())
-        d1 = float((hC[n - 256:, n - 256:].double() - C[n - 256:, n - 256:].cpu().double()).abs().max())
-        same = bool(max(d0, d1) <= 16 * 2.0 ** -53 * n) and bool(d0 > 0 or n < 4096)
-        e2e = {"value": flops / dt / 1e12, "unit": "TFLOP/s", "ms_per_step": dt * 1e3,
-               "h2d_bytes_per_step": (s2["h2d_bytes"] - s1["h2d_bytes"]) // args.steps,
-               "d2h_bytes_per_step": (s2["d2h_bytes"] - s1["d2h_bytes"]) // args.steps,
-               "host_memory": "pinned", "matches_device_result": same, "max_abs_diff_vs_resident": max(d0, d1),
-               "path": "dgemm_ on host pointers: chunked H2D of A/B and D2H of C panels overlapped with the DMMA kernel (csrc/staged_gemm.cuh)"}
-        # the reference's real miss path is plain malloc'd memory (runtime-mem.hpp:84-112), and its hit path a calloc'd block
-        # the CPU has just filled: the same call on PAGEABLE host buffers, and on tracked managed buffers at first touch
-        try:
-            e2e["pageable"] = e2e_pageable(g, n, nA, nB, C, flops)
-            e2e["managed_first_touch"] = e2e_managed_first_touch(g, lib, n, nA, nB, C, flops)
-        except Exception as exc:  # noqa: BLE001
-            e2e["pageable_error"] = repr(exc)
-        g.set_sync(False)
+            def step():
+                g.call("dgemm_", "N", "N", n, n, n, 1.0, A, n, B, n, 0.0, C, n)
 
-    probe = None
-    if rank == 0:
-        try:
-            lib.b200blas_probe_fp64_tflops.restype = ctypes.c_double
-            lib.b200blas_probe_fp64_tflops.argtypes = [ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
-            burst = ctypes.c_double(0.0)
-            probe = {"sustained": lib.b200blas_probe_fp64_tflops(1.5, ctypes.byref(burst)), "burst": burst.value,
-                     "how": "register-resident mma.sync m16n8k16 f64 (DMMA) loop, 8 warps/SM, 1.5 s, in this process (csrc/probe.cu)"}
-        except Exception as exc:  # noqa: BLE001
-            probe = {"error": repr(exc)}
-    others = None
-    if world == 1 and not args.no_others:
-        del A, B, C
-        if not args.no_e2e:
+            for _ in range(args.warmup):
+                step()
+        sync_all()
+        if rank == 0:
+            mg0 = mg_stats(lib)
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+            sampler.start()
+            time.sleep(0.3)
+            evs[0].record()
+            for i in range(args.steps):
+                step()
+                evs[i + 1].record()
+        sync_all()
+        if rank == 0:
+            clocks = sampler.stop()
+            ms_local = evs[0].elapsed_time(evs[-1])
+            per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+            mg1 = mg_stats(lib)
+        if world > 1:
+            t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_local = t.item()
+        ms_per_step = ms_local / args.steps
+        value = flops / (ms_per_step * 1e-3) / 1e12
+        scaling = "strong"
+        if rank == 0:
+            variant = g.last_variant()
+            kernel_ms = sum(per_launch_ms) / len(per_launch_ms)
+            launches = args.steps * world
+            if world > 1:
+                calls = mg1[0] - mg0[0]
+                assert calls == args.steps, "the timed calls did not take the partitioned path (%d of %d)" % (calls, args.steps)
+                P, Q = (1, 2) if world == 2 else ((2, world // 2) if world % 2 == 0 else (1, world))
+                mg = {"partitioned_calls": calls, "devices": mg1[1], "origin_gb_per_step": (mg1[2] - mg0[2]) / calls / 1e9,
+                      "forwarded_gb_per_step": (mg1[3] - mg0[3]) / calls / 1e9, "hops_per_step": (mg1[4] - mg0[4]) // calls}
+                parallelism = ("one process, devices=%d behind dgemm_: 2-D tiles on a device grid; A row-groups / B column bands leave the home GPU once and "
+                               "are forwarded along chains of the devices that need them (copy engines over NVLink, a flag per piece); one flag-polling DMMA "
+                               "launch per device; C tiles stored into the home allocation by the kernel epilogues" % world)
+            else:
+                parallelism = "single"
+            if not args.no_verify:
+                verified = verify_rows(torch, A, B, C, n)
+                if world > 1:      # and bit-for-bit against the 1-GPU kernel on the same operands
+                    lib.b200blas_set_options(b"devices=1")
+                    ref = torch.empty((n, n), dtype=torch.float64, device=dev)
+                    g.call("dgemm_", "N", "N", n, n, n, 1.0, A, n, B, n, 0.0, ref, n)
+                    torch.cuda.synchronize()
+                    verified["max_abs_diff_vs_1gpu"] = float((C - ref).abs().max().item())
+                    del ref
+                    lib.b200blas_set_options(("devices=%d" % world).encode())
+
+        # ---- end-to-end through the C ABI with pinned host buffers: the library stages A, B host->device and C back inside the call ----
+        if rank == 0 and not args.no_e2e:
+            g.set_sync(True)
+            hA = torch.empty((n, n), dtype=torch.float64).pin_memory(); hA.copy_(A.cpu())
+            hB = torch.empty((n, n), dtype=torch.float64).pin_memory(); hB.copy_(B.cpu())
+            hC = torch.empty((n, n), dtype=torch.float64).pin_memory()
+            nA, nB, nC = hA.numpy(), hB.numpy(), hC.numpy()
+            for _ in range(min(args.warmup, 2)):
+                g.call("dgemm_", "N", "N", n, n, n, 1.0, nA, n, nB, n, 0.0, nC, n)
+            torch.cuda.synchronize()
+            s1 = g.stats()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                g.call("dgemm_", "N", "N", n, n, n, 1.0, nA, n, nB, n, 0.0, nC, n)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / args.steps
+            s2 = g.stats()
+            # the result read back must agree with the device-resident one.  At N = 1 the staging pipeline accumulates C over
+            # k-chunks (another summation order than the single k loop): equal to rounding, |diff| <= 16*eps*k for U(-1,1)
+            # data; the partitioned path keeps the single k loop: equal bit for bit.  Two corners (first and last panel).
+            d0 = float((hC[:256, :256].double() - C[:256, :256].cpu().double()).abs().max())
+            d1 = float((hC[n - 256:, n - 256:].double() - C[n - 256:, n - 256:].cpu().double()).abs().max())
+            same = bool(max(d0, d1) <= 16 * 2.0 ** -53 * n)
+            e2e = {"value": flops / dt / 1e12, "unit": "TFLOP/s", "ms_per_step": dt * 1e3,
+                   "h2d_bytes_per_step": (s2["h2d_bytes"] - s1["h2d_bytes"]) // args.steps,
+                   "d2h_bytes_per_step": (s2["d2h_bytes"] - s1["d2h_bytes"]) // args.steps,
+                   "host_memory": "pinned", "matches_device_result": same, "max_abs_diff_vs_resident": max(d0, d1),
+                   "path": ("dgemm_ on host pointers: chunked H2D of A/B and D2H of C panels overlapped with the DMMA kernel (csrc/staged_gemm.cuh)" if world == 1 else
+                            "dgemm_ on host pointers, devices=%d: every GPU pulls its share of the A/B pieces over its own PCIe link, siblings "
+                            "forward them over NVLink, C tiles return device->host per GPU (csrc/multi_gemm.cu)" % world)}
+            # the reference's real miss path is plain malloc'd memory (runtime-mem.hpp:84-112), and its hit path a calloc'd block
+            # the CPU has just filled: the same call on PAGEABLE host buffers, and on tracked managed buffers at first touch
+            if world == 1:
+                try:
+                    e2e["pageable"] = e2e_pageable(g, n, nA, nB, C, flops)
+                    e2e["managed_first_touch"] = e2e_managed_first_touch(g, lib, n, nA, nB, C, flops)
+                except Exception as exc:  # noqa: BLE001
+                    e2e["pageable_error"] = repr(exc)
+            g.set_sync(False)
             del hA, hB, hC, nA, nB, nC
-        torch.cuda.empty_cache()
-        others = {}
-        try:      # the headline line must print whatever happens to a secondary measurement
-            pk = measured_peaks()
-            if probe and probe.get("sustained"):
-                pk["fp64_tflops_probe"] = probe["sustained"]
-            other_routines(g, torch, dev, pk, others)
-        except Exception as exc:  # noqa: BLE001
-            others["error"] = repr(exc)
-        try:
-            others["level1_from_c"] = l1_c_driver(measured_peaks())
-        except BaseException as exc:  # noqa: BLE001  (pytest.skip raises outside Exception)
-            others["level1_from_c"] = {"error": repr(exc)}
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_reference_run(n, args.ksample or cpu_ksample_for_budget(n, 3, 20.0), 2, 1)
-        if cpu:
-            cpu.pop("_seconds", None)
+        if rank == 0:
+            try:
+                lib.b200blas_probe_fp64_tflops.restype = ctypes.c_double
+                lib.b200blas_probe_fp64_tflops.argtypes = [ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
+                burst = ctypes.c_double(0.0)
+                probe = {"sustained": lib.b200blas_probe_fp64_tflops(1.5, ctypes.byref(burst)), "burst": burst.value,
+                         "how": "register-resident mma.sync m16n8k16 f64 (DMMA) loop, 8 warps/SM, 1.5 s, in this process (csrc/probe.cu)"}
+            except Exception as exc:  # noqa: BLE001
+                probe = {"error": repr(exc)}
+        if rank == 0 and not args.no_others:
+            del A, B, C
+            torch.cuda.empty_cache()
+            others = {}
+            try:      # the headline line must print whatever happens to a secondary measurement
+                pk = measured_peaks()
+                if probe and probe.get("sustained"):
+                    pk["fp64_tflops_probe"] = probe["sustained"]
+                if world == 1:
+                    other_routines(g, torch, dev, pk, others)
+                else:
+                    other_routines_partitioned(g, lib, torch, dev, pk, others, world)
+            except Exception as exc:  # noqa: BLE001
+                others["error"] = repr(exc)
+            if world == 1:
+                try:
+                    others["level1_from_c"] = l1_c_driver(measured_peaks())
+                except BaseException as exc:  # noqa: BLE001  (pytest.skip raises outside Exception)
+                    others["level1_from_c"] = {"error": repr(exc)}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            cpu = cpu_reference_run(n, args.ksample or cpu_ksample_for_budget(n, 3, 20.0), 2, 1)
+            if cpu:
+                cpu.pop("_seconds", None)
 
     if rank == 0:
         peaks = measured_peaks()
+        per_gpu = flops / (kernel_ms * 1e-3) / 1e12 if world == 1 else value / world
         line = {"metric": "dgemm_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": {"workload": workload, "parallelism": parallelism, "variant": variant,
                                                 "l2": "no flush needed: A+B+C = %.1f GB >> 126 MB L2" % (3 * 8.0 * n * n / 1e9)},
-                "roofline": {"bound": "tensor", "achieved": flops / world / (kernel_ms * 1e-3) / 1e12 if world == 1 else value / world,
-                             "peak": FP64_PEAK_NOMINAL, "unit": "TFLOP/s",
-                             "frac": (flops / (kernel_ms * 1e-3) / 1e12 if world == 1 else value / world) / FP64_PEAK_NOMINAL,
-                             "traffic": None,
-                             "peak_source": "FP64 tensor (DMMA) pipe: nominal 148 SM x 128 flop/clk x 1.965 GHz = 37.2; measured DMMA-only loop %.2f "
-                                            "(profiles/r01_probe_peaks_b200.txt); MEASURED_PEAKS.json has no FP64 entry (bf16 %.0f, HBM %.0f GB/s)"
-                                            % (FP64_PEAK_MEASURED, peaks.get("bf16_tflops", 0), peaks.get("hbm_gbs", 0)),
-                             "kernel_ms": kernel_ms,
-                             "peak_measured_in_process": probe,
-                             "frac_of_measured": ((flops / (kernel_ms * 1e-3) / 1e12 if world == 1 else value / world) / probe["sustained"])
-                             if probe and probe.get("sustained") else None},
+                "roofline": {"bound": "tensor", "achieved": per_gpu, "peak": FP64_PEAK_NOMINAL, "unit": "TFLOP/s",
+                             "frac": per_gpu / FP64_PEAK_NOMINAL, "traffic": None,
+                             "peak_source": "FP64 tensor (DMMA) pipe: nominal 148 SM x 128 flop/clk x 1.965 GHz = 37.2 (per GPU); MEASURED_PEAKS.json has no "
+                                            "FP64 entry (bf16 %.0f, HBM %.0f GB/s), so the ceiling is also measured in this process (peak_measured_in_process)"
+                                            % (peaks.get("bf16_tflops", 0), peaks.get("hbm_gbs", 0)),
+                             "kernel_ms": kernel_ms, "peak_measured_in_process": probe,
+                             "frac_of_measured": (per_gpu / probe["sustained"]) if probe and probe.get("sustained") else None},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "others": others}
         tr = traffic_from_profile()
         if tr and world == 1:
@@ -547,8 +624,11 @@ def main():
             line["roofline"]["traffic_source"] = tr["source"]
         if verified is not None:
             line["verified"] = verified
+        if mg is not None:
+            line["partitioned"] = mg
         print(json.dumps(line))
     if world > 1:
+        sync_all()
         dist.destroy_process_group()
     return 0
 

@@ -21,6 +21,7 @@
 #include "gemm_generic.cuh"
 #include "runtime.h"
 #include <cstdlib>
+#include <cstdio>
 
 namespace b200 {
 
@@ -57,10 +58,12 @@ struct DgemmParams {
 
 __device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch) {
     uint32_t v;
-    for (;;) {
+    for (uint32_t spins = 0;; spins++) {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if (v >= epoch) break;
         __nanosleep(200);
+        // bounded (~10 s): a panel piece that never arrives is a protocol error -- trap instead of hanging the GPU
+        if (spins > (1u << 25)) { printf("b200blas: dgemm panel flag timeout (block %d, flag %p = %u, epoch %u)\n", blockIdx.x, flag, v, epoch); __trap(); }
     }
     asm volatile("fence.proxy.async;" ::: "memory");   // order the async-proxy (TMA) reads after the acquire
 }

@@ -28,9 +28,21 @@ def _torchrun(n, script, *args, timeout=900):
 def test_tiled_dgemm_p2p_push_two_gpus():
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
-    lines = _torchrun(2, "bench.py", "--gpus", "2", "--steps", "2", "--warmup", "1", "--size", "4096", "--verify")
+    lines = _torchrun(2, "bench.py", "--gpus", "2", "--steps", "2", "--warmup", "1", "--size", "4096", "--mode", "ipc")
     assert lines and lines[-1]["n_gpus"] == 2 and lines[-1]["verified"]["max_abs_diff_vs_1gpu"] == 0.0
     assert "copy engines" in lines[-1]["config"]["parallelism"]
+
+
+def test_bench_two_gpus_behind_the_symbol():
+    """bench.py --gpus 2 as the driver launches it (torchrun, 2 ranks): rank 0 calls dgemm_ with devices=2; the line must carry the
+    partitioned-path proof, e2e from pinned host buffers, and a result bit-identical to the 1-GPU kernel."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    lines = _torchrun(2, "bench.py", "--gpus", "2", "--steps", "2", "--warmup", "1", "--size", "8192", "--no-others")
+    d = lines[-1]
+    assert d["n_gpus"] == 2 and d["partitioned"]["partitioned_calls"] == 2 and d["partitioned"]["devices"] == 2
+    assert d["verified"]["ok"] and d["verified"]["max_abs_diff_vs_1gpu"] == 0.0
+    assert d["e2e"]["matches_device_result"] and d["e2e"]["max_abs_diff_vs_resident"] == 0.0 and d["e2e"]["h2d_bytes_per_step"] == 2 * 8192 * 8192 * 8
 
 
 def test_partitioned_routines_two_gpus():
