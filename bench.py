@@ -406,6 +406,10 @@ def main():
         local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # In symbol mode rank 0's process drives ALL N GPUs.  An NCCL barrier on the waiting ranks is a kernel that spins on
+        # their GPU until rank 0 arrives and time-slices that GPU with rank 0's DGEMM (measured: 272 ms/step instead of 123 at
+        # N = 2).  So the waiting ranks block on the CPU: barriers and the max-over-ranks reduction go through a gloo group.
+        cpu_group = dist.new_group(backend="gloo") if not legacy else None
     else:
         torch.cuda.set_device(0)
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -417,7 +421,7 @@ def main():
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            dist.barrier(group=cpu_group) if cpu_group is not None else dist.barrier()
 
     verified = None
     e2e = None
@@ -497,8 +501,8 @@ def main():
             per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
             mg1 = mg_stats(lib)
         if world > 1:
-            t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t = torch.tensor([ms_local], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=cpu_group)
             ms_local = t.item()
         ms_per_step = ms_local / args.steps
         value = flops / (ms_per_step * 1e-3) / 1e12

@@ -41,6 +41,9 @@ struct SgemmParams {
     int mask;
     int tiles_m, tiles_n;
     const int* nonfinite;     // set by the split pass when an operand holds Inf/NaN: this kernel stands down, the FFMA tile kernel runs
+    // CGEMM runs on the same kernel as a real product of doubled size (see cgemm_tf32x3): C is then the interleaved (re,im)
+    // matrix viewed as 2m x n floats, rows 2i / 2i+1 = real / imaginary part of complex row i, and beta is complex.
+    int cplx; float beta_im;
 };
 
 // ------------------------------------------------------------------ split pass
@@ -170,8 +173,11 @@ sgemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
     const int m0 = tile_m * SG_BM, n0 = tile_n * BN;
     if (*p.nonfinite) return;                      // Inf/NaN in an operand: the FFMA tile kernel behind this launch does the work
-    if (p.mask == MASK_LOWER && m0 + SG_BM - 1 < n0) return;
-    if (p.mask == MASK_UPPER && n0 + BN - 1 < m0) return;
+    {
+        const int rlo = p.cplx ? (m0 >> 1) : m0, rhi = p.cplx ? ((m0 + SG_BM - 1) >> 1) : (m0 + SG_BM - 1);    // rows in C's own (complex) index space
+        if (p.mask == MASK_LOWER && rhi < n0) return;
+        if (p.mask == MASK_UPPER && n0 + BN - 1 < rlo) return;
+    }
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -284,18 +290,24 @@ sgemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             }
         }
         const int64_t row = (int64_t)m0 + 32 * q + lane;
-        const bool beta0 = p.beta == 0.f;
-        if (row < p.m) {
+        const bool beta0 = p.beta == 0.f && p.beta_im == 0.f;
+        const int64_t crow = p.cplx ? (row >> 1) : row;          // row in C's own index space (triangle masks are defined there)
+        const bool imag_row = p.cplx && (row & 1);
 #pragma unroll
-            for (int j = 0; j < HALF; j++) {
-                const int64_t col = (int64_t)n0 + half * HALF + j;
-                if (col < p.n && tri_keep(p.mask, row, col)) {
-                    float* cp = p.C + row + col * p.ldc;
-                    float r = p.alpha * acc[j];
-                    if (!beta0) r = fmaf(p.beta, *cp, r);
-                    *cp = r;
-                }
+        for (int j = 0; j < HALF; j++) {
+            const int64_t col = (int64_t)n0 + half * HALF + j;
+            const bool ok = row < p.m && col < p.n && tri_keep(p.mask, crow, col);
+            float* cp = p.C + row + col * p.ldc;
+            float r = p.alpha * acc[j];
+            if (!beta0) {
+                const float old = ok ? *cp : 0.f;
+                if (p.cplx) {
+                    // complex beta: (re, im) of one element sit in adjacent lanes (rows 2i, 2i+1 of the float view)
+                    const float other = __shfl_xor_sync(0xffffffffu, old, 1);
+                    r += imag_row ? fmaf(p.beta, old, p.beta_im * other) : fmaf(p.beta, old, -p.beta_im * other);
+                } else r = fmaf(p.beta, old, r);
             }
+            if (ok) *cp = r;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -343,7 +355,7 @@ static bool sgemm_tf32x3(cudaStream_t s, int oa, int ob, int m, int n, int k, fl
     if (ob == 0) split_kmajor_kernel<<<dim3((k + 255) / 256, n < 65535 ? n : 65535), 256, 0, s>>>(n, k, B, ldb, bs, bs + (int64_t)n * kpad, kpad, nonfinite);
     else split_transpose_kernel<<<dim3((n + 31) / 32, (k + 31) / 32), 256, 0, s>>>(n, k, B, ldb, bs, bs + (int64_t)n * kpad, kpad, nonfinite);
     SgemmParams p;
-    p.m = m; p.n = n; p.k = k; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.mask = mask; p.tiles_m = p.tiles_n = 0; p.nonfinite = nonfinite;
+    p.m = m; p.n = n; p.k = k; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.mask = mask; p.tiles_m = p.tiles_n = 0; p.nonfinite = nonfinite; p.cplx = 0; p.beta_im = 0.f;
     // tile configuration: option sgemm_cfg=<n> / B200BLAS_SGEMM_CFG override (0: 128x128 BK32 x3, 1: 128x256 BK32 x2, 2: 128x256 BK16 x4)
     static const int cfg_env = getenv("B200BLAS_SGEMM_CFG") ? atoi(getenv("B200BLAS_SGEMM_CFG")) : -1;
     const int64_t sms = sm_count() > 0 ? sm_count() : 148;
@@ -369,6 +381,106 @@ void sgemm_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, float alph
     if (variant == VAR_NONE) variant = ((double)m * n * k >= 256.0 * 256.0 * 256.0 && m >= 64 && n >= 64) ? VAR_TF32X3_TCGEN05 : VAR_GENERIC_TILE;
     if (variant == VAR_TF32X3_TCGEN05 && sgemm_tf32x3(s, op_code(ta), op_code(tb), m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mask)) return;
     gemm_generic_launch<float>(s, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mask);
+}
+
+// ------------------------------------------------------------------ CGEMM on the same tensor-core kernel
+// (reference blas_level3/gemm.cc:181-198 forwards to cublasCgemm; round 1 ran CGEMM on the FFMA tile kernel.)
+// A complex product is a real product of doubled size on the INTERLEAVED result: with C viewed as a 2m x n float matrix
+// (rows 2i / 2i+1 = re / im of complex row i, leading dimension 2*ldc)
+//     C'' = A'' * B'',   A'' (2m x 2k): row 2i = [ Re a(i,:) | -Im a(i,:) ],  row 2i+1 = [ Im a(i,:) | Re a(i,:) ],
+//                        B'' (2k x n) :  column j = [ Re b(:,j) ; Im b(:,j) ],      a = alpha * op(A), b = op(B)
+// -- 8mnk real flops, the same count as the complex product, all of them on tcgen05 (3xTF32 split per real operand).
+// The split pass builds A'' and B'' k-contiguous straight from the interleaved operands (transposes, conjugations and the
+// complex alpha folded in); the GEMM kernel is sgemm_tf32x3_kernel with a complex-beta epilogue (SgemmParams::cplx).
+// src element (r, kk) of op(X): KMAJOR -> src[kk + r*ld] (k contiguous), else src[r + kk*ld] (r contiguous, 32x32 smem transpose)
+template <bool IS_A>
+__device__ __forceinline__ void csplit_emit(cuFloatComplex v, bool conj, bool scale, cuFloatComplex alpha, int64_t r, int kk, int k, float* hi, float* lo,
+                                            int64_t kpad, int* nonfinite) {
+    if (conj) v.y = -v.y;
+    if (scale) v = make_cuFloatComplex(alpha.x * v.x - alpha.y * v.y, alpha.x * v.y + alpha.y * v.x);
+    if (IS_A) {
+        const int64_t b0 = (2 * r) * kpad, b1 = (2 * r + 1) * kpad;
+        split_store(v.x, hi + b0 + kk, lo + b0 + kk, nonfinite);
+        split_store(-v.y, hi + b0 + k + kk, lo + b0 + k + kk, nonfinite);
+        split_store(v.y, hi + b1 + kk, lo + b1 + kk, nonfinite);
+        split_store(v.x, hi + b1 + k + kk, lo + b1 + k + kk, nonfinite);
+    } else {
+        const int64_t b0 = r * kpad;
+        split_store(v.x, hi + b0 + kk, lo + b0 + kk, nonfinite);
+        split_store(v.y, hi + b0 + k + kk, lo + b0 + k + kk, nonfinite);
+    }
+}
+template <bool IS_A>
+__global__ void __launch_bounds__(256) csplit_kmajor_kernel(int rows, int k, const cuFloatComplex* __restrict__ src, int64_t ld, bool conj, bool scale,
+                                                            cuFloatComplex alpha, float* __restrict__ hi, float* __restrict__ lo, int64_t kpad, int* nonfinite) {
+    const int kk = blockIdx.x * 256 + threadIdx.x;
+    if (kk >= k) return;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y)
+        csplit_emit<IS_A>(__ldg(src + kk + (int64_t)r * ld), conj, scale, alpha, r, kk, k, hi, lo, kpad, nonfinite);
+}
+template <bool IS_A>
+__global__ void __launch_bounds__(256) csplit_transpose_kernel(int rows, int k, const cuFloatComplex* __restrict__ src, int64_t ld, bool conj, bool scale,
+                                                               cuFloatComplex alpha, float* __restrict__ hi, float* __restrict__ lo, int64_t kpad, int* nonfinite) {
+    __shared__ cuFloatComplex t[32][33];
+    const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int kk = k0 + ty + 8 * j, r = r0 + tx;
+        t[ty + 8 * j][tx] = (r < rows && kk < k) ? __ldg(src + r + (int64_t)kk * ld) : make_cuFloatComplex(0.f, 0.f);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int r = r0 + ty + 8 * j, kk = k0 + tx;
+        if (r < rows && kk < k) csplit_emit<IS_A>(t[tx][ty + 8 * j], conj, scale, alpha, r, kk, k, hi, lo, kpad, nonfinite);
+    }
+}
+
+static bool cgemm_tf32x3(cudaStream_t s, int oa, int ob, int m, int n, int k, cuFloatComplex alpha, const cuFloatComplex* A, int64_t lda,
+                         const cuFloatComplex* B, int64_t ldb, cuFloatComplex beta, cuFloatComplex* C, int64_t ldc, int mask) {
+    if (!tma_available() || (int64_t)2 * m > 0x7fffffff || (int64_t)2 * k > 0x7fffffff) return false;
+    const int M2 = 2 * m, K2 = 2 * k;
+    const int64_t kpad = ((int64_t)K2 + 3) / 4 * 4;
+    float* as = (float*)ws_alloc((size_t)2 * M2 * kpad * 4);
+    float* bs = (float*)ws_alloc((size_t)2 * n * kpad * 4);
+    int* nonfinite = (int*)ws_alloc(256);
+    B200_CUDA(cudaMemsetAsync(nonfinite, 0, 4, s));
+    const bool scale = !(alpha.x == 1.f && alpha.y == 0.f);
+    float* alo = as + (int64_t)M2 * kpad; float* blo = bs + (int64_t)n * kpad;
+    // op(A) is m x k: 'N' stores it row(m)-contiguous (transpose), 'T'/'C' k-contiguous
+    if (oa == 0) csplit_transpose_kernel<true><<<dim3((m + 31) / 32, (k + 31) / 32), 256, 0, s>>>(m, k, A, lda, false, scale, alpha, as, alo, kpad, nonfinite);
+    else csplit_kmajor_kernel<true><<<dim3((k + 255) / 256, m < 65535 ? m : 65535), 256, 0, s>>>(m, k, A, lda, oa == 2, scale, alpha, as, alo, kpad, nonfinite);
+    // op(B) is k x n: 'N' is k-contiguous per column, 'T'/'C' n-contiguous
+    if (ob == 0) csplit_kmajor_kernel<false><<<dim3((k + 255) / 256, n < 65535 ? n : 65535), 256, 0, s>>>(n, k, B, ldb, false, false, alpha, bs, blo, kpad, nonfinite);
+    else csplit_transpose_kernel<false><<<dim3((n + 31) / 32, (k + 31) / 32), 256, 0, s>>>(n, k, B, ldb, ob == 2, false, alpha, bs, blo, kpad, nonfinite);
+    SgemmParams p;
+    p.m = M2; p.n = n; p.k = K2; p.alpha = 1.f; p.beta = beta.x; p.beta_im = beta.y; p.C = (float*)C; p.ldc = 2 * ldc; p.mask = mask;
+    p.tiles_m = p.tiles_n = 0; p.nonfinite = nonfinite; p.cplx = 1;
+    static const int cfg_env = getenv("B200BLAS_SGEMM_CFG") ? atoi(getenv("B200BLAS_SGEMM_CFG")) : -1;
+    const int64_t sms = sm_count() > 0 ? sm_count() : 148;
+    int cfg = g_opts.sgemm_cfg >= 0 ? g_opts.sgemm_cfg : cfg_env;
+    if (cfg < 0) cfg = ((int64_t)((M2 + 127) / 128) * ((n + 255) / 256) >= sms) ? SG_DEFAULT_WIDE_CFG : 0;
+    bool ok;
+    if (cfg == 1) ok = launch_sg<256, 32, 2>(s, as, bs, kpad, p);
+    else if (cfg == 2) ok = launch_sg<256, 16, 4>(s, as, bs, kpad, p);
+    else ok = launch_sg<128, 32, 3>(s, as, bs, kpad, p);
+    if (!ok) return false;
+    gemm_generic_launch<cuFloatComplex>(s, "NTC"[oa], "NTC"[ob], m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mask, nonfinite);   // runs only if the flag is set
+    last_variant = VAR_TF32X3_TCGEN05;
+    return true;
+}
+
+void cgemm_dev(cudaStream_t s, char ta, char tb, int m, int n, int k, cuFloatComplex alpha, const cuFloatComplex* A,
+               int64_t lda, const cuFloatComplex* B, int64_t ldb, cuFloatComplex beta, cuFloatComplex* C, int64_t ldc,
+               int mask) {
+    if (m <= 0 || n <= 0) return;
+    if (num<cuFloatComplex>::is_zero(alpha) || k <= 0) { scale_matrix<cuFloatComplex>(s, m, n, beta, C, ldc, mask); last_variant = VAR_SCALE_ONLY; return; }
+    // same size rule as SGEMM (in real flops a complex product is 4x a real one of the same shape)
+    int variant = force_variant;
+    if (variant == VAR_NONE) variant = ((double)m * n * k >= 160.0 * 160.0 * 160.0 && m >= 32 && n >= 64) ? VAR_TF32X3_TCGEN05 : VAR_GENERIC_TILE;
+    if (variant == VAR_TF32X3_TCGEN05 && cgemm_tf32x3(s, op_code(ta), op_code(tb), m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mask)) return;
+    gemm_generic_launch<cuFloatComplex>(s, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mask);
 }
 
 #undef mbar_wait

@@ -38,6 +38,8 @@
 #include <mutex>
 #include <vector>
 #include <unistd.h>
+#include <time.h>
+#include <cstdio>
 
 namespace b200 {
 
@@ -230,6 +232,27 @@ template <> struct GemmFn<cuDoubleComplex> { static constexpr auto fn = zgemm_de
 
 MgStats g_mg_stats = {0, 0, 0, 0, 0};
 
+// B200BLAS_MG_TRACE=1: host-side timeline of one partitioned call (when each hop landed, when each device's kernel could start
+// and when it finished), from polling the events -- ~20 us resolution, debugging only.
+namespace {
+struct TraceItem { char label[48]; cudaEvent_t ev; double t_ms; };
+double now_ms() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+void trace_poll(std::vector<TraceItem>& items, double t0) {
+    size_t left = items.size();
+    for (auto& it : items) it.t_ms = -1;
+    while (left) {
+        for (auto& it : items) {
+            if (it.t_ms >= 0) continue;
+            cudaError_t e = cudaEventQuery(it.ev);
+            if (e == cudaSuccess) { it.t_ms = now_ms() - t0; left--; }
+            else if (e != cudaErrorNotReady) { cudaGetLastError(); it.t_ms = 1e9; left--; }
+        }
+    }
+    std::sort(items.begin(), items.end(), [](const TraceItem& a, const TraceItem& b) { return a.t_ms < b.t_ms; });
+    for (auto& it : items) b200_writef(STDERR_FILENO, "mgtrace %9.3f ms  %s\n", it.t_ms, it.label);
+}
+}  // namespace
+
 // Returns false when the call should take the single-GPU path (too small for the grid, mixed residency, no peer access).
 template <typename T>
 bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int64_t lda, const T* b, int64_t ldb, T beta, T* c, int64_t ldc) {
@@ -254,6 +277,18 @@ bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int6
     std::lock_guard<std::mutex> lock(g_mg.mu);
     TrackerGuard guard;
     if (!mg_init(ndev)) return false;
+    static const bool tracing = getenv("B200BLAS_MG_TRACE") != nullptr;
+    std::vector<TraceItem> trace;
+    const double trace_t0 = tracing ? now_ms() : 0.0;
+    auto trace_mark = [&](MgDev& d, cudaStream_t stream, const char* fmt, int a0, int a1, int a2, int a3) {
+        if (!tracing) return;
+        TraceItem it;
+        snprintf(it.label, sizeof it.label, fmt, a0, a1, a2, a3);
+        it.ev = next_event(d);
+        B200_CUDA(cudaEventRecord(it.ev, stream));
+        it.t_ms = -1;
+        trace.push_back(it);
+    };
     MgState& st = g_mg;
     cudaStream_t home_stream = current_stream();
     if (ra == RES_MANAGED) make_resident(a, (size_t)(((nota ? k : m) - 1) * lda + (nota ? m : k)) * es, home_stream);
@@ -324,12 +359,14 @@ bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int6
             // beta != 0 with a detached tile: bring the old C tile in first (same stream, ahead of the kernel)
             B200_CUDA(cudaMemcpy2DAsync(d.ctile, (size_t)g.ldc_t * es, c_home[s], (size_t)ldc * es, (size_t)g.tm * es, (size_t)g.tn, cudaMemcpyDefault, stream));
         }
+        trace_mark(d, stream, "dev %d kernel may start", s, 0, 0, 0);
         if constexpr (fused) {
             if (!g.in_place) dgemm_set_panel_flags(d.flags, (int)mg_a_group(g.tm), d.flags + 2048, (int)mg_b_group(), epoch);
             dgemm_out_dev(stream, ta, tb, (int)g.tm, (int)g.tn, k, alpha, a_ptr(s), a_ld(s), b_ptr(s), b_ld(s), eff_beta, out, ldo, out, ldo, MASK_FULL);
         } else {
             GemmFn<T>::fn(stream, ta, tb, (int)g.tm, (int)g.tn, k, alpha, a_ptr(s), a_ld(s), b_ptr(s), b_ld(s), eff_beta, out, ldo, MASK_FULL);
         }
+        trace_mark(d, stream, "dev %d kernel done", s, 0, 0, 0);
     };
     if (fused)
         for (int s = 0; s < ndev; s++) launch(s, s == 0 ? home_stream : st.dev[s].comp);
@@ -383,6 +420,7 @@ bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int6
         cudaEvent_t ev = next_event(ex);
         B200_CUDA(cudaEventRecord(ev, stream));
         arr(hp.dst, hp.kind, hp.piece) = ev;
+        if (tracing) { TraceItem it; snprintf(it.label, sizeof it.label, "%s piece %d: %d -> %d landed", hp.kind ? "B" : "A", hp.piece, hp.src, hp.dst); it.ev = ev; it.t_ms = -1; trace.push_back(it); }
         if (hp.src < 0) origin_bytes += (unsigned long long)width * height; else forward_bytes += (unsigned long long)width * height;
         if (hp.src < 0 && host_source) __atomic_fetch_add(&g_stats.h2d_bytes, (unsigned long long)(width * height), __ATOMIC_RELAXED);
     }
@@ -417,6 +455,10 @@ bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int6
         }
     }
     for (int s = 1; s < ndev; s++) B200_CUDA(cudaStreamWaitEvent(home_stream, st.dev[s].done, 0));
+    if (tracing) {
+        b200_writef(STDERR_FILENO, "mgtrace enqueue took %.3f ms (%zu hops)\n", now_ms() - trace_t0, plan.size());
+        trace_poll(trace, trace_t0);
+    }
     last_variant = fused ? VAR_DMMA_TMA : last_variant;
     g_mg_stats.calls++; g_mg_stats.devices = ndev; g_mg_stats.origin_bytes += origin_bytes; g_mg_stats.forward_bytes += forward_bytes;
     g_mg_stats.hops += plan.size();
