@@ -181,53 +181,49 @@ __global__ void __launch_bounds__(LEAF_RHS) trsm_leaf_kernel(int nd, int64_t nrh
     const int tid = threadIdx.x;
     const int64_t c0 = (int64_t)blockIdx.x * LEAF_RHS;
     const T zero = num<T>::zero(), one = num<T>::real(1.0);
-    // ---- Meff from the referenced triangle of the stored block (the other triangle is never read) ----
-    // Loads are issued in batches of 8 before any dependent store: a load -> store chain per element would expose one full
-    // memory latency per element (measured: 42 us per leaf of 30720 right-hand sides, against ~5 us of traffic).
-    constexpr int MBATCH = 8;
-    for (int base = tid; base < NBL * NBL; base += LEAF_RHS * MBATCH) {
-        T v[MBATCH];
+    // ---- Meff (referenced triangle only) and the right-hand sides: ALL global loads of a phase are issued before the first
+    // dependent shared-memory store -- a load -> store chain per element exposes one full memory latency per element
+    // (measured: 42 us per leaf of 30720 right-hand sides against ~5 us of traffic), and Meff's loads travel together with the
+    // first half of the right-hand sides so the two latencies overlap. ----
+    constexpr int M_PER = NBL * NBL / LEAF_RHS;      // Meff elements per thread (32 real / 8 complex)
+    constexpr int B_HALF = NBL / 2;                  // right-hand-side elements per thread and half
+    T vm[M_PER], vb[B_HALF];
 #pragma unroll
-        for (int u = 0; u < MBATCH; u++) {
-            const int idx = base + u * LEAF_RHS;
-            const int i = idx % NBL, l = idx / NBL;                  // Meff[i][l]
-            int a = left ? i : l, b = left ? l : i;                  // = op(S)[a][b]
-            if (op != 0) { const int t = a; a = b; b = t; }          // = S[a][b] (conjugated if op == 2)
-            v[u] = zero;
-            if (idx < NBL * NBL && i < nd && l < nd) {
-                if (a == b) { if (!unit) v[u] = S[a + (int64_t)b * lda]; }
-                else if (stored_upper ? a < b : a > b) v[u] = S[a + (int64_t)b * lda];
+    for (int u = 0; u < M_PER; u++) {
+        const int idx = tid + u * LEAF_RHS;
+        const int i = idx % NBL, l = idx / NBL;                  // Meff[i][l]
+        int a = left ? i : l, b = left ? l : i;                  // = op(S)[a][b]
+        if (op != 0) { const int t = a; a = b; b = t; }          // = S[a][b] (conjugated if op == 2)
+        vm[u] = zero;
+        if (i < nd && l < nd) {
+            if (a == b) { if (!unit) vm[u] = S[a + (int64_t)b * lda]; }
+            else if (stored_upper ? a < b : a > b) vm[u] = S[a + (int64_t)b * lda];
+        }
+    }
+    auto rhs_index = [&](int idx, int& i, int& c) { if (left) { i = idx % NBL; c = idx / NBL; } else { c = idx % LEAF_RHS; i = idx / LEAF_RHS; } };
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+#pragma unroll
+        for (int u = 0; u < B_HALF; u++) {
+            int i, c; rhs_index(tid + (h * B_HALF + u) * LEAF_RHS, i, c);
+            vb[u] = zero;
+            if (i < nd && c0 + c < nrhs) vb[u] = left ? B[i + (c0 + c) * ldb] : B[(c0 + c) + (int64_t)i * ldb];
+        }
+        if (h == 0) {
+#pragma unroll
+            for (int u = 0; u < M_PER; u++) {
+                const int idx = tid + u * LEAF_RHS;
+                const int i = idx % NBL, l = idx / NBL;
+                T w = vm[u];
+                if (op == 2) w = num<T>::conj(w);
+                if (i == l) w = (i < nd && !unit) ? tdiv<T>(one, w) : one;      // reciprocal pivot; unit diagonal and identity padding
+                sM[l * NBL + i] = w;
             }
         }
 #pragma unroll
-        for (int u = 0; u < MBATCH; u++) {
-            const int idx = base + u * LEAF_RHS;
-            if (idx >= NBL * NBL) continue;
-            const int i = idx % NBL, l = idx / NBL;
-            T w = v[u];
-            if (op == 2) w = num<T>::conj(w);
-            if (i == l) w = (i < nd && !unit) ? tdiv<T>(one, w) : one;      // reciprocal pivot; unit diagonal and identity padding
-            sM[l * NBL + i] = w;
-        }
-    }
-    // ---- right-hand sides: coalesced along whichever index is contiguous in memory ----
-    constexpr int BBATCH = 16;
-    for (int base = tid; base < NBL * LEAF_RHS; base += LEAF_RHS * BBATCH) {
-        T v[BBATCH];
-#pragma unroll
-        for (int u = 0; u < BBATCH; u++) {
-            const int idx = base + u * LEAF_RHS;
-            int i, c;
-            if (left) { i = idx % NBL; c = idx / NBL; } else { c = idx % LEAF_RHS; i = idx / LEAF_RHS; }
-            v[u] = zero;
-            if (i < nd && c0 + c < nrhs) v[u] = left ? B[i + (c0 + c) * ldb] : B[(c0 + c) + (int64_t)i * ldb];
-        }
-#pragma unroll
-        for (int u = 0; u < BBATCH; u++) {
-            const int idx = base + u * LEAF_RHS;
-            int i, c;
-            if (left) { i = idx % NBL; c = idx / NBL; } else { c = idx % LEAF_RHS; i = idx / LEAF_RHS; }
-            sB[c * (NBL + 1) + i] = num<T>::mul(alpha, v[u]);
+        for (int u = 0; u < B_HALF; u++) {
+            int i, c; rhs_index(tid + (h * B_HALF + u) * LEAF_RHS, i, c);
+            sB[c * (NBL + 1) + i] = num<T>::mul(alpha, vb[u]);
         }
     }
     __syncthreads();

@@ -160,3 +160,27 @@ def test_gemm_partitioned_behind_the_symbol(ndev):
         if key[0] in "dz":      # same kernel, same tile shape, k never split; (SGEMM may pick another tile configuration per device)
             assert r["bit_identical_to_1gpu"], (key, r)
         assert r["padding_untouched"] and r["err"] <= r["bound"], (key, r)
+
+
+@pytest.mark.parametrize("ndev", [2, 8])
+def test_unmodified_c_program_under_preload_uses_all_gpus(ndev, tmp_path):
+    """tests/drivers/dgemm_big.c -- a plain C program that callocs three matrices and calls dgemm_ -- under
+    LD_PRELOAD=libb200blas.so with BLAS2CUDA_OPTIONS=devices=<n>: nothing but the environment changes, the product is
+    partitioned over n GPUs (statistics.csv shows the calls, debug_exec names the path), sampled entries match long-double
+    dot products, and the steady-state call is faster than on one GPU."""
+    if _ngpu() < ndev:
+        pytest.skip("needs %d GPUs" % ndev)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_preload import build_driver, fields, run
+    exe = build_driver("dgemm_big")
+    n = 8192
+    res = {}
+    for nd in (1, ndev):
+        out, err = run(exe, [n, 4], preload=True, cwd=str(tmp_path), timeout=600,
+                       env_extra={"BLAS2CUDA_OPTIONS": "devices=%d;debug_exec" % nd})
+        r = fields([l for l in out.splitlines() if l.startswith("RESULT")][0])
+        assert float(r["max_rel_err"]) < 1e-13, out
+        res[nd] = float(r["best_ms"])
+        if nd > 1:
+            assert "partitioned over %d devices" % nd in err, err[-2000:]
+    assert res[ndev] < res[1] / (1.5 if ndev == 2 else 3.0), res
