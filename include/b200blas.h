@@ -420,6 +420,9 @@ B200_API int b200blas_device_count(void);
 B200_API int b200blas_mg_plan(int ndev, long long m, long long n, int host_source, int* out, int cap);
 B200_API void b200blas_mg_geometry(int ndev, long long m, long long n, int slot, long long* out4);
 B200_API void b200blas_mg_stats(unsigned long long* out5);
+/* The blocked Cholesky workload of BASELINE.json configs[3] (diagonal-block factorisation + DTRSM panel + DSYRK/DGEMM trailing
+ * update, look-ahead 1) as one call over the GPUs selected with devices=<n>: lower factor in place, LAPACK info returned. */
+B200_API int b200blas_cholesky_lower(int n, double* a, long long lda, int nb);
 /* FP64 tensor-pipe (DMMA) ceiling measured in this process: sustained TFLOP/s over ~`seconds` of register-resident mma.sync f64
  * loops (no memory traffic); *burst (may be NULL) = best single launch.  The denominator of bench.py's tensor rooflines. */
 B200_API double b200blas_probe_fp64_tflops(double seconds, double* burst);

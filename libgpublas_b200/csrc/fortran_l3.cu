@@ -245,6 +245,23 @@ void b200blas_mg_geometry(int ndev, long long m, long long n, int slot, long lon
     mg_block_range(m, P, slot / Q, &r0, &r1); mg_block_range(n, Q, slot % Q, &c0, &c1);
     out4[0] = r0; out4[1] = r1; out4[2] = c0; out4[3] = c1;
 }
+// Blocked right-looking Cholesky workload (BASELINE.json configs[3]) in one call: lower factor in place, a on the device /
+// managed; block size nb; runs on `devices=<n>` GPUs (1: look-ahead on one GPU).  Returns LAPACK info.
+int b200blas_cholesky_lower(int n, double* a, long long lda, int nb) {
+    if (n < 0) return -1;
+    if (!a && n > 0) return -2;
+    if (lda < (n > 1 ? n : 1)) return -3;
+    CallScope scope("cholesky_lower");
+    const Residency r = classify(a);
+    if (r == RES_HOST_PINNED || r == RES_HOST_PAGEABLE) {
+        Operand oa(a, n, n, lda, sizeof(double), ACC_INOUT);
+        const int info = multi_cholesky_lower(n, (double*)oa.dev(), oa.ld(), nb, 1);
+        oa.release();
+        return info;
+    }
+    if (r == RES_MANAGED) make_resident(a, (size_t)((int64_t)(n - 1) * lda + n) * 8, current_stream());
+    return multi_cholesky_lower(n, a, lda, nb, g_opts.devices);
+}
 void b200blas_mg_stats(unsigned long long* out5) {
     out5[0] = g_mg_stats.calls; out5[1] = g_mg_stats.devices; out5[2] = g_mg_stats.origin_bytes; out5[3] = g_mg_stats.forward_bytes; out5[4] = g_mg_stats.hops;
 }

@@ -63,6 +63,10 @@ template <typename T> void trmm_dev(cudaStream_t s, char side, char uplo, char t
 template <typename T> void trsm_dev(cudaStream_t s, char side, char uplo, char trans, char diag, int m, int n, T alpha, const T* A,
                                     int64_t lda, T* B, int64_t ldb);
 
+// lower Cholesky factor of an n x n block in place (potrf.cu); *info_dev (device int, zero on entry) receives base + the
+// 1-based index of the first non-positive pivot
+void potrf_lower_dev(cudaStream_t s, int n, double* A, int64_t lda, int* info_dev, int base = 0);
+
 // ---- Level 1 ----  x, y device-accessible; incx/incy are the BLAS increments (may be negative where
 // netlib allows it).  Reductions write their result to `out` (device memory) deterministically:
 // fixed grid, fixed combination order, independent of scheduling.

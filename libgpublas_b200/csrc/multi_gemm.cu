@@ -59,11 +59,11 @@ void mg_block_range(int64_t total, int parts, int idx, int64_t* lo, int64_t* hi)
     if (*hi < *lo) *hi = *lo;
 }
 int64_t mg_a_group(int64_t tm) { return std::max<int64_t>(128, ((tm / 16 + 127) / 128) * 128); }
-int64_t mg_b_group() { return 2048; }
+int64_t mg_b_group() { return 1024; }      // half a band of the kernel's tile schedule (16 tile columns): first tiles start sooner
 
 // Hops of the whole call in issue order.  Positions follow the tile schedule of the GEMM kernel (bands of 16 tile-columns
-// walked down the rows): B band 0, then the A row-groups top to bottom, then the remaining B bands; at every position the
-// grid rows / columns are interleaved so all devices receive their first pieces at the same time.
+// walked down the rows): B piece 0, A row-group 0, B piece 1, then the A row-groups top to bottom, then the remaining B pieces;
+// at every position the grid rows / columns are interleaved so all devices receive their first pieces at the same time.
 std::vector<MgHop> mg_plan(int ndev, int64_t m, int64_t n, bool host_source) {
     int P, Q;
     mg_grid(ndev, &P, &Q);
@@ -104,14 +104,20 @@ std::vector<MgHop> mg_plan(int ndev, int64_t m, int64_t n, bool host_source) {
             if (off < hi - lo) chain(1, q, h, off, std::min<int64_t>(mg_b_group(), hi - lo - off));
         }
     };
-    b_piece(0);
-    for (int64_t g = 0; g < max_ag; g++)
+    auto a_piece = [&](int64_t g) {
         for (int p = 0; p < P; p++) {
             int64_t lo, hi; mg_block_range(m, P, p, &lo, &hi);
             const int64_t ag = mg_a_group(hi - lo), off = g * ag;
             if (hi > lo && off < hi - lo) chain(0, p, (int)g, off, std::min<int64_t>(ag, hi - lo - off));
         }
-    for (int64_t h = 1; h < max_bb; h++) b_piece((int)h);
+    };
+    // the first tiles (tile row 0, tile columns 0..7) need B piece 0 and A row-group 0; the rest of band 0 needs B piece 1;
+    // then the schedule walks down the rows of band 0 (A row-groups in order) before it touches band 1 (B pieces 2, 3, ...)
+    b_piece(0);
+    if (max_ag > 0) a_piece(0);
+    if (max_bb > 1) b_piece(1);
+    for (int64_t g = 1; g < max_ag; g++) a_piece(g);
+    for (int64_t h = 2; h < max_bb; h++) b_piece((int)h);
     return plan;
 }
 
@@ -120,8 +126,8 @@ namespace {
 
 struct MgDev {
     int id = -1;
-    cudaStream_t comp = nullptr, in = nullptr, out = nullptr;
-    cudaStream_t fwd[kMaxDevices] = {};           // one forwarding stream per destination slot
+    cudaStream_t comp = nullptr, in = nullptr, out = nullptr, push = nullptr;
+    cudaStream_t fwd[kMaxDevices] = {};           // one forwarding stream per destination slot (Cholesky's ring and column traffic)
     char* panelA = nullptr; size_t capA = 0;
     char* panelB = nullptr; size_t capB = 0;
     char* ctile = nullptr; size_t capC = 0;
@@ -158,7 +164,7 @@ void ensure_cap(char** p, size_t* cap, size_t need) {
 // brings up `ndev` devices (home first), streams, flag arrays, peer access between every pair; false if the box cannot
 bool mg_init(int ndev) {
     MgState& st = g_mg;
-    if (st.ready && st.ndev == ndev) return true;
+    if (st.ready && st.ndev >= ndev) return true;       // st.ndev: devices brought up so far (callers use their own count)
     if (st.failed) return false;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count < ndev || ndev > kMaxDevices) { cudaGetLastError(); st.failed = true; return false; }
@@ -214,6 +220,17 @@ bool mg_init(int ndev) {
     return true;
 }
 
+// ONE push stream per device for the GEMM's pieces: a single peer copy already saturates the device's NVLink egress
+// (measured 770 GB/s for one stream), and with one stream the pieces leave in exactly the order they were queued -- the
+// order the consumers need them.  (A stream per destination let the copy engines run whole queues one after the other:
+// some devices had all their pieces after 2 ms, others saw their first one after 3.4 ms; profiles/r02e_mg_debug8.txt.)
+cudaStream_t push_stream(MgDev& d) {
+    if (!d.push) {
+        DeviceScope scope(d.id);
+        B200_CUDA(cudaStreamCreateWithFlags(&d.push, cudaStreamNonBlocking));
+    }
+    return d.push;
+}
 cudaStream_t fwd_stream(MgDev& d, int dst_slot) {
     if (!d.fwd[dst_slot]) {
         DeviceScope scope(d.id);
@@ -334,7 +351,7 @@ bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int6
         B200_CUDA(cudaStreamWaitEvent(d.comp, start, 0));
         B200_CUDA(cudaStreamWaitEvent(d.in, start, 0));
         B200_CUDA(cudaStreamWaitEvent(d.out, start, 0));
-        for (int t = 0; t < ndev; t++) if (t != s) B200_CUDA(cudaStreamWaitEvent(fwd_stream(d, t), start, 0));
+        B200_CUDA(cudaStreamWaitEvent(push_stream(d), start, 0));
     }
 
     // ---- compute launches first (DGEMM): the kernels spin on the flags while the copies below are being queued ----
@@ -410,7 +427,7 @@ bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int6
         cudaStream_t stream;
         int exec_slot;            // the device whose stream carries this hop
         if (hp.src < 0 && host_source) { exec_slot = hp.dst; stream = dst.in; }                              // H2D over the receiver's own PCIe link
-        else { exec_slot = hp.src < 0 ? 0 : hp.src; stream = fwd_stream(st.dev[exec_slot], hp.dst); }        // push over NVLink by whoever holds the piece
+        else { exec_slot = hp.src < 0 ? 0 : hp.src; stream = push_stream(st.dev[exec_slot]); }               // push over NVLink by whoever holds the piece
         MgDev& ex = st.dev[exec_slot];
         DeviceScope scope(ex.id);
         if (hp.src >= 0) B200_CUDA(cudaStreamWaitEvent(stream, arr(hp.src, hp.kind, hp.piece), 0));
@@ -446,9 +463,8 @@ bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int6
             B200_CUDA(cudaMemcpy2DAsync(c_home[s], (size_t)ldc * es, d.ctile, (size_t)g.ldc_t * es, (size_t)g.tm * es, (size_t)g.tn, cudaMemcpyDefault, stream));
             if (host_source) __atomic_fetch_add(&g_stats.d2h_bytes, (unsigned long long)(g.tm * g.tn * es), __ATOMIC_RELAXED);
         }
-        // a device's forwarding streams must drain before the call is over too (the next call reuses the panels)
-        for (int t = 0; t < ndev; t++)
-            if (t != s && d.fwd[t]) { cudaEvent_t e = next_event(d); B200_CUDA(cudaEventRecord(e, d.fwd[t])); B200_CUDA(cudaStreamWaitEvent(stream, e, 0)); }
+        // a device's push stream must drain before the call is over too (the next call reuses the panels)
+        { cudaEvent_t e = next_event(d); B200_CUDA(cudaEventRecord(e, push_stream(d))); B200_CUDA(cudaStreamWaitEvent(stream, e, 0)); }
         { cudaEvent_t e = next_event(d); B200_CUDA(cudaEventRecord(e, d.in)); B200_CUDA(cudaStreamWaitEvent(stream, e, 0)); }
         if (s) {
             B200_CUDA(cudaEventRecord(d.done, stream));
@@ -465,6 +481,195 @@ bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int6
     __atomic_fetch_add(&g_stats.hits, host_source ? 0ull : 3ull, __ATOMIC_RELAXED);
     __atomic_fetch_add(&g_stats.misses, host_source ? 3ull : 0ull, __ATOMIC_RELAXED);
     return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Blocked Cholesky WORKLOAD over the devices of the box (BASELINE.json configs[3]: "DSYRK + DTRSM + DGEMM panels, n = 32768,
+// sharded across 8 B200"; SURVEY.md section 8(e) row "Blocked Cholesky").  Round 1 ran this as one process per GPU with NCCL
+// panel broadcasts (cholesky.py: TiledCholesky, 195 ms = 2.4x at N = 8): an NCCL broadcast kernel cannot get SMs while the
+// rank-nb update occupies all of them, so the panel chain serialised.  Here one thread drives every device:
+//   * 1-D block-cyclic ownership of the nb-wide block columns (column J on device J mod N; the home GPU works in place);
+//     the other devices' columns leave the home GPU once, in the order they are needed, under the first steps;
+//   * step J: the owner factors the diagonal block (potrf.cu) and solves the panel below it (trsm_dev) on a HIGH-PRIORITY
+//     stream, so these latency-bound kernels get SMs in between the CTAs of the update running on the same device;
+//   * the panel travels round the ring owner -> owner+1 -> ... in row pieces, each hop a copy-engine push by the device that
+//     has just received the piece (copy engines need no SMs); the next owner is the first to receive it;
+//   * every device applies the rank-nb update (one masked DMMA GEMM per block column: SYRK on the diagonal tile, GEMM
+//     below) to the columns it owns, the next panel's column FIRST (look-ahead 1), then the others;
+//   * a finished column returns to the home allocation as soon as it is factored, under the remaining steps.
+// All ordering is CUDA events; nothing synchronises the host until the info words are read.
+int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
+    if (n <= 0) return 0;
+    int ndev = ndev_req < 1 ? 1 : ndev_req;
+    std::lock_guard<std::mutex> lock(g_mg.mu);
+    TrackerGuard guard;
+    if (!mg_init(ndev > 1 ? ndev : 1)) { ndev = 1; if (!mg_init(1)) fatal("multi_cholesky_lower", __FILE__, __LINE__, "device set-up failed"); }
+    MgState& st = g_mg;
+    cudaStream_t home_stream = current_stream();
+    if (nb < 128) nb = 128;
+    nb = (nb + 127) / 128 * 128;
+    const int NB = (n + nb - 1) / nb;
+    const int64_t ldw = ((int64_t)n + 1) / 2 * 2;
+    auto own = [&](int J) { return J % ndev; };
+    auto loc = [&](int J) { return J / ndev; };
+    static const int piece_rows = getenv("B200BLAS_CHOL_PIECE") ? atoi(getenv("B200BLAS_CHOL_PIECE")) : 4096;
+
+    // ---- per-device storage, streams ----
+    struct CDev { double* W; double* P[2]; int* info; cudaStream_t panel; };
+    static CDev cd[kMaxDevices] = {};
+    static size_t capW[kMaxDevices] = {}, capP[kMaxDevices] = {};
+    cudaEvent_t start;
+    { MgDev& h = st.dev[0]; h.next_event = 0; start = next_event(h); B200_CUDA(cudaEventRecord(start, home_stream)); }
+    for (int d = 0; d < ndev; d++) {
+        MgDev& md = st.dev[d];
+        if (d) md.next_event = 0;
+        DeviceScope scope(md.id);
+        ws_reset();
+        const int ncols = (NB - d + ndev - 1) / ndev;                  // block columns owned by d
+        if (d) {
+            const size_t need = (size_t)ldw * (size_t)ncols * nb * 8;
+            if (need > capW[d]) { if (cd[d].W) B200_CUDA(cudaFree(cd[d].W)); B200_CUDA(cudaMalloc((void**)&cd[d].W, need)); capW[d] = need; }
+        }
+        if (ndev > 1) {
+            const size_t need = (size_t)ldw * nb * 8;
+            if (need > capP[d]) {
+                for (int b = 0; b < 2; b++) { if (cd[d].P[b]) B200_CUDA(cudaFree(cd[d].P[b])); B200_CUDA(cudaMalloc((void**)&cd[d].P[b], need)); }
+                capP[d] = need;
+            }
+        }
+        if (!cd[d].panel) {
+            int lo = 0, hi = 0;
+            B200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            B200_CUDA(cudaStreamCreateWithPriority(&cd[d].panel, cudaStreamNonBlocking, hi));
+        }
+        cd[d].info = (int*)((char*)device_scalar() + 64);
+        B200_CUDA(cudaStreamWaitEvent(md.comp, start, 0));
+        B200_CUDA(cudaStreamWaitEvent(md.out, start, 0));
+        B200_CUDA(cudaStreamWaitEvent(cd[d].panel, start, 0));
+        for (int t = 0; t < ndev; t++) if (t != d) B200_CUDA(cudaStreamWaitEvent(fwd_stream(md, t), start, 0));
+        B200_CUDA(cudaStreamWaitEvent(push_stream(md), start, 0));
+        B200_CUDA(cudaMemsetAsync(cd[d].info, 0, sizeof(int), cd[d].panel));
+    }
+    auto colptr = [&](int d, int J) -> double* { return d == 0 ? a + (int64_t)J * nb * lda : cd[d].W + (int64_t)loc(J) * nb * ldw; };   // element (i, c): [i + c*ld]
+    auto colld = [&](int d) -> int64_t { return d == 0 ? lda : ldw; };
+    auto comp_stream = [&](int d) { return d == 0 ? home_stream : st.dev[d].comp; };
+
+    // ---- distribution: the other devices' block columns (rows on and below the diagonal block) leave home in column order ----
+    std::vector<cudaEvent_t> dist_ev(NB, nullptr), fact_ev(NB, nullptr), col_ready(NB, nullptr);
+    for (int J = 0; J < NB; J++) {
+        const int d = own(J);
+        if (d == 0) continue;
+        const int64_t j = (int64_t)J * nb; const int jb = (int)std::min<int64_t>(nb, n - j);
+        cudaStream_t s = push_stream(st.dev[0]);       // one ordered stream: columns leave in the order the steps need them
+        DeviceScope scope(st.dev[0].id);
+        B200_CUDA(cudaMemcpy2DAsync(colptr(d, J) + j, (size_t)ldw * 8, a + j + j * lda, (size_t)lda * 8, (size_t)(n - j) * 8, (size_t)jb, cudaMemcpyDefault, s));
+        dist_ev[J] = next_event(st.dev[0]);
+        B200_CUDA(cudaEventRecord(dist_ev[J], s));
+    }
+    // used[d][J]: all of device d's updates with panel J are done (its landing buffer J % 2 may be overwritten by panel J + 2)
+    std::vector<cudaEvent_t> used((size_t)ndev * NB, nullptr), arrived((size_t)ndev * NB, nullptr);
+    // last_fwd[d][slot]: the last forward that READS device d's landing buffer `slot` (it must finish before the buffer is refilled)
+    std::vector<cudaEvent_t> last_fwd((size_t)ndev * 2, nullptr);
+
+    auto factor = [&](int J) {
+        const int o = own(J);
+        const int64_t j = (int64_t)J * nb; const int jb = (int)std::min<int64_t>(nb, n - j); const int64_t rest = n - j - jb;
+        MgDev& md = st.dev[o];
+        DeviceScope scope(md.id);
+        cudaStream_t ps = cd[o].panel;
+        if (col_ready[J]) B200_CUDA(cudaStreamWaitEvent(ps, col_ready[J], 0));
+        if (dist_ev[J]) B200_CUDA(cudaStreamWaitEvent(ps, dist_ev[J], 0));
+        double* diag = colptr(o, J) + j;
+        potrf_lower_dev(ps, jb, diag, colld(o), cd[o].info, (int)j);
+        if (rest > 0) trsm_dev<double>(ps, 'R', 'L', 'T', 'N', (int)rest, jb, 1.0, diag, colld(o), diag + jb, colld(o));
+        fact_ev[J] = next_event(md);
+        B200_CUDA(cudaEventRecord(fact_ev[J], ps));
+        if (o != 0) {       // the finished column goes home under the remaining steps
+            B200_CUDA(cudaStreamWaitEvent(md.out, fact_ev[J], 0));
+            B200_CUDA(cudaMemcpy2DAsync(a + j + j * lda, (size_t)lda * 8, diag, (size_t)ldw * 8, (size_t)(n - j) * 8, (size_t)jb, cudaMemcpyDefault, md.out));
+        }
+    };
+
+    factor(0);
+    for (int J = 0; J < NB; J++) {
+        const int o = own(J);
+        const int64_t j = (int64_t)J * nb; const int jb = (int)std::min<int64_t>(nb, n - j); const int64_t rest = n - j - jb;
+        if (rest <= 0) break;
+        const int slot = J & 1;
+        // ---- ring broadcast of panel J (rows below the diagonal block) to the devices that still own columns > J ----
+        int nrecv = std::min(ndev - 1, NB - 1 - J);                   // owners of columns J+1 .. J+nrecv, in ring order
+        for (int64_t r0 = j + jb; r0 < n && nrecv > 0; r0 += piece_rows) {
+            const int64_t rows = std::min<int64_t>(piece_rows, n - r0);
+            const bool last_piece = r0 + piece_rows >= n;
+            int prev = o;
+            cudaEvent_t prev_ev = fact_ev[J];
+            for (int h = 1; h <= nrecv; h++) {
+                const int d = (o + h) % ndev;
+                MgDev& ex = st.dev[prev];
+                DeviceScope scope(ex.id);
+                cudaStream_t s = fwd_stream(ex, d);
+                B200_CUDA(cudaStreamWaitEvent(s, prev_ev, 0));
+                if (J >= 2 && used[(size_t)d * NB + (J - 2)]) B200_CUDA(cudaStreamWaitEvent(s, used[(size_t)d * NB + (J - 2)], 0));
+                if (last_fwd[(size_t)d * 2 + slot]) B200_CUDA(cudaStreamWaitEvent(s, last_fwd[(size_t)d * 2 + slot], 0));
+                const double* src = prev == o ? colptr(o, J) + r0 : cd[prev].P[slot] + r0;
+                const int64_t sld = prev == o ? colld(o) : ldw;
+                B200_CUDA(cudaMemcpy2DAsync(cd[d].P[slot] + r0, (size_t)ldw * 8, src, (size_t)sld * 8, (size_t)rows * 8, (size_t)jb, cudaMemcpyDefault, s));
+                cudaEvent_t ev = next_event(ex);
+                B200_CUDA(cudaEventRecord(ev, s));
+                if (last_piece) arrived[(size_t)d * NB + J] = ev;      // pieces of one (source, destination) pair share a stream: the last implies all
+                if (last_piece && prev != o) last_fwd[(size_t)prev * 2 + slot] = ev;
+                prev = d; prev_ev = ev;
+            }
+        }
+        // ---- rank-nb update of every owned column K > J; the owner of J + 1 takes that column first, then factors it ----
+        for (int h = 0; h < ndev; h++) {
+            const int d = (o + 1 + h) % ndev;                          // next owner first: its look-ahead work is queued earliest
+            MgDev& md = st.dev[d];
+            DeviceScope scope(md.id);
+            cudaStream_t cs = comp_stream(d);
+            bool any = false;
+            for (int K = J + 1; K < NB; K++) {
+                if (own(K) != d) continue;
+                if (!any) {
+                    if (d == o) B200_CUDA(cudaStreamWaitEvent(cs, fact_ev[J], 0));
+                    else B200_CUDA(cudaStreamWaitEvent(cs, arrived[(size_t)d * NB + J], 0));
+                    any = true;
+                }
+                if (J == 0 && dist_ev[K]) B200_CUDA(cudaStreamWaitEvent(cs, dist_ev[K], 0));
+                const int64_t kcol = (int64_t)K * nb; const int kb = (int)std::min<int64_t>(nb, n - kcol);
+                const double* Pn = d == o ? colptr(o, J) : cd[d].P[slot];     // panel J, addressed by global row
+                const int64_t pld = d == o ? colld(o) : ldw;
+                dgemm_dev(cs, 'N', 'T', (int)(n - kcol), kb, jb, -1.0, Pn + kcol, pld, Pn + kcol, pld, 1.0, colptr(d, K) + kcol, colld(d), MASK_LOWER);
+                if (K == J + 1) {
+                    col_ready[K] = next_event(md);
+                    B200_CUDA(cudaEventRecord(col_ready[K], cs));
+                    factor(K);                                         // on this device's high-priority panel stream
+                }
+            }
+            if (any) {
+                cudaEvent_t ev = next_event(md);
+                B200_CUDA(cudaEventRecord(ev, cs));
+                used[(size_t)d * NB + J] = ev;
+            }
+        }
+    }
+    // ---- completion: the caller's stream waits for every stream of every device; then the info words ----
+    int* pin = (int*)pinned_scalar();
+    for (int d = 0; d < ndev; d++) {
+        MgDev& md = st.dev[d];
+        DeviceScope scope(md.id);
+        cudaStream_t cs = comp_stream(d);
+        auto join = [&](cudaStream_t s) { if (!s || s == cs) return; cudaEvent_t e = next_event(md); B200_CUDA(cudaEventRecord(e, s)); B200_CUDA(cudaStreamWaitEvent(cs, e, 0)); };
+        join(cd[d].panel); join(md.out); join(md.push);
+        for (int t = 0; t < ndev; t++) if (t != d) join(md.fwd[t]);
+        B200_CUDA(cudaMemcpyAsync(pin + d, cd[d].info, sizeof(int), cudaMemcpyDeviceToHost, cs));
+        if (d) { B200_CUDA(cudaEventRecord(md.done, cs)); }
+    }
+    for (int d = 1; d < ndev; d++) B200_CUDA(cudaStreamWaitEvent(home_stream, st.dev[d].done, 0));
+    B200_CUDA(cudaStreamSynchronize(home_stream));
+    int info = 0;
+    for (int d = 0; d < ndev; d++) if (pin[d] > 0 && (info == 0 || pin[d] < info)) info = pin[d];
+    return info;
 }
 
 template bool multi_gemm<float>(char, char, int, int, int, float, const float*, int64_t, const float*, int64_t, float, float*, int64_t);

@@ -21,4 +21,7 @@ extern MgStats g_mg_stats;
 template <typename T>
 bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int64_t lda, const T* b, int64_t ldb, T beta, T* c, int64_t ldc);
 
+// Blocked Cholesky workload (lower, in place, `a` device-accessible on the home GPU) over ndev devices; returns LAPACK info.
+int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev);
+
 }  // namespace b200

@@ -111,10 +111,10 @@ static void potrf_rec(cudaStream_t s, int n, double* A, int64_t lda, int base, i
     potrf_rec(s, n2, A22, lda, base + n1, info);
 }
 
-// info_dev: device int, must be zero on entry
-void potrf_lower_dev(cudaStream_t s, int n, double* A, int64_t lda, int* info_dev) {
+// info_dev: device int, must be zero on entry; a failing pivot is reported as base + its 1-based index within the block
+void potrf_lower_dev(cudaStream_t s, int n, double* A, int64_t lda, int* info_dev, int base) {
     if (n <= 0) return;
-    potrf_rec(s, n, A, lda, 0, info_dev);
+    potrf_rec(s, n, A, lda, base, info_dev);
 }
 
 }  // namespace b200

@@ -68,3 +68,42 @@ def test_blocked_cholesky_workload_device_resident(nb):
     R = np.asfortranarray(A0[:k, :k].copy())
     assert load_oracle().ref_dpotrf_lower(ctypes.c_int(k), R.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(k)) == 0
     assert np.abs(L[:k, :k] - np.tril(R)).max() <= 64 * k * EPS * np.abs(R).max()
+
+
+def _chol_call(lib, n, ptr, lda, nb):
+    lib.b200blas_cholesky_lower.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int]
+    lib.b200blas_cholesky_lower.restype = ctypes.c_int
+    return lib.b200blas_cholesky_lower(n, ctypes.c_void_p(ptr), lda, nb)
+
+
+@pytest.mark.parametrize("n,nb", [(3000, 256), (2500, 1024), (1000, 2048), (130, 128)])
+def test_cholesky_workload_single_call(n, nb):
+    """b200blas_cholesky_lower: the whole blocked workload (diagonal-block factorisation, DTRSM panel, masked-GEMM trailing update,
+    look-ahead 1) issued from C++ in one call -- here on one device.  Device-resident and host matrices, ragged last block,
+    rogue padding and the strictly upper triangle untouched; residual ||A - L L^T|| and agreement with OpenBLAS dpotrf_."""
+    import torch
+    lib = g.load()
+    A0 = spd(n, seed=23)
+    lda = n + 2
+    H = np.full((lda, n), -1e10, order="F"); H[:n] = A0
+    H[:n][np.triu_indices(n, 1)] = -7e9
+    # host matrix
+    G = H.copy(order="F")
+    assert _chol_call(lib, n, G.ctypes.data, lda, nb) == 0
+    assert np.array_equal(G[n:], H[n:]) and np.array_equal(G[:n][np.triu_indices(n, 1)], H[:n][np.triu_indices(n, 1)])
+    L = np.tril(G[:n])
+    assert np.linalg.norm(L @ L.T - A0) <= 8 * n * EPS * np.linalg.norm(A0)
+    # device-resident matrix: same bits
+    D = torch.from_numpy(H.ravel(order="F").copy()).cuda()
+    torch.cuda.synchronize()
+    assert _chol_call(lib, n, D.data_ptr(), lda, nb) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(D.cpu().numpy().reshape((lda, n), order="F"), G)
+    ob = load_openblas()
+    if ob is not None:
+        O = H.copy(order="F"); info = ctypes.c_int(0)
+        ob.dpotrf_(ctypes.c_char_p(b"L"), ctypes.byref(ctypes.c_int(n)), O.ctypes.data_as(ctypes.c_void_p), ctypes.byref(ctypes.c_int(lda)), ctypes.byref(info))
+        assert info.value == 0 and np.abs(L - np.tril(O[:n])).max() <= 64 * n * EPS * np.abs(L).max()
+    # not positive definite: LAPACK info = order of the first failing leading minor
+    Bad = H.copy(order="F"); Bad[n // 2 + 3, n // 2 + 3] = -1.0
+    assert _chol_call(lib, n, Bad.ctypes.data, lda, nb) == n // 2 + 4

@@ -184,3 +184,51 @@ def test_unmodified_c_program_under_preload_uses_all_gpus(ndev, tmp_path):
         if nd > 1:
             assert "partitioned over %d devices" % nd in err, err[-2000:]
     assert res[ndev] < res[1] / (1.5 if ndev == 2 else 3.0), res
+
+
+_BODY_CHOL = r'''
+lib.b200blas_cholesky_lower.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int]
+lib.b200blas_cholesky_lower.restype = ctypes.c_int
+torch.cuda.set_device(0)
+res = {}
+for (n, nb) in CASES:
+    A = splitmix_uniform(9, (n, n)); A0 = np.asfortranarray(np.tril(A, -1) + np.tril(A, -1).T + n * np.eye(n))
+    lda = n + 2
+    H = np.full((lda, n), -1e10, order="F"); H[:n] = A0; H[:n][np.triu_indices(n, 1)] = -7e9
+    outs = []
+    for nd in (1, ndev):
+        lib.b200blas_set_options(("devices=%d" % nd).encode())
+        D = torch.from_numpy(H.ravel(order="F").copy()).cuda(); torch.cuda.synchronize()
+        info = lib.b200blas_cholesky_lower(n, ctypes.c_void_p(D.data_ptr()), lda, nb)
+        torch.cuda.synchronize()
+        outs.append((info, D.cpu().numpy().reshape((lda, n), order="F")))
+    (i1, G1), (iN, GN) = outs
+    L = np.tril(GN[:n])
+    x = splitmix_uniform(5, (n,))
+    resid = float(np.linalg.norm(A0 @ x - L @ (L.T @ x)) / (np.linalg.norm(A0) * np.linalg.norm(x)))
+    Bad = H.copy(order="F"); Bad[n // 2 + 3, n // 2 + 3] = -1.0
+    DB = torch.from_numpy(Bad.ravel(order="F").copy()).cuda(); torch.cuda.synchronize()
+    bad_info = lib.b200blas_cholesky_lower(n, ctypes.c_void_p(DB.data_ptr()), lda, nb)
+    res["n=%d nb=%d" % (n, nb)] = {"info": [int(i1), int(iN)], "identical_to_1gpu": bool(np.array_equal(G1, GN)), "resid": resid,
+                                   "untouched": bool(np.array_equal(GN[n:], H[n:]) and np.array_equal(GN[:n][np.triu_indices(n, 1)], H[:n][np.triu_indices(n, 1)])),
+                                   "bad_info": int(bad_info), "bad_expected": n // 2 + 4}
+print(json.dumps(res))
+'''
+
+
+@pytest.mark.parametrize("ndev", [2, 8])
+def test_cholesky_workload_over_the_devices(ndev):
+    """b200blas_cholesky_lower with devices=<n> (BASELINE.json configs[3]): block columns dealt round the devices, panels
+    travelling the ring by copy engine, look-ahead on a high-priority stream.  The factor must equal the 1-device factor bit
+    for bit (same kernels in the same order on every element), leave the upper triangle and the padding alone, satisfy the
+    random-vector residual ||A x - L (L^T x)|| <= 16 n eps ||A|| ||x||, and report a failing minor like LAPACK."""
+    if _ngpu() < ndev:
+        pytest.skip("needs %d GPUs" % ndev)
+    cases = [(4096, 512), (3000, 256), (5000, 1024), (1100, 1024)]
+    res = _devices_run(ndev, "CASES = %r\n" % (cases,) + _BODY_CHOL)
+    for key, r in res.items():
+        n = int(key.split()[0][2:])
+        assert r["info"] == [0, 0] and r["untouched"], (key, r)
+        assert r["resid"] <= 16 * n * 2.0 ** -53, (key, r)
+        assert r["identical_to_1gpu"], (key, r)
+        assert r["bad_info"] == r["bad_expected"], (key, r)
