@@ -165,6 +165,35 @@ def other_routines_partitioned(g, lib, torch, dev, peaks, out, world):
     out["zgemm_8192"] = {"tflops": 8.0 * n ** 3 / ms / 1e9, "ms": ms, "devices": world, "partitioned_calls": mg_stats(lib)[0] - c0,
                          "frac_of_fp64_peak_per_gpu": 8.0 * n ** 3 / ms / 1e9 / world / FP64_PEAK_NOMINAL}
     del A, B, C
+    out.update(cholesky_single_call(lib, torch, dev, world))
+
+
+def cholesky_single_call(lib, torch, dev, world, n=32768):
+    """BASELINE.json configs[3]: the blocked Cholesky workload in one call (b200blas_cholesky_lower, csrc/multi_gemm.cu) on the
+    devices selected with devices=<n>; matrix resident on GPU 0, timed span = distribute + factor + gather, wall clock."""
+    lib.b200blas_cholesky_lower.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int]
+    lib.b200blas_cholesky_lower.restype = ctypes.c_int
+    M = torch.rand((n, n), dtype=torch.float64, device=dev) * 2 - 1
+    M = torch.tril(M, -1); M = M + M.T; M.diagonal().fill_(float(n))
+    W = torch.empty_like(M)
+    x = torch.rand(n, dtype=torch.float64, device=dev)
+    res = {}
+    for nb in ((2048,) if world == 1 else (512, 1024)):
+        best, info = None, 0
+        for _ in range(3):
+            W.copy_(M); torch.cuda.synchronize()
+            t0 = time.perf_counter(); info = lib.b200blas_cholesky_lower(n, ctypes.c_void_p(W.data_ptr()), n, nb); torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        L = torch.triu(W)          # row-major upper == column-major lower
+        r = (M @ x - L.T @ (L @ x)).norm().item() / (M.norm().item() * x.norm().item())
+        cur = {"tflops": n ** 3 / 3.0 / best / 1e12, "ms": best * 1e3, "info": int(info), "nb": nb, "devices": world, "probe_residual": r,
+               "frac_of_fp64_peak_per_gpu": n ** 3 / 3.0 / best / 1e12 / world / FP64_PEAK_NOMINAL,
+               "note": "b200blas_cholesky_lower: diagonal-block factorisation + DTRSM panel + masked-GEMM trailing update, look-ahead 1; flops n^3/3"}
+        if "cholesky_32768_single_call" not in res or cur["ms"] < res["cholesky_32768_single_call"]["ms"]:
+            res["cholesky_32768_single_call"] = cur
+    del M, W
+    return res
 
 
 def l1_c_driver(peaks):
@@ -174,12 +203,14 @@ def l1_c_driver(peaks):
     from test_preload import build_driver, fields, run
     hbm = peaks.get("hbm_gbs", 6553.9)
     exe = build_driver("l1_chain")
-    out, _ = run(exe, [1 << 26, 40], preload=True, timeout=600)
+    out, _ = run(exe, [1 << 26, 40, 1 << 28], preload=True, timeout=600)
     r = dict(kv.split("=", 1) for kv in [l for l in out.splitlines() if l.startswith("GBS")][0].split() if "=" in kv)
     res = {}
-    for k in ("ddot", "daxpy", "dnrm2", "idamax"):
-        res[k + "_2^26"] = {"gbs": float(r[k]), "frac_of_measured_hbm": float(r[k]) / hbm}
-    res["how"] = "C driver (tests/drivers/l1_chain.c) under LD_PRELOAD, calloc'd managed vectors, clock_gettime per call, mean of 39 steady calls"
+    for k, size in (("ddot", "2^26"), ("daxpy", "2^26"), ("dnrm2", "2^26"), ("idamax", "2^28")):
+        res[k + "_" + size] = {"gbs": float(r[k]), "frac_of_measured_hbm": float(r[k]) / hbm}
+    chk = [l for l in out.splitlines() if l.startswith("RESULT")][0]
+    res["how"] = ("C driver (tests/drivers/l1_chain.c) under LD_PRELOAD=libb200blas.so: calloc'd (tracked -> managed) vectors filled by the CPU, "
+                  "clock_gettime around each call at the symbol, mean of 39 steady calls; " + chk)
     return res
 
 
@@ -286,6 +317,7 @@ def other_routines(g, torch, dev, peaks, out):
                              "frac_of_fp64_peak": n ** 3 / 3.0 / best / 1e12 / FP64_PEAK_NOMINAL,
                              "note": "device potrf + dtrsm_ + dsyrk_ through the Fortran symbols; flops n^3/3"}
     del M, W
+    out.update(cholesky_single_call(g.load(), torch, dev, 1))
     # banded / packed Level-2 (csrc/level2_struct.cu): algorithmic bytes = the stored part of the matrix once
     nb, kl, ku = 1 << 22, 63, 64
     ab = torch.rand((nb, kl + ku + 1), dtype=torch.float64, device=dev)       # memory == column-major (kl+ku+1) x nb band storage

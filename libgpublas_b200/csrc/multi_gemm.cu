@@ -555,7 +555,7 @@ int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
     auto comp_stream = [&](int d) { return d == 0 ? home_stream : st.dev[d].comp; };
 
     // ---- distribution: the other devices' block columns (rows on and below the diagonal block) leave home in column order ----
-    std::vector<cudaEvent_t> dist_ev(NB, nullptr), fact_ev(NB, nullptr), col_ready(NB, nullptr);
+    std::vector<cudaEvent_t> dist_ev(NB, nullptr), fact_ev(NB, nullptr), col_ready(NB, nullptr), diag_ready(NB, nullptr);
     for (int J = 0; J < NB; J++) {
         const int d = own(J);
         if (d == 0) continue;
@@ -577,10 +577,11 @@ int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
         MgDev& md = st.dev[o];
         DeviceScope scope(md.id);
         cudaStream_t ps = cd[o].panel;
-        if (col_ready[J]) B200_CUDA(cudaStreamWaitEvent(ps, col_ready[J], 0));
+        if (diag_ready[J]) B200_CUDA(cudaStreamWaitEvent(ps, diag_ready[J], 0));
         if (dist_ev[J]) B200_CUDA(cudaStreamWaitEvent(ps, dist_ev[J], 0));
         double* diag = colptr(o, J) + j;
         potrf_lower_dev(ps, jb, diag, colld(o), cd[o].info, (int)j);
+        if (col_ready[J]) B200_CUDA(cudaStreamWaitEvent(ps, col_ready[J], 0));
         if (rest > 0) trsm_dev<double>(ps, 'R', 'L', 'T', 'N', (int)rest, jb, 1.0, diag, colld(o), diag + jb, colld(o));
         fact_ev[J] = next_event(md);
         B200_CUDA(cudaEventRecord(fact_ev[J], ps));
@@ -639,11 +640,20 @@ int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
                 const int64_t kcol = (int64_t)K * nb; const int kb = (int)std::min<int64_t>(nb, n - kcol);
                 const double* Pn = d == o ? colptr(o, J) : cd[d].P[slot];     // panel J, addressed by global row
                 const int64_t pld = d == o ? colld(o) : ldw;
-                dgemm_dev(cs, 'N', 'T', (int)(n - kcol), kb, jb, -1.0, Pn + kcol, pld, Pn + kcol, pld, 1.0, colptr(d, K) + kcol, colld(d), MASK_LOWER);
+                double* Ck = colptr(d, K) + kcol;
                 if (K == J + 1) {
+                    // look-ahead column: its diagonal block first, so that the factorisation of that block (latency-bound, on
+                    // the high-priority stream) runs underneath the update of the rows below it instead of after it
+                    dgemm_dev(cs, 'N', 'T', kb, kb, jb, -1.0, Pn + kcol, pld, Pn + kcol, pld, 1.0, Ck, colld(d), MASK_LOWER);
+                    diag_ready[K] = next_event(md);
+                    B200_CUDA(cudaEventRecord(diag_ready[K], cs));
+                    const int64_t below = n - kcol - kb;
+                    if (below > 0) dgemm_dev(cs, 'N', 'T', (int)below, kb, jb, -1.0, Pn + kcol + kb, pld, Pn + kcol, pld, 1.0, Ck + kb, colld(d), MASK_FULL);
                     col_ready[K] = next_event(md);
                     B200_CUDA(cudaEventRecord(col_ready[K], cs));
                     factor(K);                                         // on this device's high-priority panel stream
+                } else {
+                    dgemm_dev(cs, 'N', 'T', (int)(n - kcol), kb, jb, -1.0, Pn + kcol, pld, Pn + kcol, pld, 1.0, Ck, colld(d), MASK_LOWER);
                 }
             }
             if (any) {
