@@ -364,6 +364,11 @@ bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int6
     // where slot s computes: straight into the caller's C (peer store / the home tile of a device-resident call) or into its ctile
     auto direct = [&](int s) { return peer_store || (s == 0 && !host_source); };
 
+    // Detached tiles of a fused (DGEMM) call with host-resident C are computed in two column halves: the first half travels
+    // device->host on the device's `out` stream underneath the second half's compute (PCIe is full duplex and the H2D side
+    // is busy with pieces anyway).  Two launches of 6.9 waves each cost 0.2 wave more than one of 13.8; four would cost 2.
+    // returned[s]: how many columns of slot s's tile have already been sent home by launch().
+    int64_t returned[kMaxDevices] = {};
     auto launch = [&](int s, cudaStream_t stream) {
         MgDev& d = st.dev[s];
         const Geo& g = geo[s];
@@ -378,8 +383,21 @@ bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int6
         }
         trace_mark(d, stream, "dev %d kernel may start", s, 0, 0, 0);
         if constexpr (fused) {
-            if (!g.in_place) dgemm_set_panel_flags(d.flags, (int)mg_a_group(g.tm), d.flags + 2048, (int)mg_b_group(), epoch);
-            dgemm_out_dev(stream, ta, tb, (int)g.tm, (int)g.tn, k, alpha, a_ptr(s), a_ld(s), b_ptr(s), b_ld(s), eff_beta, out, ldo, out, ldo, MASK_FULL);
+            const int64_t bg = mg_b_group();
+            const int64_t half = (host_source && !direct(s) && g.tn >= 4 * bg) ? (g.tn / 2) / (2 * bg) * (2 * bg) : 0;     // whole bands of the tile schedule
+            for (int part = 0; part < (half ? 2 : 1); part++) {
+                const int64_t c0 = part ? half : 0, c1 = (half && !part) ? half : g.tn;
+                if (!g.in_place) dgemm_set_panel_flags(d.flags, (int)mg_a_group(g.tm), d.flags + 2048 + c0 / bg, (int)bg, epoch);
+                const T* bp = notb ? b_ptr(s) + c0 * b_ld(s) : b_ptr(s) + c0;
+                dgemm_out_dev(stream, ta, tb, (int)g.tm, (int)(c1 - c0), k, alpha, a_ptr(s), a_ld(s), bp, b_ld(s), eff_beta, out + c0 * ldo, ldo, out + c0 * ldo, ldo, MASK_FULL);
+                if (half && !part) {
+                    cudaEvent_t e = next_event(d);
+                    B200_CUDA(cudaEventRecord(e, stream));
+                    B200_CUDA(cudaStreamWaitEvent(d.out, e, 0));
+                    B200_CUDA(cudaMemcpy2DAsync(c_home[s], (size_t)ldc * es, d.ctile, (size_t)g.ldc_t * es, (size_t)g.tm * es, (size_t)half, cudaMemcpyDefault, d.out));
+                    returned[s] = half;
+                }
+            }
         } else {
             GemmFn<T>::fn(stream, ta, tb, (int)g.tm, (int)g.tn, k, alpha, a_ptr(s), a_ld(s), b_ptr(s), b_ld(s), eff_beta, out, ldo, MASK_FULL);
         }
@@ -460,8 +478,10 @@ bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int6
         cudaStream_t stream = s == 0 ? home_stream : d.comp;
         DeviceScope scope(d.id);
         if (!direct(s) && g.tm > 0 && g.tn > 0) {
-            B200_CUDA(cudaMemcpy2DAsync(c_home[s], (size_t)ldc * es, d.ctile, (size_t)g.ldc_t * es, (size_t)g.tm * es, (size_t)g.tn, cudaMemcpyDefault, stream));
+            const int64_t c0 = returned[s];          // columns [0, c0) went home under the second half's compute
+            B200_CUDA(cudaMemcpy2DAsync(c_home[s] + c0 * ldc, (size_t)ldc * es, (T*)d.ctile + c0 * g.ldc_t, (size_t)g.ldc_t * es, (size_t)g.tm * es, (size_t)(g.tn - c0), cudaMemcpyDefault, stream));
             if (host_source) __atomic_fetch_add(&g_stats.d2h_bytes, (unsigned long long)(g.tm * g.tn * es), __ATOMIC_RELAXED);
+            if (c0) { cudaEvent_t e = next_event(d); B200_CUDA(cudaEventRecord(e, d.out)); B200_CUDA(cudaStreamWaitEvent(stream, e, 0)); }
         }
         // a device's push stream must drain before the call is over too (the next call reuses the panels)
         { cudaEvent_t e = next_event(d); B200_CUDA(cudaEventRecord(e, push_stream(d))); B200_CUDA(cudaStreamWaitEvent(stream, e, 0)); }
@@ -513,6 +533,13 @@ int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
     auto own = [&](int J) { return J % ndev; };
     auto loc = [&](int J) { return J / ndev; };
     static const int piece_rows = getenv("B200BLAS_CHOL_PIECE") ? atoi(getenv("B200BLAS_CHOL_PIECE")) : 4096;
+    static const bool tracing = getenv("B200BLAS_MG_TRACE") != nullptr;
+    std::vector<TraceItem> trace;
+    const double trace_t0 = tracing ? now_ms() : 0.0;
+    auto trace_ev = [&](cudaEvent_t ev, const char* what, int J, int d) {
+        if (!tracing || !ev) return;
+        TraceItem it; snprintf(it.label, sizeof it.label, "J=%d %s (dev %d)", J, what, d); it.ev = ev; it.t_ms = -1; trace.push_back(it);
+    };
 
     // ---- per-device storage, streams ----
     struct CDev { double* W; double* P[2]; int* info; cudaStream_t panel; };
@@ -581,10 +608,12 @@ int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
         if (dist_ev[J]) B200_CUDA(cudaStreamWaitEvent(ps, dist_ev[J], 0));
         double* diag = colptr(o, J) + j;
         potrf_lower_dev(ps, jb, diag, colld(o), cd[o].info, (int)j);
+        if (tracing) { cudaEvent_t e = next_event(md); B200_CUDA(cudaEventRecord(e, ps)); trace_ev(e, "potrf done", J, o); trace_ev(diag_ready[J], "diag ready", J, o); trace_ev(col_ready[J], "column ready", J, o); }
         if (col_ready[J]) B200_CUDA(cudaStreamWaitEvent(ps, col_ready[J], 0));
         if (rest > 0) trsm_dev<double>(ps, 'R', 'L', 'T', 'N', (int)rest, jb, 1.0, diag, colld(o), diag + jb, colld(o));
         fact_ev[J] = next_event(md);
         B200_CUDA(cudaEventRecord(fact_ev[J], ps));
+        trace_ev(fact_ev[J], "panel solved", J, o);
         if (o != 0) {       // the finished column goes home under the remaining steps
             B200_CUDA(cudaStreamWaitEvent(md.out, fact_ev[J], 0));
             B200_CUDA(cudaMemcpy2DAsync(a + j + j * lda, (size_t)lda * 8, diag, (size_t)ldw * 8, (size_t)(n - j) * 8, (size_t)jb, cudaMemcpyDefault, md.out));
@@ -618,6 +647,8 @@ int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
                 cudaEvent_t ev = next_event(ex);
                 B200_CUDA(cudaEventRecord(ev, s));
                 if (last_piece) arrived[(size_t)d * NB + J] = ev;      // pieces of one (source, destination) pair share a stream: the last implies all
+                if (last_piece && h == 1) trace_ev(ev, "panel at next owner", J, d);
+                if (last_piece && h == nrecv) trace_ev(ev, "panel at last device", J, d);
                 if (last_piece && prev != o) last_fwd[(size_t)prev * 2 + slot] = ev;
                 prev = d; prev_ev = ev;
             }
@@ -676,6 +707,7 @@ int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
         if (d) { B200_CUDA(cudaEventRecord(md.done, cs)); }
     }
     for (int d = 1; d < ndev; d++) B200_CUDA(cudaStreamWaitEvent(home_stream, st.dev[d].done, 0));
+    if (tracing) { b200_writef(STDERR_FILENO, "mgtrace cholesky enqueue took %.3f ms\n", now_ms() - trace_t0); trace_poll(trace, trace_t0); }
     B200_CUDA(cudaStreamSynchronize(home_stream));
     int info = 0;
     for (int d = 0; d < ndev; d++) if (pin[d] > 0 && (info == 0 || pin[d] < info)) info = pin[d];
