@@ -178,7 +178,7 @@ def cholesky_single_call(lib, torch, dev, world, n=32768):
     W = torch.empty_like(M)
     x = torch.rand(n, dtype=torch.float64, device=dev)
     res = {}
-    for nb in ((2048,) if world == 1 else (512, 1024)):
+    for nb in ((2048,) if world == 1 else ((1024, 2048) if world == 2 else (256, 512, 1024))):
         best, info = None, 0
         for _ in range(3):
             W.copy_(M); torch.cuda.synchronize()

@@ -533,6 +533,8 @@ int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
     auto own = [&](int J) { return J % ndev; };
     auto loc = [&](int J) { return J / ndev; };
     static const int piece_rows = getenv("B200BLAS_CHOL_PIECE") ? atoi(getenv("B200BLAS_CHOL_PIECE")) : 4096;
+    static const int hold_env = getenv("B200BLAS_CHOL_HOLD") ? atoi(getenv("B200BLAS_CHOL_HOLD")) : -1;
+    const bool hold_updates = hold_env >= 0 ? hold_env != 0 : ndev >= 4;
     static const bool tracing = getenv("B200BLAS_MG_TRACE") != nullptr;
     std::vector<TraceItem> trace;
     const double trace_t0 = tracing ? now_ms() : 0.0;
@@ -683,6 +685,11 @@ int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
                     col_ready[K] = next_event(md);
                     B200_CUDA(cudaEventRecord(col_ready[K], cs));
                     factor(K);                                         // on this device's high-priority panel stream
+                    // With many devices the panel chain (diagonal block, solve, ring) is the critical path and this device's
+                    // other updates are a small share of the step: they wait until the panel is solved, so its ~50 small
+                    // dependent kernels do not queue behind update CTAs (the DGEMM tile owns a whole SM; measured at N = 4:
+                    // potrf(512) 1.25 ms under the update against 0.59 ms alone, profiles/r02h_chol4_trace.txt).
+                    if (hold_updates) B200_CUDA(cudaStreamWaitEvent(cs, fact_ev[K], 0));
                 } else {
                     dgemm_dev(cs, 'N', 'T', (int)(n - kcol), kb, jb, -1.0, Pn + kcol, pld, Pn + kcol, pld, 1.0, Ck, colld(d), MASK_LOWER);
                 }
