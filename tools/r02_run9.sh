@@ -4,6 +4,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 timeout 900 python -m pytest tests/test_level3_gpu.py tests/test_blat3_gpu.py tests/test_cholesky_gpu.py tests/test_preload.py -m gpu -x -q -p no:cacheprovider > $OUT/${TAG}_tests.log 2>&1
 tail -8 $OUT/${TAG}_tests.log
+for CO in 0 1024; do B200BLAS_POTRF_COOP=$CO timeout 100 python tools/chol_parts.py 2>&1 | sed "s/^/potrf_coop<=$CO /"; done | tee $OUT/${TAG}_chol_parts.txt
 for S in 0 1; do B200BLAS_TRSM_SPLIT=$S timeout 100 python tools/trsm_target.py 2>&1 | sed "s/^/split=$S /"; done | tee $OUT/${TAG}_trsm_split.txt
 timeout 200 python tools/chol_perf.py 1 32768 1024,2048 2>&1 | tee $OUT/${TAG}_chol1.txt
 python - <<'PY' 2>&1 | tee gpurun_out/r02i_trsm_shapes.txt
