@@ -596,7 +596,7 @@ int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
         B200_CUDA(cudaEventRecord(dist_ev[J], s));
     }
     // used[d][J]: all of device d's updates with panel J are done (its landing buffer J % 2 may be overwritten by panel J + 2)
-    std::vector<cudaEvent_t> used((size_t)ndev * NB, nullptr), arrived((size_t)ndev * NB, nullptr);
+    std::vector<cudaEvent_t> used((size_t)ndev * NB, nullptr), arrived((size_t)ndev * NB, nullptr), first_arrived((size_t)ndev * NB, nullptr);
     // last_fwd[d][slot]: the last forward that READS device d's landing buffer `slot` (it must finish before the buffer is refilled)
     std::vector<cudaEvent_t> last_fwd((size_t)ndev * 2, nullptr);
 
@@ -649,6 +649,7 @@ int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
                 cudaEvent_t ev = next_event(ex);
                 B200_CUDA(cudaEventRecord(ev, s));
                 if (last_piece) arrived[(size_t)d * NB + J] = ev;      // pieces of one (source, destination) pair share a stream: the last implies all
+                if (r0 == j + jb) first_arrived[(size_t)d * NB + J] = ev;   // the first piece holds the rows of the next diagonal block
                 if (last_piece && h == 1) trace_ev(ev, "panel at next owner", J, d);
                 if (last_piece && h == nrecv) trace_ev(ev, "panel at last device", J, d);
                 if (last_piece && prev != o) last_fwd[(size_t)prev * 2 + slot] = ev;
@@ -665,8 +666,10 @@ int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
             for (int K = J + 1; K < NB; K++) {
                 if (own(K) != d) continue;
                 if (!any) {
+                    // the look-ahead column's diagonal block needs only the first piece (nb <= piece rows); everything else the whole panel
+                    const bool early = K == J + 1 && d != o && nb <= piece_rows;
                     if (d == o) B200_CUDA(cudaStreamWaitEvent(cs, fact_ev[J], 0));
-                    else B200_CUDA(cudaStreamWaitEvent(cs, arrived[(size_t)d * NB + J], 0));
+                    else B200_CUDA(cudaStreamWaitEvent(cs, early ? first_arrived[(size_t)d * NB + J] : arrived[(size_t)d * NB + J], 0));
                     any = true;
                 }
                 if (J == 0 && dist_ev[K]) B200_CUDA(cudaStreamWaitEvent(cs, dist_ev[K], 0));
@@ -680,6 +683,7 @@ int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
                     dgemm_dev(cs, 'N', 'T', kb, kb, jb, -1.0, Pn + kcol, pld, Pn + kcol, pld, 1.0, Ck, colld(d), MASK_LOWER);
                     diag_ready[K] = next_event(md);
                     B200_CUDA(cudaEventRecord(diag_ready[K], cs));
+                    if (d != o) B200_CUDA(cudaStreamWaitEvent(cs, arrived[(size_t)d * NB + J], 0));      // the rows below need the whole panel
                     const int64_t below = n - kcol - kb;
                     if (below > 0) dgemm_dev(cs, 'N', 'T', (int)below, kb, jb, -1.0, Pn + kcol + kb, pld, Pn + kcol, pld, 1.0, Ck + kb, colld(d), MASK_FULL);
                     col_ready[K] = next_event(md);
