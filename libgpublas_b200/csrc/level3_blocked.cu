@@ -327,27 +327,6 @@ void trsm_dev(cudaStream_t s, char side, char uplo, char trans, char diag, int m
     c.trans = op_code(trans) == 0 ? 'N' : (op_code(trans) == 1 ? 'T' : 'C');
     c.A = A; c.lda = lda; c.B = B; c.ldb = ldb;
     const int nd = c.left ? m : n, other = c.left ? n : m;
-    // The right-hand sides are independent, and below the top levels the recursion is a chain of short kernels (leaves and
-    // k <= 256 updates) whose ramps and tails leave SMs idle.  With many right-hand sides the call is therefore run as two
-    // independent halves on two streams, so one half's short kernels fill the gaps of the other's (the large updates lose
-    // nothing: each half still has several waves of tiles).  Only for calls on the thread's own stream (the BLAS entry
-    // points); internal callers that chose a stream themselves (priorities, other devices) keep it.
-    static const int split_env = getenv("B200BLAS_TRSM_SPLIT") ? atoi(getenv("B200BLAS_TRSM_SPLIT")) : 1;
-    int prio = 0;
-    if (split_env && other >= 16384 && nd >= 256 && s == current_stream() && cudaStreamGetPriority(s, &prio) == cudaSuccess && prio >= 0) {   // (a caller's high-priority stream is left alone)
-        const int h1 = (other / 2 + 127) / 128 * 128, h2 = other - h1;
-        cudaStream_t s2 = aux_stream(0);
-        cudaEvent_t fork = pooled_event(62), join = pooled_event(63);
-        B200_CUDA(cudaEventRecord(fork, s));
-        B200_CUDA(cudaStreamWaitEvent(s2, fork, 0));
-        TsCtx<T> c2 = c;
-        c2.s = s2; c2.B = c.left ? B + (int64_t)h1 * ldb : B + h1;
-        trsm_rec(c, alpha, 0, nd, h1);
-        trsm_rec(c2, alpha, 0, nd, h2);
-        B200_CUDA(cudaEventRecord(join, s2));
-        B200_CUDA(cudaStreamWaitEvent(s, join, 0));
-        return;
-    }
     trsm_rec(c, alpha, 0, nd, other);
 }
 template void trsm_dev<float>(cudaStream_t, char, char, char, char, int, int, float, const float*, int64_t, float*, int64_t);

@@ -341,7 +341,7 @@ bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int6
         MgDev& d = st.dev[s];
         if (s) d.next_event = 0;
         DeviceScope scope(d.id);
-        ws_reset();
+        if (s) ws_reset();               // (the home context was reset by the entry point; its workspace may already hold a staged operand)
         const Geo& g = geo[s];
         if (!g.in_place) {
             ensure_cap(&d.panelA, &d.capA, (size_t)g.lda_p * (nota ? k : g.tm) * es);
@@ -553,7 +553,7 @@ int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
         MgDev& md = st.dev[d];
         if (d) md.next_event = 0;
         DeviceScope scope(md.id);
-        ws_reset();
+        if (d) ws_reset();               // (the home context was reset by the entry point; its workspace may already hold a staged operand)
         const int ncols = (NB - d + ndev - 1) / ndev;                  // block columns owned by d
         if (d) {
             const size_t need = (size_t)ldw * (size_t)ncols * nb * 8;
