@@ -544,7 +544,7 @@ int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
     };
 
     // ---- per-device storage, streams ----
-    struct CDev { double* W; double* P[2]; int* info; cudaStream_t panel; };
+    struct CDev { double* W; double* P[2]; int* info; cudaStream_t panel, la; };     // la: look-ahead column updates (high priority)
     static CDev cd[kMaxDevices] = {};
     static size_t capW[kMaxDevices] = {}, capP[kMaxDevices] = {};
     cudaEvent_t start;
@@ -570,11 +570,13 @@ int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
             int lo = 0, hi = 0;
             B200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
             B200_CUDA(cudaStreamCreateWithPriority(&cd[d].panel, cudaStreamNonBlocking, hi));
+            B200_CUDA(cudaStreamCreateWithPriority(&cd[d].la, cudaStreamNonBlocking, hi));
         }
         cd[d].info = (int*)((char*)device_scalar() + 64);
         B200_CUDA(cudaStreamWaitEvent(md.comp, start, 0));
         B200_CUDA(cudaStreamWaitEvent(md.out, start, 0));
         B200_CUDA(cudaStreamWaitEvent(cd[d].panel, start, 0));
+        B200_CUDA(cudaStreamWaitEvent(cd[d].la, start, 0));
         for (int t = 0; t < ndev; t++) if (t != d) B200_CUDA(cudaStreamWaitEvent(fwd_stream(md, t), start, 0));
         B200_CUDA(cudaStreamWaitEvent(push_stream(md), start, 0));
         B200_CUDA(cudaMemsetAsync(cd[d].info, 0, sizeof(int), cd[d].panel));
@@ -599,6 +601,8 @@ int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
     std::vector<cudaEvent_t> used((size_t)ndev * NB, nullptr), arrived((size_t)ndev * NB, nullptr), first_arrived((size_t)ndev * NB, nullptr);
     // last_fwd[d][slot]: the last forward that READS device d's landing buffer `slot` (it must finish before the buffer is refilled)
     std::vector<cudaEvent_t> last_fwd((size_t)ndev * 2, nullptr);
+    std::vector<cudaEvent_t> col_done(NB, nullptr);            // last update of column K so far (event on whichever stream ran it)
+
 
     auto factor = [&](int J) {
         const int o = own(J);
@@ -656,47 +660,57 @@ int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
                 prev = d; prev_ev = ev;
             }
         }
-        // ---- rank-nb update of every owned column K > J; the owner of J + 1 takes that column first, then factors it ----
+        // ---- rank-nb update of every owned column K > J ----
+        // The next panel's column (K = J + 1) is updated on its owner's HIGH-PRIORITY look-ahead stream, not behind that device's
+        // other updates: the compute stream is in order, and at step J it still holds the device's step J-1 updates of its other
+        // columns (measured at N = 8: 2.5 ms per early step instead of ~1.4, profiles/r02k_chol8_trace.txt).  col_done[K] orders the
+        // successive updates of one column across the two streams.
         for (int h = 0; h < ndev; h++) {
             const int d = (o + 1 + h) % ndev;                          // next owner first: its look-ahead work is queued earliest
             MgDev& md = st.dev[d];
             DeviceScope scope(md.id);
             cudaStream_t cs = comp_stream(d);
-            bool any = false;
+            bool any = false, comp_has_panel = false;
+            cudaEvent_t panel_here = d == o ? fact_ev[J] : arrived[(size_t)d * NB + J];
             for (int K = J + 1; K < NB; K++) {
                 if (own(K) != d) continue;
-                if (!any) {
-                    // the look-ahead column's diagonal block needs only the first piece (nb <= piece rows); everything else the whole panel
-                    const bool early = K == J + 1 && d != o && nb <= piece_rows;
-                    if (d == o) B200_CUDA(cudaStreamWaitEvent(cs, fact_ev[J], 0));
-                    else B200_CUDA(cudaStreamWaitEvent(cs, early ? first_arrived[(size_t)d * NB + J] : arrived[(size_t)d * NB + J], 0));
-                    any = true;
-                }
-                if (J == 0 && dist_ev[K]) B200_CUDA(cudaStreamWaitEvent(cs, dist_ev[K], 0));
                 const int64_t kcol = (int64_t)K * nb; const int kb = (int)std::min<int64_t>(nb, n - kcol);
                 const double* Pn = d == o ? colptr(o, J) : cd[d].P[slot];     // panel J, addressed by global row
                 const int64_t pld = d == o ? colld(o) : ldw;
                 double* Ck = colptr(d, K) + kcol;
                 if (K == J + 1) {
-                    // look-ahead column: its diagonal block first, so that the factorisation of that block (latency-bound, on
-                    // the high-priority stream) runs underneath the update of the rows below it instead of after it
-                    dgemm_dev(cs, 'N', 'T', kb, kb, jb, -1.0, Pn + kcol, pld, Pn + kcol, pld, 1.0, Ck, colld(d), MASK_LOWER);
+                    cudaStream_t ls = cd[d].la;
+                    // its diagonal block needs only the first piece of the panel (nb <= piece rows) ...
+                    const bool early = d != o && nb <= piece_rows;
+                    B200_CUDA(cudaStreamWaitEvent(ls, early ? first_arrived[(size_t)d * NB + J] : panel_here, 0));
+                    if (col_done[K]) B200_CUDA(cudaStreamWaitEvent(ls, col_done[K], 0));
+                    if (J == 0 && dist_ev[K]) B200_CUDA(cudaStreamWaitEvent(ls, dist_ev[K], 0));
+                    // ... and goes first, so that its factorisation (panel stream) runs underneath the update of the rows below it
+                    dgemm_dev(ls, 'N', 'T', kb, kb, jb, -1.0, Pn + kcol, pld, Pn + kcol, pld, 1.0, Ck, colld(d), MASK_LOWER);
                     diag_ready[K] = next_event(md);
-                    B200_CUDA(cudaEventRecord(diag_ready[K], cs));
-                    if (d != o) B200_CUDA(cudaStreamWaitEvent(cs, arrived[(size_t)d * NB + J], 0));      // the rows below need the whole panel
+                    B200_CUDA(cudaEventRecord(diag_ready[K], ls));
+                    if (early) B200_CUDA(cudaStreamWaitEvent(ls, panel_here, 0));                        // the rows below need the whole panel
                     const int64_t below = n - kcol - kb;
-                    if (below > 0) dgemm_dev(cs, 'N', 'T', (int)below, kb, jb, -1.0, Pn + kcol + kb, pld, Pn + kcol, pld, 1.0, Ck + kb, colld(d), MASK_FULL);
+                    if (below > 0) dgemm_dev(ls, 'N', 'T', (int)below, kb, jb, -1.0, Pn + kcol + kb, pld, Pn + kcol, pld, 1.0, Ck + kb, colld(d), MASK_FULL);
                     col_ready[K] = next_event(md);
-                    B200_CUDA(cudaEventRecord(col_ready[K], cs));
+                    B200_CUDA(cudaEventRecord(col_ready[K], ls));
+                    col_done[K] = col_ready[K];
                     factor(K);                                         // on this device's high-priority panel stream
                     // With many devices the panel chain (diagonal block, solve, ring) is the critical path and this device's
                     // other updates are a small share of the step: they wait until the panel is solved, so its ~50 small
                     // dependent kernels do not queue behind update CTAs (the DGEMM tile owns a whole SM; measured at N = 4:
                     // potrf(512) 1.25 ms under the update against 0.59 ms alone, profiles/r02h_chol4_trace.txt).
-                    if (hold_updates) B200_CUDA(cudaStreamWaitEvent(cs, fact_ev[K], 0));
-                } else {
-                    dgemm_dev(cs, 'N', 'T', (int)(n - kcol), kb, jb, -1.0, Pn + kcol, pld, Pn + kcol, pld, 1.0, Ck, colld(d), MASK_LOWER);
+                    // (the wait also makes `used` below cover the look-ahead stream's reads of the panel, and gives the compute stream the panel)
+                    B200_CUDA(cudaStreamWaitEvent(cs, hold_updates ? fact_ev[K] : col_ready[K], 0));
+                    any = comp_has_panel = true;
+                    continue;
                 }
+                if (!comp_has_panel) { B200_CUDA(cudaStreamWaitEvent(cs, panel_here, 0)); comp_has_panel = true; }
+                any = true;
+                if (J == 0 && dist_ev[K]) B200_CUDA(cudaStreamWaitEvent(cs, dist_ev[K], 0));
+                dgemm_dev(cs, 'N', 'T', (int)(n - kcol), kb, jb, -1.0, Pn + kcol, pld, Pn + kcol, pld, 1.0, Ck, colld(d), MASK_LOWER);
+                // the column that becomes the look-ahead column of the NEXT step: mark this, its last update on the compute stream
+                if (K == J + 2) { col_done[K] = next_event(md); B200_CUDA(cudaEventRecord(col_done[K], cs)); }
             }
             if (any) {
                 cudaEvent_t ev = next_event(md);
@@ -712,7 +726,7 @@ int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev_req) {
         DeviceScope scope(md.id);
         cudaStream_t cs = comp_stream(d);
         auto join = [&](cudaStream_t s) { if (!s || s == cs) return; cudaEvent_t e = next_event(md); B200_CUDA(cudaEventRecord(e, s)); B200_CUDA(cudaStreamWaitEvent(cs, e, 0)); };
-        join(cd[d].panel); join(md.out); join(md.push);
+        join(cd[d].panel); join(cd[d].la); join(md.out); join(md.push);
         for (int t = 0; t < ndev; t++) if (t != d) join(md.fwd[t]);
         B200_CUDA(cudaMemcpyAsync(pin + d, cd[d].info, sizeof(int), cudaMemcpyDeviceToHost, cs));
         if (d) { B200_CUDA(cudaEventRecord(md.done, cs)); }
