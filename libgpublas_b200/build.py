@@ -1,6 +1,7 @@
 """Build libb200blas.so in-tree with nvcc for sm_100a (no torch extension machinery: the product
 is a plain C-ABI shared object).  Used by __graft_entry__.build() and `python -m libgpublas_b200.build`."""
 import os
+import re
 import subprocess
 import sys
 
@@ -13,6 +14,10 @@ CXX = os.environ.get("CXX", "g++")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+INTERPOSED = ["malloc", "calloc", "realloc", "free", "memalign", "posix_memalign", "aligned_alloc", "valloc", "malloc_usable_size",
+              "pthread_create"]          # csrc/tracker.cpp
 
 
 def sources():
@@ -57,8 +62,15 @@ def build(verbose=False, force=False):
     if failed:
         raise RuntimeError("nvcc failed")
     if procs or not os.path.exists(OUT) or force:
+        # exactly the C ABI of include/b200blas.h plus the allocator interposers leave the library: weak libstdc++ template
+        # instantiations (std::thread, std::vector) must not be visible to -- or interposable by -- the program it is preloaded into
+        hdr = open(os.path.join(os.path.dirname(HERE), "include", "b200blas.h")).read()
+        names = sorted(set(re.findall(r"^B200_API [^;(]*?(\w+)\(", hdr, re.M)) | set(INTERPOSED))
+        vs = os.path.join(OBJDIR, "exports.map")
+        with open(vs, "w") as f:
+            f.write("{\n  global:\n" + "".join("    %s;\n" % n for n in names) + "  local: *;\n};\n")
         # -e: running the .so prints the option help (reference entry.c / meson.build:25)
-        link = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-Xlinker", "--no-undefined", "-Xlinker", "-e,b200blas_entry",
+        link = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-Xlinker", "--no-undefined", "-Xlinker", "-e,b200blas_entry", "-Xlinker", "--version-script=" + vs,
                                                                 "-ldl", "-lpthread", "-cudart", "static"]
         subprocess.check_call(link)
     return OUT

@@ -362,6 +362,7 @@ Operand::Operand(const void* host, int64_t rows, int64_t cols, int64_t ld, size_
       staged_(false), done_(false) {
     if (rows <= 0 || cols <= 0 || host == nullptr) { dev_ = (void*)host; done_ = true; return; }
     Residency r = classify(host);
+    pageable_ = r == RES_HOST_PAGEABLE;
     cudaStream_t s = current_stream();
     if (r == RES_DEVICE || r == RES_MANAGED) {
         dev_ = (void*)host;
@@ -381,7 +382,9 @@ Operand::Operand(const void* host, int64_t rows, int64_t cols, int64_t ld, size_
     if (access & ACC_IN) {
         TrackerGuard guard;
         // one column (every vector, packed matrices): a flat copy -- a 2-D copy's pitch is capped at cudaDeviceProp::memPitch (2 GiB)
-        if (cols == 1) B200_CUDA(cudaMemcpyAsync(dev_, host, (size_t)rows * elem, cudaMemcpyHostToDevice, s));
+        const bool bounce = pageable_ && staged_copy_worthwhile((size_t)rows * cols * elem);     // host_stager.cu
+        if (bounce) staged_copy_2d(dev_, (size_t)dld_ * elem, host, (size_t)ld * elem, (size_t)rows * elem, (size_t)cols, true, s);
+        else if (cols == 1) B200_CUDA(cudaMemcpyAsync(dev_, host, (size_t)rows * elem, cudaMemcpyHostToDevice, s));
         else B200_CUDA(cudaMemcpy2DAsync(dev_, (size_t)dld_ * elem, host, (size_t)ld * elem, (size_t)rows * elem, (size_t)cols,
                                          cudaMemcpyHostToDevice, s));
         __atomic_fetch_add(&g_stats.h2d_bytes, (unsigned long long)(rows * cols * elem), __ATOMIC_RELAXED);
@@ -395,7 +398,9 @@ void Operand::release() {
     done_ = true;
     if (staged_ && (access_ & ACC_OUT)) {
         TrackerGuard guard;
-        if (cols_ == 1 && vec_inc_ > 1 && vec_n_ > 0)   // strided vector: only its own elements go back (see runtime.h)
+        const bool bounce = pageable_ && !(cols_ == 1 && vec_inc_ > 1) && staged_copy_worthwhile((size_t)rows_ * cols_ * elem_);
+        if (bounce) staged_copy_2d((void*)host_, (size_t)ld_ * elem_, dev_, (size_t)dld_ * elem_, (size_t)rows_ * elem_, (size_t)cols_, false, current_stream());
+        else if (cols_ == 1 && vec_inc_ > 1 && vec_n_ > 0)   // strided vector: only its own elements go back (see runtime.h)
             B200_CUDA(cudaMemcpy2DAsync((void*)host_, (size_t)vec_inc_ * elem_, dev_, (size_t)vec_inc_ * elem_, elem_, (size_t)vec_n_,
                                         cudaMemcpyDeviceToHost, current_stream()));
         else if (cols_ == 1) B200_CUDA(cudaMemcpyAsync((void*)host_, dev_, (size_t)rows_ * elem_, cudaMemcpyDeviceToHost, current_stream()));

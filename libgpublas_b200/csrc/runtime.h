@@ -75,6 +75,11 @@ void* armed_scalar(size_t bytes);
 void wait_scalar(const void* slot, size_t bytes, size_t word_bytes);   // word_bytes: size of the stores the kernel makes (4 or 8)
 void* device_scalar();              // 64 B of device memory for scalar results (per thread)
 
+// Pageable host memory <-> device through pinned bounce buffers filled by a pool of host threads (host_stager.cu).  dst/src: `height`
+// rows of `width` bytes.  to_device: returns once everything is queued on `stream`; from device: returns once the data is on the host.
+void staged_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, bool to_device, cudaStream_t stream);
+bool staged_copy_worthwhile(size_t bytes);
+
 enum Access { ACC_IN = 1, ACC_OUT = 2, ACC_INOUT = 3 };
 enum Residency { RES_DEVICE = 0, RES_MANAGED = 1, RES_HOST_PINNED = 2, RES_HOST_PAGEABLE = 3 };
 Residency classify(const void* p);
@@ -103,6 +108,7 @@ public:
 private:
     const void* host_; void* dev_; int64_t rows_, cols_, ld_, dld_; size_t elem_; int access_; bool staged_, done_;
     int64_t vec_n_ = 0, vec_inc_ = 1;
+    bool pageable_ = false;
 };
 struct VecOperand : Operand {
     VecOperand(const void* p, int64_t n, int64_t inc, size_t elem, int access) : Operand(VecTag{}, p, n, inc, elem, access) {}

@@ -22,7 +22,7 @@
 namespace b200 {
 
 struct StagedMat {
-    const char* host; char* dev; int64_t ld, dld, rows, cols; size_t es; bool staged;
+    const char* host; char* dev; int64_t ld, dld, rows, cols; size_t es; bool staged; bool pageable;
 };
 
 static inline StagedMat stage_matrix(const void* p, int64_t rows, int64_t cols, int64_t ld, size_t es, cudaStream_t s) {
@@ -30,6 +30,7 @@ static inline StagedMat stage_matrix(const void* p, int64_t rows, int64_t cols, 
     m.host = (const char*)p; m.rows = rows; m.cols = cols; m.ld = ld; m.es = es;
     const Residency r = classify(p);
     m.staged = !(r == RES_DEVICE || r == RES_MANAGED);
+    m.pageable = r == RES_HOST_PAGEABLE;
     if (m.staged) {
         int64_t per16 = 16 / (int64_t)es; if (per16 < 1) per16 = 1;
         m.dld = (rows + per16 - 1) / per16 * per16;          // TMA-addressable pitch
@@ -49,11 +50,16 @@ static inline void copy_region(const StagedMat& m, int64_t r0, int64_t c0, int64
     TrackerGuard guard;
     const char* h = m.host + (size_t)(r0 + c0 * m.ld) * m.es;
     char* d = m.dev + (size_t)(r0 + c0 * m.dld) * m.es;
+    // pageable memory goes through the pinned bounce ring packed by the host-thread pool (host_stager.cu): the driver's own
+    // staging of a pageable cudaMemcpy2DAsync is one thread at ~11 GB/s
+    const bool bounce = m.pageable && staged_copy_worthwhile((size_t)nr * nc * m.es);
     if (to_device) {
-        B200_CUDA(cudaMemcpy2DAsync(d, (size_t)m.dld * m.es, h, (size_t)m.ld * m.es, (size_t)nr * m.es, (size_t)nc, cudaMemcpyHostToDevice, st));
+        if (bounce) staged_copy_2d(d, (size_t)m.dld * m.es, h, (size_t)m.ld * m.es, (size_t)nr * m.es, (size_t)nc, true, st);
+        else B200_CUDA(cudaMemcpy2DAsync(d, (size_t)m.dld * m.es, h, (size_t)m.ld * m.es, (size_t)nr * m.es, (size_t)nc, cudaMemcpyHostToDevice, st));
         __atomic_fetch_add(&g_stats.h2d_bytes, (unsigned long long)(nr * nc * m.es), __ATOMIC_RELAXED);
     } else {
-        B200_CUDA(cudaMemcpy2DAsync((void*)h, (size_t)m.ld * m.es, d, (size_t)m.dld * m.es, (size_t)nr * m.es, (size_t)nc, cudaMemcpyDeviceToHost, st));
+        if (bounce) staged_copy_2d((void*)h, (size_t)m.ld * m.es, d, (size_t)m.dld * m.es, (size_t)nr * m.es, (size_t)nc, false, st);
+        else B200_CUDA(cudaMemcpy2DAsync((void*)h, (size_t)m.ld * m.es, d, (size_t)m.dld * m.es, (size_t)nr * m.es, (size_t)nc, cudaMemcpyDeviceToHost, st));
         __atomic_fetch_add(&g_stats.d2h_bytes, (unsigned long long)(nr * nc * m.es), __ATOMIC_RELAXED);
     }
     if (g_opts.trace_copy)
@@ -145,12 +151,19 @@ bool gemm_pipelined(GEMM gemm, char ta, char tb, int m, int n, int k, T alpha, c
     copy_b(kL, k - kL, 0, n);
     record(EV_TAIL, h2d);
     wait(s, EV_TAIL);
-    for (int p = 0; p < P; p++) {
-        const int64_t n0 = pb[p]; const int nn = pb[p + 1] - pb[p];
-        gemm(s, ta, tb, m, nn, (int)(k - kL), alpha, a_chunk(kL), A.dld, b_block(kL, n0), B.dld, NCH ? one : beta, c_panel(n0), C.dld, MASK_FULL);
-        record(EV_DONE + p, s);
-        wait(d2h, EV_DONE + p);
-        copy_region(C, 0, n0, m, nn, d2h, false);
+    // (panel p's copy back is issued AFTER panel p+1's multiply has been launched: with pageable memory the copy blocks the host
+    // until the panel is in host memory, and the next multiply must already be running underneath it)
+    for (int p = 0; p <= P; p++) {
+        if (p < P) {
+            const int64_t n0 = pb[p]; const int nn = pb[p + 1] - pb[p];
+            gemm(s, ta, tb, m, nn, (int)(k - kL), alpha, a_chunk(kL), A.dld, b_block(kL, n0), B.dld, NCH ? one : beta, c_panel(n0), C.dld, MASK_FULL);
+            record(EV_DONE + p, s);
+        }
+        if (p > 0) {
+            const int64_t n0 = pb[p - 1]; const int nn = pb[p] - pb[p - 1];
+            wait(d2h, EV_DONE + p - 1);
+            copy_region(C, 0, n0, m, nn, d2h, false);
+        }
     }
     record(EV_END, d2h);
     wait(s, EV_END);      // the call's own stream completes only when C is back: finish_call() then covers everything

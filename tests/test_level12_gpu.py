@@ -342,3 +342,49 @@ def test_level2_more_vs_oracle(p):
         v1 = [np.array([v], dtype=dt) for v in (a, b, 0, 0)]; v2 = [np.array([v], dtype=dt) for v in (a, b, 0, 0)]
         f77(lib, p + "rotg_", *v1); oracle_call(p + "rotg", *v2, restype=None)
         assert np.allclose([v[0] for v in v1], [v[0] for v in v2], rtol=4 * EPS[p])
+
+
+def test_pageable_operands_through_the_bounce_ring():
+    """Pageable host operands of >= 4 MiB travel through pinned bounce slots packed by host threads (csrc/host_stager.cu; the
+    reference's miss path is a whole-array blocking cudaMemcpy, runtime-mem.hpp:84-112).  Covered here: a flat vector larger than
+    one 32 MiB slot (in and in/out), a strided in/out vector (element-wise write-back stays), and a 2-D matrix with an odd leading
+    dimension that needs several slots.  Results must be bit-identical to the same calls on device-resident copies."""
+    import torch
+    lib = g.load()
+    n = (5 << 20) + 3                                     # 40 MiB of doubles: two slot-sized chunks
+    x = splitmix_uniform(91, (n,)); y0 = splitmix_uniform(92, (n,))
+    xd = torch.from_numpy(x).cuda(); yd = torch.from_numpy(y0).cuda()
+    y = y0.copy()
+    s0 = g.stats()
+    f77(lib, "daxpy_", n, -0.37, x, 1, y, 1)
+    s1 = g.stats()
+    f77(lib, "daxpy_", n, -0.37, xd, 1, yd, 1)
+    torch.cuda.synchronize()
+    assert np.array_equal(y, yd.cpu().numpy())
+    assert s1["h2d_bytes"] - s0["h2d_bytes"] == 2 * n * 8 and s1["d2h_bytes"] - s0["d2h_bytes"] == n * 8
+    r = f77(lib, "ddot_", n, x, 1, y, 1, restype=ctypes.c_double)
+    rd = f77(lib, "ddot_", n, xd, 1, yd, 1, restype=ctypes.c_double)
+    assert r == rd
+    # strided in/out vector: the gaps keep their contents
+    m = 700001
+    v0 = splitmix_uniform(93, (1 + (m - 1) * 2,)); v = v0.copy()
+    f77(lib, "dscal_", m, 3.0, v, 2)
+    assert np.array_equal(v[::2], v0[::2] * 3.0) and np.array_equal(v[1::2], v0[1::2])
+    # 2-D: 3000 x 2500 inside lda = 3001 (57 MiB of columns -> several slots), dgemv both ways and dger in place
+    rows, cols, lda = 3000, 2500, 3001
+    A0 = np.asfortranarray(splitmix_uniform(94, (lda, cols))); A = A0.copy(order="F")
+    u = splitmix_uniform(95, (rows,)); w = splitmix_uniform(96, (cols,))
+    Ad = torch.from_numpy(np.ascontiguousarray(A0.T)).cuda()            # row-major (cols, lda) == column-major lda x cols
+    ud = torch.from_numpy(u).cuda(); wd = torch.from_numpy(w).cuda()
+    for trans, nx, ny, xin, xin_d in [("N", cols, rows, w, wd), ("T", rows, cols, u, ud)]:
+        out = np.zeros(ny); outd = torch.zeros(ny, dtype=torch.float64, device="cuda")
+        f77(lib, "dgemv_", trans, rows, cols, 1.0, A, lda, xin, 1, 0.0, out, 1)
+        f77(lib, "dgemv_", trans, rows, cols, 1.0, Ad, lda, xin_d, 1, 0.0, outd, 1)
+        torch.cuda.synchronize()
+        assert np.array_equal(out, outd.cpu().numpy()), trans
+    f77(lib, "dger_", rows, cols, 0.5, u, 1, w, 1, A, lda)
+    f77(lib, "dger_", rows, cols, 0.5, ud, 1, wd, 1, Ad, lda)
+    torch.cuda.synchronize()
+    got_d = Ad.cpu().numpy().T
+    assert np.array_equal(A[:rows], got_d[:rows])
+    assert np.array_equal(A[rows:], A0[rows:])                           # the padding row of lda is not written
