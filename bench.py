@@ -138,7 +138,8 @@ def mg_stats(lib):
 
 
 def other_routines_partitioned(g, lib, torch, dev, peaks, out, world):
-    """SGEMM 16384^3 and ZGEMM 8192^3 through sgemm_/zgemm_ with devices=N (bulk mode: panels land, then the ordinary kernel)."""
+    """SGEMM 16384^3, ZGEMM 8192^3, DSYRK / DTRSM / DTRMM 16384 through the Fortran symbols with devices=N (bulk mode: operands land,
+    then the ordinary kernels), and the Cholesky workload."""
     def timed(fn, reps=3, warm=1):
         for _ in range(warm):
             fn()
@@ -165,6 +166,22 @@ def other_routines_partitioned(g, lib, torch, dev, peaks, out, world):
     out["zgemm_8192"] = {"tflops": 8.0 * n ** 3 / ms / 1e9, "ms": ms, "devices": world, "partitioned_calls": mg_stats(lib)[0] - c0,
                          "frac_of_fp64_peak_per_gpu": 8.0 * n ** 3 / ms / 1e9 / world / FP64_PEAK_NOMINAL}
     del A, B, C
+    # DSYRK 16384^2 x 16384 and DTRSM / DTRMM 16384^2 through dsyrk_ / dtrsm_ / dtrmm_ with devices=N (csrc/multi_level3.cu)
+    n = 16384
+    A = torch.rand((n, n), dtype=torch.float64, device=dev) * 2 - 1
+    C = torch.zeros((n, n), dtype=torch.float64, device=dev)
+    c0 = mg_stats(lib)[0]
+    ms = timed(lambda: g.call("dsyrk_", "L", "N", n, n, 1.0, A, n, 0.0, C, n))
+    out["dsyrk_LN_16384"] = {"tflops": float(n) ** 3 / ms / 1e9, "ms": ms, "devices": world, "partitioned_calls": mg_stats(lib)[0] - c0,
+                             "frac_of_fp64_peak_per_gpu": float(n) ** 3 / ms / 1e9 / world / FP64_PEAK_NOMINAL}
+    T = torch.triu(A).contiguous(); T.mul_(1.0 / n); T.diagonal().fill_(1.0)          # row-major upper == column-major lower, well conditioned
+    for name in ("dtrsm_", "dtrmm_"):
+        C.uniform_(-1, 1)
+        c0 = mg_stats(lib)[0]
+        ms = timed(lambda: g.call(name, "L", "L", "N", "N", n, n, 1.0, T, n, C, n))
+        out[name + "LLNN_16384"] = {"tflops": float(n) ** 3 / ms / 1e9, "ms": ms, "devices": world, "partitioned_calls": mg_stats(lib)[0] - c0,
+                                    "frac_of_fp64_peak_per_gpu": float(n) ** 3 / ms / 1e9 / world / FP64_PEAK_NOMINAL}
+    del A, C, T
     out.update(cholesky_single_call(lib, torch, dev, world))
 
 

@@ -420,6 +420,12 @@ B200_API int b200blas_device_count(void);
 B200_API int b200blas_mg_plan(int ndev, long long m, long long n, int host_source, int* out, int cap);
 B200_API void b200blas_mg_geometry(int ndev, long long m, long long n, int slot, long long* out4);
 B200_API void b200blas_mg_stats(unsigned long long* out5);
+/* ?syrk_, ?trsm_, ?trmm_ with devices=<n> (csrc/multi_level3.cu; reference blas_level3/syrk.cc:43-76, trsm.cc:40-73, trmm.cc:42-79).
+ * b200blas_ml3_strips: the ndev + 1 boundaries of the equal-area strips a partitioned ?syrk_ of order n cuts its triangle into.
+ * b200blas_ml3_plan: hop list as above; which = 0: ?syrk_ row pieces of op(A) (grid index = strip the piece lies in, consumed by
+ * slots 0..strip; offset = global row), which = 1: ?trsm_/?trmm_ column groups of the order-n triangle (consumed by every slot). */
+B200_API void b200blas_ml3_strips(long long n, int ndev, long long* out);
+B200_API int b200blas_ml3_plan(int which, int ndev, long long n, int host_source, int* out, int cap);
 /* The blocked Cholesky workload of BASELINE.json configs[3] (diagonal-block factorisation + DTRSM panel + DSYRK/DGEMM trailing
  * update, look-ahead 1) as one call over the GPUs selected with devices=<n>: lower factor in place, LAPACK info returned. */
 B200_API int b200blas_cholesky_lower(int n, double* a, long long lda, int nb);

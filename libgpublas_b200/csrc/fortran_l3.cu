@@ -81,6 +81,11 @@ void syrk_entry(const char* name, bool cplx, const char* uplo, const char* trans
     if (*n == 0 || ((is0(*alpha) || *k == 0) && is1(*beta))) return;
     CallScope scope(name);
     const bool scale_only = is0(*alpha) || *k == 0;
+    // devices=<n>: equal-area strips of the triangle, one masked GEMM per device (multi_level3.cu)
+    if (!scale_only && g_opts.devices > 1 && multi_syrk<T>(upper ? 'U' : 'L', nota ? 'N' : 'T', *n, *k, *alpha, a, (int64_t)*lda, *beta, c, (int64_t)*ldc)) {
+        log_exec(name, "%c%c n=%d k=%d lda=%d ldc=%d (partitioned over %d devices)", upper ? 'U' : 'L', nota ? 'N' : 'T', *n, *k, *lda, *ldc, g_opts.devices);
+        return;
+    }
     Operand oa(scale_only ? nullptr : a, nrowa, nota ? *k : *n, *lda, sizeof(T), ACC_IN);
     // C is read even when beta == 0: the unreferenced triangle must survive a staged round trip
     Operand oc(c, *n, *n, *ldc, sizeof(T), ACC_INOUT);
@@ -108,6 +113,11 @@ void tr_entry(const char* name, bool solve, const char* side, const char* uplo, 
     if (*m == 0 || *n == 0) return;
     CallScope scope(name);
     const char t = lsame(transa, 'N') ? 'N' : (lsame(transa, 'T') ? 'T' : 'C');
+    // devices=<n>: independent right-hand sides, one block per device (multi_level3.cu)
+    if (g_opts.devices > 1 && multi_trxm<T>(solve, lside ? 'L' : 'R', upper ? 'U' : 'L', t, lsame(diag, 'U') ? 'U' : 'N', *m, *n, *alpha, a, (int64_t)*lda, b, (int64_t)*ldb)) {
+        log_exec(name, "%c%c%c%c m=%d n=%d lda=%d ldb=%d (partitioned over %d devices)", lside ? 'L' : 'R', upper ? 'U' : 'L', t, lsame(diag, 'U') ? 'U' : 'N', *m, *n, *lda, *ldb, g_opts.devices);
+        return;
+    }
     Operand oa(is0(*alpha) ? nullptr : a, nrowa, nrowa, *lda, sizeof(T), ACC_IN);
     Operand ob(b, *m, *n, *ldb, sizeof(T), is0(*alpha) ? ACC_OUT : ACC_INOUT);
     if (solve) trsm_dev<T>(current_stream(), lside ? 'L' : 'R', upper ? 'U' : 'L', t, lsame(diag, 'U') ? 'U' : 'N', *m, *n, *alpha, (const T*)oa.dev(), oa.ld(), (T*)ob.dev(), ob.ld());
@@ -238,6 +248,26 @@ int b200blas_mg_plan(int ndev, long long m, long long n, int host_source, int* o
         w++;
     }
     return w;
+}
+// The same for ?syrk_ (which = 0: row pieces of op(A), n = order of C) and ?trsm_/?trmm_ (which = 1: column groups of the triangle, n = its order)
+int b200blas_ml3_plan(int which, int ndev, long long n, int host_source, int* out, int cap) {
+    const std::vector<MgHop> plan = which == 0 ? ml3_syrk_plan(ndev, n, host_source != 0) : ml3_tri_plan(ndev, n, host_source != 0);
+    int w = 0;
+    for (const MgHop& h : plan) {
+        if (w < cap) {
+            int* o = out + 7 * w;
+            o[0] = h.kind; o[1] = h.gidx; o[2] = h.piece; o[3] = (int)h.off; o[4] = (int)h.len; o[5] = h.src; o[6] = h.dst;
+        }
+        w++;
+    }
+    return w;
+}
+// strip boundaries of a partitioned ?syrk_: out[0..ndev]
+void b200blas_ml3_strips(long long n, int ndev, long long* out) {
+    int64_t b[kMaxDevices + 1];
+    if (ndev < 1 || ndev > kMaxDevices) return;
+    ml3_strips(n, ndev, b);
+    for (int i = 0; i <= ndev; i++) out[i] = b[i];
 }
 void b200blas_mg_geometry(int ndev, long long m, long long n, int slot, long long* out4) {
     int P, Q; mg_grid(ndev, &P, &Q);

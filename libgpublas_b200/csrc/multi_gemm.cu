@@ -33,6 +33,7 @@
 #include "abi_common.h"
 #include "gemm_generic.cuh"
 #include "multi_gemm.h"
+#include "multi_state.h"
 #include <algorithm>
 #include <cmath>
 #include <mutex>
@@ -122,27 +123,7 @@ std::vector<MgHop> mg_plan(int ndev, int64_t m, int64_t n, bool host_source) {
 }
 
 // ---------------------------------------------------------------------------------------------
-namespace {
-
-struct MgDev {
-    int id = -1;
-    cudaStream_t comp = nullptr, in = nullptr, out = nullptr, push = nullptr;
-    cudaStream_t fwd[kMaxDevices] = {};           // one forwarding stream per destination slot (Cholesky's ring and column traffic)
-    char* panelA = nullptr; size_t capA = 0;
-    char* panelB = nullptr; size_t capB = 0;
-    char* ctile = nullptr; size_t capC = 0;
-    uint32_t* flags = nullptr;                    // [0,2048): A row-groups, [2048,4096): B column bands
-    uint32_t* consts = nullptr;                   // consts[v] = v (device copy, for flag writes into a peer)
-    std::vector<cudaEvent_t> events; size_t next_event = 0;
-    cudaEvent_t done = nullptr;
-};
-struct MgState {
-    std::mutex mu;                                // one partitioned call at a time
-    int ndev = 0; bool ready = false, failed = false;
-    MgDev dev[kMaxDevices];
-    uint32_t* host_consts = nullptr;              // pinned: flag writes that follow a host->device copy
-    uint32_t epoch = 0;
-};
+// per-device streams / panels and the process-wide state: multi_state.h (shared with multi_level3.cu)
 MgState g_mg;
 
 cudaEvent_t next_event(MgDev& d) {
@@ -239,12 +220,12 @@ cudaStream_t fwd_stream(MgDev& d, int dst_slot) {
     return d.fwd[dst_slot];
 }
 
+namespace {
 template <typename T> struct GemmFn;
 template <> struct GemmFn<float> { static constexpr auto fn = sgemm_dev; };
 template <> struct GemmFn<double> { static constexpr auto fn = dgemm_dev; };
 template <> struct GemmFn<cuFloatComplex> { static constexpr auto fn = cgemm_dev; };
 template <> struct GemmFn<cuDoubleComplex> { static constexpr auto fn = zgemm_dev; };
-
 }  // namespace
 
 MgStats g_mg_stats = {0, 0, 0, 0, 0};

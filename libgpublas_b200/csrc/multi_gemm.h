@@ -21,6 +21,16 @@ extern MgStats g_mg_stats;
 template <typename T>
 bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int64_t lda, const T* b, int64_t ldb, T beta, T* c, int64_t ldc);
 
+// multi_level3.cu: ?syrk_ on equal-area strips of the triangle, ?trsm_ / ?trmm_ on blocks of independent right-hand sides.  Same
+// contract: false = not partitioned.  (uplo, trans, side, diag already normalised to upper case; trans 'N' | 'T' | 'C'.)
+template <typename T>
+bool multi_syrk(char uplo, char trans, int n, int k, T alpha, const T* a, int64_t lda, T beta, T* c, int64_t ldc);
+template <typename T>
+bool multi_trxm(bool solve, char side, char uplo, char trans, char diag, int m, int n, T alpha, const T* a, int64_t lda, T* b, int64_t ldb);
+void ml3_strips(int64_t n, int ndev, int64_t* bounds);                       // ndev + 1 strip boundaries of equal referenced area
+std::vector<MgHop> ml3_syrk_plan(int ndev, int64_t n, bool host_source);     // row pieces of op(A): gidx = strip, off = global row
+std::vector<MgHop> ml3_tri_plan(int ndev, int64_t na, bool host_source);     // column groups of the triangle: off = first column
+
 // Blocked Cholesky workload (lower, in place, `a` device-accessible on the home GPU) over ndev devices; returns LAPACK info.
 int multi_cholesky_lower(int n, double* a, int64_t lda, int nb, int ndev);
 

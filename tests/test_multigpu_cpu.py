@@ -249,3 +249,107 @@ def test_partitioned_gemm_hop_list_delivers_every_panel_once(ndev, host):
                 r0, r1, c0, c1 = geo[s]
                 C[r0:r1, c0:c1] = panelA[s] @ panelB[s]
             assert np.allclose(C, A @ B, rtol=1e-12, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Partitioned ?syrk_ / ?trsm_ / ?trmm_ behind the symbol (csrc/multi_level3.cu): strip boundaries and hop lists are pure host
+# logic exported by the library; executed here as numpy copies, with the per-device work done by numpy (test infrastructure).
+def _ml3_plan(lib, which, ndev, n, host):
+    cap = 8192
+    buf = (ctypes.c_int * (7 * cap))()
+    cnt = lib.b200blas_ml3_plan(which, ndev, ctypes.c_longlong(n), int(host), buf, cap)
+    assert 0 <= cnt <= cap
+    return [tuple(buf[7 * i + j] for j in range(7)) for i in range(cnt)]
+
+
+def _ml3_strips(lib, n, ndev):
+    out = (ctypes.c_longlong * (ndev + 1))()
+    lib.b200blas_ml3_strips(ctypes.c_longlong(n), ndev, out)
+    return list(out)
+
+
+@pytest.mark.parametrize("ndev", [2, 3, 4, 8])
+@pytest.mark.parametrize("host", [False, True])
+def test_partitioned_syrk_strips_and_hop_list(ndev, host):
+    import libgpublas_b200 as g
+    lib = g.load()
+    for n in [1024 * ndev, 16384, 8192 + 77]:
+        b = _ml3_strips(lib, n, ndev)
+        assert b[0] == 0 and b[-1] == n and all(b[i] < b[i + 1] for i in range(ndev))
+        assert all(v % 128 == 0 for v in b[:-1])
+        # referenced elements per strip (lower: column j holds n - j of them): equal shares within the rounding to whole CTA tiles
+        area = [(b[s + 1] - b[s]) * n - (b[s + 1] * (b[s + 1] - 1) - b[s] * (b[s] - 1)) // 2 for s in range(ndev)]
+        assert sum(area) == n * (n + 1) // 2
+        if n >= 16384:
+            assert max(area) <= 1.08 * (sum(area) / ndev), area
+        plan = _ml3_plan(lib, 0, ndev, n, host)
+        k = 8
+        rng = np.random.default_rng(n + ndev)
+        A = rng.standard_normal((n, k))
+        panel = [np.full((n - b[s], k), np.nan) for s in range(ndev)]
+        if not host:
+            panel[0][:] = A
+        have, origin, fwd = set(), 0, 0
+        first_dst = []
+        for (kind, strip, piece, off, ln, src, dst) in plan:
+            assert kind == 0 and dst <= strip, "only devices 0..strip consume a piece of that strip"
+            assert b[strip] <= off and off + ln <= b[strip + 1]
+            assert (dst, piece) not in have
+            assert not (dst == 0 and not host)
+            if src >= 0:
+                assert (src, piece) in have, "forwarded before it arrived"
+                blk = panel[src][off - b[src]:off - b[src] + ln]; fwd += blk.size
+            else:
+                blk = A[off:off + ln]; origin += blk.size
+                first_dst.append(dst)
+            assert not np.isnan(blk).any()
+            panel[dst][off - b[dst]:off - b[dst] + ln] = blk
+            have.add((dst, piece))
+        for s in range(ndev):
+            assert np.array_equal(panel[s], A[b[s]:]), (ndev, host, s)
+        # each row leaves the origin once (device-resident: rows of strip 0 never leave -- only the home GPU uses them)
+        assert origin == (A.size if host else (n - b[1]) * k)
+        assert origin + fwd == sum((n - b[s]) * k for s in range(0 if host else 1, ndev))
+        # the last strip is queued first: the device with the shortest panel starts first
+        assert plan[0][1] == ndev - 1
+        if ndev >= 4:
+            assert len(set(first_dst)) >= ndev - 1, "first receivers rotate over the devices"
+        # lower and upper triangles assembled from the per-device trapezoids
+        if n > 9000:
+            continue
+        full = A @ A.T
+        L = np.zeros((n, n)); U = np.zeros((n, n))
+        for s in range(ndev):
+            w = b[s + 1] - b[s]
+            P = panel[s]
+            L[b[s]:, b[s]:b[s + 1]] = np.tril(P @ P[:w].T)
+            U[b[s]:b[s + 1], b[s]:] = np.triu(P[:w] @ P.T)
+        assert np.allclose(L, np.tril(full), rtol=1e-12, atol=1e-12) and np.allclose(U, np.triu(full), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("ndev", [2, 3, 4, 8])
+@pytest.mark.parametrize("host", [False, True])
+def test_partitioned_triangular_hop_list(ndev, host):
+    """?trsm_/?trmm_: every device receives the referenced trapezoid of every column group of A exactly once."""
+    import libgpublas_b200 as g
+    lib = g.load()
+    for na in [2048, 8192, 5000]:
+        plan = _ml3_plan(lib, 1, ndev, na, host)
+        have = set()
+        cols = [np.zeros(na, dtype=np.int32) for _ in range(ndev)]
+        origin_cols = 0
+        firsts = []
+        for (kind, gidx, piece, off, ln, src, dst) in plan:
+            assert 0 <= off and off + ln <= na and ln > 0
+            assert (dst, piece) not in have and not (dst == 0 and not host)
+            if src >= 0:
+                assert (src, piece) in have
+            else:
+                origin_cols += ln; firsts.append(dst)
+            cols[dst][off:off + ln] += 1
+            have.add((dst, piece))
+        for s in range(0 if host else 1, ndev):
+            assert (cols[s] == 1).all()
+        assert origin_cols == na, "A leaves its origin once"
+        if ndev >= 3:
+            assert len(set(firsts)) == (ndev if host else ndev - 1)

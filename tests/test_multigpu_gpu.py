@@ -162,6 +162,122 @@ def test_gemm_partitioned_behind_the_symbol(ndev):
         assert r["padding_untouched"] and r["err"] <= r["bound"], (key, r)
 
 
+_BODY_L3 = r"""
+def mg_stats():
+    buf = (ctypes.c_ulonglong * 5)(); lib.b200blas_mg_stats(buf); return list(buf)
+res = {}
+lib.b200blas_set_options(b"multi_min=1024;pipeline_min=1000000000000")
+torch.cuda.set_device(0)
+def place(X, where, dt):
+    # returns (argument for f77, function that reads the array back)
+    flat = np.ascontiguousarray(X.ravel(order="F").view(np.float64 if dt in (np.float64, np.complex128) else np.float32))
+    if where == "device":
+        t = torch.from_numpy(flat.copy()).cuda(); torch.cuda.synchronize()
+        return t, lambda: (torch.cuda.synchronize(), t.cpu().numpy().view(dt).reshape(X.shape, order="F"))[1]
+    if where == "pinned":
+        t = torch.from_numpy(flat.copy()).pin_memory()
+        return t, lambda: t.numpy().view(dt).reshape(X.shape, order="F").copy(order="F")
+    H = np.array(X, order="F")
+    return H, lambda: H
+for case in CASES:
+    p = case[1]; where = case[-1]
+    dt = {"d": np.float64, "s": np.float32, "z": np.complex128, "c": np.complex64}[p]
+    hi = np.complex128 if p in "cz" else np.float64
+    eps = 2.0 ** -53 if p in "dz" else 2.0 ** -24
+    outs = []
+    if case[0] == "syrk":
+        _, _, uplo, trans, n, k, alpha, beta, _ = case
+        ra, ca = (n, k) if trans == "N" else (k, n)
+        lda, ldc = ra + 2, n + 6
+        A = splitmix_uniform(81, (lda, ca), dt); C0 = splitmix_uniform(82, (ldc, n), dt)
+        for nd in (1, ndev):
+            lib.b200blas_set_options(("devices=%d" % nd).encode())
+            s0 = mg_stats()
+            a_arg, _ = place(A, where, dt); c_arg, c_read = place(C0, where, dt)
+            f77(lib, p + "syrk_", uplo, trans, n, k, alpha, a_arg, lda, beta, c_arg, ldc)
+            outs.append((np.array(c_read(), order="F"), mg_stats()[0] - s0[0]))
+        (C1, calls1), (CN, callsN) = outs
+        opA = A[:ra, :ca].astype(hi); opA = opA if trans == "N" else opA.T
+        full = alpha * (opA @ opA.T) + beta * C0[:n].astype(hi)
+        tri = np.tril if uplo == "L" else np.triu
+        other = (np.triu_indices(n, 1) if uplo == "L" else np.tril_indices(n, -1))
+        err = float(np.linalg.norm(tri(CN[:n].astype(hi) - full)))
+        bound = 4 * (k + 2) * eps * (abs(alpha) * float(np.linalg.norm(opA)) ** 2 + abs(beta) * float(np.linalg.norm(C0[:n])))
+        untouched = bool(np.array_equal(CN[n:], C0[n:]) and np.array_equal(CN[:n][other], C0[:n][other]))
+        close = float(np.abs(tri(CN[:n].astype(hi) - C1[:n].astype(hi))).max())
+    else:
+        kind, _, side, uplo, trans, diag, m, n, alpha, _ = case
+        na = m if side == "L" else n
+        lda, ldb = na + 2, m + 6
+        A = splitmix_uniform(83, (lda, na), dt)
+        A[:na] = A[:na] / na + np.eye(na, dtype=dt) * (1.0 if diag == "U" else 2.0)          # well conditioned; the unit diagonal is implicit for diag = U
+        if diag == "U":
+            A[:na][np.diag_indices(na)] = 77.0                                               # must never be read
+        tri_ref = (np.tril if uplo == "L" else np.triu)(A[:na].astype(hi), 0)
+        if diag == "U":
+            tri_ref[np.diag_indices(na)] = 1.0
+        unref = (np.triu_indices(na, 1) if uplo == "L" else np.tril_indices(na, -1))
+        A[:na][unref] = np.nan                                                               # the unreferenced triangle is never read
+        B0 = splitmix_uniform(84, (ldb, n), dt)
+        for nd in (1, ndev):
+            lib.b200blas_set_options(("devices=%d" % nd).encode())
+            s0 = mg_stats()
+            a_arg, _ = place(A, where, dt); b_arg, b_read = place(B0, where, dt)
+            f77(lib, p + kind + "_", side, uplo, trans, diag, m, n, alpha, a_arg, lda, b_arg, ldb)
+            outs.append((np.array(b_read(), order="F"), mg_stats()[0] - s0[0]))
+        (C1, calls1), (CN, callsN) = outs
+        opT = tri_ref if trans == "N" else (tri_ref.T if trans == "T" else tri_ref.conj().T)
+        X = CN[:m].astype(hi); Bh = B0[:m].astype(hi)
+        if kind == "trmm":
+            ref = alpha * (opT @ Bh if side == "L" else Bh @ opT)
+            err = float(np.linalg.norm(X - ref)); bound = 8 * na * eps * abs(alpha) * float(np.linalg.norm(opT)) * float(np.linalg.norm(Bh))
+        else:   # backward error of the solve
+            r = (opT @ X if side == "L" else X @ opT) - alpha * Bh
+            err = float(np.linalg.norm(r)); bound = 8 * na * eps * (float(np.linalg.norm(opT)) * float(np.linalg.norm(X)) + abs(alpha) * float(np.linalg.norm(Bh)))
+        untouched = bool(np.array_equal(CN[m:], B0[m:]))
+        close = float(np.abs(CN[:m].astype(hi) - C1[:m].astype(hi)).max())
+    res[" ".join(str(c) for c in case)] = {"partitioned_calls": int(callsN), "single_calls": int(calls1), "err": err, "bound": bound, "untouched": untouched,
+                                          "finite": bool(np.isfinite(CN[:(n if case[0] == "syrk" else m)].view(np.float64 if p in "dz" else np.float32)).all()) if case[0] != "syrk" else True,
+                                          "max_abs_diff_vs_1gpu": close}
+print(json.dumps(res))
+"""
+
+
+@pytest.mark.parametrize("ndev", [2, 4, 8])
+def test_syrk_trsm_trmm_partitioned_behind_the_symbol(ndev):
+    """devices=<n>: ?syrk_ on equal-area strips of the triangle, ?trsm_/?trmm_ on blocks of independent right-hand sides
+    (csrc/multi_level3.cu; north_star (4) "partitioned GEMM/SYRK/TRSM"; reference blas_level3/syrk.cc:43-76, trsm.cc:40-73,
+    trmm.cc:42-79).  Device, pinned-host and pageable-host operands; both triangles, transposes, sides, unit diagonals, beta = 0
+    and != 0, ragged sizes, odd leading dimensions.  Bars: SYRK ||tri(C - C_ref)||_F <= 4(k+2) eps (|alpha| ||A||_F^2 + |beta| ||C||_F);
+    TRMM 8 n eps |alpha| ||A|| ||B||; TRSM backward error ||op(A) X - alpha B||_F <= 8 n eps (||A|| ||X|| + |alpha| ||B||); the other
+    triangle, the padding rows of ldc / ldb untouched; the unreferenced triangle of A (NaN here) never read."""
+    if _ngpu() < ndev:
+        pytest.skip("needs %d GPUs" % ndev)
+    n0 = 1024 * ndev
+    f0 = 512 * ndev
+    cases = [("syrk", "d", "L", "N", n0 + 130, 600, 0.7, 1.3, "device"),
+             ("syrk", "d", "U", "T", n0 + 77, 520, 1.0, 0.0, "device"),
+             ("syrk", "d", "L", "T", n0 + 256, 700, 0.7, 0.0, "pinned"),
+             ("syrk", "d", "U", "N", n0 + 5, 600, 0.7, 1.3, "pageable"),
+             ("syrk", "s", "L", "N", n0 + 64, 600, 0.7, 1.3, "device"),
+             ("syrk", "z", "U", "N", n0 + 3, 400, 0.7 - 0.9j, 1.3 - 1.1j, "device"),
+             ("syrk", "c", "L", "T", n0, 512, 0.7 - 0.9j, 0.0j, "device"),
+             ("trsm", "d", "L", "L", "N", "N", 2048 + 70, f0 + 33, 0.7, "device"),
+             ("trsm", "d", "R", "L", "T", "N", f0 + 129, 2048 + 8, 1.0, "device"),
+             ("trsm", "d", "L", "U", "T", "U", 2100, f0 + 64, 0.7, "pinned"),
+             ("trsm", "d", "R", "U", "N", "N", f0 + 7, 2304, 0.7, "pageable"),
+             ("trsm", "s", "L", "L", "N", "N", 2048, f0 + 10, 1.0, "device"),
+             ("trsm", "z", "L", "U", "C", "N", 2048 + 6, f0, 0.7 - 0.9j, "device"),
+             ("trmm", "d", "L", "L", "N", "N", 2048 + 70, f0 + 33, 0.7, "device"),
+             ("trmm", "d", "R", "U", "T", "U", f0 + 19, 2048 + 40, 0.7, "pinned"),
+             ("trmm", "c", "R", "L", "C", "N", f0, 2048, 0.7 - 0.9j, "device")]
+    res = _devices_run(ndev, "CASES = %r\n" % (cases,) + _BODY_L3)
+    assert len(res) == len(cases)
+    for key, r in res.items():
+        assert r["partitioned_calls"] == 1 and r["single_calls"] == 0, (key, r)
+        assert r["untouched"] and r["finite"] and r["err"] <= r["bound"], (key, r)
+
+
 @pytest.mark.parametrize("ndev", [2, 8])
 def test_unmodified_c_program_under_preload_uses_all_gpus(ndev, tmp_path):
     """tests/drivers/dgemm_big.c -- a plain C program that callocs three matrices and calls dgemm_ -- under
