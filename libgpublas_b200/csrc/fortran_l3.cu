@@ -4,6 +4,7 @@
 // problems pick a small-tile GPU variant instead.
 #include "abi_common.h"
 #include "staged_gemm.cuh"
+#include "staged_level3.cuh"
 #include "multi_gemm.h"
 #include <type_traits>
 #include "../../include/b200blas.h"
@@ -86,6 +87,11 @@ void syrk_entry(const char* name, bool cplx, const char* uplo, const char* trans
         log_exec(name, "%c%c n=%d k=%d lda=%d ldc=%d (partitioned over %d devices)", upper ? 'U' : 'L', nota ? 'N' : 'T', *n, *k, *lda, *ldc, g_opts.devices);
         return;
     }
+    // large host-resident operands: k-chunks of A in, finished trapezoids of C out, under the multiply (staged_level3.cuh)
+    if (!scale_only && syrk_pipelined<T>(upper ? 'U' : 'L', nota ? 'N' : 'T', *n, *k, *alpha, a, (int64_t)*lda, *beta, c, (int64_t)*ldc)) {
+        log_exec(name, "%c%c n=%d k=%d lda=%d ldc=%d (pipelined staging)", upper ? 'U' : 'L', nota ? 'N' : 'T', *n, *k, *lda, *ldc);
+        return;
+    }
     Operand oa(scale_only ? nullptr : a, nrowa, nota ? *k : *n, *lda, sizeof(T), ACC_IN);
     // C is read even when beta == 0: the unreferenced triangle must survive a staged round trip
     Operand oc(c, *n, *n, *ldc, sizeof(T), ACC_INOUT);
@@ -116,6 +122,11 @@ void tr_entry(const char* name, bool solve, const char* side, const char* uplo, 
     // devices=<n>: independent right-hand sides, one block per device (multi_level3.cu)
     if (g_opts.devices > 1 && multi_trxm<T>(solve, lside ? 'L' : 'R', upper ? 'U' : 'L', t, lsame(diag, 'U') ? 'U' : 'N', *m, *n, *alpha, a, (int64_t)*lda, b, (int64_t)*ldb)) {
         log_exec(name, "%c%c%c%c m=%d n=%d lda=%d ldb=%d (partitioned over %d devices)", lside ? 'L' : 'R', upper ? 'U' : 'L', t, lsame(diag, 'U') ? 'U' : 'N', *m, *n, *lda, *ldb, g_opts.devices);
+        return;
+    }
+    // large host-resident B: blocks of right-hand sides travel in and out under the solve / product (staged_level3.cuh)
+    if (trxm_pipelined<T>(solve, lside ? 'L' : 'R', upper ? 'U' : 'L', t, lsame(diag, 'U') ? 'U' : 'N', *m, *n, *alpha, a, (int64_t)*lda, b, (int64_t)*ldb)) {
+        log_exec(name, "%c%c%c%c m=%d n=%d lda=%d ldb=%d (pipelined staging)", lside ? 'L' : 'R', upper ? 'U' : 'L', t, lsame(diag, 'U') ? 'U' : 'N', *m, *n, *lda, *ldb);
         return;
     }
     Operand oa(is0(*alpha) ? nullptr : a, nrowa, nrowa, *lda, sizeof(T), ACC_IN);

@@ -227,3 +227,83 @@ def test_next_family_larger_shapes_vs_oracle(p):
                 assert oracle_call(p + r, side, uplo, m, n, al, S, na + 1, Bm, m + 2, be, R, m + 1) == 0
                 assert np.array_equal(C[m:], C0[m:])
                 assert fro(C[:m] - R[:m]) <= abs(al) * tol(na, S, Bm) + 8 * EPS[p] * abs(be) * fro(C0)
+
+
+@pytest.mark.parametrize("p", ["d", "s", "z"])
+def test_syrk_pipelined_staging_host_operands(p):
+    """Host-resident ?syrk_ operands above pipeline_min bytes: A in k-chunks, C out trapezoid by trapezoid under the multiply
+    (csrc/staged_level3.cuh; the reference's miss path is whole-array blocking copies, runtime-mem.hpp:84-165).  Both triangles,
+    both transposes, beta = 0 and != 0, ragged sizes, odd leading dimensions; same bar as the resident path, the other triangle
+    and the padding rows untouched, and the strictly unreferenced part of C never crosses PCIe (byte counters)."""
+    lib = g.load(); dt = DT[p]
+    lib.b200blas_set_options(b"pipeline_min=1000")
+    try:
+        al, be = ((0.7 - 0.9j), (1.3 - 1.1j)) if p in "cz" else (0.7, 1.3)
+        hi = np.complex128 if p in "cz" else np.float64
+        n, k = 1500, 2300
+        for uplo in "UL":
+            for tr in "NT":
+                for beta in (be, 0.0 * be):
+                    ra, ca = (n, k) if tr == "N" else (k, n)
+                    A = splitmix_uniform(11, (ra + 1, ca), dt); C0 = splitmix_uniform(12, (n + 3, n), dt)
+                    C = F(C0)
+                    s0 = g.stats()
+                    f77(lib, p + "syrk_", uplo, tr, n, k, al, A, ra + 1, beta, C, n + 3)
+                    s1 = g.stats()
+                    opA = A[:ra].astype(hi); opA = opA if tr == "N" else opA.T
+                    ref = complex(al) * (opA @ opA.T) + complex(beta) * C0[:n].astype(hi) if p in "cz" else al * (opA @ opA.T) + beta * C0[:n].astype(hi)
+                    tri = np.triu(np.ones((n, n), bool)) if uplo == "U" else np.tril(np.ones((n, n), bool))
+                    full = np.zeros((n + 3, n), bool); full[:n] = tri
+                    assert np.array_equal(C[~full], C0[~full]), "outside the referenced triangle must be untouched"
+                    err = fro((C[:n] - ref)[tri]); bound = 4 * (k + 2) * EPS[p] * (abs(al) * fro(A[:ra]) ** 2 + abs(beta) * fro(C0[:n]))
+                    assert err <= bound, (p, uplo, tr, beta, err, bound)
+                    es = np.dtype(dt).itemsize
+                    assert s1["h2d_bytes"] - s0["h2d_bytes"] < (n * k + (0.66 if beta != 0 else 0.25) * n * n) * es, "A once, at most the trapezoids of C"
+                    assert s1["d2h_bytes"] - s0["d2h_bytes"] < 0.66 * n * n * es, "only the trapezoids return"
+    finally:
+        lib.b200blas_set_options(b"pipeline_min=67108864")
+
+
+@pytest.mark.parametrize("which", ["trsm", "trmm"])
+@pytest.mark.parametrize("p", ["d", "s", "z"])
+def test_trxm_pipelined_staging_host_operands(p, which):
+    """Host-resident B above pipeline_min bytes goes through ?trsm_/?trmm_ in blocks of right-hand sides (columns for side L,
+    rows for side R), block p+1 travelling in and block p-1 out under block p's work (csrc/staged_level3.cuh).  A in host memory
+    or already on the device."""
+    import torch
+    lib = g.load(); dt = DT[p]
+    lib.b200blas_set_options(b"pipeline_min=1000")
+    try:
+        al = (0.7 - 0.9j) if p in "cz" else 0.7
+        hi = np.complex128 if p in "cz" else np.float64
+        for (side, m, n) in [("L", 300, 2300), ("R", 2500, 260)]:
+            na = m if side == "L" else n
+            T = F(splitmix_uniform(13, (na + 1, na), dt)); T[:na] = T[:na] / dt(na); T[np.arange(na), np.arange(na)] = dt(2.0)
+            for uplo in "UL":
+                for ta in "NC":
+                    for diag, a_on_device in (("N", False), ("U", True)):
+                        B0 = splitmix_uniform(14, (m + 2, n), dt); B = F(B0)
+                        a_arg = T
+                        if a_on_device:
+                            a_arg = torch.from_numpy(np.ascontiguousarray(T.ravel(order="F").view(np.float64 if p in "dz" else np.float32))).cuda()
+                        s0 = g.stats()
+                        f77(lib, p + which + "_", side, uplo, ta, diag, m, n, al, a_arg, na + 1, B, m + 2)
+                        s1 = g.stats()
+                        es = np.dtype(dt).itemsize
+                        assert s1["d2h_bytes"] - s0["d2h_bytes"] == m * n * es
+                        assert s1["h2d_bytes"] - s0["h2d_bytes"] == (m * n + (0 if a_on_device else na * na)) * es
+                        assert np.array_equal(B[m:], B0[m:])
+                        Tm = (np.triu(T[:na]) if uplo == "U" else np.tril(T[:na])).astype(hi)
+                        if diag == "U":
+                            Tm[np.arange(na), np.arange(na)] = 1
+                        opT = Tm if ta == "N" else Tm.conj().T
+                        X = B[:m].astype(hi); Bh = B0[:m].astype(hi)
+                        a_s = complex(dt(al)) if p in "cz" else float(dt(al))
+                        if which == "trmm":
+                            ref = a_s * (opT @ Bh if side == "L" else Bh @ opT)
+                            assert fro(X - ref) <= 4 * (na + 2) * EPS[p] * abs(al) * fro(Tm) * fro(Bh), (p, side, uplo, ta, diag)
+                        else:
+                            resid = (opT @ X if side == "L" else X @ opT) - a_s * Bh
+                            assert fro(resid) <= 4 * na * EPS[p] * (fro(Tm) * fro(X) + abs(al) * fro(Bh)), (p, side, uplo, ta, diag, fro(resid))
+    finally:
+        lib.b200blas_set_options(b"pipeline_min=67108864")
