@@ -318,6 +318,26 @@ def other_routines(g, torch, dev, peaks, out):
     ms = timed(lambda: g.call("dtrsm_", "R", "L", "T", "N", mm, nn, 1.0, Lp, nn, Bp, mm), reps=3, warm=1)
     tf = float(mm) * nn * nn / ms / 1e9
     out["dtrsm_RLTN_30720x2048"] = {"tflops": tf, "ms": ms, "frac_of_fp64_peak": tf / FP64_PEAK_NOMINAL, "frac_of_fp64_probe": tf / fp64}
+    # the same routines on HOST operands (pinned), through the symbol: chunked staging under the compute (csrc/staged_level3.cuh);
+    # wall clock around the synchronous call, best of 3; "serial_copy_ms" = what whole-array copies at 50 GB/s would add in series
+    try:
+        hn = 8192
+        hA = (torch.rand((hn, hn), dtype=torch.float64) * 2 - 1).pin_memory(); hC = torch.zeros((hn, hn), dtype=torch.float64).pin_memory()
+        hT = torch.triu(hA).contiguous(); hT.mul_(1.0 / hn); hT.diagonal().fill_(1.0); hT = hT.pin_memory()
+        def wall(fn, reps=3):
+            fn(); torch.cuda.synchronize(); best = None
+            for _ in range(reps):
+                t0 = time.perf_counter(); fn(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            return best * 1e3
+        ms = wall(lambda: g.call("dsyrk_", "L", "N", hn, hn, 1.0, hA, hn, 0.0, hC, hn))
+        out["dsyrk_LN_8192_host_pinned"] = {"tflops": float(hn) * hn * (hn + 1) / ms / 1e9, "ms": ms, "h2d_bytes": 8 * hn * hn, "d2h_bytes_max": int(0.66 * 8 * hn * hn)}
+        hC.uniform_(-1, 1)
+        ms = wall(lambda: g.call("dtrsm_", "L", "L", "N", "N", hn, hn, 1.0, hT, hn, hC, hn))
+        out["dtrsm_LLNN_8192_host_pinned"] = {"tflops": float(hn) ** 3 / ms / 1e9, "ms": ms, "h2d_bytes": 16 * hn * hn, "d2h_bytes": 8 * hn * hn}
+        del hA, hC, hT
+    except Exception as exc:      # pinned allocation can fail on a small host; the resident lines above stand on their own
+        out["level3_host_pinned_error"] = repr(exc)
     del A, T, Bm, Lp, Bp
     # blocked Cholesky workload (BASELINE.json configs[3]) on one GPU: wall clock, the driver synchronises per panel
     from libgpublas_b200.cholesky import blocked_cholesky

@@ -1,6 +1,6 @@
 #!/bin/sh
 # round 2: full single-GPU suite with the pageable bounce ring + version-scripted exports, then the N=1 bench line
-TAG=r02m
+TAG=r02o
 OUT=gpurun_out
 mkdir -p $OUT
 timeout 1500 python -m pytest tests -m gpu -x -q -p no:cacheprovider > $OUT/${TAG}_tests.log 2>&1
