@@ -113,10 +113,12 @@ bool trxm_pipelined(bool solve, char side, char uplo, char trans, char diag, int
     cudaStream_t s = current_stream(), h2d = aux_stream(0), d2h = aux_stream(1);
     StagedMat A = stage_matrix(a, na, na, lda, es, s);
     StagedMat B = stage_matrix(b, m, n, ldb, es, s);
-    // blocks: a short first one (the exposed head is its H2D), equal ones after, a short last one (the exposed tail is its D2H)
+    // blocks: a short first one (the exposed head is its H2D), equal ones after, short last ones (the exposed tail is the last D2H)
     int bb[24], P = 0;
     {
-        const int64_t body = std::max<int64_t>(512, round_up((nfree + 7) / 8, 128));
+        // few, wide blocks: the substitution leaves of trsm_dev run one right-hand side per thread, so a block's leaf chain costs
+        // the same whatever its width (8 blocks of 1024 columns: 68 ms for DTRSM 8192^2 against 20.5 ms resident, profiles/r02o_bench_n1.json)
+        const int64_t body = std::max<int64_t>(1024, round_up((nfree + 3) / 4, 128));
         bb[0] = 0;
         int64_t c0 = std::min<int64_t>(nfree, round_up(body / 2, 128));
         bb[++P] = (int)c0;
@@ -134,7 +136,13 @@ bool trxm_pipelined(bool solve, char side, char uplo, char trans, char diag, int
     auto copy_b = [&](int p, cudaStream_t st, bool to_device) {
         if (lside) copy_region(B, 0, bb[p], m, bb[p + 1] - bb[p], st, to_device); else copy_region(B, bb[p], 0, bb[p + 1] - bb[p], n, st, to_device);
     };
-    copy_region(A, 0, 0, na, na, h2d, true);
+    {   // only the referenced trapezoids of A cross PCIe (column groups: rows [c, na) of a lower, [0, c + w) of an upper triangle)
+        const int64_t cg = std::max<int64_t>(256, round_up((na + 7) / 8, 128));
+        for (int64_t c0 = 0; c0 < na; c0 += cg) {
+            const int64_t w = std::min(cg, na - c0);
+            if (uplo == 'U') copy_region(A, 0, c0, c0 + w, w, h2d, true); else copy_region(A, c0, c0, na - c0, w, h2d, true);
+        }
+    }
     copy_b(0, h2d, true);
     record(EV_IN + 0, h2d);
     for (int p = 0; p <= P; p++) {
