@@ -76,6 +76,73 @@ __global__ void __launch_bounds__(COL_WARPS * 32) tpart_kernel(Desc D, const T* 
     const T acc = warp_sum(tpart_lane<T>(D, A, v, j, lane, 32, r0, r1, flags));
     if (lane == 0) tpart[j] = acc;
 }
+// ---- one-pass symmetric product (structured.cuh: sym_row) ----
+template <typename T> __device__ __forceinline__ T shfl_xor_any(T x, int m) {
+    union { T t; unsigned u[sizeof(T) / 4]; } a;
+    a.t = x;
+#pragma unroll
+    for (int q = 0; q < (int)(sizeof(T) / 4); q++) a.u[q] = __shfl_xor_sync(0xffffffffu, a.u[q], m);
+    return a.t;
+}
+// Per-warp sink of sym_row: t[u] is this lane's (row's) product for column j + u.  Transposing butterfly: at mask 16 the lanes
+// with that bit clear keep the low half of the columns and hand the high half to their partner (and vice versa), at 8 and 4 the
+// same on what is left -- after log2(NU) exchanges a lane holds ONE column's sum over 32 / NU... lanes, the remaining masks finish
+// it.  NU + log2(32) - 1 shuffles per step instead of 5 NU.  The lane with the low bits clear stores the column's sum.
+template <typename T> struct WarpStripSink {
+    enum { NU = unroll_of<T>::N };
+    T* strip; int cw0, cw1, lane;
+    __device__ __forceinline__ void step(int j, T (&t)[NU]) {
+        int col = 0, m = 16;
+#pragma unroll
+        for (int cnt = NU / 2; cnt >= 1; cnt >>= 1, m >>= 1) {
+            const bool up = (lane & m) != 0;
+#pragma unroll
+            for (int u = 0; u < cnt; u++) {
+                const T keep = up ? t[u + cnt] : t[u], send = up ? t[u] : t[u + cnt];
+                t[u] = el<T>::add(keep, shfl_xor_any<T>(send, m));
+            }
+            col += up ? cnt : 0;
+        }
+        T sum = t[0];
+#pragma unroll
+        for (; m >= 1; m >>= 1) sum = el<T>::add(sum, shfl_xor_any<T>(sum, m));
+        const int jj = j + col;
+        if ((lane & (32 / NU - 1)) == 0 && jj >= cw0 && jj < cw1) strip[jj - cw0] = sum;
+    }
+};
+// grid (row blocks, column chunks); dynamic shared memory: one strip of `wstride` sums per warp
+template <typename T>
+__global__ void __launch_bounds__(ROW_THREADS) sympart_kernel(Desc D, const T* __restrict__ A, const T* __restrict__ v, int cpc, int nflags, int tflags, T* __restrict__ part,
+                                                               int64_t npad, T* __restrict__ tp2, int64_t npadw, int wstride) {
+    extern __shared__ __align__(16) unsigned char sym_smem[];
+    T* strips = reinterpret_cast<T*>(sym_smem);
+    const int r0 = blockIdx.x * ROW_THREADS, i = r0 + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.y * cpc, c1 = st_min(D.n, c0 + cpc);
+    int cw0, cw1;
+    sym_window(D, r0, c0, c1, cw0, cw1);
+    for (int t = threadIdx.x; t < (ROW_THREADS / 32) * wstride; t += ROW_THREADS) strips[t] = el<T>::zero();
+    __syncthreads();
+    WarpStripSink<T> sink = {strips + warp * wstride, cw0, cw1, lane};
+    const T r = sym_row<T>(D, A, v, i, i - lane, c0, c1, nflags, tflags, sink);
+    if (i < D.n) part[(int64_t)blockIdx.y * npad + i] = r;
+    __syncthreads();
+    T* row = tp2 + (int64_t)blockIdx.x * npadw - sym_jw0(D, r0);
+    for (int t = threadIdx.x; t < cw1 - cw0; t += ROW_THREADS) {
+        T s = strips[t];
+#pragma unroll
+        for (int w = 1; w < ROW_THREADS / 32; w++) s = el<T>::add(s, strips[w * wstride + t]);
+        row[cw0 + t] = s;
+    }
+}
+template <typename T>
+__global__ void sym_finish_kernel(Desc D, int nparts, const T* __restrict__ part, int64_t npad, const T* __restrict__ tp2, int64_t npadw, T alpha, T beta,
+                                  T* __restrict__ out, int64_t inco) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= D.n) return;
+    T* p = out + vpos(j, D.n, inco);
+    const bool beta0 = el<T>::is_zero(beta);
+    *p = sym_finish_elem<T>(D, j, nparts, part, npad, tp2, npadw, alpha, beta, beta0, beta0 ? el<T>::zero() : *p);
+}
 template <typename T>
 __global__ void smv_finish_kernel(int n, int nparts, const T* __restrict__ part, int64_t npad, const T* __restrict__ tpart, const T* __restrict__ vunit, T alpha,
                                   T beta, T* __restrict__ out, int64_t inco) {
@@ -191,6 +258,22 @@ struct DeviceBackend {
     template <typename T>
     void finish(int n, int nparts, const T* part, int64_t npad, const T* tp, const T* vunit, T alpha, T beta, T* out, int64_t inco) {
         smv_finish_kernel<T><<<(n + 255) / 256, 256, 0, s>>>(n, nparts, part, npad, tp, vunit, alpha, beta, out, inco);
+        last_variant = VAR_GENERIC_TILE;
+    }
+    // one-pass symmetric product: a strip of 1024 doubles (512 double-complex) per warp = 32 KB per CTA, 7 CTAs per SM
+    template <typename T> int sym_max_cols() const {
+        static const bool off = getenv("B200BLAS_SYM_TWO_PASS") != nullptr;
+        return off ? 0 : (int)(8192 / sizeof(T));
+    }
+    template <typename T>
+    void sympart(const Desc& D, const T* A, const T* v, int cpc, int nchunks, int nflags, int tflags, T* part, int64_t npad, T* tp2, int64_t npadw) {
+        const int64_t w = sym_width(D) < cpc ? sym_width(D) : (int64_t)cpc;
+        const int wstride = (int)((w + 7) / 8 * 8);
+        sympart_kernel<T><<<dim3((D.n + ROW_THREADS - 1) / ROW_THREADS, nchunks), ROW_THREADS, (size_t)(ROW_THREADS / 32) * wstride * sizeof(T), s>>>(
+            D, A, v, cpc, nflags, tflags, part, npad, tp2, npadw, wstride);
+    }
+    template <typename T> void sym_finish(const Desc& D, int nparts, const T* part, int64_t npad, const T* tp2, int64_t npadw, T alpha, T beta, T* out, int64_t inco) {
+        sym_finish_kernel<T><<<(D.n + 255) / 256, 256, 0, s>>>(D, nparts, part, npad, tp2, npadw, alpha, beta, out, inco);
         last_variant = VAR_GENERIC_TILE;
     }
     template <typename T> void rank(const Desc& D, T* A, int rows, int ncols, int cpc, int nchunks, T alpha, const T* x, const T* y, int mode) {

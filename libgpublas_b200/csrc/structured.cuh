@@ -250,6 +250,92 @@ template <typename T> ST_HD T tpart_lane(const Desc& D, const T* A, const T* v, 
     for (; i < i1; i += nlanes, p += nlanes) acc0 = mad_elem<T>(*p, v[i], i, j, flags, acc0);
     return el<T>::add(el<T>::add(acc0, acc1), el<T>::add(acc2, acc3));
 }
+// ---- symmetric / Hermitian products in ONE pass over the stored triangle ----
+// The two-pass form (N part over the triangle, T part over its strict half) reads every stored element twice: at most 50 % of
+// the HBM peak (measured 41-44 %, profiles/r01g_level2_struct_summary.txt).  Here a CTA of ROW_THREADS rows x one column chunk
+// walks its rows exactly like npart_row, and every loaded element S(i,j) also feeds the mirrored product op_t(S(i,j)) * v(i)
+// for out(j).  The 32 rows of a warp hold NU such products per step, one per column: a transposing butterfly (sym_step in
+// level2_struct.cu) leaves each column's sum over the warp's rows in one lane, which stores it in the warp's strip of shared
+// memory -- every column is visited by exactly one step of a warp, so the strip needs no read-modify-write.  At the end the
+// CTA adds its warps' strips and writes them to tp2[row block][column - jw0(row block)]; sym_finish_elem adds, for out(j), the
+// row blocks that hold stored rows of column j.  Extra traffic: tp2 is written and read once, n/ROW_THREADS values per column
+// against ~n/2 stored ones (1.6 %).  Deterministic: fixed grid, fixed order.
+// first column of the tp2 row of the row block that starts at row r0 (bands keep only the block's window of columns)
+ST_HD int sym_jw0(const Desc& D, int r0) {
+    if (D.kind != K_BAND_TRI) return 0;
+    int j0, j1;
+    row_cols(D, r0, j0, j1);
+    return j0;
+}
+// width of a tp2 row: the whole matrix, or (bands) the columns a row block can touch
+ST_HD int64_t sym_width(const Desc& D) { return D.kind == K_BAND_TRI ? (int64_t)ROW_THREADS + st_max(D.kl, D.ku) : (int64_t)D.n; }
+// columns [cw0, cw1) of chunk [c0, c1) that the rows [r0, r0 + ROW_THREADS) of an n x n triangle can touch (row ranges never move left as i grows)
+ST_HD void sym_window(const Desc& D, int r0, int c0, int c1, int& cw0, int& cw1) {
+    const int rl = st_min(r0 + ROW_THREADS, D.n) - 1;
+    int ja0, ja1, jb0, jb1;
+    row_cols(D, r0, ja0, ja1);
+    row_cols(D, rl, jb0, jb1);
+    cw0 = st_max(c0, ja0); cw1 = st_min(c1, jb1);
+    if (cw1 < cw0) cw1 = cw0;
+}
+// One row's walk.  Every lane of a warp runs the SAME steps (the butterfly in sink.step needs all 32): the loop bounds come from
+// the warp's first and last row, a lane masks the columns outside its own range (rows past n: everything).  Returns the N part
+// of row i; sink.step(j, t) receives the NU mirrored products of the step, t[u] = op_t(S(i, j+u)) * v(i) (zero where masked).
+template <typename T, typename SINK> ST_HD T sym_row(const Desc& D, const T* A, const T* v, int i, int i_first, int c0, int c1, int nflags, int tflags, SINK& sink) {
+    enum { NU = unroll_of<T>::N };
+    const int n = D.n, i_last = st_min(i_first + 31, n - 1);
+    if (i_first >= n) return el<T>::zero();                  // the whole warp is past the last row
+    int j0 = 0, j1 = 0, jf0, jf1, jl0, jl1;
+    if (i < n) row_cols(D, i, j0, j1);
+    j0 = st_max(j0, c0); j1 = st_min(j1, c1);
+    row_cols(D, i_first, jf0, jf1);
+    row_cols(D, i_last, jl0, jl1);
+    const int jstart = st_max(jf0, c0), jend = st_min(jl1, c1);
+    T acc[NU];
+ST_UNROLL
+    for (int u = 0; u < NU; u++) acc[u] = el<T>::zero();
+    const T vi = i < n ? v[i] : el<T>::zero();
+    const T* p = A + off(D, i < n ? i : i_first, jstart);   // outside the stored part it is never dereferenced
+    for (int j = jstart; j < jend; j += NU) {
+        T a[NU], w[NU], t[NU];
+        int64_t s = 0;
+        if (j >= j0 && j + NU <= j1) {
+ST_UNROLL
+            for (int u = 0; u < NU; u++) { a[u] = p[s]; w[u] = v[j + u]; s += col_step(D, j + u); }
+        } else {
+ST_UNROLL
+            for (int u = 0; u < NU; u++) {
+                const bool in = j + u >= j0 && j + u < j1;
+                a[u] = in ? p[s] : el<T>::zero();
+                w[u] = in ? v[j + u] : el<T>::zero();
+                s += col_step(D, j + u);
+            }
+        }
+        p += s;
+ST_UNROLL
+        for (int u = 0; u < NU; u++) {
+            acc[u] = mad_elem<T>(a[u], w[u], i, j + u, nflags, acc[u]);
+            t[u] = mad_elem<T>(a[u], vi, i, j + u, tflags, el<T>::zero());
+        }
+        sink.step(j, t);
+    }
+    T r = acc[0];
+ST_UNROLL
+    for (int u = 1; u < NU; u++) r = el<T>::add(r, acc[u]);
+    return r;
+}
+// out(j) = alpha*(N partials + mirrored partials of the row blocks that hold stored rows of column j) + beta*old
+template <typename T>
+ST_HD T sym_finish_elem(const Desc& D, int j, int nparts, const T* part, int64_t npad, const T* tp2, int64_t npadw, T alpha, T beta, bool beta0, T old) {
+    T s = el<T>::zero();
+    for (int c = 0; c < nparts; c++) s = el<T>::add(s, part[(int64_t)c * npad + j]);
+    int i0, i1;
+    col_rows(D, j, i0, i1);
+    for (int rb = i0 / ROW_THREADS; rb <= (i1 - 1) / ROW_THREADS; rb++) s = el<T>::add(s, tp2[(int64_t)rb * npadw + (j - sym_jw0(D, rb * ROW_THREADS))]);
+    s = el<T>::mul(alpha, s);
+    return beta0 ? s : el<T>::mad(beta, old, s);
+}
+
 // out = alpha*(sum of the partial rows + tpart + vunit) + beta*old   (beta == 0: old is never read, like netlib)
 template <typename T>
 ST_HD T finish_elem(int i, int nparts, const T* part, int64_t npad, const T* tpart, const T* vunit, T alpha, T beta, bool beta0, T old) {
@@ -340,6 +426,8 @@ ST_HD int64_t vpos(int64_t i, int64_t n, int64_t inc) { return inc >= 0 ? i * in
 //   BE::npart(D, A, v, row0, row1, c_lo, c_hi, cpc, nchunks, flags, part, npad)
 //   BE::tpart(D, A, v, col0, col1, r0, r1, flags, tpart)
 //   BE::finish(n, nparts, part, npad, tpart, vunit, alpha, beta, out, inco)
+//   BE::sym_max_cols<T>()                              widest column strip a one-pass symmetric CTA can hold (0: two-pass form)
+//   BE::sympart(D, A, v, cpc, nchunks, nflags, tflags, part, npad, tp2, npadw) / sym_finish(D, nparts, part, npad, tp2, npadw, alpha, beta, out, inco)
 //   BE::rank(D, A, rows, ncols, cpc, nchunks, alpha, x, y, mode)
 //   BE::solve_panel(D, A, x, p0, p1, trans, conj, unit, forward)     one CTA: the whole panel [p0,p1) in place
 //   BE::solve_nupdate(D, A, x, row0, row1, b0, b1, flags) / solve_tupdate(D, A, x, col0, col1, b0, b1, flags)
@@ -451,6 +539,24 @@ inline void plan_symv_like(BE& be, int kind, bool herm, bool rowmajor, bool uppe
     const T* xc = gathered<T>(be, n, x, incx, false);
     const int nf = herm ? (F_HERM | (rowmajor ? F_CONJ : 0)) : 0;
     const int tf = F_NODIAG | ((herm && !rowmajor) ? F_CONJ : 0);
+    // one pass over the triangle when a CTA's strip of mirrored sums fits in shared memory (bands: ROW_THREADS + k columns)
+    const int wmax = be.template sym_max_cols<T>();
+    if (wmax > 0 && (kind != K_BAND_TRI || (int64_t)ROW_THREADS + k <= wmax)) {
+        int cpc = n, nch = 1;
+        if (kind != K_BAND_TRI) {
+            const int ch = st_max(col_chunks(be, D, n, n), (n + wmax - 1) / wmax);
+            cpc = ((n + ch - 1) / ch + 7) / 8 * 8;
+            if (cpc > wmax) cpc = wmax;
+            nch = (n + cpc - 1) / cpc;
+        }
+        const int64_t npad = ((int64_t)n + 31) / 32 * 32, npadw = (sym_width(D) + 31) / 32 * 32;
+        const int nrb = (n + ROW_THREADS - 1) / ROW_THREADS;
+        T* part = (T*)be.alloc((size_t)nch * npad * sizeof(T));
+        T* tp2 = (T*)be.alloc((size_t)nrb * npadw * sizeof(T));
+        be.sympart(D, a, xc, cpc, nch, nf, tf, part, npad, tp2, npadw);
+        be.sym_finish(D, nch, part, npad, tp2, npadw, alpha, beta, y, incy);
+        return;
+    }
     smv<T>(be, D, a, xc, nf, tf, (const T*)nullptr, alpha, beta, n, y, incy);
 }
 // TBMV / TPMV / TRMV (solve = false) and TBSV / TPSV (solve = true)

@@ -7,6 +7,7 @@
 // kernels themselves are verified on the GPU by tests/test_zz_level2_struct_gpu.py.  libb200blas.so never loads this file.
 #include "../../libgpublas_b200/csrc/structured.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -67,6 +68,52 @@ struct HostBackend {
             T* p = out + vpos(i, n, inco);
             const bool beta0 = el<T>::is_zero(beta);
             *p = finish_elem<T>(i, nparts, part, npad, tp, vunit, alpha, beta, beta0, beta0 ? el<T>::zero() : *p);
+        }
+    }
+    // one-pass symmetric product: the grid and the per-warp strips of sympart_kernel; the lanes of a warp run one after the other, so
+    // the sink adds into the strip where the device's butterfly stores one finished sum (the butterfly itself is checked on the GPU)
+    template <typename T> struct HostStripSink {
+        enum { NU = unroll_of<T>::N };
+        T* strip; int cw0, cw1;
+        void step(int j, T (&t)[NU]) {
+            for (int u = 0; u < NU; u++)
+                if (j + u >= cw0 && j + u < cw1) strip[j + u - cw0] = el<T>::add(strip[j + u - cw0], t[u]);
+        }
+    };
+    int sym_two_pass = 0;
+    template <typename T> int sym_max_cols() const { return sym_two_pass ? 0 : (int)(8192 / sizeof(T)); }
+    template <typename T>
+    void sympart(const Desc& D, const T* A, const T* v, int cpc, int nchunks, int nflags, int tflags, T* part, int64_t npad, T* tp2, int64_t npadw) {
+        const int64_t w = sym_width(D) < cpc ? sym_width(D) : (int64_t)cpc;
+        const int wstride = (int)((w + 7) / 8 * 8), nwarps = ROW_THREADS / 32;
+        std::vector<T> strips((size_t)nwarps * wstride);
+        for (int by = 0; by < nchunks; by++)
+            for (int bx = 0; bx < (D.n + ROW_THREADS - 1) / ROW_THREADS; bx++) {
+                const int r0 = bx * ROW_THREADS, c0 = by * cpc, c1 = st_min(D.n, c0 + cpc);
+                int cw0, cw1;
+                sym_window(D, r0, c0, c1, cw0, cw1);
+                if (cw1 - cw0 > wstride) std::abort();                     // the strip must hold the CTA's window
+                for (auto& x : strips) x = el<T>::zero();
+                for (int tx = 0; tx < ROW_THREADS; tx++) {
+                    const int i = r0 + tx, lane = tx & 31, warp = tx >> 5;
+                    HostStripSink<T> sink = {strips.data() + (size_t)warp * wstride, cw0, cw1};
+                    const T r = sym_row<T>(D, A, v, i, i - lane, c0, c1, nflags, tflags, sink);
+                    if (i < D.n) part[(int64_t)by * npad + i] = r;
+                }
+                T* row = tp2 + (int64_t)bx * npadw - sym_jw0(D, r0);
+                for (int t = 0; t < cw1 - cw0; t++) {
+                    T sacc = strips[t];
+                    for (int wv = 1; wv < nwarps; wv++) sacc = el<T>::add(sacc, strips[(size_t)wv * wstride + t]);
+                    if (cw0 + t - sym_jw0(D, r0) < 0 || cw0 + t - sym_jw0(D, r0) >= npadw) std::abort();
+                    row[cw0 + t] = sacc;
+                }
+            }
+    }
+    template <typename T> void sym_finish(const Desc& D, int nparts, const T* part, int64_t npad, const T* tp2, int64_t npadw, T alpha, T beta, T* out, int64_t inco) {
+        for (int j = 0; j < D.n; j++) {
+            T* p = out + vpos(j, D.n, inco);
+            const bool beta0 = el<T>::is_zero(beta);
+            *p = sym_finish_elem<T>(D, j, nparts, part, npad, tp2, npadw, alpha, beta, beta0, beta0 ? el<T>::zero() : *p);
         }
     }
     template <typename T> void rank(const Desc& D, T* A, int rows, int ncols, int cpc, int nchunks, T alpha, const T* x, const T* y, int mode) {

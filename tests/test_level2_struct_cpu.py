@@ -399,3 +399,17 @@ def test_cblas_rotmg_rotg_host_paths_vs_openblas():
                     fn(l2x._ptr(ca), l2x._ptr(cb), l2x._ptr(c), l2x._ptr(s))
                 outs.append(np.array([ca[0], c[0], s[0]], dtype=np.complex128))
             assert np.allclose(outs[0], outs[1], rtol=16 * tol, atol=16 * tol), (p, a_, b_, outs)
+
+
+@pytest.mark.parametrize("p", ["d", "z", "s"])
+def test_emulated_one_pass_symmetric_products(p):
+    """SBMV/HBMV/SPMV/HPMV/SYMV/HEMV read the stored triangle ONCE (structured.cuh: sym_row -- every loaded element feeds its own
+    row and, mirrored, its column; per-row-block column sums in tp2, sym_finish_elem).  Sizes that span several 128-row blocks and
+    several column chunks, bands narrower and wider than a row block, a band too wide for the strip (the two-pass form), both
+    storage orders -- the window / tp2 indexing is what this checks where there is no GPU (the device butterfly: GPU tests)."""
+    names = ("sbmv", "hbmv", "spmv", "hpmv", "symv", "hemv")
+    for rowmajor in (False, True):
+        cs = [c for c in l2x.cases(p, rowmajor=rowmajor, sizes=(127, 129, 300), big=(1100,) if p == "d" and not rowmajor else ()) if c.name[1:] in names]
+        assert len(cs) >= 30
+        w, tag = _worst(cs, lambda c, args: l2x.emu_call(c.name, *args, rowmajor=rowmajor))
+        assert w < 1.0, (tag, w)

@@ -347,3 +347,63 @@ def test_threaded_allocator_churn_under_preload(tmp_path):
         out, _ = run(exe, args, preload=True, cwd=str(tmp_path), timeout=300)
         r = fields([l for l in out.splitlines() if l.startswith("RESULT")][0])
         assert r["ok"] == "1" and int(r["big"]) > 300 and int(r["tracked_seen"]) >= int(r["big"]), out
+
+
+def test_one_pass_symmetric_products_larger_device_resident():
+    """SPMV / SYMV / SBMV / HEMV / HPMV / HBMV at sizes that span many row blocks and column chunks of the one-pass kernel
+    (level2_struct.cu: sympart_kernel -- every stored element read once, mirrored sums by a transposing warp butterfly), operands
+    on the device, against a float64 / complex128 numpy product.  Bar: |y - y_ref| <= 16 n eps (|alpha| |S| |x| + |beta| |y0|)
+    element-wise (the GEMV bound with c = 16)."""
+    import torch
+    lib = g.load()
+    rng = np.random.default_rng(11)
+    for p, n, k in (("d", 3001, 200), ("z", 1409, 77), ("s", 2050, 5)):
+        dt = {"d": np.float64, "z": np.complex128, "s": np.float32}[p]
+        eps = 2.0 ** -24 if p == "s" else 2.0 ** -53
+        cplx = p == "z"
+        def rnd(shape):
+            a = rng.uniform(-1, 1, shape)
+            return (a + 1j * rng.uniform(-1, 1, shape)).astype(dt) if cplx else a.astype(dt)
+        M = rnd((n, n))
+        x = rnd(n); y0 = rnd(n)
+        alpha, beta = ((0.7 - 0.9j), (1.3 - 1.1j)) if cplx else (0.7, 1.3)
+        fl = np.float64 if p in "dz" else np.float32
+        def dev(a):
+            return torch.from_numpy(np.ascontiguousarray(a).view(fl).copy()).cuda()
+        for ul in "UL":
+            tri = np.triu(M) if ul == "U" else np.tril(M)
+            if cplx:
+                tri[np.diag_indices(n)] = tri[np.diag_indices(n)].real + 5j      # the imaginary part of a Hermitian diagonal is never used
+                S = tri + tri.conj().T; S[np.diag_indices(n)] = tri[np.diag_indices(n)].real
+            else:
+                S = tri + tri.T - np.diag(np.diag(tri))
+            hi = np.complex128 if cplx else np.float64
+            ref = alpha * (S.astype(hi) @ x.astype(hi)) + beta * y0.astype(hi)
+            bound = 16 * n * eps * (abs(alpha) * (np.abs(S).astype(np.float64) @ np.abs(x).astype(np.float64)) + abs(beta) * np.abs(y0))
+            # full storage (lda = n + 3), the unreferenced triangle poisoned
+            Af = np.full((n + 3, n), np.nan, dtype=dt, order="F"); Af[:n][(np.triu if ul == "U" else np.tril)(np.ones((n, n), bool))] = tri[(np.triu if ul == "U" else np.tril)(np.ones((n, n), bool))]
+            # packed by columns
+            ap = np.concatenate([tri[: j + 1, j] if ul == "U" else tri[j:, j] for j in range(n)]).astype(dt)
+            xd = dev(x)
+            for name, a_args in ((("hemv" if cplx else "symv"), (dev(Af.ravel(order="F")), n + 3)), (("hpmv" if cplx else "spmv"), (dev(ap),))):
+                yd = dev(y0)
+                f77(lib, p + name + "_", ul, n, alpha, *a_args, xd, 1, beta, yd, 1)
+                torch.cuda.synchronize()
+                got = yd.cpu().numpy().view(dt)
+                assert np.all(np.abs(got.astype(hi) - ref) <= bound), (p, name, ul, float(np.abs(got - ref).max()))
+            # band: keep k off-diagonals
+            i, j = np.indices((n, n))
+            bt = np.where(np.abs(i - j) <= k, tri, 0)
+            Sb = np.where(np.abs(i - j) <= k, S, 0)
+            AB = np.full((k + 2, n), np.nan, dtype=dt, order="F")
+            for jj in range(n):
+                if ul == "U":
+                    lo = max(0, jj - k); AB[k + lo - jj: k + 1, jj] = bt[lo: jj + 1, jj]
+                else:
+                    hi_r = min(n, jj + k + 1); AB[0: hi_r - jj, jj] = bt[jj: hi_r, jj]
+            refb = alpha * (Sb.astype(hi) @ x.astype(hi)) + beta * y0.astype(hi)
+            yd = dev(y0)
+            f77(lib, p + ("hbmv" if cplx else "sbmv") + "_", ul, n, k, alpha, dev(AB.ravel(order="F")), k + 2, xd, 1, beta, yd, 1)
+            torch.cuda.synchronize()
+            got = yd.cpu().numpy().view(dt)
+            assert np.all(np.abs(got.astype(hi) - refb) <= bound), (p, "band", ul, float(np.abs(got - refb).max()))

@@ -63,5 +63,13 @@ Z = torch.rand((m, m), dtype=torch.complex128, device="cuda"); zx = torch.rand(m
 rows.append(("zhemv U n=16384", 16.0 * m * (m + 1) / 2, time_call(lambda: g.call("zhemv_", "U", m, 1.0 + 0j, Z, m, zx, 1, 0j, zy, 1))))
 rows.append(("zher2 L n=16384", 2 * 16.0 * m * (m + 1) / 2, time_call(lambda: g.call("zher2_", "L", m, 1e-9 + 0j, zx, 1, zy, 1, Z, m))))
 rows.append(("zgeru n=16384", 2 * 16.0 * m * m, time_call(lambda: g.call("zgeru_", m, m, 1e-9 + 0j, zx, 1, zy, 1, Z, m))))
+del Z
+nn = 32768
+Sf = torch.rand((nn, nn), dtype=torch.float64, device="cuda"); sx = torch.rand(nn, dtype=torch.float64, device="cuda"); sy = torch.zeros(nn, dtype=torch.float64, device="cuda")
+for ul in "UL":
+    rows.append(("dsymv %s n=32768" % ul, 8.0 * nn * (nn + 1) / 2, time_call(lambda: g.call("dsymv_", ul, nn, 1.0, Sf, nn, sx, 1, 0.0, sy, 1))))
+del Sf
+ab = torch.rand((nb, k + 1), dtype=torch.float64, device="cuda")
+rows.append(("dsbmv L n=2^22 k=127", 8.0 * nb * (k + 1), time_call(lambda: g.call("dsbmv_", "L", nb, k, 1.0, ab, k + 1, xb, 1, 0.0, yb, 1))))
 for name, byts, ms in rows:
     print(f"{name:30s} {ms:9.4f} ms  {byts/ms/1e6:8.1f} GB/s  {byts/ms/1e6/PEAK*100:5.1f}% of measured HBM peak", flush=True)
