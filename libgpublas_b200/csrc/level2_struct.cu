@@ -112,7 +112,7 @@ template <typename T> struct WarpStripSink {
 };
 // grid (row blocks, column chunks); dynamic shared memory: one strip of `wstride` sums per warp
 template <typename T>
-__global__ void __launch_bounds__(ROW_THREADS) sympart_kernel(Desc D, const T* __restrict__ A, const T* __restrict__ v, int cpc, int nflags, int tflags, T* __restrict__ part,
+__global__ void __launch_bounds__(ROW_THREADS, 5) sympart_kernel(Desc D, const T* __restrict__ A, const T* __restrict__ v, int cpc, int nflags, int tflags, T* __restrict__ part,
                                                                int64_t npad, T* __restrict__ tp2, int64_t npadw, int wstride) {
     extern __shared__ __align__(16) unsigned char sym_smem[];
     T* strips = reinterpret_cast<T*>(sym_smem);

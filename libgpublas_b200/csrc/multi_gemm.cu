@@ -59,18 +59,18 @@ void mg_block_range(int64_t total, int parts, int idx, int64_t* lo, int64_t* hi)
     *hi = idx < parts - 1 ? std::min<int64_t>(total, base * (idx + 1)) : total;
     if (*hi < *lo) *hi = *lo;
 }
-int64_t mg_a_group(int64_t tm) { return std::max<int64_t>(128, ((tm / 16 + 127) / 128) * 128); }
+int64_t mg_a_group(int64_t tm, int pieces) { return std::max<int64_t>(128, ((tm / pieces + 127) / 128) * 128); }
 int64_t mg_b_group() { return 1024; }      // half a band of the kernel's tile schedule (16 tile columns): first tiles start sooner
 
 // Hops of the whole call in issue order.  Positions follow the tile schedule of the GEMM kernel (bands of 16 tile-columns
 // walked down the rows): B piece 0, A row-group 0, B piece 1, then the A row-groups top to bottom, then the remaining B pieces;
 // at every position the grid rows / columns are interleaved so all devices receive their first pieces at the same time.
-std::vector<MgHop> mg_plan(int ndev, int64_t m, int64_t n, bool host_source) {
+std::vector<MgHop> mg_plan(int ndev, int64_t m, int64_t n, bool host_source, int a_pieces) {
     int P, Q;
     mg_grid(ndev, &P, &Q);
     std::vector<MgHop> plan;
     int64_t max_ag = 0, max_bb = 0;
-    for (int p = 0; p < P; p++) { int64_t lo, hi; mg_block_range(m, P, p, &lo, &hi); if (hi > lo) max_ag = std::max(max_ag, (hi - lo + mg_a_group(hi - lo) - 1) / mg_a_group(hi - lo)); }
+    for (int p = 0; p < P; p++) { int64_t lo, hi; mg_block_range(m, P, p, &lo, &hi); if (hi > lo) max_ag = std::max(max_ag, (hi - lo + mg_a_group(hi - lo, a_pieces) - 1) / mg_a_group(hi - lo, a_pieces)); }
     for (int q = 0; q < Q; q++) { int64_t lo, hi; mg_block_range(n, Q, q, &lo, &hi); max_bb = std::max(max_bb, (hi - lo + mg_b_group() - 1) / mg_b_group()); }
     auto chain = [&](int kind, int gidx, int piece, int64_t off, int64_t len) {
         // members of the chain: the devices that consume this piece
@@ -108,7 +108,7 @@ std::vector<MgHop> mg_plan(int ndev, int64_t m, int64_t n, bool host_source) {
     auto a_piece = [&](int64_t g) {
         for (int p = 0; p < P; p++) {
             int64_t lo, hi; mg_block_range(m, P, p, &lo, &hi);
-            const int64_t ag = mg_a_group(hi - lo), off = g * ag;
+            const int64_t ag = mg_a_group(hi - lo, a_pieces), off = g * ag;
             if (hi > lo && off < hi - lo) chain(0, p, (int)g, off, std::min<int64_t>(ag, hi - lo - off));
         }
     };
@@ -368,7 +368,7 @@ bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int6
             const int64_t half = (host_source && !direct(s) && g.tn >= 4 * bg) ? (g.tn / 2) / (2 * bg) * (2 * bg) : 0;     // whole bands of the tile schedule
             for (int part = 0; part < (half ? 2 : 1); part++) {
                 const int64_t c0 = part ? half : 0, c1 = (half && !part) ? half : g.tn;
-                if (!g.in_place) dgemm_set_panel_flags(d.flags, (int)mg_a_group(g.tm), d.flags + 2048 + c0 / bg, (int)bg, epoch);
+                if (!g.in_place) dgemm_set_panel_flags(d.flags, (int)mg_a_group(g.tm, 16), d.flags + 2048 + c0 / bg, (int)bg, epoch);
                 const T* bp = notb ? b_ptr(s) + c0 * b_ld(s) : b_ptr(s) + c0;
                 dgemm_out_dev(stream, ta, tb, (int)g.tm, (int)(c1 - c0), k, alpha, a_ptr(s), a_ld(s), bp, b_ld(s), eff_beta, out + c0 * ldo, ldo, out + c0 * ldo, ldo, MASK_FULL);
                 if (half && !part) {
@@ -386,39 +386,66 @@ bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int6
     };
     if (fused)
         for (int s = 0; s < ndev; s++) launch(s, s == 0 ? home_stream : st.dev[s].comp);
+    // bulk types: columns/rows [k0, k0 + kk) of the panels; the first chunk applies beta (after bringing a detached tile's old C in)
+    auto launch_chunk = [&](int s, cudaStream_t stream, int64_t k0, int64_t kk, bool first) {
+        MgDev& d = st.dev[s];
+        const Geo& g = geo[s];
+        if (g.tm <= 0 || g.tn <= 0) return;
+        DeviceScope scope(d.id);
+        T* out = direct(s) ? c_home[s] : (T*)d.ctile;
+        const int64_t ldo = direct(s) ? ldc : g.ldc_t;
+        if (first && !direct(s) && !beta0)
+            B200_CUDA(cudaMemcpy2DAsync(d.ctile, (size_t)g.ldc_t * es, c_home[s], (size_t)ldc * es, (size_t)g.tm * es, (size_t)g.tn, cudaMemcpyDefault, stream));
+        const T* ap = nota ? a_ptr(s) + k0 * a_ld(s) : a_ptr(s) + k0;
+        const T* bp = notb ? b_ptr(s) + k0 : b_ptr(s) + k0 * b_ld(s);
+        if (first) trace_mark(d, stream, "dev %d kernel may start", s, 0, 0, 0);
+        GemmFn<T>::fn(stream, ta, tb, (int)g.tm, (int)g.tn, (int)kk, alpha, ap, a_ld(s), bp, b_ld(s), first ? beta : num<T>::real(1.0), out, ldo, MASK_FULL);
+        if (k0 + kk >= k) trace_mark(d, stream, "dev %d kernel done", s, 0, 0, 0);
+    };
 
     // ---- the piece chains ----
-    const std::vector<MgHop> plan = mg_plan(ndev, m, n, host_source);
+    // Bulk types (S/C/Z): k is consumed in NCH chunks -- every piece travels chunk by chunk, a device multiplies chunk c (beta on the
+    // first chunk, then accumulating into its tile) as soon as that chunk of its panels has landed, while chunk c+1 is still on
+    // the wires.  (One chunk = the old behaviour: at N = 8 the SGEMM 16384^3 call was 2.5 ms of transfers, then the split pass, then
+    // 4.7 ms of tensor work in series -- 4.3x; profiles/r02j_bench_n8.json.)  Coarser A pieces keep the hop count per call the same.
+    const int NCH = fused ? 1 : (k >= 8192 ? 4 : (k >= 4096 ? 2 : 1));
+    const int64_t kstep = ((k + NCH - 1) / NCH + 255) / 256 * 256;
+    const std::vector<MgHop> plan = mg_plan(ndev, m, n, host_source, NCH > 1 ? 4 : 16);
     // arrival events: [slot][kind][piece]
     std::vector<cudaEvent_t> arrived((size_t)ndev * 2 * 2048, nullptr);
     auto arr = [&](int s, int kind, int piece) -> cudaEvent_t& { return arrived[((size_t)s * 2 + kind) * 2048 + piece]; };
     unsigned long long origin_bytes = 0, forward_bytes = 0;
+    for (int ch = 0; ch < NCH; ch++) {
+    const int64_t k0 = (int64_t)ch * kstep, kk = std::min<int64_t>(kstep, k - k0);
+    if (kk <= 0) break;
+    std::fill(arrived.begin(), arrived.end(), nullptr);
     for (const MgHop& hp : plan) {
         MgDev& dst = st.dev[hp.dst];
         const Geo& gd = geo[hp.dst];
         // geometry of the piece inside a panel / inside the original operand
         size_t width, height, spitch, dpitch;
         const char* src; char* dstp;
+        // (k range [k0, k0 + kk) of the piece: columns of an 'N' A / rows of a 'T' A, rows of an 'N' B / columns of a 'T' B)
         if (hp.kind == 0) {       // rows [off, off+len) of op(A)'s row block
-            if (nota) { width = (size_t)hp.len * es; height = (size_t)k; dstp = dst.panelA + (size_t)hp.off * es; dpitch = (size_t)gd.lda_p * es; }
-            else      { width = (size_t)k * es; height = (size_t)hp.len; dstp = dst.panelA + (size_t)hp.off * gd.lda_p * es; dpitch = (size_t)gd.lda_p * es; }
+            if (nota) { width = (size_t)hp.len * es; height = (size_t)kk; dstp = dst.panelA + ((size_t)hp.off + (size_t)k0 * gd.lda_p) * es; dpitch = (size_t)gd.lda_p * es; }
+            else      { width = (size_t)kk * es; height = (size_t)hp.len; dstp = dst.panelA + ((size_t)hp.off * gd.lda_p + (size_t)k0) * es; dpitch = (size_t)gd.lda_p * es; }
             if (hp.src < 0) {
-                src = nota ? (const char*)(a + gd.r0 + hp.off) : (const char*)(a + (gd.r0 + hp.off) * lda);
+                src = nota ? (const char*)(a + gd.r0 + hp.off + k0 * lda) : (const char*)(a + (gd.r0 + hp.off) * lda + k0);
                 spitch = (size_t)lda * es;
             } else {
                 const Geo& gs = geo[hp.src];
-                src = nota ? st.dev[hp.src].panelA + (size_t)hp.off * es : st.dev[hp.src].panelA + (size_t)hp.off * gs.lda_p * es;
+                src = nota ? st.dev[hp.src].panelA + ((size_t)hp.off + (size_t)k0 * gs.lda_p) * es : st.dev[hp.src].panelA + ((size_t)hp.off * gs.lda_p + (size_t)k0) * es;
                 spitch = (size_t)gs.lda_p * es;
             }
         } else {                  // columns [off, off+len) of op(B)'s column block
-            if (notb) { width = (size_t)k * es; height = (size_t)hp.len; dstp = dst.panelB + (size_t)hp.off * gd.ldb_p * es; dpitch = (size_t)gd.ldb_p * es; }
-            else      { width = (size_t)hp.len * es; height = (size_t)k; dstp = dst.panelB + (size_t)hp.off * es; dpitch = (size_t)gd.ldb_p * es; }
+            if (notb) { width = (size_t)kk * es; height = (size_t)hp.len; dstp = dst.panelB + ((size_t)hp.off * gd.ldb_p + (size_t)k0) * es; dpitch = (size_t)gd.ldb_p * es; }
+            else      { width = (size_t)hp.len * es; height = (size_t)kk; dstp = dst.panelB + ((size_t)hp.off + (size_t)k0 * gd.ldb_p) * es; dpitch = (size_t)gd.ldb_p * es; }
             if (hp.src < 0) {
-                src = notb ? (const char*)(b + (gd.c0 + hp.off) * ldb) : (const char*)(b + gd.c0 + hp.off);
+                src = notb ? (const char*)(b + (gd.c0 + hp.off) * ldb + k0) : (const char*)(b + gd.c0 + hp.off + k0 * ldb);
                 spitch = (size_t)ldb * es;
             } else {
                 const Geo& gs = geo[hp.src];
-                src = notb ? st.dev[hp.src].panelB + (size_t)hp.off * gs.ldb_p * es : st.dev[hp.src].panelB + (size_t)hp.off * es;
+                src = notb ? st.dev[hp.src].panelB + ((size_t)hp.off * gs.ldb_p + (size_t)k0) * es : st.dev[hp.src].panelB + ((size_t)hp.off + (size_t)k0 * gs.ldb_p) * es;
                 spitch = (size_t)gs.ldb_p * es;
             }
         }
@@ -440,7 +467,7 @@ bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int6
         if (hp.src < 0) origin_bytes += (unsigned long long)width * height; else forward_bytes += (unsigned long long)width * height;
         if (hp.src < 0 && host_source) __atomic_fetch_add(&g_stats.h2d_bytes, (unsigned long long)(width * height), __ATOMIC_RELAXED);
     }
-    // ---- bulk types: the ordinary kernel once every piece of the device's panels has landed ----
+    // ---- bulk types: the ordinary kernel on this chunk of k once the chunk's pieces of the device's panels have landed ----
     if (!fused)
         for (int s = 0; s < ndev; s++) {
             cudaStream_t stream = s == 0 ? home_stream : st.dev[s].comp;
@@ -450,8 +477,9 @@ bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int6
                     for (int piece = 0; piece < 2048; piece++)
                         if (arr(s, kind, piece)) B200_CUDA(cudaStreamWaitEvent(stream, arr(s, kind, piece), 0));
             }
-            launch(s, stream);
+            launch_chunk(s, stream, k0, kk, ch == 0);
         }
+    }   // chunks of k
     // ---- C return for detached tiles, completion ----
     for (int s = 0; s < ndev; s++) {
         MgDev& d = st.dev[s];

@@ -10,9 +10,9 @@ namespace b200 {
 struct MgHop { int kind, gidx, piece; int64_t off, len; int src, dst; };
 void mg_grid(int ndev, int* P, int* Q);
 void mg_block_range(int64_t total, int parts, int idx, int64_t* lo, int64_t* hi);
-int64_t mg_a_group(int64_t tile_rows);
+int64_t mg_a_group(int64_t tile_rows, int pieces = 16);
 int64_t mg_b_group();
-std::vector<MgHop> mg_plan(int ndev, int64_t m, int64_t n, bool host_source);
+std::vector<MgHop> mg_plan(int ndev, int64_t m, int64_t n, bool host_source, int a_pieces = 16);
 
 struct MgStats { unsigned long long calls, devices, origin_bytes, forward_bytes, hops; };
 extern MgStats g_mg_stats;

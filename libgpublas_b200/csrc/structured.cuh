@@ -291,25 +291,65 @@ template <typename T, typename SINK> ST_HD T sym_row(const Desc& D, const T* A, 
     row_cols(D, i_first, jf0, jf1);
     row_cols(D, i_last, jl0, jl1);
     const int jstart = st_max(jf0, c0), jend = st_min(jl1, c1);
+    // INTERIOR steps (warp-uniform test): all 32 rows exist, the step lies inside every row's range and meets no diagonal.  They
+    // are nearly all of the work and run without masks, flag tests or per-column stride look-ups, with the next step's matrix
+    // elements already in flight while this step's butterfly runs (the first version did all of that per element: 215 issue slots
+    // per step, 57 % of the HBM peak with the DRAM pipe half idle; profiles/r02p_level2_sym_one_pass_v1.txt).
+    const bool whole = i_first + 31 < n;
+    const int jin0 = st_max(jl0, c0), jin1 = st_min(jf1, c1);          // the last row starts last, the first row ends first
+    const bool packed = D.kind == K_PACKED, up = D.upper != 0;
+    const int64_t cs = packed ? 0 : col_step(D, 0);
+    const bool cn = (nflags & F_CONJ) != 0, ct = (tflags & F_CONJ) != 0;
     T acc[NU];
 ST_UNROLL
     for (int u = 0; u < NU; u++) acc[u] = el<T>::zero();
     const T vi = i < n ? v[i] : el<T>::zero();
     const T* p = A + off(D, i < n ? i : i_first, jstart);   // outside the stored part it is never dereferenced
-    for (int j = jstart; j < jend; j += NU) {
+    int j = jstart;
+    while (j < jend) {
         T a[NU], w[NU], t[NU];
-        int64_t s = 0;
-        if (j >= j0 && j + NU <= j1) {
+        const bool interior = whole && j >= jin0 && j + NU <= jin1 && (j + NU <= i_first || j > i_last);
+        if (interior) {
+            T an[NU];
+            auto fetch = [&](T (&dst)[NU], int jj) {       // NU loads along the row, p moves to column jj + NU
+                if (packed) {
+                    int64_t s = 0;
 ST_UNROLL
-            for (int u = 0; u < NU; u++) { a[u] = p[s]; w[u] = v[j + u]; s += col_step(D, j + u); }
-        } else {
+                    for (int u = 0; u < NU; u++) { dst[u] = p[s]; s += up ? (int64_t)jj + u + 1 : (int64_t)n - jj - u - 1; }
+                    p += s;
+                } else {
 ST_UNROLL
-            for (int u = 0; u < NU; u++) {
-                const bool in = j + u >= j0 && j + u < j1;
-                a[u] = in ? p[s] : el<T>::zero();
-                w[u] = in ? v[j + u] : el<T>::zero();
-                s += col_step(D, j + u);
+                    for (int u = 0; u < NU; u++) dst[u] = p[u * cs];
+                    p += NU * cs;
+                }
+            };
+            fetch(a, j);
+            for (;;) {
+                const int jn = j + NU;
+                const bool more = jn < jend && jn >= jin0 && jn + NU <= jin1 && (jn + NU <= i_first || jn > i_last);
+                if (more) fetch(an, jn);
+ST_UNROLL
+                for (int u = 0; u < NU; u++) w[u] = v[j + u];
+ST_UNROLL
+                for (int u = 0; u < NU; u++) {
+                    acc[u] = el<T>::mad(cn ? el<T>::conj(a[u]) : a[u], w[u], acc[u]);
+                    t[u] = el<T>::mul(ct ? el<T>::conj(a[u]) : a[u], vi);
+                }
+                sink.step(j, t);
+                j = jn;
+                if (!more) break;
+ST_UNROLL
+                for (int u = 0; u < NU; u++) a[u] = an[u];
             }
+            continue;
+        }
+        int64_t s = 0;
+ST_UNROLL
+        for (int u = 0; u < NU; u++) {
+            const bool in = j + u >= j0 && j + u < j1;
+            a[u] = in ? p[s] : el<T>::zero();
+            w[u] = in ? v[j + u] : el<T>::zero();
+            s += col_step(D, j + u);
         }
         p += s;
 ST_UNROLL
@@ -318,6 +358,7 @@ ST_UNROLL
             t[u] = mad_elem<T>(a[u], vi, i, j + u, tflags, el<T>::zero());
         }
         sink.step(j, t);
+        j += NU;
     }
     T r = acc[0];
 ST_UNROLL
