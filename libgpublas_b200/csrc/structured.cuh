@@ -204,13 +204,29 @@ template <typename T> ST_HD T npart_row(const Desc& D, const T* A, const T* v, i
 ST_UNROLL
     for (int u = 0; u < NU; u++) acc[u] = el<T>::zero();
     if (j0 >= j1) return acc[0];
+    const bool packed = D.kind == K_PACKED, up = D.upper != 0, cj = (flags & F_CONJ) != 0;
+    const int64_t cs = packed ? 0 : col_step(D, 0);
     const T* p = A + off(D, i, jstart);   // may point outside the stored part for columns left of j0: never dereferenced there
     for (int j = jstart; j < j1; j += NU) {
         T a[NU], w[NU];
         int64_t s = 0;
-        if (j >= j0 && j + NU <= j1) {   // interior step: no masks
+        if (j >= j0 && j + NU <= j1) {   // interior step: no masks, a constant stride where the scheme has one
+            if (packed) {
 ST_UNROLL
-            for (int u = 0; u < NU; u++) { a[u] = p[s]; w[u] = v[j + u]; s += col_step(D, j + u); }
+                for (int u = 0; u < NU; u++) { a[u] = p[s]; s += up ? (int64_t)j + u + 1 : (int64_t)D.n - j - u - 1; }
+            } else {
+ST_UNROLL
+                for (int u = 0; u < NU; u++) a[u] = p[u * cs];
+                s = NU * cs;
+            }
+ST_UNROLL
+            for (int u = 0; u < NU; u++) w[u] = v[j + u];
+            p += s;
+            if (i < j || i >= j + NU) {  // ... and no diagonal element in it: no flag tests either
+ST_UNROLL
+                for (int u = 0; u < NU; u++) acc[u] = el<T>::mad(cj ? el<T>::conj(a[u]) : a[u], w[u], acc[u]);
+                continue;
+            }
         } else {                         // head (columns left of this row's range) or tail
 ST_UNROLL
             for (int u = 0; u < NU; u++) {
@@ -219,8 +235,8 @@ ST_UNROLL
                 w[u] = in ? v[j + u] : el<T>::zero();
                 s += col_step(D, j + u);
             }
+            p += s;
         }
-        p += s;
 ST_UNROLL
         for (int u = 0; u < NU; u++) acc[u] = mad_elem<T>(a[u], w[u], i, j + u, flags, acc[u]);
     }
@@ -421,13 +437,21 @@ template <typename T> ST_HD void rank_row(const Desc& D, T* A, int i, int c0, in
     const T yi = (mode == R_SYR2 || mode == R_HER2) ? y[i] : el<T>::zero();
     const T axi = el<T>::mul(alpha, xi);                                          // alpha x(i)
     const T ayi = el<T>::mul(mode == R_HER2 ? el<T>::conj(alpha) : alpha, yi);     // alpha y(i)  /  conj(alpha) y(i)
+    const bool packed = D.kind == K_PACKED, up = D.upper != 0;
+    const int64_t cs = packed ? 0 : col_step(D, 0);
     T* p = A + off(D, i, jstart);
     for (int j = jstart; j < j1; j += NU) {   // NU read-modify-writes per step, loads first
         T a[NU];
         int64_t st[NU], s = 0;
-        if (j >= j0 && j + NU <= j1) {        // interior step: no masks
+        if (j >= j0 && j + NU <= j1) {        // interior step: no masks, a constant stride where the scheme has one
+            if (packed) {
 ST_UNROLL
-            for (int u = 0; u < NU; u++) { st[u] = s; a[u] = p[s]; s += col_step(D, j + u); }
+                for (int u = 0; u < NU; u++) { st[u] = s; a[u] = p[s]; s += up ? (int64_t)j + u + 1 : (int64_t)D.n - j - u - 1; }
+            } else {
+ST_UNROLL
+                for (int u = 0; u < NU; u++) { st[u] = u * cs; a[u] = p[u * cs]; }
+                s = NU * cs;
+            }
 ST_UNROLL
             for (int u = 0; u < NU; u++) p[st[u]] = rank_elem<T>(a[u], i, j + u, axi, ayi, x, y, mode);
         } else {                              // head (columns left of this row's range) or tail
