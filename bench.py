@@ -174,6 +174,18 @@ def other_routines_partitioned(g, lib, torch, dev, peaks, out, world):
     ms = timed(lambda: g.call("dsyrk_", "L", "N", n, n, 1.0, A, n, 0.0, C, n))
     out["dsyrk_LN_16384"] = {"tflops": float(n) ** 3 / ms / 1e9, "ms": ms, "devices": world, "partitioned_calls": mg_stats(lib)[0] - c0,
                              "frac_of_fp64_peak_per_gpu": float(n) ** 3 / ms / 1e9 / world / FP64_PEAK_NOMINAL}
+    # check (outside the timed region): 64 sampled columns of the lower triangle against a float64 product of the same operands;
+    # torch tensors are row-major, so the column-major operand the library saw is A^T and its C := A_cm A_cm^T lower is torch's upper
+    eps = 2.0 ** -53
+    cols = torch.randperm(n, device=dev)[:64]
+    Acm_cols = A[:, cols]                                    # column-major rows `cols` of the operand = torch columns
+    ref = A.T @ Acm_cols                                     # (A_cm A_cm^T)[:, cols]
+    got = C[cols, :].T                                       # column-major C[:, cols]
+    mask = torch.arange(n, device=dev)[:, None] >= cols[None, :]          # referenced (lower) part of those columns
+    err = ((got - ref) * mask).norm().item(); bound = 4 * (n + 2) * eps * (A.norm().item() * Acm_cols.norm().item())
+    out["dsyrk_LN_16384"]["verified"] = {"ok": bool(err <= bound), "err_fro_64_columns": err, "bound": bound,
+                                         "upper_untouched": bool((torch.tril(C, -1) == 0).all().item())}
+    del ref, got, mask, Acm_cols
     T = torch.triu(A).contiguous(); T.mul_(1.0 / n); T.diagonal().fill_(1.0)          # row-major upper == column-major lower, well conditioned
     for name in ("dtrsm_", "dtrmm_"):
         C.uniform_(-1, 1)
@@ -181,6 +193,17 @@ def other_routines_partitioned(g, lib, torch, dev, peaks, out, world):
         ms = timed(lambda: g.call(name, "L", "L", "N", "N", n, n, 1.0, T, n, C, n))
         out[name + "LLNN_16384"] = {"tflops": float(n) ** 3 / ms / 1e9, "ms": ms, "devices": world, "partitioned_calls": mg_stats(lib)[0] - c0,
                                     "frac_of_fp64_peak_per_gpu": float(n) ** 3 / ms / 1e9 / world / FP64_PEAK_NOMINAL}
+        # one more call on known right-hand sides, checked on 64 of them: column-major B[:, j] is torch row j
+        C.uniform_(-1, 1); B0 = C[:64].clone()
+        g.call(name, "L", "L", "N", "N", n, n, 1.0, T, n, C, n); torch.cuda.synchronize()
+        Lcm = T.T                                            # the column-major lower triangle as a torch matrix
+        X = C[:64].T
+        if name == "dtrsm_":
+            err = (Lcm @ X - B0.T).norm().item(); bound = 4 * n * eps * (Lcm.norm().item() * X.norm().item() + B0.norm().item())
+        else:
+            err = (X - Lcm @ B0.T).norm().item(); bound = 4 * (n + 2) * eps * Lcm.norm().item() * B0.norm().item()
+        out[name + "LLNN_16384"]["verified"] = {"ok": bool(err <= bound), "err_fro_64_rhs": err, "bound": bound}
+        del B0, X
     del A, C, T
     out.update(cholesky_single_call(lib, torch, dev, world))
 
