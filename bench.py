@@ -287,7 +287,8 @@ def other_routines(g, torch, dev, peaks, out):
     tf32_peak = peaks.get("bf16_tflops", 1667.5) / 2.0     # tf32 dense = half the bf16 rate; 3 MMAs per product
     out["sgemm_16384"] = {"tflops": tf, "ms": ms, "variant": g.last_variant(), "frac_of_fp32_ffma_peak_74.4": tf / 74.4,
                           "frac_of_tf32_pipe_div3": tf / (tf32_peak / 3.0),
-                          "note": "3xTF32 on tcgen05 incl. the split pass; tensor denominator = measured bf16 burst / 2 / 3; cuBLAS SGEMM (FFMA) on this part: 67 TFLOP/s"}
+                          "frac_of_tf32_pipe_div3_sustained": (tf / (peaks["bf16_tflops_sustained"] / 2.0 / 3.0)) if peaks.get("bf16_tflops_sustained") else None,
+                          "note": "3xTF32 on tcgen05 incl. the split pass; tensor denominator = measured bf16 burst / 2 / 3 (and, second key, the sustained bf16 figure: back-to-back launches run power-limited); cuBLAS SGEMM (FFMA) on this part: 67 TFLOP/s"}
     del A, B, C
     n = 8192
     A = torch.rand((n, n), dtype=torch.complex128, device=dev); B = torch.rand((n, n), dtype=torch.complex128, device=dev)
