@@ -47,6 +47,11 @@ void gemm_entry(const char* name, const char* transa, const char* transb, const 
         log_exec(name, "%c%c m=%d n=%d k=%d lda=%d ldb=%d ldc=%d (partitioned over %d devices)", ta, tb, *m, *n, *k, *lda, *ldb, *ldc, g_opts.devices);
         return;
     }
+    // tracked managed operands the CPU has just filled: range-by-range migration with the multiply behind it (staged_gemm.cuh)
+    if (!scale_only && gemm_first_touch<T>(GemmDev<T>::fn, ta, tb, *m, *n, *k, *alpha, a, (int64_t)*lda, b, (int64_t)*ldb, *beta, c, (int64_t)*ldc)) {
+        log_exec(name, "%c%c m=%d n=%d k=%d lda=%d ldb=%d ldc=%d (first-touch migration under the multiply)", ta, tb, *m, *n, *k, *lda, *ldb, *ldc);
+        return;
+    }
     // large host-resident operands: chunked staging overlapped with the multiply (staged_gemm.cuh)
     if (!scale_only && gemm_pipelined<T>(GemmDev<T>::fn, ta, tb, *m, *n, *k, *alpha, a, (int64_t)*lda, b, (int64_t)*ldb, *beta, c, (int64_t)*ldc)) {
         log_exec(name, "%c%c m=%d n=%d k=%d lda=%d ldb=%d ldc=%d (pipelined staging)", ta, tb, *m, *n, *k, *lda, *ldb, *ldc);

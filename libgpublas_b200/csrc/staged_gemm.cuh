@@ -170,4 +170,84 @@ bool gemm_pipelined(GEMM gemm, char ta, char tb, int m, int n, int k, T alpha, c
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// First use of TRACKED MANAGED operands the CPU has just filled -- the reference's hit path (an unmodified program callocs its
+// matrices under the interposer and calls dgemm_): the pages live in host memory.  make_resident() migrates whole blocks before the
+// kernel starts: 6.4 GB at ~43 GB/s = 150 ms in front of 245 ms of DMMA for 16384^3 (profiles/r02a_bench_n1.json:
+// e2e.managed_first_touch = 22 TFLOP/s).  Here the migration is issued as cudaMemPrefetchAsync of CONTIGUOUS ranges on a second
+// stream in the order the multiply needs them, and the multiply follows range by range, in place (no staging buffers):
+//   column panel 0 of B and C, then A in k-chunks (panel 0 is multiplied chunk by chunk as A arrives), then the panels 1.. of
+//   B and C under the multiplies of the panels before them.
+// Ranges are contiguous only for 'N' operands (columns of a column-major array); a transposed operand is migrated whole, first.
+// Operands that are already resident (or not tracked: the application manages those) take part without prefetches.
+template <typename T, typename GEMM>
+bool gemm_first_touch(GEMM gemm, char ta, char tb, int m, int n, int k, T alpha, const T* a, int64_t lda, const T* b, int64_t ldb,
+                      T beta, T* c, int64_t ldc) {
+    const size_t es = sizeof(T);
+    if (g_opts.prefetch != 1 || n < 2048 || k < 2048 || m < 128) return false;
+    const size_t total = ((size_t)m * k + (size_t)k * n + (size_t)m * n) * es;
+    if (total < g_opts.pipeline_min_bytes) return false;
+    if (classify(a) != RES_MANAGED || classify(b) != RES_MANAGED || classify(c) != RES_MANAGED) return false;
+    const bool fresh_a = tracker_peek_resident(a) == 0, fresh_b = tracker_peek_resident(b) == 0, fresh_c = tracker_peek_resident(c) == 0;
+    if (!fresh_a && !fresh_b) return false;                       // nothing large to migrate: the plain path
+    const bool nota = ta == 'N', notb = tb == 'N';
+    cudaStream_t s = current_stream(), pf = aux_stream(0);
+    const int dev = current_device();
+    const T one = num<T>::real(1.0);
+    auto record = [&](int ev, cudaStream_t on) { TrackerGuard guard; B200_CUDA(cudaEventRecord(pooled_event(ev), on)); };
+    auto wait = [&](cudaStream_t who, int ev) { TrackerGuard guard; B200_CUDA(cudaStreamWaitEvent(who, pooled_event(ev), 0)); };
+    auto prefetch = [&](const void* p, size_t bytes) {
+        TrackerGuard guard;
+        if (cudaMemPrefetchAsync(p, bytes, dev, pf) == cudaSuccess) __atomic_fetch_add(&g_stats.prefetch_bytes, (unsigned long long)bytes, __ATOMIC_RELAXED);
+        else cudaGetLastError();
+    };
+    auto advise = [&](const void* p) {        // whole block: preferred location = this device, marked as migrated
+        TrackerGuard guard;
+        void* base = nullptr; size_t bsize = 0;
+        if (tracker_lookup(p, &base, &bsize)) cudaMemAdvise(base, bsize, cudaMemAdviseSetPreferredLocation, dev);
+        cudaGetLastError();
+        tracker_test_and_set_resident(p);
+    };
+    enum { EV_START = 0, EV_CHUNK = 1, EV_PANEL = 20, EV_END = 60 };
+    record(EV_START, s);
+    wait(pf, EV_START);
+    if (fresh_a) advise(a);
+    if (fresh_b) advise(b);
+    if (fresh_c) advise(c);
+    __atomic_fetch_add(&g_stats.hits, 3ull, __ATOMIC_RELAXED);
+    const int P = 8;
+    const int64_t np = round_up((n + P - 1) / P, 128);
+    const int NCH = 8;
+    const int64_t kc = round_up((k + NCH - 1) / NCH, 256);
+    const size_t a_bytes = (size_t)(((nota ? k : m) - 1) * lda + (nota ? m : k)) * es;
+    const size_t b_bytes = (size_t)(((notb ? n : k) - 1) * ldb + (notb ? k : n)) * es;
+    auto b_panel = [&](int64_t n0, int64_t nn) { if (fresh_b && notb) prefetch(b + n0 * ldb, (size_t)((nn - 1) * ldb + k) * es); };
+    auto c_panel = [&](int64_t n0, int64_t nn) { if (fresh_c) prefetch(c + n0 * ldc, (size_t)((nn - 1) * ldc + m) * es); };
+    if (fresh_b && !notb) prefetch(b, b_bytes);
+    if (fresh_a && !nota) prefetch(a, a_bytes);
+    // ---- panel 0: B and C first, then A chunk by chunk with the multiply behind it ----
+    const int64_t n00 = std::min<int64_t>(np, n);
+    b_panel(0, n00);
+    c_panel(0, n00);
+    int nev = 0;
+    for (int64_t k0 = 0; k0 < k; k0 += kc, nev++) {
+        const int64_t kk = std::min<int64_t>(kc, k - k0);
+        if (fresh_a && nota) prefetch(a + k0 * lda, (size_t)((kk - 1) * lda + m) * es);
+        record(EV_CHUNK + nev, pf);
+        wait(s, EV_CHUNK + nev);
+        gemm(s, ta, tb, m, (int)n00, (int)kk, alpha, nota ? a + k0 * lda : a + k0, lda, notb ? b + k0 : b + k0 * ldb, ldb, k0 == 0 ? beta : one, c, ldc, MASK_FULL);
+    }
+    // ---- the other panels: their B and C columns travel under the multiplies before them ----
+    int pe = 0;
+    for (int64_t n0 = n00; n0 < n; n0 += np, pe++) {
+        const int64_t nn = std::min<int64_t>(np, n - n0);
+        b_panel(n0, nn);
+        c_panel(n0, nn);
+        record(EV_PANEL + pe, pf);
+        wait(s, EV_PANEL + pe);
+        gemm(s, ta, tb, m, (int)nn, k, alpha, a, lda, notb ? b + n0 * ldb : b + n0, ldb, beta, c + n0 * ldc, ldc, MASK_FULL);
+    }
+    return true;
+}
+
 }  // namespace b200

@@ -211,6 +211,16 @@ int tracker_test_and_set_resident(const void* ptr) {
     pthread_rwlock_unlock(&g_lock);
     return prev;
 }
+int tracker_peek_resident(const void* ptr) {
+    uintptr_t p = (uintptr_t)ptr;
+    if (p < g_lo || p >= g_hi) return -1;
+    int cur = -1;
+    pthread_rwlock_rdlock(&g_lock);
+    long i = find_block(p);
+    if (i >= 0) cur = __atomic_load_n(&g_blocks[i].resident, __ATOMIC_RELAXED);
+    pthread_rwlock_unlock(&g_lock);
+    return cur;
+}
 void tracker_set_trace(int on) { g_trace = on; }
 // "C" line for a tracked operand of a BLAS call (reference OBJPRINT_CALL): which allocation the routine `fun` used
 void tracker_trace_call(const void* ptr, const char* fun) {

@@ -19,6 +19,7 @@ int tracker_lookup(const void* p, void** base, size_t* size);
 // Residency bookkeeping for a tracked block containing p: returns 1 if the block has already been bulk-migrated to
 // the device since it was allocated, 0 if not (and marks it), -1 if p is not in a tracked block.
 int tracker_test_and_set_resident(const void* p);
+int tracker_peek_resident(const void* p);    // the same answer without marking the block
 // re-entrancy guard (reference obj_tracker_internal_enter/leave, obj_tracker.c:343-349): while a
 // thread is inside, its allocations go straight to glibc.
 void tracker_enter(void);

@@ -497,3 +497,49 @@ def test_entry_points_are_thread_safe():
     for t in range(8):
         assert np.abs(got[t][0] - want[t][0]).max() <= 16 * 2.0 ** -53 * jobs[t][2]
         assert abs(got[t][1] - want[t][1]) <= 1e-12 * want[t][1]
+
+
+@pytest.mark.parametrize("ta,tb", [("N", "N"), ("T", "N"), ("N", "T"), ("T", "T")])
+def test_dgemm_first_touch_of_tracked_managed_operands(ta, tb):
+    """The reference's hit path: matrices calloc'd under the interposer (tracked managed blocks), filled by the CPU, then dgemm_.
+    The first call migrates them range by range (cudaMemPrefetchAsync of contiguous column ranges in the order the multiply needs
+    them) with the multiply following behind, in place (staged_gemm.cuh: gemm_first_touch; the reference bulk-copies, then calls
+    cuBLAS: runtime-mem.hpp:84-112).  Result within the GEMM bound of a float64 numpy product; the blocks are resident afterwards
+    (a second call prefetches nothing) and both calls agree to the bound."""
+    lib = g.load()
+    lib.b200blas_set_options(b"pipeline_min=1000")
+    try:
+        m, n, k = 300, 2048 + 260, 2048 + 90
+        ra, ca = (m, k) if ta == "N" else (k, m)
+        rb, cb = (k, n) if tb == "N" else (n, k)
+        lda, ldb, ldc = ra + 2, rb + 4, m + 6
+        A = splitmix_uniform(81, (lda, ca)); B = splitmix_uniform(82, (ldb, cb)); C0 = splitmix_uniform(83, (ldc, n))
+        ptrs, views = [], []
+        for X in (A, B, C0):
+            nb = X.size * 8
+            ptr = lib.b200blas_malloc_managed(nb); assert ptr
+            v = np.frombuffer((ctypes.c_char * nb).from_address(ptr), dtype=np.float64).reshape(X.shape, order="F")
+            v[...] = X                                             # first touch on the CPU
+            ptrs.append(ptr); views.append(v)
+        s0 = g.stats()
+        f77(lib, "dgemm_", ta, tb, m, n, k, 0.7, g.DevPtr(ptrs[0]), lda, g.DevPtr(ptrs[1]), ldb, 1.3, g.DevPtr(ptrs[2]), ldc)
+        s1 = g.stats()
+        C1 = np.array(views[2], order="F")
+        assert s1["prefetch_bytes"] - s0["prefetch_bytes"] >= (ra * ca + rb * cb + m * n) * 8 * 0.95, "every operand range was migrated"
+        assert s1["h2d_bytes"] == s0["h2d_bytes"] and s1["hits"] - s0["hits"] == 3
+        views[2][...] = C0
+        f77(lib, "dgemm_", ta, tb, m, n, k, 0.7, g.DevPtr(ptrs[0]), lda, g.DevPtr(ptrs[1]), ldb, 1.3, g.DevPtr(ptrs[2]), ldc)
+        s2 = g.stats()
+        C2 = np.array(views[2], order="F")
+        assert s2["prefetch_bytes"] == s1["prefetch_bytes"], "resident now: nothing left to migrate"
+        opA = A[:ra] if ta == "N" else A[:ra].T
+        opB = B[:rb] if tb == "N" else B[:rb].T
+        ref = 0.7 * (opA @ opB) + 1.3 * C0[:m]
+        bound = 4 * (k + 2) * 2.0 ** -53 * (0.7 * np.linalg.norm(opA) * np.linalg.norm(opB) + 1.3 * np.linalg.norm(C0[:m]))
+        for Cx in (C1, C2):
+            assert np.linalg.norm(Cx[:m] - ref) <= bound and np.array_equal(Cx[m:], C0[m:])
+        del views, v
+        for ptr in ptrs:
+            lib.b200blas_free_managed(ptr)
+    finally:
+        lib.b200blas_set_options(b"pipeline_min=67108864")
