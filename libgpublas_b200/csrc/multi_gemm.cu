@@ -404,16 +404,16 @@ bool multi_gemm(char ta, char tb, int m, int n, int k, T alpha, const T* a, int6
     };
 
     // ---- the piece chains ----
-    // Bulk types (S/C/Z): k is consumed in NCH chunks -- every piece travels chunk by chunk, a device multiplies chunk c (beta on the
+    // Bulk types (S/C/Z) CAN consume k in NCH chunks -- every piece travels chunk by chunk, a device multiplies chunk c (beta on the
     // first chunk, then accumulating into its tile) as soon as that chunk of its panels has landed, while chunk c+1 is still on
     // the wires.  (One chunk: at N = 8 the SGEMM 16384^3 call was 2.5 ms of transfers, then the split pass, then 4.7 ms of tensor
     // work in series -- 4.3x; profiles/r02j_bench_n8.json.)  Coarser A pieces keep the hop count per call the same.
     static const int nch_env = getenv("B200BLAS_MG_KCHUNKS") ? atoi(getenv("B200BLAS_MG_KCHUNKS")) : 0;      // experiments: force the chunk count
-    // Each chunk costs a pass of the tile's epilogues (not overlapped with the next tile's main loop in the tcgen05 kernel: ~30 us per
-    // wave of tiles) and hides 1/NCH less of the distribution, which only weighs enough on large grids: measured at N = 2, SGEMM
-    // 16384^3 19.6 ms in one chunk, 20.4 in two, 24.1 in four (profiles/r02r_kchunks_n2.txt) -- so one chunk up to 3 devices.
-    const int want = ndev >= 8 ? 4 : (ndev >= 4 ? 2 : 1);
-    const int NCH = fused ? 1 : std::min(nch_env > 0 ? nch_env : want, std::max(1, k / (nch_env > 0 ? 1024 : 4096)));
+    // Measured, and OFF by default: each chunk costs a pass of the tile's epilogues (not overlapped with the next tile's main loop
+    // in the tcgen05 kernel), a split pass launch and a round of hops.  SGEMM 16384^3 at N = 2: 19.6 ms in one chunk, 20.4 in two,
+    // 24.1 in four (profiles/r02r_kchunks_n2.txt); at N = 8 four chunks took 22.2 ms against 9.5 ms in one (profiles/r02v_bench_n8.json
+    // vs r02j_bench_n8.json).  B200BLAS_MG_KCHUNKS=<n> keeps the path reachable (tests run it with 3 chunks).
+    const int NCH = fused ? 1 : std::min(nch_env > 0 ? nch_env : 1, std::max(1, k / 1024));
     const int64_t kstep = ((k + NCH - 1) / NCH + 255) / 256 * 256;
     const std::vector<MgHop> plan = mg_plan(ndev, m, n, host_source, NCH > 1 ? 4 : 16);
     // arrival events: [slot][kind][piece]
