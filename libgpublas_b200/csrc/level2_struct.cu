@@ -110,9 +110,9 @@ template <typename T> struct WarpStripSink {
         if ((lane & (32 / NU - 1)) == 0 && jj >= cw0 && jj < cw1) strip[jj - cw0] = sum;
     }
 };
-// grid (row blocks, column chunks); dynamic shared memory: one strip of `wstride` sums per warp
-template <typename T>
-__global__ void __launch_bounds__(ROW_THREADS, 5) sympart_kernel(Desc D, const T* __restrict__ A, const T* __restrict__ v, int cpc, int nflags, int tflags, T* __restrict__ part,
+// grid (row blocks, column chunks); dynamic shared memory: one strip of `wstride` sums per warp + `wstride` elements of v
+template <typename T, int MINB>
+__global__ void __launch_bounds__(ROW_THREADS, MINB) sympart_kernel(Desc D, const T* __restrict__ A, const T* __restrict__ v, int cpc, int nflags, int tflags, T* __restrict__ part,
                                                                int64_t npad, T* __restrict__ tp2, int64_t npadw, int wstride) {
     extern __shared__ __align__(16) unsigned char sym_smem[];
     T* strips = reinterpret_cast<T*>(sym_smem);
@@ -120,10 +120,12 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) sympart_kernel(Desc D, const T
     const int c0 = blockIdx.y * cpc, c1 = st_min(D.n, c0 + cpc);
     int cw0, cw1;
     sym_window(D, r0, c0, c1, cw0, cw1);
+    T* vwin = strips + (ROW_THREADS / 32) * wstride;           // v over the CTA's window of columns
     for (int t = threadIdx.x; t < (ROW_THREADS / 32) * wstride; t += ROW_THREADS) strips[t] = el<T>::zero();
+    for (int t = threadIdx.x; t < cw1 - cw0; t += ROW_THREADS) vwin[t] = v[cw0 + t];
     __syncthreads();
     WarpStripSink<T> sink = {strips + warp * wstride, cw0, cw1, lane};
-    const T r = sym_row<T>(D, A, v, i, i - lane, c0, c1, nflags, tflags, sink);
+    const T r = sym_row<T>(D, A, v, vwin - cw0, i, i - lane, c0, c1, nflags, tflags, sink);
     if (i < D.n) part[(int64_t)blockIdx.y * npad + i] = r;
     __syncthreads();
     T* row = tp2 + (int64_t)blockIdx.x * npadw - sym_jw0(D, r0);
@@ -260,7 +262,7 @@ struct DeviceBackend {
         smv_finish_kernel<T><<<(n + 255) / 256, 256, 0, s>>>(n, nparts, part, npad, tp, vunit, alpha, beta, out, inco);
         last_variant = VAR_GENERIC_TILE;
     }
-    // one-pass symmetric product: a strip of 1024 doubles (512 double-complex) per warp = 32 KB per CTA, 7 CTAs per SM
+    // one-pass symmetric product: a strip of 1024 doubles (512 double-complex) per warp + v over the window = 40 KB per CTA, 5 CTAs per SM
     template <typename T> int sym_max_cols() const {
         static const bool off = getenv("B200BLAS_SYM_TWO_PASS") != nullptr;
         return off ? 0 : (int)(8192 / sizeof(T));
@@ -269,11 +271,15 @@ struct DeviceBackend {
     void sympart(const Desc& D, const T* A, const T* v, int cpc, int nchunks, int nflags, int tflags, T* part, int64_t npad, T* tp2, int64_t npadw) {
         const int64_t w = sym_width(D) < cpc ? sym_width(D) : (int64_t)cpc;
         const int wstride = (int)((w + 7) / 8 * 8);
-        sympart_kernel<T><<<dim3((D.n + ROW_THREADS - 1) / ROW_THREADS, nchunks), ROW_THREADS, (size_t)(ROW_THREADS / 32) * wstride * sizeof(T), s>>>(
-            D, A, v, cpc, nflags, tflags, part, npad, tp2, npadw, wstride);
+        // 5 CTAs per SM (96 registers, a few spilled words) or 4 (no spills): B200BLAS_SYM_MINB picks, measured in profiles/
+        static const int minb = getenv("B200BLAS_SYM_MINB") ? atoi(getenv("B200BLAS_SYM_MINB")) : 5;
+        const dim3 grid((D.n + ROW_THREADS - 1) / ROW_THREADS, nchunks);
+        const size_t smem = (size_t)(ROW_THREADS / 32 + 1) * wstride * sizeof(T);
+        if (minb == 4) sympart_kernel<T, 4><<<grid, ROW_THREADS, smem, s>>>(D, A, v, cpc, nflags, tflags, part, npad, tp2, npadw, wstride);
+        else sympart_kernel<T, 5><<<grid, ROW_THREADS, smem, s>>>(D, A, v, cpc, nflags, tflags, part, npad, tp2, npadw, wstride);
     }
     template <typename T> void sym_finish(const Desc& D, int nparts, const T* part, int64_t npad, const T* tp2, int64_t npadw, T alpha, T beta, T* out, int64_t inco) {
-        sym_finish_kernel<T><<<(D.n + 255) / 256, 256, 0, s>>>(D, nparts, part, npad, tp2, npadw, alpha, beta, out, inco);
+        sym_finish_kernel<T><<<(D.n + 63) / 64, 64, 0, s>>>(D, nparts, part, npad, tp2, npadw, alpha, beta, out, inco);
         last_variant = VAR_GENERIC_TILE;
     }
     template <typename T> void rank(const Desc& D, T* A, int rows, int ncols, int cpc, int nchunks, T alpha, const T* x, const T* y, int mode) {

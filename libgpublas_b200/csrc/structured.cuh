@@ -297,7 +297,9 @@ ST_HD void sym_window(const Desc& D, int r0, int c0, int c1, int& cw0, int& cw1)
 // One row's walk.  Every lane of a warp runs the SAME steps (the butterfly in sink.step needs all 32): the loop bounds come from
 // the warp's first and last row, a lane masks the columns outside its own range (rows past n: everything).  Returns the N part
 // of row i; sink.step(j, t) receives the NU mirrored products of the step, t[u] = op_t(S(i, j+u)) * v(i) (zero where masked).
-template <typename T, typename SINK> ST_HD T sym_row(const Desc& D, const T* A, const T* v, int i, int i_first, int c0, int c1, int nflags, int tflags, SINK& sink) {
+// vcol[j] = v[j] for the columns of the CTA's window (the kernel keeps them in shared memory: the per-step v(j) loads were the
+// largest stall of the first two versions -- long scoreboard 6.3 of 11 cycles per issued instruction, profiles/r02s_ncu_full_raw.csv).
+template <typename T, typename SINK> ST_HD T sym_row(const Desc& D, const T* A, const T* v, const T* vcol, int i, int i_first, int c0, int c1, int nflags, int tflags, SINK& sink) {
     enum { NU = unroll_of<T>::N };
     const int n = D.n, i_last = st_min(i_first + 31, n - 1);
     if (i_first >= n) return el<T>::zero();                  // the whole warp is past the last row
@@ -339,23 +341,29 @@ ST_UNROLL
                     p += NU * cs;
                 }
             };
-            fetch(a, j);
-            for (;;) {
-                const int jn = j + NU;
-                const bool more = jn < jend && jn >= jin0 && jn + NU <= jin1 && (jn + NU <= i_first || jn > i_last);
-                if (more) fetch(an, jn);
+            auto compute = [&](T (&x)[NU], int jj) {
 ST_UNROLL
-                for (int u = 0; u < NU; u++) w[u] = v[j + u];
+                for (int u = 0; u < NU; u++) w[u] = vcol[jj + u];
 ST_UNROLL
                 for (int u = 0; u < NU; u++) {
-                    acc[u] = el<T>::mad(cn ? el<T>::conj(a[u]) : a[u], w[u], acc[u]);
-                    t[u] = el<T>::mul(ct ? el<T>::conj(a[u]) : a[u], vi);
+                    acc[u] = el<T>::mad(cn ? el<T>::conj(x[u]) : x[u], w[u], acc[u]);
+                    t[u] = el<T>::mul(ct ? el<T>::conj(x[u]) : x[u], vi);
                 }
-                sink.step(j, t);
-                j = jn;
+                sink.step(jj, t);
+            };
+            auto is_interior = [&](int jj) { return jj < jend && jj >= jin0 && jj + NU <= jin1 && (jj + NU <= i_first || jj > i_last); };
+            fetch(a, j);
+            for (;;) {                                     // the two register sets take turns: no copies between steps
+                bool more = is_interior(j + NU);
+                if (more) fetch(an, j + NU);
+                compute(a, j);
+                j += NU;
                 if (!more) break;
-ST_UNROLL
-                for (int u = 0; u < NU; u++) a[u] = an[u];
+                more = is_interior(j + NU);
+                if (more) fetch(a, j + NU);
+                compute(an, j);
+                j += NU;
+                if (!more) break;
             }
             continue;
         }
@@ -364,7 +372,7 @@ ST_UNROLL
         for (int u = 0; u < NU; u++) {
             const bool in = j + u >= j0 && j + u < j1;
             a[u] = in ? p[s] : el<T>::zero();
-            w[u] = in ? v[j + u] : el<T>::zero();
+            w[u] = in ? vcol[j + u] : el<T>::zero();
             s += col_step(D, j + u);
         }
         p += s;
@@ -388,7 +396,18 @@ ST_HD T sym_finish_elem(const Desc& D, int j, int nparts, const T* part, int64_t
     for (int c = 0; c < nparts; c++) s = el<T>::add(s, part[(int64_t)c * npad + j]);
     int i0, i1;
     col_rows(D, j, i0, i1);
-    for (int rb = i0 / ROW_THREADS; rb <= (i1 - 1) / ROW_THREADS; rb++) s = el<T>::add(s, tp2[(int64_t)rb * npadw + (j - sym_jw0(D, rb * ROW_THREADS))]);
+    // four independent partial sums (fixed order): a column of a full triangle collects up to n / ROW_THREADS values, and one
+    // dependent chain of loads per thread left this pass latency-bound (63 us for n = 32768, 7 % of the product)
+    T q0 = el<T>::zero(), q1 = q0, q2 = q0, q3 = q0;
+    const int rb_lo = i0 / ROW_THREADS, rb_hi = (i1 - 1) / ROW_THREADS;
+    auto at = [&](int rb) { return tp2[(int64_t)rb * npadw + (j - sym_jw0(D, rb * ROW_THREADS))]; };
+    int rb = rb_lo;
+    for (; rb + 3 <= rb_hi; rb += 4) {
+        const T x0 = at(rb), x1 = at(rb + 1), x2 = at(rb + 2), x3 = at(rb + 3);
+        q0 = el<T>::add(q0, x0); q1 = el<T>::add(q1, x1); q2 = el<T>::add(q2, x2); q3 = el<T>::add(q3, x3);
+    }
+    for (; rb <= rb_hi; rb++) q0 = el<T>::add(q0, at(rb));
+    s = el<T>::add(s, el<T>::add(el<T>::add(q0, q1), el<T>::add(q2, q3)));
     s = el<T>::mul(alpha, s);
     return beta0 ? s : el<T>::mad(beta, old, s);
 }

@@ -97,7 +97,7 @@ struct HostBackend {
                 for (int tx = 0; tx < ROW_THREADS; tx++) {
                     const int i = r0 + tx, lane = tx & 31, warp = tx >> 5;
                     HostStripSink<T> sink = {strips.data() + (size_t)warp * wstride, cw0, cw1};
-                    const T r = sym_row<T>(D, A, v, i, i - lane, c0, c1, nflags, tflags, sink);
+                    const T r = sym_row<T>(D, A, v, v, i, i - lane, c0, c1, nflags, tflags, sink);
                     if (i < D.n) part[(int64_t)by * npad + i] = r;
                 }
                 T* row = tp2 + (int64_t)bx * npadw - sym_jw0(D, r0);
