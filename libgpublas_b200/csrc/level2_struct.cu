@@ -271,8 +271,11 @@ struct DeviceBackend {
     void sympart(const Desc& D, const T* A, const T* v, int cpc, int nchunks, int nflags, int tflags, T* part, int64_t npad, T* tp2, int64_t npadw) {
         const int64_t w = sym_width(D) < cpc ? sym_width(D) : (int64_t)cpc;
         const int wstride = (int)((w + 7) / 8 * 8);
-        // 5 CTAs per SM (96 registers, a few spilled words) or 4 (no spills): B200BLAS_SYM_MINB picks, measured in profiles/
-        static const int minb = getenv("B200BLAS_SYM_MINB") ? atoi(getenv("B200BLAS_SYM_MINB")) : 5;
+        // 4 CTAs per SM (120 registers, no spills) or 5 (96 registers, a few spilled words in the loop).  Measured
+        // (profiles/r02w_level2_sym_one_pass_v3.txt): packed / full triangles 80 / 83 % of the HBM peak with 4 against 55 / 74 % with 5;
+        // bands (short rows, mostly masked steps) 57.5 % with 5 against 54 % with 4.  B200BLAS_SYM_MINB overrides.
+        static const int minb_env = getenv("B200BLAS_SYM_MINB") ? atoi(getenv("B200BLAS_SYM_MINB")) : 0;
+        const int minb = minb_env ? minb_env : (D.kind == K_BAND_TRI ? 5 : 4);
         const dim3 grid((D.n + ROW_THREADS - 1) / ROW_THREADS, nchunks);
         const size_t smem = (size_t)(ROW_THREADS / 32 + 1) * wstride * sizeof(T);
         if (minb == 4) sympart_kernel<T, 4><<<grid, ROW_THREADS, smem, s>>>(D, A, v, cpc, nflags, tflags, part, npad, tp2, npadw, wstride);
