@@ -182,19 +182,20 @@ __global__ void __launch_bounds__(COL_WARPS * 32) solve_tupdate_kernel(Desc D, c
 // reciprocal of its pivot; each step scales on the pivot lane, broadcasts the solved unknown by shuffle and eliminates it
 // from the lanes still waiting.  (x * (1/d) instead of x / d: one FP64 division per lane off the critical path instead
 // of 32 in sequence; within the solves' stated tolerance.)
+// Split in two so that a block's coefficient loads can be in flight while the block before it is being solved:
+//   diag_load   addresses and loads only (nothing here consumes a loaded value).  Every load is unconditional (a lane with
+//               nothing to fetch re-reads its own diagonal element, which always exists), so the 32 loads issue back to back;
+//               behind a branch each one waited for the previous (32 memory latencies per block: 30 us, the whole cost of the
+//               first version -- profiles/r01f_level2_struct_perf_v2.txt).
+//   diag_solve  conjugate, mask, pivot reciprocal, then the 32 elimination steps.
 template <typename T>
-__device__ __forceinline__ void solve_diag_warp(const Desc& D, const T* __restrict__ A, T* x, int b0, int nb, bool trans, bool conj, bool unit, bool forward) {
+__device__ __forceinline__ void diag_load(const Desc& D, const T* __restrict__ A, int b0, int nb, bool trans, bool unit, bool forward, T (&coef)[32], unsigned& okmask) {
     const int lane = threadIdx.x & 31, r = b0 + lane;
-    T coef[32];
-    T dinv = el<T>::one();
-    // Every load is unconditional (a lane with nothing to fetch re-reads its own diagonal element, which always exists), so
-    // the 32 loads issue back to back; behind a branch each one waited for the previous (32 memory latencies per block:
-    // 30 us, the whole cost of the first version -- profiles/r01f_level2_struct_perf_v2.txt).
     const int rs = r < D.n ? r : D.n - 1;
     const int64_t safe = off(D, rs, rs);
-    unsigned okmask = 0;
+    okmask = 0;
 #pragma unroll
-    for (int step = 0; step < 32; step++) {   // pass 1: addresses and loads only -- nothing here consumes a loaded value
+    for (int step = 0; step < 32; step++) {
         const int jj = forward ? step : nb - 1 - step;
         const int c = b0 + jj, ci = trans ? c : r, cj = trans ? r : c;
         const bool waiting = forward ? lane > jj : lane < jj;
@@ -203,8 +204,14 @@ __device__ __forceinline__ void solve_diag_warp(const Desc& D, const T* __restri
         coef[step] = A[ok ? off(D, ci, cj) : safe];
         okmask |= (ok ? 1u : 0u) << step;
     }
+}
+// xs (shared memory, may be null): the block's solved unknowns for the CTA's update phase
+template <typename T>
+__device__ __forceinline__ void diag_solve(T (&coef)[32], unsigned okmask, T* x, T* xs, int b0, int nb, bool conj, bool unit, bool forward) {
+    const int lane = threadIdx.x & 31, r = b0 + lane;
+    T dinv = el<T>::one();
 #pragma unroll
-    for (int step = 0; step < 32; step++) {   // pass 2: conjugate, mask, pivot reciprocal
+    for (int step = 0; step < 32; step++) {
         const int jj = forward ? step : nb - 1 - step;
         const bool ok = (okmask >> step) & 1u;
         T a = coef[step];
@@ -224,20 +231,80 @@ __device__ __forceinline__ void solve_diag_warp(const Desc& D, const T* __restri
         }
     }
     if (lane < nb) x[r] = xv;
+    if (xs) xs[lane] = lane < nb ? xv : el<T>::zero();
 }
-// One CTA solves the panel [p0,p1) of op(S) in place: per 32-block, warp 0 solves the diagonal block, then every thread
-// takes panel rows the block reaches and subtracts its contribution (x lives in global memory; __syncthreads orders the
-// phases).  See structured.cuh: solve().
+template <typename T>
+__device__ __forceinline__ void solve_diag_warp(const Desc& D, const T* __restrict__ A, T* x, int b0, int nb, bool trans, bool conj, bool unit, bool forward) {
+    T coef[32];
+    unsigned okmask;
+    diag_load<T>(D, A, b0, nb, trans, unit, forward, coef, okmask);
+    diag_solve<T>(coef, okmask, x, (T*)nullptr, b0, nb, conj, unit, forward);
+}
+// One CTA solves the panel [p0,p1) of op(S) in place, 32-block by 32-block (structured.cuh: solve(), panel_block()).  The
+// dependency chain through x is what bounds a triangular solve, so nothing that does NOT depend on x may sit on it:
+//   * warp 1 loads the NEXT block's diagonal coefficients into shared memory (two buffers take turns) while warp 0 solves the
+//     current block from the buffer filled one block earlier;
+//   * warps 2..7 load the coefficients op(S)(r, b0..b1) of the panel row r they will update while warp 0 solves, and after the
+//     barrier only multiply them with the 32 solved unknowns (shared memory) and subtract;
+//   * rows beyond the 192 those warps hold (wide bands, the last rows of a packed panel) take the plain path (panel_update).
+// Before: diagonal loads, solve, barrier, update loads, update, barrier in series -- two memory latencies per block on the chain,
+// 17.8 us per block (DTBSV n = 2^18, k = 127: 146 ms; profiles/r01g_level2_struct_summary.txt).
 template <typename T>
 __global__ void __launch_bounds__(SOLVE_THREADS) solve_panel_kernel(Desc D, const T* __restrict__ A, T* x, int p0, int p1, bool trans, bool conj, bool unit,
                                                                     bool forward) {
+    __shared__ T xs[32];
+    __shared__ T dco[2][32][33];                       // [buffer][step][lane]: diagonal coefficients in elimination order
+    __shared__ unsigned dok[2][32];
     const int nblk = (p1 - p0 + SOLVE_NB - 1) / SOLVE_NB, flags = conj ? F_CONJ : 0;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int HELD = SOLVE_THREADS - 64;            // panel rows whose update coefficients are preloaded (warps 2..7)
+    auto stage_diag = [&](int bi) {                     // warp 1: block bi's diagonal coefficients -> dco[bi & 1]
+        int b0, b1, u0, u1;
+        panel_block(D, p0, p1, forward, bi, b0, b1, u0, u1);
+        T c[32];
+        unsigned ok;
+        diag_load<T>(D, A, b0, b1 - b0, trans, unit, forward, c, ok);
+#pragma unroll
+        for (int st = 0; st < 32; st++) dco[bi & 1][st][lane] = c[st];
+        dok[bi & 1][lane] = ok;
+    };
+    if (warp == 1 && nblk > 0) stage_diag(0);
+    __syncthreads();
     for (int bi = 0; bi < nblk; bi++) {
         int b0, b1, u0, u1;
         panel_block(D, p0, p1, forward, bi, b0, b1, u0, u1);
-        if (threadIdx.x < 32) solve_diag_warp<T>(D, A, x, b0, b1 - b0, trans, conj, unit, forward);
+        const int nb = b1 - b0;
+        T cu[32];                                       // warp 0: the diagonal coefficients; warps 2..7: the update row's
+        unsigned uok = 0;
+        const int r = u0 + (tid - 64);
+        const bool mine = tid >= 64 && r < u1;
+        if (warp == 0) {
+#pragma unroll
+            for (int st = 0; st < 32; st++) cu[st] = dco[bi & 1][st][lane];
+            diag_solve<T>(cu, dok[bi & 1][lane], x, xs, b0, nb, conj, unit, forward);
+        } else if (warp == 1) {
+            if (bi + 1 < nblk) stage_diag(bi + 1);
+        } else if (mine) {
+            const int64_t safe = off(D, b0, b0);
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int c = b0 + j, ci = trans ? c : r, cj = trans ? r : c;
+                const bool ok = j < nb && stored(D, ci, cj);
+                cu[j] = A[ok ? off(D, ci, cj) : safe];
+                uok |= (ok ? 1u : 0u) << j;
+            }
+        }
         __syncthreads();
-        for (int r = u0 + threadIdx.x; r < u1; r += SOLVE_THREADS) x[r] = el<T>::sub(x[r], panel_update<T>(D, A, x, r, b0, b1, trans, flags));
+        if (mine) {
+            T acc = el<T>::zero();
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const T a = conj ? el<T>::conj(cu[j]) : cu[j];
+                if ((uok >> j) & 1u) acc = el<T>::mad(a, xs[j], acc);
+            }
+            x[r] = el<T>::sub(x[r], acc);
+        }
+        for (int r2 = u0 + HELD + tid; r2 < u1; r2 += SOLVE_THREADS) x[r2] = el<T>::sub(x[r2], panel_update<T>(D, A, x, r2, b0, b1, trans, flags));
         __syncthreads();
     }
 }
