@@ -243,6 +243,7 @@ template <> __device__ __forceinline__ double num_div(double a, double b) { retu
 template <> __device__ __forceinline__ cuFloatComplex num_div(cuFloatComplex a, cuFloatComplex b) { return cuCdivf(a, b); }
 template <> __device__ __forceinline__ cuDoubleComplex num_div(cuDoubleComplex a, cuDoubleComplex b) { return cuCdiv(a, b); }
 
+template <typename T> __device__ __forceinline__ T plus_one_dev() { return num<T>::real(1.0); }
 // solves op(Ablk) x = x for one nb x nb block; opupper: op(A) is upper triangular (back substitution)
 template <typename T>
 __global__ void __launch_bounds__(TvNb<T>::value) trsv_diag_kernel(int nb, const T* __restrict__ A, int64_t lda, int op, bool opupper, bool unit, T* x) {
@@ -260,9 +261,14 @@ __global__ void __launch_bounds__(TvNb<T>::value) trsv_diag_kernel(int nb, const
     }
     if (t < nb) sx[t] = x[t];
     __syncthreads();
+    // pivot reciprocals, all at once: a division by one thread inside the loop below put an FP64 division sequence (hundreds of
+    // cycles) on every step of the dependency chain (x * (1/d) instead of x / d: within the solves' stated tolerance)
+    __shared__ T sr[TV_NB];
+    if (t < nb && !unit) sr[t] = num_div<T>(plus_one_dev<T>(), sA[t][t]);
+    __syncthreads();
     for (int step = 0; step < nb; step++) {
         const int j = opupper ? nb - 1 - step : step;
-        if (t == j && !unit) sx[j] = num_div<T>(sx[j], sA[j][j]);
+        if (t == j && !unit) sx[j] = num<T>::mul(sx[j], sr[j]);
         __syncthreads();
         const bool mine = opupper ? (t < j) : (t > j && t < nb);
         if (mine) sx[t] = num<T>::sub(sx[t], num<T>::mul(sA[t][j], sx[j]));

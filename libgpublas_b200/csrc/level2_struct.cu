@@ -209,7 +209,7 @@ __device__ __forceinline__ void diag_load(const Desc& D, const T* __restrict__ A
 template <typename T>
 __device__ __forceinline__ void diag_solve(T (&coef)[32], unsigned okmask, T* x, T* xs, int b0, int nb, bool conj, bool unit, bool forward) {
     const int lane = threadIdx.x & 31, r = b0 + lane;
-    T dinv = el<T>::one();
+    T piv = el<T>::one();
 #pragma unroll
     for (int step = 0; step < 32; step++) {
         const int jj = forward ? step : nb - 1 - step;
@@ -217,8 +217,11 @@ __device__ __forceinline__ void diag_solve(T (&coef)[32], unsigned okmask, T* x,
         T a = coef[step];
         if (conj) a = el<T>::conj(a);
         coef[step] = (ok && lane != jj) ? a : el<T>::zero();
-        if (ok && lane == jj) dinv = el<T>::div(el<T>::one(), a);
+        piv = (ok && lane == jj) ? a : piv;              // a select: the division must not sit inside this loop (see below)
     }
+    // ONE division per lane, all lanes at once.  (It used to be written inside the loop above under `lane == jj`: a divergent
+    // branch taken by one lane per step, i.e. 32 FP64 division sequences one after the other -- ~8 us of the 16 us a block took.)
+    const T dinv = el<T>::div(el<T>::one(), piv);
     T xv = lane < nb ? x[r] : el<T>::zero();
 #pragma unroll
     for (int step = 0; step < 32; step++) {
