@@ -21,6 +21,7 @@
 #include "structured.cuh"
 #include "../../include/b200blas.h"
 #include <cstdlib>
+#include <type_traits>
 
 namespace b200 {
 using namespace st;
@@ -188,22 +189,51 @@ __global__ void __launch_bounds__(COL_WARPS * 32) solve_tupdate_kernel(Desc D, c
 //               behind a branch each one waited for the previous (32 memory latencies per block: 30 us, the whole cost of the
 //               first version -- profiles/r01f_level2_struct_perf_v2.txt).
 //   diag_solve  conjugate, mask, pivot reciprocal, then the 32 elimination steps.
+// Row r of op(S) over the columns of one diagonal block: the stored range [lo, hi) of c and the address of element (r, c) as an
+// affine walk from c = b0 (packed rows of the untransposed triangle: the closed form).  The generic stored() / off() pair costs a
+// switch and 64-bit multiplies per ELEMENT; written per element in four fully unrolled 32-step loops it made this kernel 20 600
+// instructions (320 KB of SASS): the single CTA spent its time on instruction fetch ("no instruction" + barrier stalls 15 of 20
+// cycles per issue, 30 900 cycles per 32-block; ncu source page of run r02z).
+struct OpRow { int lo, hi, r, n; int64_t a0, cs; bool packed_row, up; };
+__device__ __forceinline__ OpRow op_row(const Desc& D, int r, int b0, bool trans) {
+    OpRow w;
+    const int rs = r < D.n ? r : D.n - 1;
+    if (trans) col_rows(D, rs, w.lo, w.hi); else row_cols(D, rs, w.lo, w.hi);
+    if (r >= D.n) w.lo = w.hi = 0;
+    w.r = rs; w.n = D.n; w.up = D.upper != 0;
+    w.packed_row = D.kind == K_PACKED && !trans;
+    w.a0 = trans ? off(D, b0, rs) : off(D, rs, b0);
+    w.cs = trans ? 1 : (D.kind == K_PACKED ? 0 : col_step(D, 0));
+    return w;
+}
+template <bool PACKED_ROW> __device__ __forceinline__ int64_t op_row_addr(const OpRow& w, int b0, int c) {
+    if (PACKED_ROW) return (int64_t)w.r + (w.up ? (int64_t)c * ((int64_t)c + 1) / 2 : (int64_t)c * (2 * (int64_t)w.n - c - 1) / 2);
+    return w.a0 + (int64_t)(c - b0) * w.cs;
+}
+// Split in two so that a block's coefficient loads can be in flight while the block before it is being solved:
+//   diag_load   addresses and loads only (nothing here consumes a loaded value).  Every load is unconditional (a lane with
+//               nothing to fetch re-reads its own diagonal element, which always exists), so the 32 loads issue back to back;
+//               behind a branch each one waited for the previous (32 memory latencies per block: 30 us, the whole cost of the
+//               first version -- profiles/r01f_level2_struct_perf_v2.txt).
+//   diag_solve  conjugate, mask, pivot reciprocal, then the 32 elimination steps.
 template <typename T>
 __device__ __forceinline__ void diag_load(const Desc& D, const T* __restrict__ A, int b0, int nb, bool trans, bool unit, bool forward, T (&coef)[32], unsigned& okmask) {
     const int lane = threadIdx.x & 31, r = b0 + lane;
-    const int rs = r < D.n ? r : D.n - 1;
-    const int64_t safe = off(D, rs, rs);
+    const OpRow w = op_row(D, r, b0, trans);
+    const int64_t safe = off(D, w.r, w.r);
     okmask = 0;
+    auto body = [&](auto packed_tag) {
 #pragma unroll
-    for (int step = 0; step < 32; step++) {
-        const int jj = forward ? step : nb - 1 - step;
-        const int c = b0 + jj, ci = trans ? c : r, cj = trans ? r : c;
-        const bool waiting = forward ? lane > jj : lane < jj;
-        const bool want = step < nb && lane < nb && (waiting || (lane == jj && !unit));
-        const bool ok = want && stored(D, ci, cj);
-        coef[step] = A[ok ? off(D, ci, cj) : safe];
-        okmask |= (ok ? 1u : 0u) << step;
-    }
+        for (int step = 0; step < 32; step++) {
+            const int jj = forward ? step : nb - 1 - step;
+            const int c = b0 + jj;
+            const bool waiting = forward ? lane > jj : lane < jj;
+            const bool ok = step < nb && lane < nb && (waiting || (lane == jj && !unit)) && c >= w.lo && c < w.hi;
+            coef[step] = A[ok ? op_row_addr<decltype(packed_tag)::value>(w, b0, c) : safe];
+            okmask |= (ok ? 1u : 0u) << step;
+        }
+    };
+    if (w.packed_row) body(std::true_type{}); else body(std::false_type{});     // (uniform: the closed form stays out of the common loop)
 }
 // xs (shared memory, may be null): the block's solved unknowns for the CTA's update phase
 template <typename T>
@@ -242,6 +272,10 @@ __device__ __forceinline__ void solve_diag_warp(const Desc& D, const T* __restri
     unsigned okmask;
     diag_load<T>(D, A, b0, nb, trans, unit, forward, coef, okmask);
     diag_solve<T>(coef, okmask, x, (T*)nullptr, b0, nb, conj, unit, forward);
+}
+// (the rarely taken plain path, kept out of line: its inlined N / T bodies are thousands of instructions)
+template <typename T> __device__ __noinline__ T panel_update_call(const Desc& D, const T* A, const T* x, int r, int b0, int b1, bool trans, int flags) {
+    return panel_update<T>(D, A, x, r, b0, b1, trans, flags);
 }
 // One CTA solves the panel [p0,p1) of op(S) in place, 32-block by 32-block (structured.cuh: solve(), panel_block()).  The
 // dependency chain through x is what bounds a triangular solve, so nothing that does NOT depend on x may sit on it:
@@ -288,14 +322,18 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_panel_kernel(Desc D, cons
         } else if (warp == 1) {
             if (bi + 1 < nblk) stage_diag(bi + 1);
         } else if (mine) {
+            const OpRow w = op_row(D, r, b0, trans);
             const int64_t safe = off(D, b0, b0);
+            auto body = [&](auto packed_tag) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const int c = b0 + j, ci = trans ? c : r, cj = trans ? r : c;
-                const bool ok = j < nb && stored(D, ci, cj);
-                cu[j] = A[ok ? off(D, ci, cj) : safe];
-                uok |= (ok ? 1u : 0u) << j;
-            }
+                for (int j = 0; j < 32; j++) {
+                    const int c = b0 + j;
+                    const bool ok = j < nb && c >= w.lo && c < w.hi;
+                    cu[j] = A[ok ? op_row_addr<decltype(packed_tag)::value>(w, b0, c) : safe];
+                    uok |= (ok ? 1u : 0u) << j;
+                }
+            };
+            if (w.packed_row) body(std::true_type{}); else body(std::false_type{});
         }
         __syncthreads();
         if (mine) {
@@ -307,7 +345,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_panel_kernel(Desc D, cons
             }
             x[r] = el<T>::sub(x[r], acc);
         }
-        for (int r2 = u0 + HELD + tid; r2 < u1; r2 += SOLVE_THREADS) x[r2] = el<T>::sub(x[r2], panel_update<T>(D, A, x, r2, b0, b1, trans, flags));
+        for (int r2 = u0 + HELD + tid; r2 < u1; r2 += SOLVE_THREADS) x[r2] = el<T>::sub(x[r2], panel_update_call<T>(D, A, x, r2, b0, b1, trans, flags));
         __syncthreads();
     }
 }
