@@ -278,47 +278,75 @@ template <typename T> __device__ __noinline__ T panel_update_call(const Desc& D,
     return panel_update<T>(D, A, x, r, b0, b1, trans, flags);
 }
 // One CTA solves the panel [p0,p1) of op(S) in place, 32-block by 32-block (structured.cuh: solve(), panel_block()).  The
-// dependency chain through x is what bounds a triangular solve, so nothing that does NOT depend on x may sit on it:
-//   * warp 1 loads the NEXT block's diagonal coefficients into shared memory (two buffers take turns) while warp 0 solves the
-//     current block from the buffer filled one block earlier;
+// dependency chain through x is what bounds a triangular solve, so nothing that does NOT depend on x may sit on it, and the code
+// on it must be short enough to stay in the instruction cache:
+//   * warp 1 STAGES the next block's diagonal coefficients in shared memory -- already conjugated, masked (zero for lanes that
+//     do not wait on that step) and with the pivot reciprocals -- while warp 0 solves the current block from the buffer filled one
+//     block earlier (two buffers take turns);
+//   * warp 0's elimination is then a rolled loop of one shared-memory load, one broadcast and one FMA per step;
 //   * warps 2..7 load the coefficients op(S)(r, b0..b1) of the panel row r they will update while warp 0 solves, and after the
 //     barrier only multiply them with the 32 solved unknowns (shared memory) and subtract;
 //   * rows beyond the 192 those warps hold (wide bands, the last rows of a packed panel) take the plain path (panel_update).
-// Before: diagonal loads, solve, barrier, update loads, update, barrier in series -- two memory latencies per block on the chain,
-// 17.8 us per block (DTBSV n = 2^18, k = 127: 146 ms; profiles/r01g_level2_struct_summary.txt).
+// History (DTBSV n = 2^18, k = 127; profiles/r01g_level2_struct_summary.txt, r02y_solves.txt): loads, solve, barrier, update loads,
+// update, barrier in series 146 ms; loads off the chain 127 ms -- ncu showed the real cost: 20 600 instructions of unrolled
+// per-element stored()/off() logic, the single CTA stalled on instruction fetch; affine address walks 57 ms; this form: see profiles/.
 template <typename T>
 __global__ void __launch_bounds__(SOLVE_THREADS) solve_panel_kernel(Desc D, const T* __restrict__ A, T* x, int p0, int p1, bool trans, bool conj, bool unit,
                                                                     bool forward) {
     __shared__ T xs[32];
-    __shared__ T dco[2][32][33];                       // [buffer][step][lane]: diagonal coefficients in elimination order
-    __shared__ unsigned dok[2][32];
+    __shared__ T dco[2][32][33];                       // [buffer][step][lane]: masked diagonal coefficients in elimination order
+    __shared__ T dinv[2][32];                          // pivot reciprocals (one for a unit diagonal)
     const int nblk = (p1 - p0 + SOLVE_NB - 1) / SOLVE_NB, flags = conj ? F_CONJ : 0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int HELD = SOLVE_THREADS - 64;            // panel rows whose update coefficients are preloaded (warps 2..7)
-    auto stage_diag = [&](int bi) {                     // warp 1: block bi's diagonal coefficients -> dco[bi & 1]
+    auto stage_diag = [&](int bi) {                     // warp 1: block bi's diagonal coefficients -> dco[bi & 1], dinv[bi & 1]
         int b0, b1, u0, u1;
         panel_block(D, p0, p1, forward, bi, b0, b1, u0, u1);
-        T c[32];
-        unsigned ok;
-        diag_load<T>(D, A, b0, b1 - b0, trans, unit, forward, c, ok);
-#pragma unroll
-        for (int st = 0; st < 32; st++) dco[bi & 1][st][lane] = c[st];
-        dok[bi & 1][lane] = ok;
+        const int nb = b1 - b0, r = b0 + lane, buf = bi & 1;
+        const OpRow w = op_row(D, r, b0, trans);
+        const int64_t safe = off(D, w.r, w.r);
+        T piv = el<T>::one();
+        auto body = [&](auto packed_tag) {
+#pragma unroll 8
+            for (int step = 0; step < 32; step++) {     // 8 loads in flight per batch; off the critical path
+                const int jj = forward ? step : nb - 1 - step;
+                const int c = b0 + jj;
+                const bool waiting = forward ? lane > jj : lane < jj;
+                const bool ok = step < nb && lane < nb && (waiting || (lane == jj && !unit)) && c >= w.lo && c < w.hi;
+                T a = A[ok ? op_row_addr<decltype(packed_tag)::value>(w, b0, c) : safe];
+                if (conj) a = el<T>::conj(a);
+                dco[buf][step][lane] = (ok && lane != jj) ? a : el<T>::zero();
+                piv = (ok && lane == jj) ? a : piv;
+            }
+        };
+        if (w.packed_row) body(std::true_type{}); else body(std::false_type{});
+        dinv[buf][lane] = el<T>::div(el<T>::one(), piv);     // one division per lane, all lanes at once
     };
     if (warp == 1 && nblk > 0) stage_diag(0);
     __syncthreads();
     for (int bi = 0; bi < nblk; bi++) {
         int b0, b1, u0, u1;
         panel_block(D, p0, p1, forward, bi, b0, b1, u0, u1);
-        const int nb = b1 - b0;
-        T cu[32];                                       // warp 0: the diagonal coefficients; warps 2..7: the update row's
+        const int nb = b1 - b0, buf = bi & 1;
+        T cu[32];                                       // warps 2..7: the update row's coefficients
         unsigned uok = 0;
         const int r = u0 + (tid - 64);
         const bool mine = tid >= 64 && r < u1;
         if (warp == 0) {
-#pragma unroll
-            for (int st = 0; st < 32; st++) cu[st] = dco[bi & 1][st][lane];
-            diag_solve<T>(cu, dok[bi & 1][lane], x, xs, b0, nb, conj, unit, forward);
+            const int rr = b0 + lane;
+            T xv = lane < nb ? x[rr] : el<T>::zero();
+            const T di = dinv[buf][lane];
+#pragma unroll 4
+            for (int step = 0; step < nb; step++) {
+                const int jj = forward ? step : nb - 1 - step;
+                const T c = dco[buf][step][lane];
+                if (lane == jj) xv = el<T>::mul(xv, di);          // (di = 1 for a unit diagonal)
+                const T xj = warp_bcast(xv, jj);
+                const bool waiting = forward ? (lane > jj && lane < nb) : lane < jj;
+                if (waiting) xv = el<T>::sub(xv, el<T>::mul(c, xj));   // (guarded, not just masked: an Inf in x must not reach solved lanes as 0 * Inf)
+            }
+            if (lane < nb) x[rr] = xv;
+            xs[lane] = lane < nb ? xv : el<T>::zero();
         } else if (warp == 1) {
             if (bi + 1 < nblk) stage_diag(bi + 1);
         } else if (mine) {
