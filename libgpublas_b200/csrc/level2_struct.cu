@@ -306,20 +306,28 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_panel_kernel(Desc D, cons
         const OpRow w = op_row(D, r, b0, trans);
         const int64_t safe = off(D, w.r, w.r);
         T piv = el<T>::one();
+        T cf[32];
+        unsigned okm = 0;
         auto body = [&](auto packed_tag) {
-#pragma unroll 8
-            for (int step = 0; step < 32; step++) {     // 8 loads in flight per batch; off the critical path
-                const int jj = forward ? step : nb - 1 - step;
+#pragma unroll
+            for (int step = 0; step < 32; step++) {     // pass 1: all 32 loads in flight at once (batches of 8 made this warp the
+                const int jj = forward ? step : nb - 1 - step;   // slowest of the CTA: four memory latencies per block, 156 ms)
                 const int c = b0 + jj;
                 const bool waiting = forward ? lane > jj : lane < jj;
                 const bool ok = step < nb && lane < nb && (waiting || (lane == jj && !unit)) && c >= w.lo && c < w.hi;
-                T a = A[ok ? op_row_addr<decltype(packed_tag)::value>(w, b0, c) : safe];
-                if (conj) a = el<T>::conj(a);
-                dco[buf][step][lane] = (ok && lane != jj) ? a : el<T>::zero();
-                piv = (ok && lane == jj) ? a : piv;
+                cf[step] = A[ok ? op_row_addr<decltype(packed_tag)::value>(w, b0, c) : safe];
+                okm |= (ok ? 1u : 0u) << step;
             }
         };
         if (w.packed_row) body(std::true_type{}); else body(std::false_type{});
+#pragma unroll
+        for (int step = 0; step < 32; step++) {         // pass 2: conjugate, mask, store
+            const int jj = forward ? step : nb - 1 - step;
+            const bool ok = (okm >> step) & 1u;
+            const T a = conj ? el<T>::conj(cf[step]) : cf[step];
+            dco[buf][step][lane] = (ok && lane != jj) ? a : el<T>::zero();
+            piv = (ok && lane == jj) ? a : piv;
+        }
         dinv[buf][lane] = el<T>::div(el<T>::one(), piv);     // one division per lane, all lanes at once
     };
     if (warp == 1 && nblk > 0) stage_diag(0);
