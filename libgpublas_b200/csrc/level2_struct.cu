@@ -296,6 +296,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_panel_kernel(Desc D, cons
     __shared__ T xs[32];
     __shared__ T dco[2][32][33];                       // [buffer][step][lane]: masked diagonal coefficients in elimination order
     __shared__ T dinv[2][32];                          // pivot reciprocals (one for a unit diagonal)
+    __shared__ T xn[32];                               // the next block's unknowns after this block's update
+    bool xn_valid = false;
     const int nblk = (p1 - p0 + SOLVE_NB - 1) / SOLVE_NB, flags = conj ? F_CONJ : 0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int HELD = SOLVE_THREADS - 64;            // panel rows whose update coefficients are preloaded (warps 2..7)
@@ -321,14 +323,21 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_panel_kernel(Desc D, cons
         };
         if (w.packed_row) body(std::true_type{}); else body(std::false_type{});
 #pragma unroll
-        for (int step = 0; step < 32; step++) {         // pass 2: conjugate, mask, store
+        for (int step = 0; step < 32; step++) {         // pass 2: conjugate, pick the lane's pivot
             const int jj = forward ? step : nb - 1 - step;
             const bool ok = (okm >> step) & 1u;
-            const T a = conj ? el<T>::conj(cf[step]) : cf[step];
-            dco[buf][step][lane] = (ok && lane != jj) ? a : el<T>::zero();
-            piv = (ok && lane == jj) ? a : piv;
+            cf[step] = conj ? el<T>::conj(cf[step]) : cf[step];
+            piv = (ok && lane == jj) ? cf[step] : piv;
         }
-        dinv[buf][lane] = el<T>::div(el<T>::one(), piv);     // one division per lane, all lanes at once
+        const T di = el<T>::div(el<T>::one(), piv);     // one division per lane, all lanes at once
+        dinv[buf][lane] = di;
+#pragma unroll
+        for (int step = 0; step < 32; step++) {         // pass 3: mask and scale column jj by 1/pivot(jj): the solve then carries the
+            const int jj = forward ? step : nb - 1 - step;   // UNSCALED unknowns y (x = y/d applied at the end, off the chain)
+            const bool ok = (okm >> step) & 1u;
+            const T dj = warp_bcast(di, jj & 31);
+            dco[buf][step][lane] = (ok && lane != jj) ? el<T>::mul(cf[step], dj) : el<T>::zero();
+        }
     };
     if (warp == 1 && nblk > 0) stage_diag(0);
     __syncthreads();
@@ -341,18 +350,18 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_panel_kernel(Desc D, cons
         const int r = u0 + (tid - 64);
         const bool mine = tid >= 64 && r < u1;
         if (warp == 0) {
+            // per step on the chain: one broadcast and one FMA (coefficients pre-scaled by the pivot reciprocals; y = d x)
             const int rr = b0 + lane;
-            T xv = lane < nb ? x[rr] : el<T>::zero();
-            const T di = dinv[buf][lane];
+            T yv = lane < nb ? (xn_valid ? xn[lane] : x[rr]) : el<T>::zero();
 #pragma unroll 4
             for (int step = 0; step < nb; step++) {
                 const int jj = forward ? step : nb - 1 - step;
                 const T c = dco[buf][step][lane];
-                if (lane == jj) xv = el<T>::mul(xv, di);          // (di = 1 for a unit diagonal)
-                const T xj = warp_bcast(xv, jj);
+                const T yj = warp_bcast(yv, jj);
                 const bool waiting = forward ? (lane > jj && lane < nb) : lane < jj;
-                if (waiting) xv = el<T>::sub(xv, el<T>::mul(c, xj));   // (guarded, not just masked: an Inf in x must not reach solved lanes as 0 * Inf)
+                if (waiting) yv = el<T>::sub(yv, el<T>::mul(c, yj));   // (guarded, not just masked: an Inf in x must not reach solved lanes as 0 * Inf)
             }
+            const T xv = el<T>::mul(yv, dinv[buf][lane]);         // (1 for a unit diagonal)
             if (lane < nb) x[rr] = xv;
             xs[lane] = lane < nb ? xv : el<T>::zero();
         } else if (warp == 1) {
@@ -371,16 +380,32 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_panel_kernel(Desc D, cons
             };
             if (w.packed_row) body(std::true_type{}); else body(std::false_type{});
         }
+        // the next block's unknowns also go to shared memory (saves warp 0 a round trip through L2 at the head of its chain) when
+        // all of them are among the held rows -- a narrow band or a wide one leaves some to the plain path: then warp 0 reads x
+        int nb0 = 0, nb1 = 0;
+        bool cover = false;
+        if (bi + 1 < nblk) {
+            int t0, t1;
+            panel_block(D, p0, p1, forward, bi + 1, nb0, nb1, t0, t1);
+            cover = nb0 >= u0 && nb1 <= u1 && nb0 - u0 < HELD && nb1 - u0 <= HELD;
+        }
         __syncthreads();
         if (mine) {
-            T acc = el<T>::zero();
+            T q0 = el<T>::zero(), q1 = q0, q2 = q0, q3 = q0;      // four chains of 8, not one of 32
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const T a = conj ? el<T>::conj(cu[j]) : cu[j];
-                if ((uok >> j) & 1u) acc = el<T>::mad(a, xs[j], acc);
+            for (int j = 0; j < 32; j += 4) {
+                const T a0 = conj ? el<T>::conj(cu[j]) : cu[j], a1 = conj ? el<T>::conj(cu[j + 1]) : cu[j + 1];
+                const T a2 = conj ? el<T>::conj(cu[j + 2]) : cu[j + 2], a3 = conj ? el<T>::conj(cu[j + 3]) : cu[j + 3];
+                if ((uok >> j) & 1u) q0 = el<T>::mad(a0, xs[j], q0);
+                if ((uok >> (j + 1)) & 1u) q1 = el<T>::mad(a1, xs[j + 1], q1);
+                if ((uok >> (j + 2)) & 1u) q2 = el<T>::mad(a2, xs[j + 2], q2);
+                if ((uok >> (j + 3)) & 1u) q3 = el<T>::mad(a3, xs[j + 3], q3);
             }
-            x[r] = el<T>::sub(x[r], acc);
+            const T nx = el<T>::sub(x[r], el<T>::add(el<T>::add(q0, q1), el<T>::add(q2, q3)));
+            x[r] = nx;
+            if (cover && r >= nb0 && r < nb1) xn[r - nb0] = nx;
         }
+        xn_valid = cover;
         for (int r2 = u0 + HELD + tid; r2 < u1; r2 += SOLVE_THREADS) x[r2] = el<T>::sub(x[r2], panel_update_call<T>(D, A, x, r2, b0, b1, trans, flags));
         __syncthreads();
     }
