@@ -280,13 +280,13 @@ template <typename T> __device__ __noinline__ T panel_update_call(const Desc& D,
 // One CTA solves the panel [p0,p1) of op(S) in place, 32-block by 32-block (structured.cuh: solve(), panel_block()).  The
 // dependency chain through x is what bounds a triangular solve, so nothing that does NOT depend on x may sit on it, and the code
 // on it must be short enough to stay in the instruction cache:
-//   * warp 1 STAGES the next block's diagonal coefficients in shared memory -- already conjugated, masked (zero for lanes that
-//     do not wait on that step) and with the pivot reciprocals -- while warp 0 solves the current block from the buffer filled one
+//   * warps 1 and 2 STAGE the next block's diagonal coefficients in shared memory -- already conjugated, masked (zero for lanes that
+//     do not wait on that step) and scaled by the pivot reciprocals -- while warp 0 solves the current block from the buffer filled one
 //     block earlier (two buffers take turns);
 //   * warp 0's elimination is then a rolled loop of one shared-memory load, one broadcast and one FMA per step;
-//   * warps 2..7 load the coefficients op(S)(r, b0..b1) of the panel row r they will update while warp 0 solves, and after the
+//   * warps 3..7 load the coefficients op(S)(r, b0..b1) of the panel row r they will update while warp 0 solves, and after the
 //     barrier only multiply them with the 32 solved unknowns (shared memory) and subtract;
-//   * rows beyond the 192 those warps hold (wide bands, the last rows of a packed panel) take the plain path (panel_update).
+//   * rows beyond the 160 those warps hold (wide bands, the last rows of a packed panel) take the plain path (panel_update).
 // History (DTBSV n = 2^18, k = 127; profiles/r01g_level2_struct_summary.txt, r02y_solves.txt): loads, solve, barrier, update loads,
 // update, barrier in series 146 ms; loads off the chain 127 ms -- ncu showed the real cost: 20 600 instructions of unrolled
 // per-element stored()/off() logic, the single CTA stalled on instruction fetch; affine address walks 57 ms; this form: see profiles/.
@@ -300,46 +300,45 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_panel_kernel(Desc D, cons
     bool xn_valid = false;
     const int nblk = (p1 - p0 + SOLVE_NB - 1) / SOLVE_NB, flags = conj ? F_CONJ : 0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int HELD = SOLVE_THREADS - 64;            // panel rows whose update coefficients are preloaded (warps 2..7)
-    auto stage_diag = [&](int bi) {                     // warp 1: block bi's diagonal coefficients -> dco[bi & 1], dinv[bi & 1]
+    constexpr int HELD = SOLVE_THREADS - 96;            // panel rows whose update coefficients are preloaded (warps 3..7)
+    // warps 1 and 2, half the elimination steps each (one warp doing all 32 was the slowest warp of the CTA: ~2000 straight-line
+    // instructions per block against ~250 on warp 0's chain -- ncu source page, run r02z2)
+    auto stage_diag = [&](int bi, int half) {           // block bi's diagonal coefficients -> dco[bi & 1], dinv[bi & 1]
         int b0, b1, u0, u1;
         panel_block(D, p0, p1, forward, bi, b0, b1, u0, u1);
         const int nb = b1 - b0, r = b0 + lane, buf = bi & 1;
         const OpRow w = op_row(D, r, b0, trans);
-        const int64_t safe = off(D, w.r, w.r);
-        T piv = el<T>::one();
-        T cf[32];
+        const int64_t dpos = off(D, w.r, w.r);           // the lane's own diagonal element: always stored
+        T cf[16];
         unsigned okm = 0;
         auto body = [&](auto packed_tag) {
 #pragma unroll
-            for (int step = 0; step < 32; step++) {     // pass 1: all 32 loads in flight at once (batches of 8 made this warp the
-                const int jj = forward ? step : nb - 1 - step;   // slowest of the CTA: four memory latencies per block, 156 ms)
+            for (int q = 0; q < 16; q++) {               // all loads in flight at once
+                const int step = half * 16 + q;
+                const int jj = forward ? step : nb - 1 - step;
                 const int c = b0 + jj;
                 const bool waiting = forward ? lane > jj : lane < jj;
-                const bool ok = step < nb && lane < nb && (waiting || (lane == jj && !unit)) && c >= w.lo && c < w.hi;
-                cf[step] = A[ok ? op_row_addr<decltype(packed_tag)::value>(w, b0, c) : safe];
-                okm |= (ok ? 1u : 0u) << step;
+                const bool ok = step < nb && lane < nb && waiting && c >= w.lo && c < w.hi;
+                cf[q] = A[ok ? op_row_addr<decltype(packed_tag)::value>(w, b0, c) : dpos];
+                okm |= (ok ? 1u : 0u) << q;
             }
         };
         if (w.packed_row) body(std::true_type{}); else body(std::false_type{});
-#pragma unroll
-        for (int step = 0; step < 32; step++) {         // pass 2: conjugate, pick the lane's pivot
-            const int jj = forward ? step : nb - 1 - step;
-            const bool ok = (okm >> step) & 1u;
-            cf[step] = conj ? el<T>::conj(cf[step]) : cf[step];
-            piv = (ok && lane == jj) ? cf[step] : piv;
-        }
+        T piv = (unit || lane >= nb) ? el<T>::one() : A[dpos];
+        if (conj) piv = el<T>::conj(piv);
         const T di = el<T>::div(el<T>::one(), piv);     // one division per lane, all lanes at once
-        dinv[buf][lane] = di;
+        if (half == 0) dinv[buf][lane] = di;
 #pragma unroll
-        for (int step = 0; step < 32; step++) {         // pass 3: mask and scale column jj by 1/pivot(jj): the solve then carries the
-            const int jj = forward ? step : nb - 1 - step;   // UNSCALED unknowns y (x = y/d applied at the end, off the chain)
-            const bool ok = (okm >> step) & 1u;
+        for (int q = 0; q < 16; q++) {                   // conjugate, mask and scale column jj by 1/pivot(jj): the solve then carries the
+            const int step = half * 16 + q;              // UNSCALED unknowns y (x = y/d applied at the end, off the chain)
+            const int jj = forward ? step : nb - 1 - step;
+            const bool ok = (okm >> q) & 1u;
+            const T a = conj ? el<T>::conj(cf[q]) : cf[q];
             const T dj = warp_bcast(di, jj & 31);
-            dco[buf][step][lane] = (ok && lane != jj) ? el<T>::mul(cf[step], dj) : el<T>::zero();
+            dco[buf][step][lane] = ok ? el<T>::mul(a, dj) : el<T>::zero();
         }
     };
-    if (warp == 1 && nblk > 0) stage_diag(0);
+    if ((warp == 1 || warp == 2) && nblk > 0) stage_diag(0, warp - 1);
     __syncthreads();
     for (int bi = 0; bi < nblk; bi++) {
         int b0, b1, u0, u1;
@@ -347,8 +346,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_panel_kernel(Desc D, cons
         const int nb = b1 - b0, buf = bi & 1;
         T cu[32];                                       // warps 2..7: the update row's coefficients
         unsigned uok = 0;
-        const int r = u0 + (tid - 64);
-        const bool mine = tid >= 64 && r < u1;
+        const int r = u0 + (tid - 96);
+        const bool mine = tid >= 96 && r < u1;
         if (warp == 0) {
             // per step on the chain: one broadcast and one FMA (coefficients pre-scaled by the pivot reciprocals; y = d x)
             const int rr = b0 + lane;
@@ -364,8 +363,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_panel_kernel(Desc D, cons
             const T xv = el<T>::mul(yv, dinv[buf][lane]);         // (1 for a unit diagonal)
             if (lane < nb) x[rr] = xv;
             xs[lane] = lane < nb ? xv : el<T>::zero();
-        } else if (warp == 1) {
-            if (bi + 1 < nblk) stage_diag(bi + 1);
+        } else if (warp <= 2) {
+            if (bi + 1 < nblk) stage_diag(bi + 1, warp - 1);
         } else if (mine) {
             const OpRow w = op_row(D, r, b0, trans);
             const int64_t safe = off(D, b0, b0);
