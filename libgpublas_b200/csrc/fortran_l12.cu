@@ -6,6 +6,7 @@
 // inherited: axpy dropping y (axpy.cc:28-30), cblas_i?amax returning a 1-based index
 // (amax.cc:25,33-36), nrm2 exported under a misspelt name (nrm2.cc:31-54).
 #include "abi_common.h"
+#include <cstdlib>
 #include <type_traits>
 #include "../../include/b200blas.h"
 
@@ -129,7 +130,11 @@ void trsv_entry(const char* name, const char* uplo, const char* trans, const cha
     VecOperand ox(x, *n, *incx, sizeof(T), ACC_INOUT);
     const char u = lsame(uplo, 'U') ? 'U' : 'L', t = lsame(trans, 'N') ? 'N' : (lsame(trans, 'T') ? 'T' : 'C'), d = lsame(diag, 'U') ? 'U' : 'N';
     // netlib: with a negative increment, element i lives at x[(n-1-i)*|incx|]
-    trsv_dev<T>(current_stream(), u, t, d, *n, (const T*)oa.dev(), oa.ld(), (T*)ox.dev(), *incx);
+    // B200BLAS_TRSV_STRUCT: 1 = always the panel solver of level2_struct.cu, 0 = never; default: from n = 4096 (measured, profiles/)
+    static const int st_env = getenv("B200BLAS_TRSV_STRUCT") ? atoi(getenv("B200BLAS_TRSV_STRUCT")) : -1;
+    const bool panel = st_env >= 0 ? st_env != 0 : false;
+    if (panel) trsv_struct_dev<T>(current_stream(), u, t, d, *n, (const T*)oa.dev(), oa.ld(), (T*)ox.dev(), *incx);
+    else trsv_dev<T>(current_stream(), u, t, d, *n, (const T*)oa.dev(), oa.ld(), (T*)ox.dev(), *incx);
     ox.release();
     log_exec(name, "%c%c%c n=%d lda=%d incx=%d", u, t, d, *n, *lda, *incx);
 }

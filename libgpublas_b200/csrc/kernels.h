@@ -86,5 +86,8 @@ template <typename T> void gemv_dev(cudaStream_t s, char trans, int m, int n, T 
                                     int64_t incx, T beta, T* y, int64_t incy);
 template <typename T> void trsv_dev(cudaStream_t s, char uplo, char trans, char diag, int n, const T* A, int64_t lda, T* x,
                                     int64_t incx);
+// the same solve through the panel solver of level2_struct.cu (32-wide diagonal blocks staged ahead of the dependency chain)
+template <typename T> void trsv_struct_dev(cudaStream_t s, char uplo, char trans, char diag, int n, const T* A, int64_t lda, T* x,
+                                           int64_t incx);
 
 }  // namespace b200

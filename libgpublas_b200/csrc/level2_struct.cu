@@ -469,6 +469,17 @@ struct DeviceBackend {
     }
 };
 
+// real / complex full-storage TRSV through the panel solver above (fortran_l12.cu: trsv_entry picks it for large n)
+template <typename T>
+void trsv_struct_dev(cudaStream_t s, char uplo, char trans, char diag, int n, const T* A, int64_t lda, T* x, int64_t incx) {
+    DeviceBackend be(s);
+    plan_tri<T>(be, K_FULL_TRI, true, false, uplo == 'U', trans, diag == 'U', n, 0, A, lda, x, incx);
+}
+template void trsv_struct_dev<float>(cudaStream_t, char, char, char, int, const float*, int64_t, float*, int64_t);
+template void trsv_struct_dev<double>(cudaStream_t, char, char, char, int, const double*, int64_t, double*, int64_t);
+template void trsv_struct_dev<cuFloatComplex>(cudaStream_t, char, char, char, int, const cuFloatComplex*, int64_t, cuFloatComplex*, int64_t);
+template void trsv_struct_dev<cuDoubleComplex>(cudaStream_t, char, char, char, int, const cuDoubleComplex*, int64_t, cuDoubleComplex*, int64_t);
+
 }  // namespace b200
 
 using namespace b200;
