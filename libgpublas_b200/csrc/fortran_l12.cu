@@ -130,9 +130,11 @@ void trsv_entry(const char* name, const char* uplo, const char* trans, const cha
     VecOperand ox(x, *n, *incx, sizeof(T), ACC_INOUT);
     const char u = lsame(uplo, 'U') ? 'U' : 'L', t = lsame(trans, 'N') ? 'N' : (lsame(trans, 'T') ? 'T' : 'C'), d = lsame(diag, 'U') ? 'U' : 'N';
     // netlib: with a negative increment, element i lives at x[(n-1-i)*|incx|]
-    // B200BLAS_TRSV_STRUCT: 1 = always the panel solver of level2_struct.cu, 0 = never; default: from n = 4096 (measured, profiles/)
+    // The panel solver of level2_struct.cu (32-wide diagonal blocks staged ahead of the dependency chain, one CTA per 256-column
+    // panel) against this file's diagonal kernel + GEMV update per 64 columns: 0.33 vs 0.73 ms at n = 2048, 1.96 vs 3.54 at 8192,
+    // 8.1 vs 16.3 at 32768 (profiles/r02y7_trsv_panel_solver.txt).  B200BLAS_TRSV_STRUCT=0/1 forces one or the other.
     static const int st_env = getenv("B200BLAS_TRSV_STRUCT") ? atoi(getenv("B200BLAS_TRSV_STRUCT")) : -1;
-    const bool panel = st_env >= 0 ? st_env != 0 : false;
+    const bool panel = st_env >= 0 ? st_env != 0 : *n >= 512;
     if (panel) trsv_struct_dev<T>(current_stream(), u, t, d, *n, (const T*)oa.dev(), oa.ld(), (T*)ox.dev(), *incx);
     else trsv_dev<T>(current_stream(), u, t, d, *n, (const T*)oa.dev(), oa.ld(), (T*)ox.dev(), *incx);
     ox.release();
