@@ -395,7 +395,30 @@ def other_routines(g, torch, dev, peaks, out):
         ms = timed(lambda: g.call("dtpmv_", "U", tr, "N", npk, ap, xp, 1))
         gbs = 8.0 * npk * (npk + 1) / 2 / ms / 1e6
         out["dtpmv_U%s_32768" % tr] = {"gbs": gbs, "ms": ms, "frac_of_measured_hbm": gbs / hbm}
-    del ap, xp
+    # symmetric / Hermitian products in one pass over the stored triangle (level2_struct.cu: sympart_kernel), the packed solve
+    try:
+        yp = torch.zeros(npk, dtype=torch.float64, device=dev)
+        for ul in "UL":
+            ms = timed(lambda: g.call("dspmv_", ul, npk, 1.0, ap, xp, 1, 0.0, yp, 1))
+            gbs = 8.0 * npk * (npk + 1) / 2 / ms / 1e6
+            out["dspmv_%s_32768" % ul] = {"gbs": gbs, "ms": ms, "frac_of_measured_hbm": gbs / hbm}
+        idx = torch.arange(npk, device=dev, dtype=torch.int64)
+        ap[idx * (idx + 1) // 2 + idx] = 2.0                     # diagonal of the packed upper triangle: a well-conditioned solve
+        xp.fill_(1.0)
+        ms = timed(lambda: g.call("dtpsv_", "U", "T", "N", npk, ap, xp, 1), reps=3, warm=1)
+        out["dtpsv_UT_32768"] = {"ms": ms, "gbs": 8.0 * npk * (npk + 1) / 2 / ms / 1e6, "note": "latency-bound: 1024 dependent 32-blocks"}
+        del ap, xp, yp, idx
+        Sf = torch.rand((npk, npk), dtype=torch.float64, device=dev) * (1.0 / npk); Sf.diagonal().fill_(2.0)
+        sx = torch.rand(npk, dtype=torch.float64, device=dev); sy = torch.zeros(npk, dtype=torch.float64, device=dev)
+        ms = timed(lambda: g.call("dsymv_", "U", npk, 1.0, Sf, npk, sx, 1, 0.0, sy, 1))
+        gbs = 8.0 * npk * (npk + 1) / 2 / ms / 1e6
+        out["dsymv_U_32768"] = {"gbs": gbs, "ms": ms, "frac_of_measured_hbm": gbs / hbm}
+        sx.fill_(1.0)
+        ms = timed(lambda: g.call("dtrsv_", "L", "N", "N", npk, Sf, npk, sx, 1), reps=3, warm=1)
+        out["dtrsv_LN_32768"] = {"ms": ms, "gbs": 8.0 * npk * (npk + 1) / 2 / ms / 1e6, "note": "latency-bound: 1024 dependent 32-blocks (panel solver)"}
+        del Sf, sx, sy
+    except Exception as exc:
+        out["level2_sym_error"] = repr(exc)
     return out
 
 
