@@ -178,17 +178,10 @@ __global__ void __launch_bounds__(COL_WARPS * 32) solve_tupdate_kernel(Desc D, c
     const T acc = warp_sum(tpart_lane<T>(D, A, x, j, lane, 32, b0, b1, flags));
     if (lane == 0) x[j] = el<T>::sub(x[j], acc);
 }
-// One warp solves the nb <= 32 unknowns of a diagonal block of op(S): lane l owns x(b0+l).  The lane's row of
-// coefficients is loaded up front (independent loads, one memory latency) in elimination order together with the
-// reciprocal of its pivot; each step scales on the pivot lane, broadcasts the solved unknown by shuffle and eliminates it
-// from the lanes still waiting.  (x * (1/d) instead of x / d: one FP64 division per lane off the critical path instead
-// of 32 in sequence; within the solves' stated tolerance.)
-// Split in two so that a block's coefficient loads can be in flight while the block before it is being solved:
-//   diag_load   addresses and loads only (nothing here consumes a loaded value).  Every load is unconditional (a lane with
-//               nothing to fetch re-reads its own diagonal element, which always exists), so the 32 loads issue back to back;
-//               behind a branch each one waited for the previous (32 memory latencies per block: 30 us, the whole cost of the
-//               first version -- profiles/r01f_level2_struct_perf_v2.txt).
-//   diag_solve  conjugate, mask, pivot reciprocal, then the 32 elimination steps.
+// ---- triangular panel solve ----
+// One warp solves the nb <= 32 unknowns of a diagonal block of op(S): lane l owns x(b0+l); each step broadcasts the solved
+// unknown by shuffle and eliminates it from the lanes still waiting (x * (1/d) instead of x / d: one FP64 division per lane off
+// the critical path instead of 32 in sequence; within the solves' stated tolerance).  See solve_panel_kernel.
 // Row r of op(S) over the columns of one diagonal block: the stored range [lo, hi) of c and the address of element (r, c) as an
 // affine walk from c = b0 (packed rows of the untransposed triangle: the closed form).  The generic stored() / off() pair costs a
 // switch and 64-bit multiplies per ELEMENT; written per element in four fully unrolled 32-step loops it made this kernel 20 600
@@ -209,69 +202,6 @@ __device__ __forceinline__ OpRow op_row(const Desc& D, int r, int b0, bool trans
 template <bool PACKED_ROW> __device__ __forceinline__ int64_t op_row_addr(const OpRow& w, int b0, int c) {
     if (PACKED_ROW) return (int64_t)w.r + (w.up ? (int64_t)c * ((int64_t)c + 1) / 2 : (int64_t)c * (2 * (int64_t)w.n - c - 1) / 2);
     return w.a0 + (int64_t)(c - b0) * w.cs;
-}
-// Split in two so that a block's coefficient loads can be in flight while the block before it is being solved:
-//   diag_load   addresses and loads only (nothing here consumes a loaded value).  Every load is unconditional (a lane with
-//               nothing to fetch re-reads its own diagonal element, which always exists), so the 32 loads issue back to back;
-//               behind a branch each one waited for the previous (32 memory latencies per block: 30 us, the whole cost of the
-//               first version -- profiles/r01f_level2_struct_perf_v2.txt).
-//   diag_solve  conjugate, mask, pivot reciprocal, then the 32 elimination steps.
-template <typename T>
-__device__ __forceinline__ void diag_load(const Desc& D, const T* __restrict__ A, int b0, int nb, bool trans, bool unit, bool forward, T (&coef)[32], unsigned& okmask) {
-    const int lane = threadIdx.x & 31, r = b0 + lane;
-    const OpRow w = op_row(D, r, b0, trans);
-    const int64_t safe = off(D, w.r, w.r);
-    okmask = 0;
-    auto body = [&](auto packed_tag) {
-#pragma unroll
-        for (int step = 0; step < 32; step++) {
-            const int jj = forward ? step : nb - 1 - step;
-            const int c = b0 + jj;
-            const bool waiting = forward ? lane > jj : lane < jj;
-            const bool ok = step < nb && lane < nb && (waiting || (lane == jj && !unit)) && c >= w.lo && c < w.hi;
-            coef[step] = A[ok ? op_row_addr<decltype(packed_tag)::value>(w, b0, c) : safe];
-            okmask |= (ok ? 1u : 0u) << step;
-        }
-    };
-    if (w.packed_row) body(std::true_type{}); else body(std::false_type{});     // (uniform: the closed form stays out of the common loop)
-}
-// xs (shared memory, may be null): the block's solved unknowns for the CTA's update phase
-template <typename T>
-__device__ __forceinline__ void diag_solve(T (&coef)[32], unsigned okmask, T* x, T* xs, int b0, int nb, bool conj, bool unit, bool forward) {
-    const int lane = threadIdx.x & 31, r = b0 + lane;
-    T piv = el<T>::one();
-#pragma unroll
-    for (int step = 0; step < 32; step++) {
-        const int jj = forward ? step : nb - 1 - step;
-        const bool ok = (okmask >> step) & 1u;
-        T a = coef[step];
-        if (conj) a = el<T>::conj(a);
-        coef[step] = (ok && lane != jj) ? a : el<T>::zero();
-        piv = (ok && lane == jj) ? a : piv;              // a select: the division must not sit inside this loop (see below)
-    }
-    // ONE division per lane, all lanes at once.  (It used to be written inside the loop above under `lane == jj`: a divergent
-    // branch taken by one lane per step, i.e. 32 FP64 division sequences one after the other -- ~8 us of the 16 us a block took.)
-    const T dinv = el<T>::div(el<T>::one(), piv);
-    T xv = lane < nb ? x[r] : el<T>::zero();
-#pragma unroll
-    for (int step = 0; step < 32; step++) {
-        if (step < nb) {   // uniform across the warp
-            const int jj = forward ? step : nb - 1 - step;
-            if (lane == jj && !unit) xv = el<T>::mul(xv, dinv);
-            const T xj = warp_bcast(xv, jj);
-            const bool waiting = forward ? (lane > jj && lane < nb) : lane < jj;
-            if (waiting) xv = el<T>::sub(xv, el<T>::mul(coef[step], xj));
-        }
-    }
-    if (lane < nb) x[r] = xv;
-    if (xs) xs[lane] = lane < nb ? xv : el<T>::zero();
-}
-template <typename T>
-__device__ __forceinline__ void solve_diag_warp(const Desc& D, const T* __restrict__ A, T* x, int b0, int nb, bool trans, bool conj, bool unit, bool forward) {
-    T coef[32];
-    unsigned okmask;
-    diag_load<T>(D, A, b0, nb, trans, unit, forward, coef, okmask);
-    diag_solve<T>(coef, okmask, x, (T*)nullptr, b0, nb, conj, unit, forward);
 }
 // (the rarely taken plain path, kept out of line: its inlined N / T bodies are thousands of instructions)
 template <typename T> __device__ __noinline__ T panel_update_call(const Desc& D, const T* A, const T* x, int r, int b0, int b1, bool trans, int flags) {
