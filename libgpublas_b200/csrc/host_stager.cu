@@ -140,10 +140,11 @@ void staged_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, si
     stager_init();
     if (width > kSlotBytes) {      // a single row larger than a slot (a flat vector copy): re-shape it into slot-sized rows
         const size_t chunk = kSlotBytes;
+        size_t turn = 0;
         for (size_t r = 0; r < height; r++)
-            for (size_t off = 0; off < width; off += chunk) {
+            for (size_t off = 0; off < width; off += chunk, turn++) {
                 const size_t w = std::min(chunk, width - off);
-                const int i = 0;
+                const int i = (int)(turn % kSlots);          // the slots take turns: chunk c+1 is packed while chunk c is on the wire
                 if (st.busy[i]) { B200_CUDA(cudaEventSynchronize(st.ev[i])); st.busy[i] = false; }
                 char* d = (char*)dst + r * dpitch + off; const char* s = (const char*)src + r * spitch + off;
                 if (to_device) {

@@ -233,7 +233,7 @@ MgStats g_mg_stats = {0, 0, 0, 0, 0};
 // B200BLAS_MG_TRACE=1: host-side timeline of one partitioned call (when each hop landed, when each device's kernel could start
 // and when it finished), from polling the events -- ~20 us resolution, debugging only.
 namespace {
-struct TraceItem { char label[48]; cudaEvent_t ev; double t_ms; };
+struct TraceItem { char label[80]; cudaEvent_t ev; double t_ms; };
 double now_ms() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 void trace_poll(std::vector<TraceItem>& items, double t0) {
     size_t left = items.size();
