@@ -389,27 +389,38 @@ ST_UNROLL
     for (int u = 1; u < NU; u++) r = el<T>::add(r, acc[u]);
     return r;
 }
-// out(j) = alpha*(N partials + mirrored partials of the row blocks that hold stored rows of column j) + beta*old
-template <typename T>
-ST_HD T sym_finish_elem(const Desc& D, int j, int nparts, const T* part, int64_t npad, const T* tp2, int64_t npadw, T alpha, T beta, bool beta0, T old) {
-    T s = el<T>::zero();
-    for (int c = 0; c < nparts; c++) s = el<T>::add(s, part[(int64_t)c * npad + j]);
-    int i0, i1;
-    col_rows(D, j, i0, i1);
-    // four independent partial sums (fixed order): a column of a full triangle collects up to n / ROW_THREADS values, and one
-    // dependent chain of loads per thread left this pass latency-bound (63 us for n = 32768, 7 % of the product)
+// sum over the row blocks [rb0, rb1] of their mirrored partial for column j: four independent chains in a fixed order (one chain of
+// dependent loads per thread left the finish pass latency-bound)
+template <typename T> ST_HD T sym_tp2_sum(const Desc& D, int j, const T* tp2, int64_t npadw, int rb0, int rb1) {
     T q0 = el<T>::zero(), q1 = q0, q2 = q0, q3 = q0;
-    const int rb_lo = i0 / ROW_THREADS, rb_hi = (i1 - 1) / ROW_THREADS;
     auto at = [&](int rb) { return tp2[(int64_t)rb * npadw + (j - sym_jw0(D, rb * ROW_THREADS))]; };
-    int rb = rb_lo;
-    for (; rb + 3 <= rb_hi; rb += 4) {
+    int rb = rb0;
+    for (; rb + 3 <= rb1; rb += 4) {
         const T x0 = at(rb), x1 = at(rb + 1), x2 = at(rb + 2), x3 = at(rb + 3);
         q0 = el<T>::add(q0, x0); q1 = el<T>::add(q1, x1); q2 = el<T>::add(q2, x2); q3 = el<T>::add(q3, x3);
     }
-    for (; rb <= rb_hi; rb++) q0 = el<T>::add(q0, at(rb));
-    s = el<T>::add(s, el<T>::add(el<T>::add(q0, q1), el<T>::add(q2, q3)));
-    s = el<T>::mul(alpha, s);
+    for (; rb <= rb1; rb++) q0 = el<T>::add(q0, at(rb));
+    return el<T>::add(el<T>::add(q0, q1), el<T>::add(q2, q3));
+}
+// the row blocks that hold stored rows of column j
+ST_HD void sym_col_blocks(const Desc& D, int j, int& rb_lo, int& rb_hi) {
+    int i0, i1;
+    col_rows(D, j, i0, i1);
+    rb_lo = i0 / ROW_THREADS; rb_hi = (i1 - 1) / ROW_THREADS;
+}
+// out(j) = alpha*(N partials + mirrored) + beta*old
+template <typename T>
+ST_HD T sym_finish_value(int j, int nparts, const T* part, int64_t npad, T mirrored, T alpha, T beta, bool beta0, T old) {
+    T s = el<T>::zero();
+    for (int c = 0; c < nparts; c++) s = el<T>::add(s, part[(int64_t)c * npad + j]);
+    s = el<T>::mul(alpha, el<T>::add(s, mirrored));
     return beta0 ? s : el<T>::mad(beta, old, s);
+}
+template <typename T>
+ST_HD T sym_finish_elem(const Desc& D, int j, int nparts, const T* part, int64_t npad, const T* tp2, int64_t npadw, T alpha, T beta, bool beta0, T old) {
+    int rb_lo, rb_hi;
+    sym_col_blocks(D, j, rb_lo, rb_hi);
+    return sym_finish_value<T>(j, nparts, part, npad, sym_tp2_sum<T>(D, j, tp2, npadw, rb_lo, rb_hi), alpha, beta, beta0, old);
 }
 
 // out = alpha*(sum of the partial rows + tpart + vunit) + beta*old   (beta == 0: old is never read, like netlib)
