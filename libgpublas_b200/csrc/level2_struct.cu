@@ -145,13 +145,13 @@ template <typename T>
 __global__ void __launch_bounds__(FIN_COLS * FIN_SPLIT) sym_finish_kernel(Desc D, int nparts, const T* __restrict__ part, int64_t npad, const T* __restrict__ tp2, int64_t npadw,
                                                                             T alpha, T beta, T* __restrict__ out, int64_t inco) {
     __shared__ T quarter[FIN_SPLIT][FIN_COLS];
-    const int c = threadIdx.x % FIN_COLS, g = threadIdx.x / FIN_COLS;
+    const int c = threadIdx.x % FIN_COLS, g = threadIdx.x / FIN_COLS, split = blockDim.x / FIN_COLS;   // bands launch with split = 1
     const int j = blockIdx.x * FIN_COLS + c;
     T q = el<T>::zero();
     if (j < D.n) {
         int rb_lo, rb_hi;
         sym_col_blocks(D, j, rb_lo, rb_hi);
-        const int cnt = rb_hi - rb_lo + 1, per = (cnt + FIN_SPLIT - 1) / FIN_SPLIT;
+        const int cnt = rb_hi - rb_lo + 1, per = (cnt + split - 1) / split;
         const int r0 = rb_lo + g * per, r1 = st_min(rb_hi, r0 + per - 1);
         if (r0 <= r1) q = sym_tp2_sum<T>(D, j, tp2, npadw, r0, r1);
     }
@@ -159,8 +159,7 @@ __global__ void __launch_bounds__(FIN_COLS * FIN_SPLIT) sym_finish_kernel(Desc D
     __syncthreads();
     if (g == 0 && j < D.n) {
         T m = quarter[0][c];
-#pragma unroll
-        for (int t = 1; t < FIN_SPLIT; t++) m = el<T>::add(m, quarter[t][c]);
+        for (int t = 1; t < split; t++) m = el<T>::add(m, quarter[t][c]);
         T* p = out + vpos(j, D.n, inco);
         const bool beta0 = el<T>::is_zero(beta);
         *p = sym_finish_value<T>(j, nparts, part, npad, m, alpha, beta, beta0, beta0 ? el<T>::zero() : *p);
@@ -400,7 +399,9 @@ struct DeviceBackend {
         else sympart_kernel<T, 5><<<grid, ROW_THREADS, smem, s>>>(D, A, v, cpc, nflags, tflags, part, npad, tp2, npadw, wstride);
     }
     template <typename T> void sym_finish(const Desc& D, int nparts, const T* part, int64_t npad, const T* tp2, int64_t npadw, T alpha, T beta, T* out, int64_t inco) {
-        sym_finish_kernel<T><<<(D.n + FIN_COLS - 1) / FIN_COLS, FIN_COLS * FIN_SPLIT, 0, s>>>(D, nparts, part, npad, tp2, npadw, alpha, beta, out, inco);
+        // a band column collects at most (k + 128) / 128 + 1 row blocks: one thread per column (the split cost 2.5 % there)
+        const int split = D.kind == K_BAND_TRI ? 1 : FIN_SPLIT;
+        sym_finish_kernel<T><<<(D.n + FIN_COLS - 1) / FIN_COLS, FIN_COLS * split, 0, s>>>(D, nparts, part, npad, tp2, npadw, alpha, beta, out, inco);
         last_variant = VAR_GENERIC_TILE;
     }
     template <typename T> void rank(const Desc& D, T* A, int rows, int ncols, int cpc, int nchunks, T alpha, const T* x, const T* y, int mode) {
