@@ -76,6 +76,10 @@ __host__ __device__ __forceinline__ bool tri_keep(int mask, int64_t i, int64_t j
     return mask == MASK_FULL || (mask == MASK_LOWER ? i >= j : i <= j);
 }
 
+static inline int op_code(char t) { return (t == 'N' || t == 'n') ? 0 : ((t == 'T' || t == 't') ? 1 : 2); }
+
+#ifdef __CUDACC__      // kernels and their launchers: nvcc only (the multi-device drivers that include this header for num<T> are
+                       // also compiled by g++ against a stream simulator, tests/drivers/mgsim.cpp)
 // C := beta*C over the masked region (the alpha==0 / k==0 quick path of netlib xGEMM/xSYRK, which the
 // reference runs as a HOST loop over managed memory, gemm.cc:118-125 -- here it stays on the GPU).
 template <typename T>
@@ -174,8 +178,6 @@ __global__ void __launch_bounds__(256) gemm_generic_kernel(int m, int n, int k, 
     }
 }
 
-static inline int op_code(char t) { return (t == 'N' || t == 'n') ? 0 : ((t == 'T' || t == 't') ? 1 : 2); }
-
 template <typename T>
 void gemm_generic_launch(cudaStream_t s, char ta, char tb, int m, int n, int k, T alpha, const T* A, int64_t lda,
                          const T* B, int64_t ldb, T beta, T* C, int64_t ldc, int mask, const int* gate = nullptr) {
@@ -197,5 +199,6 @@ void gemm_generic_launch(cudaStream_t s, char ta, char tb, int m, int n, int k, 
 #undef B200_GG
     last_variant = VAR_GENERIC_TILE;
 }
+#endif  // __CUDACC__
 
 }  // namespace b200
