@@ -374,7 +374,7 @@ def test_multi_device_drivers_under_the_stream_simulator(tmp_path):
     exe = os.path.join(build, "mgsim")
     csrc = os.path.join(ROOT, "libgpublas_b200", "csrc")
     srcs = [os.path.join(drv, "mgsim.cpp"), os.path.join(csrc, "multi_gemm.cu"), os.path.join(csrc, "multi_level3.cu")]
-    deps = srcs + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".h", ".cuh"))]
+    deps = srcs + [os.path.join(drv, "simcuda.inc")] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".h", ".cuh"))]
     if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-Wall", "-I/usr/local/cuda/include", "-o", exe, srcs[0], "-x", "c++", srcs[1], srcs[2], "-ldl", "-lpthread"])
     env = dict(os.environ, MGSIM_OPENBLAS=ob, OPENBLAS_CORETYPE="SkylakeX", OPENBLAS_NUM_THREADS=str(min(8, os.cpu_count() or 1)))
