@@ -51,9 +51,14 @@ static void fill(std::vector<double>& v, double scale = 1.0) {      // xorshift6
 }
 // a buffer in "device" memory (cudaMalloc: classified as device-resident) or host memory declared pinned / left pageable
 struct Buf {
-    double* p = nullptr; size_t n = 0; int where = 0;      // 0 device, 1 pinned host, 2 pageable host
+    double* p = nullptr; size_t n = 0; int where = 0;      // 0 device, 1 pinned host, 2 pageable host, 3 tracked managed
     Buf(const std::vector<double>& src, int where_) : n(src.size()), where(where_) {
-        if (where == 0) { cudaMalloc((void**)&p, n * 8); } else { p = (double*)malloc(n * 8); if (where == 1) sim::registered[(const char*)p] = {n * 8, (int)b200::RES_HOST_PINNED}; }
+        if (where == 0) { cudaMalloc((void**)&p, n * 8); }
+        else {
+            p = (double*)malloc(n * 8);
+            if (where == 1) sim::registered[(const char*)p] = {n * 8, (int)b200::RES_HOST_PINNED};
+            if (where == 3) sim::registered[(const char*)p] = {n * 8, (int)b200::RES_MANAGED};
+        }
         memcpy(p, src.data(), n * 8);
     }
     ~Buf() { sim::run_all(); if (where == 0) cudaFree(p); else { sim::registered.erase((const char*)p); free(p); } }
@@ -68,7 +73,7 @@ static void verdict(const char* what, int ndev, int where, double err, double to
     g_cases++;
     const bool ok = partitioned && err <= tol && sim::deadlocks == 0;
     if (!ok) g_fail++;
-    printf("%s %-28s devices=%d operands=%s policy=%d err=%.3e tol=%.1e%s\n", ok ? "ok  " : "FAIL", what, ndev, where == 0 ? "device" : (where == 1 ? "pinned" : "pageable"), sim::policy, err,
+    printf("%s %-28s devices=%d operands=%s policy=%d err=%.3e tol=%.1e%s\n", ok ? "ok  " : "FAIL", what, ndev, where == 0 ? "device" : (where == 1 ? "pinned" : (where == 2 ? "pageable" : "managed")), sim::policy, err,
            tol, partitioned ? "" : " (NOT PARTITIONED)");
     sim::deadlocks = 0;
 }
@@ -156,14 +161,14 @@ int main(int argc, char** argv) {
             sim::rng.seed(1000 + 17 * nd + pol);
             case_gemm(nd, 'N', 'N', 0);
             case_gemm(nd, 'T', 'N', pol & 1 ? 1 : 2);
-            if (pol == 0) case_gemm(nd, 'N', 'T', 1);
+            if (pol == 0) { case_gemm(nd, 'N', 'T', 1); case_gemm(nd, 'T', 'T', 3); }
             case_syrk(nd, 'L', 'N', 1.3, 0);
             case_syrk(nd, 'U', 'T', 0.0, pol & 1 ? 2 : 1);
-            if (pol == 0) { case_syrk(nd, 'U', 'N', 1.3, 0); case_syrk(nd, 'L', 'T', 0.0, 1); }
+            if (pol == 0) { case_syrk(nd, 'U', 'N', 1.3, 0); case_syrk(nd, 'L', 'T', 0.0, 1); case_syrk(nd, 'L', 'N', 0.0, 3); }
             case_trxm(nd, true, 'L', 'L', 'N', 0);
             case_trxm(nd, true, 'R', 'U', 'T', pol & 1 ? 1 : 2);
             case_trxm(nd, false, 'L', 'U', 'N', pol & 1 ? 0 : 1);
-            if (pol == 0) case_trxm(nd, false, 'R', 'L', 'T', 0);
+            if (pol == 0) { case_trxm(nd, false, 'R', 'L', 'T', 0); case_trxm(nd, true, 'L', 'U', 'T', 3); }
             case_cholesky(nd, 128);
             if (pol == 0) case_cholesky(nd, 256);
         }

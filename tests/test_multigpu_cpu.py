@@ -387,5 +387,5 @@ def test_multi_device_drivers_under_the_stream_simulator(tmp_path):
     assert "DEADLOCK" not in out.stderr
     # every device count, every routine, the three residencies were exercised
     for needle in ("devices=2", "devices=3", "devices=4", "devices=6", "devices=8", "dgemm NN", "dsyrk LN", "dtrsm LLNN", "dtrmm LUNN", "cholesky",
-                   "operands=device", "operands=pinned", "operands=pageable", "policy=1", "policy=2"):
+                   "operands=device", "operands=pinned", "operands=pageable", "operands=managed", "policy=1", "policy=2"):
         assert needle in out.stdout, needle
